@@ -67,9 +67,147 @@ int b200seg_conv2d_fwd_direct(const b200seg_conv_desc* d, const void* x, const v
 
 /* Repack fp32 OIHW master weights (the nn.Parameter layout the reference checkpoints use) into the kernel layouts:
  *   w_ohwi  bf16 [O][kh*kw][I]            forward operand
- *   w_dgrad bf16 [I][kh*kw (flipped)][O]  data-gradient operand (may be NULL) */
+ *   w_dgrad bf16 [I][kh*kw (flipped)][o_pad]  data-gradient operand (may be NULL); o_pad >= O is a multiple of 8 and
+ *           the pad columns must have been zeroed by the caller once (they are never written). */
 int b200seg_pack_weight(const float* w_oihw, int32_t o, int32_t i, int32_t ksize, void* w_ohwi, void* w_dgrad,
+                        int32_t o_pad, void* stream);
+
+/* Data gradient: dx[n,h,w,cin] = conv_transpose(dy, W) (+ addend, e.g. a gradient that already arrived at x).
+ * d describes the FORWARD convolution; dy: bf16 [n,ho,wo,*] whose channel extent is roundup8(cout) (pad channels
+ * zero); w_dgrad from b200seg_pack_weight with o_pad = roundup8(cout). Stride-2 convolutions run as four parity-class
+ * launches of the same tcgen05 kernel. Replaces cuDNN convolution_backward (input part). */
+int b200seg_conv2d_dgrad(const b200seg_conv_desc* d, const void* dy, int32_t dy_ld, const void* w_dgrad,
+                         const void* addend, int32_t addend_ld, void* dx, int32_t dx_ld, void* stream);
+
+
+/* Weight gradient: dw_oihw[co][ci][kh][kw] (fp32, the nn.Parameter .grad layout) += sum_pixels dy * x_shifted.
+ * d describes the FORWARD convolution (input geometry, stride, pad); dy is bf16 NHWC [n,ho,wo,cout] with pitch dy_ld.
+ * cin multiple of 16. Accumulates with red.global (zero the buffer once per optimizer step). */
+int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, int32_t dy_ld, float* dw_oihw,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm around the convolutions. Replaces cuDNN/Apex BN behind Norm2d (network/mynn.py:18-24),
+ * in-place ReLU (network/hrnetv2.py:28,44) and the residual add (network/hrnetv2.py:63-64,103-104).
+ * ------------------------------------------------------------------------------------------------ */
+/* partials[grid][2][cpad] (conv epilogue) -> scale = gamma*invstd, shift = beta - mean*scale, saved mean/invstd;
+ * running stats updated with `momentum` (unbiased variance), num_batches_tracked += 1 (all optional). */
+int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t c, int32_t cpad, float count, const float* gamma,
+                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                        int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
                         void* stream);
+/* eval mode: scale/shift from running statistics */
+int b200seg_bn_eval_params(int32_t c, const float* gamma, const float* beta, float eps, const float* running_mean,
+                           const float* running_var, float* scale, float* shift, void* stream);
+/* z = relu?(y*scale + shift [+ res]) [* post_scale[n][c]]   (post_scale carries the Dropout2d mask/(1-p),
+ * network/ocr_utils.py:146). npix = n*h*w, hw = h*w. */
+int b200seg_bn_apply(const void* y, int32_t y_ld, const float* scale, const float* shift, const void* res,
+                     int32_t res_ld, const float* post_scale, int32_t relu, void* z, int32_t z_ld, int64_t npix,
+                     int32_t hw, int32_t c, void* stream);
+/* backward: g = dz * post_scale * (mask > 0); partials[grid][2][c] of (sum g, sum g*xhat), grid from _bn_bwd_grid */
+int32_t b200seg_bn_bwd_grid(int64_t npix, int32_t c);
+int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld, const float* post_scale,
+                          const void* y, int32_t y_ld, const float* mean, const float* invstd, int64_t npix, int32_t hw,
+                          int32_t c, float* partials, void* stream);
+/* dgamma += sum g*xhat, dbeta += sum g (accumulating), c1 = sum g / count, c2 = sum g*xhat / count */
+int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int32_t c, float count, float* dgamma, float* dbeta,
+                            float* c1, float* c2, void* stream);
+/* dy = gamma*invstd*(g - c1 - xhat*c2); optionally g_out (=|+=) g for the residual / identity branch */
+int b200seg_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld, const float* post_scale,
+                         const void* y, int32_t y_ld, const float* mean, const float* invstd, const float* gamma,
+                         const float* c1, const float* c2, void* dy, int32_t dy_ld, void* g_out, int32_t g_ld,
+                         int32_t g_accumulate, int64_t npix, int32_t hw, int32_t c, void* stream);
+/* dst (=|+=) src * (mask > 0) */
+int b200seg_masked_accum(const void* src, int32_t src_ld, const void* mask, int32_t mask_ld, void* dst, int32_t dst_ld,
+                         int32_t accumulate, int64_t npix, int32_t c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-resolution fuse / upsample+concat / their adjoint / image preparation.
+ * Replaces F.interpolate + add + ReLU chains at network/hrnetv2.py:230-254,438-447 and ResizeX (network/mynn.py:102-114).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200seg_fuse_term {
+  const void* x;        /* bf16 NHWC [n, h, w, c] */
+  const float* scale;   /* optional per-channel affine (BN folded), both or neither */
+  const float* shift;
+  int32_t ld, h, w;
+  int32_t reserved;
+} b200seg_fuse_term;
+typedef struct b200seg_fuse_desc {
+  b200seg_fuse_term term[4];
+  int32_t nterms;
+  int32_t n, h, w, c;   /* output geometry */
+  int32_t relu;
+  int32_t reserved[2];
+} b200seg_fuse_desc;
+/* out[n,Y,X,:] = relu?( sum_j affine_j( bilinear_j(x_j)[Y,X,:] ) ), summed in term order */
+int b200seg_fuse_fwd(const b200seg_fuse_desc* d, void* out, int32_t out_ld, void* stream);
+/* out[n,y,x,:] (=|+=) sum_{Y,X} w(Y,y) w(X,x) g[n,Y,X,:] * (mask>0): adjoint of the align_corners=False bilinear upsample */
+int b200seg_upsample_adjoint(const void* g, int32_t g_ld, const void* mask, int32_t mask_ld, int32_t n, int32_t H,
+                             int32_t W, int32_t c, void* out, int32_t out_ld, int32_t h, int32_t w, int32_t accumulate,
+                             void* stream);
+/* fp32 NCHW [n,3,H,W] -> bf16 NHWC [n,h,w,16] (zero padded channels), bilinear resize to (h,w) */
+int b200seg_image_prep(const float* img_nchw, int32_t n, int32_t H, int32_t W, void* out_nhwc16, int32_t h, int32_t w,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * OCR glue: softmaxes around the skinny GEMMs of SpatialGather (network/ocr_utils.py:34-46) and
+ * ObjectAttentionBlock (network/ocr_utils.py:95-119). The GEMMs themselves run on b200seg_conv2d_fwd /
+ * b200seg_conv2d_wgrad with the class dimension padded to a 32-wide bf16 operand.
+ * ------------------------------------------------------------------------------------------------ */
+int32_t b200seg_spatial_softmax_blocks(int32_t P);   /* partial_ws needs n * blocks * 32 * 2 floats */
+/* probs[n][pix][k<32] = softmax over the P pixels of logits[n][pix][k] (fp32, pitch ld); k >= K -> 0 */
+int b200seg_spatial_softmax_fwd(const float* logits, int32_t ld, int32_t n, int32_t P, int32_t K, float* partial_ws,
+                                void* probs_bf16, float* stat_out, void* stream);
+/* dlogit[n][pix][k<32] (bf16, =|+=) probs * (dprobs - sum_pix probs*dprobs) */
+int b200seg_spatial_softmax_bwd(const float* dprobs, int32_t ldd, const void* probs_bf16, int32_t n, int32_t P, int32_t K,
+                                float* partial_ws, void* dlogit_bf16, int32_t accumulate, void* stream);
+/* sim[pix][k<32] = softmax_k(scale * x[pix][k]); ds = scale * sim * (dsim - <sim, dsim>) */
+int b200seg_class_softmax_fwd(const float* x, int32_t ld, int64_t P, int32_t K, float scale, void* sim_bf16, void* stream);
+int b200seg_class_softmax_bwd(const float* dsim, int32_t ld, const void* sim_bf16, int64_t P, int32_t K, float scale,
+                              void* ds_bf16, void* stream);
+/* dst[c][r] (bf16, pitch rpad, zero padded) = src[r][c]; src is bf16 or fp32 with pitch ld */
+int b200seg_transpose_pad(const void* src, int32_t src_fp32, int32_t R, int32_t C, int32_t ld, void* dst_bf16, int32_t rpad,
+                          void* stream);
+/* dst bf16 [rows][dst_ld] (=|+=) src fp32 [rows][src_ld], first C columns */
+int b200seg_cast_rows(const float* src, int32_t src_ld, void* dst_bf16, int32_t dst_ld, int64_t rows, int32_t C,
+                      int32_t accumulate, void* stream);
+
+/* db[c] += sum_rows dy[row][c], c < C <= 32 (bias gradient of the logit heads, network/ocrnet.py:66-76) */
+int b200seg_bias_grad(const void* dy_bf16, int32_t ld, int64_t rows, int32_t C, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-scale attention blend + cross-entropy, forward and backward (network/ocrnet.py:170-183,264-319,
+ * network/mscale.py:182-220, loss/utils.py:133-134). Logit maps are fp32 [n][h][w][20] (19 classes + 1 pad),
+ * class-gradient outputs bf16 [pixels][32] (zero padded) ready for b200seg_conv2d_dgrad/_wgrad.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200seg_mscale_desc {
+  int32_t n, h, w;          /* labels / full resolution */
+  int32_t hq, wq;           /* hi-pass quarter-resolution maps */
+  int32_t hm, wm;           /* mid grid = lo-pass input size (0,0: single-scale, no lo pass) */
+  int32_t hl, wl;           /* lo-pass quarter-resolution maps */
+  int32_t nheads;           /* 1: cls only, 2: cls + aux */
+  float w_head0, w_head1;   /* loss weights (1.0, cfg.LOSS.OCR_ALPHA) */
+  float sup_wt;             /* cfg.LOSS.SUPERVISED_MSCALE_WT (0 disables) */
+  int32_t ignore_index;     /* 255 */
+  int32_t reserved[2];
+} b200seg_mscale_desc;
+/* counter_ws: one uint64; inv_count <- 1 / #(labels != ignore) */
+int b200seg_count_valid(const int64_t* labels, int64_t total, int32_t ignore_index, uint64_t* counter_ws,
+                        float* inv_count, void* stream);
+/* mid[n][hm][wm][40] fp32 (attn4*cls4, attn4*aux4, attn4, 0); mid_sup[n][hm][wm][20] = cls4 when sup_wt != 0 */
+int b200seg_mscale_mid_fwd(const b200seg_mscale_desc* d, const float* lo_cls, const float* lo_aux,
+                           const float* lo_attn_logit, float* mid, float* mid_sup, void* stream);
+int32_t b200seg_mscale_loss_blocks(const b200seg_mscale_desc* d);   /* partial_ws: blocks * 4 floats */
+/* loss_out[0] = total loss, [1..4] = mean NLL of {cls, aux, supervised lo, supervised hi};
+ * g_hi / g_lo / g_sup: bf16 [n*h*w][40] per-pixel gradients consumed by the two backward entry points below */
+int b200seg_mscale_loss_fwd(const b200seg_mscale_desc* d, const int64_t* labels, const float* inv_count,
+                            const float* hi_cls, const float* hi_aux, const float* mid, const float* mid_sup, void* g_hi,
+                            void* g_lo, void* g_sup, float* partial_ws, float* loss_out, void* stream);
+int b200seg_mscale_hi_bwd(const b200seg_mscale_desc* d, const void* g_hi, void* d_cls, void* d_aux, void* stream);
+/* dmid_ws: fp32 [n*hm*wm][40]; d_attn: bf16 [n*hl*wl][8] gradient w.r.t. the PRE-sigmoid attention logit */
+int b200seg_mscale_lo_bwd(const b200seg_mscale_desc* d, const void* g_lo, const void* g_sup, const float* lo_cls,
+                          const float* lo_aux, const float* lo_attn_logit, const float* mid, float* dmid_ws, void* d_cls,
+                          void* d_aux, void* d_attn, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,13 +44,62 @@ BN_MOMENTUM = 0.1          # hrnetv2.py:25 and torch default
 ALIGN_CORNERS = False      # config.py:127
 
 
-class Ctx:
-    """Execution context: the state dict, train/eval flag and the dropout policy."""
+class _RoundBF16(torch.autograd.Function):
+    """Round-trip through bf16 in forward AND backward: emulates a tensor (and its gradient) being stored in bf16."""
 
-    def __init__(self, sd, training=True, drop_mask_fn=None):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundGradBF16(torch.autograd.Function):
+    """Identity forward, bf16 round-trip of the gradient (fp32 logits whose gradients are stored in bf16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundFwdOnly(torch.autograd.Function):
+    """bf16 round-trip in forward, exact (fp32) gradient: conv weights are read as bf16, their gradients are fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class Ctx:
+    """Execution context: the state dict, train/eval flag and the dropout policy.
+
+    ``emulate_bf16=False`` (default) is the reference algorithm in fp32, pinned by the golden vectors.
+    ``emulate_bf16=True`` additionally rounds to bf16 at exactly the points where the B200 path stores bf16
+    (conv operands and outputs, activations after BN/ReLU/fuse, class-probability operands, activation gradients);
+    all arithmetic stays fp32. It is the matched-precision comparison target for end-to-end GPU tests, because an
+    fp32-vs-bf16 comparison of a randomly initialised 300-layer batch-stat-BN network is chaotic."""
+
+    def __init__(self, sd, training=True, drop_mask_fn=None, emulate_bf16=False):
         self.sd = sd
         self.training = training
         self.drop_mask_fn = drop_mask_fn   # callable(shape)->mask or None (None => dropout disabled, p=0 comparison mode)
+        self.emulate_bf16 = emulate_bf16
+
+    def q(self, x):
+        return _RoundBF16.apply(x) if self.emulate_bf16 else x
+
+    def qg(self, x):
+        return _RoundGradBF16.apply(x) if self.emulate_bf16 else x
 
 
 # ----------------------------------------------------------------------------------------------- primitives
@@ -58,6 +107,8 @@ def conv(ctx, name, x, stride=1, padding=0):
     """nn.Conv2d call sites, e.g. hrnetv2.py:31-34; bias present only where the reference leaves bias=True."""
     w = ctx.sd[name + ".weight"]
     b = ctx.sd.get(name + ".bias")
+    if ctx.emulate_bf16:
+        w = _RoundFwdOnly.apply(w)
     return F.conv2d(x, w, b, stride=stride, padding=padding)
 
 
@@ -85,20 +136,22 @@ def resize_x(x, scale):
 # ----------------------------------------------------------------------------------------------- HRNet backbone
 def basic_block(ctx, p, x):
     """hrnetv2.BasicBlock.forward (hrnetv2.py:50-66); HRNet branches never use a downsample here."""
-    out = F.relu(bn(ctx, p + ".bn1", conv(ctx, p + ".conv1", x, 1, 1)))
-    out = bn(ctx, p + ".bn2", conv(ctx, p + ".conv2", out, 1, 1))
-    return F.relu(out + x)
+    q = ctx.q
+    out = q(F.relu(bn(ctx, p + ".bn1", q(conv(ctx, p + ".conv1", x, 1, 1)))))
+    out = bn(ctx, p + ".bn2", q(conv(ctx, p + ".conv2", out, 1, 1)))
+    return q(F.relu(out + x))
 
 
 def bottleneck(ctx, p, x, has_downsample):
     """hrnetv2.Bottleneck.forward (hrnetv2.py:86-106), 1x1 -> 3x3 -> 1x1 (x4) with optional 1x1+BN residual."""
-    out = F.relu(bn(ctx, p + ".bn1", conv(ctx, p + ".conv1", x)))
-    out = F.relu(bn(ctx, p + ".bn2", conv(ctx, p + ".conv2", out, 1, 1)))
-    out = bn(ctx, p + ".bn3", conv(ctx, p + ".conv3", out))
+    q = ctx.q
+    out = q(F.relu(bn(ctx, p + ".bn1", q(conv(ctx, p + ".conv1", x)))))
+    out = q(F.relu(bn(ctx, p + ".bn2", q(conv(ctx, p + ".conv2", out, 1, 1)))))
+    out = bn(ctx, p + ".bn3", q(conv(ctx, p + ".conv3", out)))
     res = x
     if has_downsample:
-        res = bn(ctx, p + ".downsample.1", conv(ctx, p + ".downsample.0", x))
-    return F.relu(out + res)
+        res = bn(ctx, p + ".downsample.1", q(conv(ctx, p + ".downsample.0", x)))
+    return q(F.relu(out + res))
 
 
 def hr_module(ctx, p, xs, num_blocks):
@@ -116,23 +169,25 @@ def hr_module(ctx, p, xs, num_blocks):
             if j == i:
                 t = xs[j]
             elif j > i:
-                t = bn(ctx, fp + ".1", conv(ctx, fp + ".0", xs[j]))
+                t = bn(ctx, fp + ".1", ctx.q(conv(ctx, fp + ".0", xs[j])))
                 t = bilinear(t, xs[i].shape[-2:])
             else:
                 t = xs[j]
                 for k in range(i - j):
-                    t = bn(ctx, "%s.%d.1" % (fp, k), conv(ctx, "%s.%d.0" % (fp, k), t, 2, 1))
+                    t = bn(ctx, "%s.%d.1" % (fp, k), ctx.q(conv(ctx, "%s.%d.0" % (fp, k), t, 2, 1)))
                     if k != i - j - 1:
-                        t = F.relu(t)
+                        t = ctx.q(F.relu(t))
             y = t if y is None else y + t
-        outs.append(F.relu(y))
+        outs.append(ctx.q(F.relu(y)))
     return outs
 
 
 def hrnet_forward(ctx, p, x, cfg=HRNET_W48):
     """HighResolutionNet.forward (hrnetv2.py:399-449). Returns the concatenated high-resolution features."""
-    x = F.relu(bn(ctx, p + ".bn1", conv(ctx, p + ".conv1", x, 2, 1)))
-    x = F.relu(bn(ctx, p + ".bn2", conv(ctx, p + ".conv2", x, 2, 1)))
+    q = ctx.q
+    x = q(x)   # the B200 path reads the image as bf16
+    x = q(F.relu(bn(ctx, p + ".bn1", q(conv(ctx, p + ".conv1", x, 2, 1)))))
+    x = q(F.relu(bn(ctx, p + ".bn2", q(conv(ctx, p + ".conv2", x, 2, 1)))))
     s1 = cfg["stage1"]
     for k in range(s1["num_blocks"][0]):   # _make_layer (hrnetv2.py:353-368): 1x1+BN residual iff channel count changes
         x = bottleneck(ctx, "%s.layer1.%d" % (p, k), x,
@@ -147,36 +202,37 @@ def hrnet_forward(ctx, p, x, cfg=HRNET_W48):
         for i in range(len(chans)):
             if i < len(pre):
                 if chans[i] != pre[i]:   # hrnetv2.py:324-336 (3x3 s1 + BN + ReLU)
-                    xs.append(F.relu(bn(ctx, "%s.%d.1" % (tp, i), conv(ctx, "%s.%d.0" % (tp, i), ys[i], 1, 1))))
+                    xs.append(q(F.relu(bn(ctx, "%s.%d.1" % (tp, i), q(conv(ctx, "%s.%d.0" % (tp, i), ys[i], 1, 1))))))
                 else:
                     xs.append(ys[i])
             else:                        # hrnetv2.py:338-349: new branch from the LAST previous branch, 3x3 s2 chain
                 t = ys[-1]
                 for j in range(i + 1 - len(pre)):
-                    t = F.relu(bn(ctx, "%s.%d.%d.1" % (tp, i, j), conv(ctx, "%s.%d.%d.0" % (tp, i, j), t, 2, 1)))
+                    t = q(F.relu(bn(ctx, "%s.%d.%d.1" % (tp, i, j), q(conv(ctx, "%s.%d.%d.0" % (tp, i, j), t, 2, 1)))))
                 xs.append(t)
         for m in range(sc["num_modules"]):
             xs = hr_module(ctx, "%s.%s.%d" % (p, key, m), xs, sc["num_blocks"])
         ys = xs
         pre = chans
     size = ys[0].shape[-2:]
-    feats = torch.cat([ys[0]] + [bilinear(t, size) for t in ys[1:]], 1)   # hrnetv2.py:438-447
+    feats = torch.cat([ys[0]] + [q(bilinear(t, size)) for t in ys[1:]], 1)   # hrnetv2.py:438-447
     return feats
 
 
 # ----------------------------------------------------------------------------------------------- OCR head
 def bn_relu(ctx, name, x):
     """network.utils.BNReLU (utils.py:314-317): Sequential(Norm2d, ReLU) -> sub-module '0' is the BN."""
-    return F.relu(bn(ctx, name + ".0", x))
+    return ctx.q(F.relu(bn(ctx, name + ".0", ctx.q(x))))
 
 
-def spatial_gather(feats, probs):
+def spatial_gather(feats, probs, ctx=None):
     """SpatialGather_Module.forward (ocr_utils.py:34-46), scale = 1."""
+    q = ctx.q if ctx is not None else (lambda t: t)
     n, k = probs.shape[:2]
     c = feats.shape[1]
-    pr = F.softmax(probs.reshape(n, k, -1), dim=2)
+    pr = q(F.softmax(probs.reshape(n, k, -1), dim=2))
     ft = feats.reshape(n, c, -1).permute(0, 2, 1)
-    ctxv = torch.matmul(pr, ft)                       # n x k x c
+    ctxv = q(torch.matmul(pr, ft))                    # n x k x c
     return ctxv.permute(0, 2, 1).unsqueeze(3)         # n x c x k x 1
 
 
@@ -191,38 +247,40 @@ def object_attention(ctx, p, x, proxy, key_ch):
     q = q.reshape(n, key_ch, -1).permute(0, 2, 1)
     k = k.reshape(n, key_ch, -1)
     v = v.reshape(n, key_ch, -1).permute(0, 2, 1)
-    sim = F.softmax((key_ch ** -0.5) * torch.matmul(q, k), dim=-1)
-    c = torch.matmul(sim, v).permute(0, 2, 1).contiguous().reshape(n, key_ch, h, w)
+    sim = ctx.q(F.softmax((key_ch ** -0.5) * torch.matmul(q, k), dim=-1))
+    c = ctx.q(torch.matmul(sim, v)).permute(0, 2, 1).contiguous().reshape(n, key_ch, h, w)
     return bn_relu(ctx, p + ".f_up.1", conv(ctx, p + ".f_up.0", c))
 
 
 def ocr_block(ctx, p, feats_in, ocfg=OCR_CFG):
     """OCR_block.forward (ocrnet.py:85-91) + SpatialOCR_Module.forward (ocr_utils.py:149-158)."""
     feats = bn_relu(ctx, p + ".conv3x3_ocr.1", conv(ctx, p + ".conv3x3_ocr.0", feats_in, 1, 1))
-    aux = conv(ctx, p + ".aux_head.2", bn_relu(ctx, p + ".aux_head.1", conv(ctx, p + ".aux_head.0", feats_in)))
-    context = spatial_gather(feats, aux)
+    aux = ctx.qg(conv(ctx, p + ".aux_head.2", bn_relu(ctx, p + ".aux_head.1", conv(ctx, p + ".aux_head.0", feats_in))))
+    context = spatial_gather(feats, aux, ctx)
     dp = p + ".ocr_distri_head"
     oc = object_attention(ctx, dp + ".object_context_block", feats, context, ocfg["key_channels"])
     out = bn_relu(ctx, dp + ".conv_bn_dropout.1", conv(ctx, dp + ".conv_bn_dropout.0", torch.cat([oc, feats], 1)))
     if ctx.training and ctx.drop_mask_fn is not None:   # nn.Dropout2d(0.05): per-(n,c) mask scaled by 1/(1-p)
         mask = ctx.drop_mask_fn((out.shape[0], out.shape[1], 1, 1)).to(out.dtype)
         out = out * mask / (1.0 - ocfg["dropout"])
-    cls = conv(ctx, p + ".cls_head", out)
+    cls = ctx.qg(conv(ctx, p + ".cls_head", out))
     return cls, aux, out
 
 
 def attn_head(ctx, p, x):
     """make_attn_head new-arch (utils.py:343-367): 3x3-BN-ReLU, 3x3-BN-ReLU, 1x1, Sigmoid; all bias-free."""
-    x = F.relu(bn(ctx, p + ".bn0", conv(ctx, p + ".conv0", x, 1, 1)))
-    x = F.relu(bn(ctx, p + ".bn1", conv(ctx, p + ".conv1", x, 1, 1)))
-    return torch.sigmoid(conv(ctx, p + ".conv2", x))
+    q = ctx.q
+    x = q(F.relu(bn(ctx, p + ".bn0", q(conv(ctx, p + ".conv0", x, 1, 1)))))
+    x = q(F.relu(bn(ctx, p + ".bn1", q(conv(ctx, p + ".conv1", x, 1, 1)))))
+    return torch.sigmoid(ctx.qg(conv(ctx, p + ".conv2", x)))
 
 
 def seg_head(ctx, p, x):
     """make_seg_head (utils.py:320-329), used by basic.HRNet (basic.py:38-64)."""
-    x = F.relu(bn(ctx, p + ".1", conv(ctx, p + ".0", x, 1, 1)))
-    x = F.relu(bn(ctx, p + ".4", conv(ctx, p + ".3", x, 1, 1)))
-    return conv(ctx, p + ".6", x)
+    q = ctx.q
+    x = q(F.relu(bn(ctx, p + ".1", q(conv(ctx, p + ".0", x, 1, 1)))))
+    x = q(F.relu(bn(ctx, p + ".4", q(conv(ctx, p + ".3", x, 1, 1)))))
+    return ctx.qg(conv(ctx, p + ".6", x))
 
 
 # ----------------------------------------------------------------------------------------------- losses

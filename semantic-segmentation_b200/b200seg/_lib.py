@@ -1,7 +1,7 @@
 """ctypes binding of libb200seg.so (the C ABI declared in include/b200seg.h).
 
 The library is built in-tree by ``__graft_entry__.build()`` / ``make -C csrc`` and loaded from ``b200seg/lib``.
-There is deliberately no fallback: if the shared object is missing, importing a kernel-backed op raises.
+There is deliberately no fallback: if the shared object is missing, using a kernel-backed op raises.
 """
 import ctypes
 import os
@@ -10,13 +10,34 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200seg.so")
 
 c_int32 = ctypes.c_int32
+c_int64 = ctypes.c_int64
+c_float = ctypes.c_float
 c_void_p = ctypes.c_void_p
+c_size_t = ctypes.c_size_t
+P32 = ctypes.POINTER(c_int32)
 
 
 class ConvDesc(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "n", "h", "w", "cin", "cout", "ksize", "stride", "pad", "x_ld", "y_ld",
         "out_fp32", "has_bias", "emit_stats", "reserved")]
+
+
+class FuseTerm(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+                ("ld", c_int32), ("h", c_int32), ("w", c_int32), ("reserved", c_int32)]
+
+
+class FuseDesc(ctypes.Structure):
+    _fields_ = [("term", FuseTerm * 4), ("nterms", c_int32), ("n", c_int32), ("h", c_int32), ("w", c_int32),
+                ("c", c_int32), ("relu", c_int32), ("reserved", c_int32 * 2)]
+
+
+class MscaleDesc(ctypes.Structure):
+    _fields_ = [("n", c_int32), ("h", c_int32), ("w", c_int32), ("hq", c_int32), ("wq", c_int32),
+                ("hm", c_int32), ("wm", c_int32), ("hl", c_int32), ("wl", c_int32), ("nheads", c_int32),
+                ("w_head0", c_float), ("w_head1", c_float), ("sup_wt", c_float), ("ignore_index", c_int32),
+                ("reserved", c_int32 * 2)]
 
 
 class ProbeOperand(ctypes.Structure):
@@ -31,6 +52,49 @@ class ProbeDesc(ctypes.Structure):
         "a_off", "a_lbo", "a_sbo", "a_layout", "a_base", "a_major", "a_kstep",
         "b_off", "b_lbo", "b_sbo", "b_layout", "b_base", "b_major", "b_kstep")]
 
+
+# name -> (restype, argtypes). Must list every symbol include/b200seg.h declares (tests/test_abi.py checks this).
+V, I32, I64, F = c_void_p, c_int32, c_int64, c_float
+SIGNATURES = {
+    "b200seg_abi_version": (ctypes.c_int, []),
+    "b200seg_build_info": (ctypes.c_char_p, []),
+    "b200seg_conv2d_stats_elems": (c_size_t, [ctypes.POINTER(ConvDesc)]),
+    "b200seg_conv2d_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V, P32, V]),
+    "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
+    "b200seg_pack_weight": (ctypes.c_int, [V, I32, I32, I32, V, V, I32, V]),
+    "b200seg_conv2d_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, I32, V, V, I32, V, I32, V]),
+    "b200seg_conv2d_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, I32, V, V]),
+    "b200seg_bn_finalize": (ctypes.c_int, [V, I32, I32, I32, F, V, V, F, F, V, V, V, V, V, V, V, V]),
+    "b200seg_bn_eval_params": (ctypes.c_int, [I32, V, V, F, V, V, V, V, V]),
+    "b200seg_bn_apply": (ctypes.c_int, [V, I32, V, V, V, I32, V, I32, V, I32, I64, I32, I32, V]),
+    "b200seg_bn_bwd_grid": (I32, [I64, I32]),
+    "b200seg_bn_bwd_reduce": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, I64, I32, I32, V, V]),
+    "b200seg_bn_bwd_finalize": (ctypes.c_int, [V, I32, I32, F, V, V, V, V, V]),
+    "b200seg_bn_bwd_apply": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, V, V, V, V, I32, V, I32, I32, I64, I32,
+                                            I32, V]),
+    "b200seg_masked_accum": (ctypes.c_int, [V, I32, V, I32, V, I32, I32, I64, I32, V]),
+    "b200seg_fuse_fwd": (ctypes.c_int, [ctypes.POINTER(FuseDesc), V, I32, V]),
+    "b200seg_upsample_adjoint": (ctypes.c_int, [V, I32, V, I32, I32, I32, I32, I32, V, I32, I32, I32, I32, V]),
+    "b200seg_image_prep": (ctypes.c_int, [V, I32, I32, I32, V, I32, I32, V]),
+    "b200seg_spatial_softmax_blocks": (I32, [I32]),
+    "b200seg_spatial_softmax_fwd": (ctypes.c_int, [V, I32, I32, I32, I32, V, V, V, V]),
+    "b200seg_spatial_softmax_bwd": (ctypes.c_int, [V, I32, V, I32, I32, I32, V, V, I32, V]),
+    "b200seg_class_softmax_fwd": (ctypes.c_int, [V, I32, I64, I32, F, V, V]),
+    "b200seg_class_softmax_bwd": (ctypes.c_int, [V, I32, V, I64, I32, F, V, V]),
+    "b200seg_transpose_pad": (ctypes.c_int, [V, I32, I32, I32, I32, V, I32, V]),
+    "b200seg_cast_rows": (ctypes.c_int, [V, I32, V, I32, I64, I32, I32, V]),
+    "b200seg_bias_grad": (ctypes.c_int, [V, I32, I64, I32, V, V]),
+    "b200seg_count_valid": (ctypes.c_int, [V, I64, I32, V, V, V]),
+    "b200seg_mscale_mid_fwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V, V, V]),
+    "b200seg_mscale_loss_blocks": (I32, [ctypes.POINTER(MscaleDesc)]),
+    "b200seg_mscale_loss_fwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V, V, V, V, V, V, V, V, V]),
+    "b200seg_mscale_hi_bwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V]),
+    "b200seg_mscale_lo_bwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V, V, V, V, V, V, V, V]),
+}
+# test-only probe entry point (csrc/probe.h), not part of include/b200seg.h
+PROBE_SIGNATURES = {
+    "b200seg_umma_probe": (ctypes.c_int, [ctypes.POINTER(ProbeDesc), V, V, V, V]),
+}
 
 _lib = None
 
@@ -47,26 +111,14 @@ def lib():
             raise B200SegError(
                 "libb200seg.so not found at %s - run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU / PyTorch fallback for the hot path)" % LIB_PATH)
-        _lib = ctypes.CDLL(LIB_PATH)
-        _declare(_lib)
+        L = ctypes.CDLL(LIB_PATH)
+        for table in (SIGNATURES, PROBE_SIGNATURES):
+            for name, (res, args) in table.items():
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+        _lib = L
     return _lib
-
-
-def _declare(L):
-    L.b200seg_abi_version.restype = ctypes.c_int
-    L.b200seg_build_info.restype = ctypes.c_char_p
-    L.b200seg_conv2d_stats_elems.restype = ctypes.c_size_t
-    L.b200seg_conv2d_stats_elems.argtypes = [ctypes.POINTER(ConvDesc)]
-    L.b200seg_conv2d_fwd.restype = ctypes.c_int
-    L.b200seg_conv2d_fwd.argtypes = [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     ctypes.POINTER(c_int32), c_void_p]
-    L.b200seg_conv2d_fwd_direct.restype = ctypes.c_int
-    L.b200seg_conv2d_fwd_direct.argtypes = [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p,
-                                            c_void_p]
-    L.b200seg_pack_weight.restype = ctypes.c_int
-    L.b200seg_pack_weight.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
-    L.b200seg_umma_probe.restype = ctypes.c_int
-    L.b200seg_umma_probe.argtypes = [ctypes.POINTER(ProbeDesc), c_void_p, c_void_p, c_void_p, c_void_p]
 
 
 def check(rc, what):
@@ -76,9 +128,9 @@ def check(rc, what):
 
 def ptr(t):
     """Raw device pointer of a torch tensor (or None)."""
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    return None if t is None else t.data_ptr()
 
 
 def stream_ptr():
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch.cuda.current_stream().cuda_stream

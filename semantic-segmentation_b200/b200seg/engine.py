@@ -1,0 +1,220 @@
+"""Executor for the HRNet-OCR-MScale hot path: fused-op forward with an explicit reverse tape.
+
+Design notes
+  * Every op is one or a few C-ABI kernel launches (``raw``); there is no per-op autograd graph. The forward pushes
+    closures on a tape; ``run_backward`` pops them in reverse. Tapes are static for a given input shape, which is
+    what lets ``B200SegModule`` capture the whole fwd+bwd step in one CUDA graph.
+  * ``Act`` is an NHWC bf16 activation (possibly a channel-slice view of a wider buffer, so concat is a no-op).
+    ``Act.grad`` accumulates in place: producers of a gradient either create it or pass the existing buffer as the
+    kernel's addend.
+  * conv -> training BatchNorm -> (residual) -> ReLU is three passes: the tcgen05 conv emits the batch statistics from
+    its epilogue, ``bn_finalize`` turns them into scale/shift (+ running stats), ``bn_apply`` fuses affine, residual,
+    ReLU and the Dropout2d mask. The backward mirrors it (``bn_bwd`` = reduce + finalize + apply, then wgrad, dgrad).
+"""
+import torch
+
+from . import raw
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1   # network/hrnetv2.py:25 and the nn.BatchNorm2d default
+
+
+class Act:
+    __slots__ = ("t", "grad", "needs_grad")
+
+    def __init__(self, t, needs_grad=True):
+        self.t = t
+        self.grad = None
+        self.needs_grad = needs_grad
+
+
+class ConvBNRec:
+    """A convolution + batch-statistics record whose affine/activation is applied later (bn_act or inside a fuse)."""
+    __slots__ = ("x", "y", "cname", "bname", "ksize", "stride", "cout", "scale", "shift", "mean", "invstd", "has_bias")
+
+
+class HeadRec:
+    """A logit-head convolution (no BN); ``dlogits`` (bf16 [N,h,w,32|8]) is filled in by the loss backward."""
+    __slots__ = ("x", "cname", "cout", "logits", "dlogits", "has_bias")
+
+
+class Engine:
+    def __init__(self, params, grads, packed, training, drop_mask=None):
+        """params: name -> tensor (weights, BN buffers); grads: name -> fp32 tensor accumulated into (training);
+        packed: name -> (w_fwd, w_dgrad) bf16 operand caches; drop_mask: fp32 [N, mid] post-ReLU multiplier."""
+        self.p = params
+        self.g = grads
+        self.packed = packed
+        self.training = training
+        self.drop_mask = drop_mask
+        self.tape = []
+
+    # ------------------------------------------------------------------------------------------ tape
+    def run_backward(self):
+        tape = self.tape
+        while tape:
+            fn = tape.pop()
+            fn()
+
+    def _push(self, fn):
+        if self.training:
+            self.tape.append(fn)
+
+    @staticmethod
+    def _accumulate(act, new_grad_fn):
+        """new_grad_fn(addend, out) must write out = new (+ addend). Creates act.grad when absent."""
+        if act.grad is None:
+            act.grad = new_grad_fn(None)
+        else:
+            new_grad_fn(act.grad)
+
+    # ------------------------------------------------------------------------------------------ conv + BN
+    def conv_stats(self, x, cname, bname, ksize, stride=1, bias=False):
+        w_f, _ = self.packed[cname]
+        rec = ConvBNRec()
+        rec.x, rec.cname, rec.bname, rec.ksize, rec.stride, rec.has_bias = x, cname, bname, ksize, stride, bias
+        rec.cout = w_f.shape[0]
+        b = self.p[cname + ".bias"] if bias else None
+        if self.training:
+            y, stats = raw.conv2d_fwd(x.t, w_f, b, stride=stride, emit_stats=True)
+            n, ho, wo, _ = y.shape
+            par = raw.bn_finalize(stats, n * ho * wo, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
+                                  BN_MOMENTUM, self.p[bname + ".running_mean"], self.p[bname + ".running_var"],
+                                  self.p[bname + ".num_batches_tracked"], rec.cout)
+            rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], par[2], par[3]
+        else:
+            y = raw.conv2d_fwd(x.t, w_f, b, stride=stride)
+            par = raw.bn_eval_params(self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
+                                     self.p[bname + ".running_mean"], self.p[bname + ".running_var"])
+            rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], None, None
+        rec.y = y
+        return rec
+
+    def rec_backward(self, rec, dz, mask, post_scale=None, g_out=None, g_accumulate=False):
+        """Backward of BN(conv(x)) given the gradient w.r.t. the BN output (dz, optionally ReLU-masked by `mask`)."""
+        dy = raw.bn_bwd(dz, mask, post_scale, rec.y, rec.mean, rec.invstd, self.p[rec.bname + ".weight"],
+                        self.g[rec.bname + ".weight"], self.g[rec.bname + ".bias"], g_out=g_out,
+                        g_accumulate=g_accumulate)
+        x = rec.x
+        raw.conv2d_wgrad(x.t, dy, self.g[rec.cname + ".weight"], rec.cout, rec.ksize, rec.stride)
+        # a conv bias in front of a training-mode BN has an exactly zero gradient (BN removes the mean): left at 0
+        if x.needs_grad:
+            _, w_d = self.packed[rec.cname]
+            if x.grad is None:
+                x.grad = raw.conv2d_dgrad(dy, w_d, tuple(x.t.shape), rec.ksize, rec.stride)
+            else:
+                raw.conv2d_dgrad(dy, w_d, tuple(x.t.shape), rec.ksize, rec.stride, addend=x.grad, out=x.grad)
+
+    def bn_act(self, rec, relu=True, residual=None, out=None, post_scale=None):
+        z = raw.bn_apply(rec.y, rec.scale, rec.shift, residual.t if residual is not None else None, post_scale, relu,
+                         out=out)
+        za = Act(z)
+
+        def bwd():
+            dz = za.grad
+            if dz is None:
+                return   # dead branch (autograd would prune it too)
+            g_out, g_acc = None, False
+            if residual is not None and residual.needs_grad:
+                if residual.grad is None:
+                    residual.grad = torch.empty(residual.t.shape, dtype=BF16, device=z.device)
+                else:
+                    g_acc = True
+                g_out = residual.grad
+            self.rec_backward(rec, dz, z if relu else None, post_scale, g_out, g_acc)
+            za.grad = None
+        self._push(bwd)
+        return za
+
+    def conv_bn(self, x, cname, bname, ksize, stride=1, relu=True, residual=None, out=None, bias=False,
+                post_scale=None):
+        rec = self.conv_stats(x, cname, bname, ksize, stride, bias)
+        return self.bn_act(rec, relu, residual, out, post_scale)
+
+    # ------------------------------------------------------------------------------------------ fuse / resample
+    def fuse(self, out_shape, terms, relu=True, out=None):
+        """terms: list of ('id', Act) | ('rec', ConvBNRec) (affine folded in, upsampled when coarser)."""
+        n, h, w, c = out_shape
+        tl = []
+        for kind, obj in terms:
+            if kind == "id":
+                tl.append((obj.t, None, None))
+            else:
+                tl.append((obj.y, obj.scale, obj.shift))
+        z = raw.fuse_fwd(tl, n, h, w, c, relu, out=out)
+        za = Act(z)
+
+        def bwd():
+            dz = za.grad
+            if dz is None:
+                return
+            mask = z if relu else None
+            for kind, obj in terms:
+                if kind == "id":
+                    if not obj.needs_grad:
+                        continue
+                    if obj.t.shape[1] == h and obj.t.shape[2] == w:
+                        if obj.grad is None:
+                            obj.grad = torch.empty(obj.t.shape, dtype=BF16, device=z.device)
+                            raw.masked_accum(dz, mask, obj.grad, False)
+                        else:
+                            raw.masked_accum(dz, mask, obj.grad, True)
+                    else:
+                        hh, ww = obj.t.shape[1], obj.t.shape[2]
+                        if obj.grad is None:
+                            obj.grad = raw.upsample_adjoint(dz, mask, hh, ww)
+                        else:
+                            raw.upsample_adjoint(dz, mask, hh, ww, out=obj.grad, accumulate=True)
+                else:
+                    yh, yw = obj.y.shape[1], obj.y.shape[2]
+                    if yh == h and yw == w:
+                        self.rec_backward(obj, dz, mask)
+                    else:
+                        gl = raw.upsample_adjoint(dz, mask, yh, yw)
+                        self.rec_backward(obj, gl, None)
+            za.grad = None
+        self._push(bwd)
+        return za
+
+    def slice_marker(self, parent, pieces):
+        """pieces: list of (Act view, c0, c1). In backward, hands each view its slice of parent.grad."""
+        def bwd():
+            if parent.grad is None:
+                return
+            for act, c0, c1 in pieces:
+                sl = parent.grad[..., c0:c1]
+                if act.grad is None:
+                    act.grad = sl
+                else:   # already has a gradient elsewhere: accumulate into the slice and alias it
+                    raw.masked_accum(act.grad, None, sl, True)
+                    act.grad = sl
+        self._push(bwd)
+
+    # ------------------------------------------------------------------------------------------ logit heads
+    def conv_head(self, x, cname, bias=True, ld=20):
+        w_f, _ = self.packed[cname]
+        cout = w_f.shape[0]
+        b = self.p[cname + ".bias"] if bias else None
+        logits = raw.conv2d_fwd(x.t, w_f, b, out_fp32=True, out_ld=max(ld, cout))
+        rec = HeadRec()
+        rec.x, rec.cname, rec.cout, rec.logits, rec.dlogits, rec.has_bias = x, cname, cout, logits, None, bias
+
+        def bwd():
+            dl = rec.dlogits
+            if dl is None:
+                return   # dead head (e.g. the 1x pass' attention, network/ocrnet.py:284-287)
+            raw.conv2d_wgrad(x.t, dl, self.g[cname + ".weight"], cout, 1, 1)
+            if bias:
+                raw.bias_grad(dl, cout, self.g[cname + ".bias"])
+            _, w_d = self.packed[cname]
+            cpad = w_d.shape[2]
+            dlv = dl[..., :cpad]
+            if x.grad is None:
+                x.grad = raw.conv2d_dgrad(dlv, w_d, tuple(x.t.shape), 1, 1)
+            else:
+                raw.conv2d_dgrad(dlv, w_d, tuple(x.t.shape), 1, 1, addend=x.grad, out=x.grad)
+            rec.dlogits = None
+        self._push(bwd)
+        return rec

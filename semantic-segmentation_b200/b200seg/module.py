@@ -1,0 +1,258 @@
+"""``B200SegModule`` — the nn.Module the reference's ``network.get_model`` factory returns on the B200 path.
+
+Contract mirrored from the reference:
+  * constructor ``f(num_classes, criterion)``; ``module(inputs)`` with ``inputs = {'images': fp32 [N,3,H,W],
+    'gts': int64 [N,H,W]}``; train mode -> 0-dim loss tensor whose ``.backward()`` populates ``param.grad``; eval mode
+    -> ``{'pred': [N,C,H,W], ...}`` (network/ocrnet.py:300-327, utils/trnval_utils.py:134-143);
+  * ``state_dict()`` names / shapes / registration order identical to the reference module, parameters are ordinary
+    fp32 ``nn.Parameter`` leaves (optimizers, DDP and checkpoints keep working); the bf16 operand layouts the kernels
+    read are private caches refreshed from the master weights at the start of every step.
+
+The training step executes forward AND backward inside ``forward()`` (the tape is static, so the whole step is one
+CUDA graph after the first call); ``loss.backward()`` then only publishes the already-computed gradients into
+``param.grad`` (accumulating if gradients are already present) and, under the DDP shim, all-reduces the flat buffer.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import arch as A
+from . import model as M
+from . import raw
+from .engine import Engine
+
+F32 = torch.float32
+
+
+def _criterion_kind(criterion):
+    """Map the reference criterion object (loss/utils.py:40-67) to the fused loss implementation."""
+    if criterion is None:
+        return "ce"
+    name = type(criterion).__name__
+    if name in ("CrossEntropyLoss2d", "CrossEntropyLoss", "str") or criterion == "ce":
+        return "ce"
+    if name == "RMILoss" or criterion == "rmi":
+        return "rmi"
+    raise NotImplementedError("criterion %s is outside the B200 hot path (CE and RMI are covered)" % name)
+
+
+class _PublishGrads(torch.autograd.Function):
+    """Bridges the engine's eagerly computed gradients into autograd: forward returns the loss, backward hands every
+    parameter its slice of the flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, module, loss, anchor):
+        ctx.module = module
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        # Gradients were computed for a unit upstream gradient (bf16 needs no loss scaling; the apex.amp shim is a
+        # pass-through), so grad_out is not applied.
+        ctx.module._publish()
+        return None, None, None
+
+
+class B200SegModule(nn.Module):
+    def __init__(self, arch, num_classes=19, criterion=None, hcfg=None, ocfg=None, lo_scale=0.5, ocr_alpha=0.4,
+                 supervised_mscale_wt=0.0, ignore_index=255, n_scales=None, use_cuda_graph=True):
+        super().__init__()
+        self.arch = arch
+        self.criterion = criterion
+        self.loss_kind = _criterion_kind(criterion)
+        self.hcfg = hcfg or A.HRNET_W48
+        self.ocfg = dict(ocfg or A.OCR_DEFAULT)
+        self.ocfg["num_classes"] = num_classes
+        assert num_classes == 19, "kernels are instantiated for the 19 Cityscapes classes"
+        self.lo_scale, self.ocr_alpha, self.sup_wt, self.ignore_index = lo_scale, ocr_alpha, supervised_mscale_wt, ignore_index
+        self.n_scales = n_scales
+        self.use_cuda_graph = use_cuda_graph
+        self._specs = A.tensor_specs(arch, self.hcfg, self.ocfg)
+        self._build_parameters()
+        self._flat_grad = None
+        self._packed = None
+        self._graphs = {}
+        self._ddp_allreduce = False
+        self._anchor = None
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def _container(self, dotted):
+        mod = self
+        for part in dotted:
+            if part not in mod._modules:
+                mod.add_module(part, nn.Module())
+            mod = mod._modules[part]
+        return mod
+
+    def _build_parameters(self):
+        """Registers tensors under the reference names and reproduces its initialisation policy:
+        backbone convs N(0, 1e-3), BN (1, 0) (network/hrnetv2.py:451-461); OCR / attention / seg heads keep the
+        nn.Conv2d default (kaiming_uniform(a=sqrt(5)), bias U(+-1/sqrt(fan_in))) as in network/ocrnet.py:46-83."""
+        for name, shape, kind in self._specs:
+            parts = name.split(".")
+            owner = self._container(parts[:-1])
+            leaf = parts[-1]
+            in_backbone = parts[0] == "backbone"
+            if kind == "conv_w":
+                w = torch.empty(shape)
+                if in_backbone:
+                    nn.init.normal_(w, std=0.001)
+                else:
+                    nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+                owner.register_parameter(leaf, nn.Parameter(w))
+            elif kind == "conv_b":
+                wname = ".".join(parts[:-1]) + ".weight"
+                fan_in = 1
+                for nm, shp, _k in self._specs:
+                    if nm == wname:
+                        fan_in = shp[1] * shp[2] * shp[3]
+                bound = 1.0 / math.sqrt(fan_in)
+                owner.register_parameter(leaf, nn.Parameter(torch.empty(shape).uniform_(-bound, bound)))
+            elif kind == "bn_w":
+                owner.register_parameter(leaf, nn.Parameter(torch.ones(shape)))
+            elif kind == "bn_b":
+                owner.register_parameter(leaf, nn.Parameter(torch.zeros(shape)))
+            elif kind == "bn_rm":
+                owner.register_buffer(leaf, torch.zeros(shape))
+            elif kind == "bn_rv":
+                owner.register_buffer(leaf, torch.ones(shape))
+            elif kind == "bn_nbt":
+                owner.register_buffer(leaf, torch.tensor(0, dtype=torch.long))
+
+    def _tensors(self):
+        out = dict(self.named_parameters())
+        out.update(dict(self.named_buffers()))
+        return out
+
+    def _ensure_device_state(self):
+        """(Re)build the flat fp32 gradient buffer and the packed bf16 weight caches on the parameters' device."""
+        params = [(n, p) for n, p in self.named_parameters()]
+        dev = params[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError("B200SegModule runs on CUDA only (sm_100a); there is no CPU path - call .cuda() first")
+        if self._flat_grad is None or self._flat_grad.device != dev:
+            total = sum((p.numel() + 63) // 64 * 64 for _, p in params)
+            self._flat_grad = torch.zeros(total, dtype=F32, device=dev)
+            self._grad_views = {}
+            off = 0
+            for n, p in params:
+                self._grad_views[n] = self._flat_grad[off:off + p.numel()].view(p.shape)
+                off += (p.numel() + 63) // 64 * 64
+            self._packed = {}
+            for n, p in params:
+                if p.dim() == 4:
+                    o, i, k, _ = p.shape
+                    if i == 3:      # stem: the image is padded to 16 channels (see resample_kernels.cu image_prep)
+                        i = 16
+                    w_f = torch.zeros((o, k * k, i), dtype=torch.bfloat16, device=dev)
+                    w_d = torch.zeros((i, k * k, (o + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
+                    self._packed[n[: -len(".weight")]] = (w_f, w_d)
+            self._stem_pad = None
+            self._graphs = {}
+
+    def _repack(self):
+        """fp32 OIHW master weights -> bf16 kernel layouts (inside the captured step: weights change every step)."""
+        for n, p in self.named_parameters():
+            if p.dim() != 4:
+                continue
+            w_f, w_d = self._packed[n[: -len(".weight")]]
+            src = p.detach()
+            if src.shape[1] == 3:
+                if self._stem_pad is None:
+                    self._stem_pad = torch.zeros((src.shape[0], 16, 3, 3), dtype=F32, device=src.device)
+                self._stem_pad[:, :3].copy_(src)
+                src = self._stem_pad
+            raw.pack_weight_into(src.contiguous(), w_f, w_d)
+
+    # ------------------------------------------------------------------------------------------ training step
+    def _step_eager(self, images, gts, drop_mask):
+        self._repack()
+        tensors = {k: v.detach() for k, v in self._tensors().items()}
+        grads = dict(self._grad_views)
+        stem = "backbone.conv1.weight"
+        stem_pad_grad = torch.zeros((grads[stem].shape[0], 16, 3, 3), dtype=F32, device=images.device)
+        grads[stem] = stem_pad_grad          # the stem runs on the 16-channel padded image
+        E = Engine(tensors, grads, self._packed, True, drop_mask)
+        if self.loss_kind != "ce":
+            raise NotImplementedError("RMI loss kernels are not wired into the fused step yet")
+        loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,
+                            self.ignore_index)
+        E.run_backward()
+        self._grad_views[stem].add_(stem_pad_grad[:, :3])
+        return loss
+
+    def _drop_mask(self, n, device):
+        """Dropout2d(0.05) channel mask (network/ocr_utils.py:146) drawn from torch's generator, folded with 1/(1-p)."""
+        if self.arch == "basic.HRNet":
+            return None
+        p = self.ocfg["dropout"]
+        c = self.ocfg["mid_channels"]
+        if p == 0.0:
+            return torch.ones((n, c), dtype=F32, device=device)
+        keep = torch.bernoulli(torch.full((n, c), 1.0 - p, dtype=F32, device=device))
+        return keep / (1.0 - p)
+
+    def _train_forward(self, images, gts):
+        self._ensure_device_state()
+        images = images.contiguous().float()
+        gts = gts.contiguous().long()
+        key = (tuple(images.shape), str(images.device))
+        mask = self._drop_mask(images.shape[0], images.device)
+        # Gradient accumulation contract: zero the flat buffer only when the caller dropped the gradients
+        # (optimizer.zero_grad(set_to_none=True)); an in-place zero_grad already cleared it through the aliased views,
+        # and live .grad tensors mean the caller wants this step accumulated on top.
+        first = next(self.parameters())
+        if first.grad is None:
+            self._flat_grad.zero_()
+        if not self.use_cuda_graph:
+            return self._step_eager(images, gts, mask)
+        st = self._graphs.get(key)
+        if st is None:
+            st = dict(images=images.clone(), gts=gts.clone(), mask=None if mask is None else mask.clone(), calls=0,
+                      graph=None, loss=None)
+            self._graphs[key] = st
+        st["images"].copy_(images)
+        st["gts"].copy_(gts)
+        if mask is not None:
+            st["mask"].copy_(mask)
+        st["calls"] += 1
+        if st["graph"] is None:
+            if st["calls"] < 2:      # first call: eager warm-up (sets kernel attributes, fills the allocator pools)
+                return self._step_eager(st["images"], st["gts"], st["mask"])
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["loss"] = self._step_eager(st["images"], st["gts"], st["mask"])
+            st["graph"] = g
+        st["graph"].replay()
+        return st["loss"]
+
+    def _publish(self):
+        """Called from loss.backward(): aliases every ``param.grad`` to its slice of the flat gradient buffer (or adds
+        into a foreign .grad tensor) and, under the data-parallel shim, averages the buffer across ranks (C1)."""
+        if self._ddp_allreduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+            ws = torch.distributed.get_world_size()
+            if ws > 1:
+                torch.distributed.all_reduce(self._flat_grad)
+                self._flat_grad.mul_(1.0 / ws)
+        for n, p in self.named_parameters():
+            g = self._grad_views[n]
+            if p.grad is None:
+                p.grad = g
+            elif p.grad.data_ptr() != g.data_ptr():
+                p.grad.add_(g)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, inputs):
+        assert "images" in inputs
+        images = inputs["images"]
+        if self.training:
+            assert "gts" in inputs
+            loss5 = self._train_forward(images, inputs["gts"])
+            self.last_loss_terms = loss5
+            if self._anchor is None or self._anchor.device != loss5.device:
+                self._anchor = torch.zeros(1, device=loss5.device, requires_grad=True)
+            return _PublishGrads.apply(self, loss5[0], self._anchor)
+        from .evalpath import eval_forward
+        return eval_forward(self, images)

@@ -1,54 +1,80 @@
 """Functional (no-autograd) wrappers: torch tensors in, C-ABI calls on the current CUDA stream, torch tensors out.
 
-Tensors are NHWC ("pixels x channels") bf16 unless stated. PyTorch only provides device memory and streams here.
+Activations are NHWC bf16 tensors (or channel-slice views of wider NHWC buffers: ``t.stride(3) == 1`` and
+``t.stride(2)`` is the pixel pitch). PyTorch only provides device memory and streams here.
 """
 import ctypes
 
 import torch
 
-from . import _lib
-from ._lib import ConvDesc, check, lib, ptr, stream_ptr
+from ._lib import ConvDesc, FuseDesc, MscaleDesc, check, lib, ptr, stream_ptr
+
+BF16 = torch.bfloat16
+F32 = torch.float32
 
 
+def _ld(t):
+    assert t.stride(-1) == 1, "channel dimension must be contiguous"
+    return t.stride(-2)
+
+
+def _dev(t):
+    return t.device
+
+
+def empty_act(n, h, w, c, device, dtype=BF16):
+    return torch.empty((n, h, w, c), dtype=dtype, device=device)
+
+
+# ----------------------------------------------------------------------------------------------- convolution
 def pack_weight(w_oihw, want_dgrad=True):
-    """fp32 OIHW master weight -> (bf16 [O][k*k][I], bf16 [I][k*k flipped][O])."""
-    assert w_oihw.is_cuda and w_oihw.dtype == torch.float32 and w_oihw.is_contiguous()
+    """fp32 OIHW master weight -> (bf16 [O][k*k][I], bf16 [I][k*k flipped][roundup8(O)])."""
+    assert w_oihw.is_cuda and w_oihw.dtype == F32 and w_oihw.is_contiguous()
     o, i, k, _ = w_oihw.shape
-    w_f = torch.empty((o, k * k, i), dtype=torch.bfloat16, device=w_oihw.device)
-    w_d = torch.empty((i, k * k, o), dtype=torch.bfloat16, device=w_oihw.device) if want_dgrad else None
-    check(lib().b200seg_pack_weight(ptr(w_oihw), o, i, k, ptr(w_f), ptr(w_d), stream_ptr()), "pack_weight")
+    o_pad = (o + 7) // 8 * 8
+    w_f = torch.empty((o, k * k, i), dtype=BF16, device=w_oihw.device)
+    w_d = torch.zeros((i, k * k, o_pad), dtype=BF16, device=w_oihw.device) if want_dgrad else None
+    check(lib().b200seg_pack_weight(ptr(w_oihw), o, i, k, ptr(w_f), ptr(w_d), o_pad, stream_ptr()), "pack_weight")
     return w_f, w_d
 
 
-def _conv_desc(x, cout, ksize, stride, y_ld, out_fp32, has_bias, emit_stats, force_kc=0, cin=None):
-    n, h, w, _ = x.shape
+def pack_weight_into(w_oihw, w_f, w_d):
+    o, i, k, _ = w_oihw.shape
+    o_pad = w_d.shape[2] if w_d is not None else 0
+    check(lib().b200seg_pack_weight(ptr(w_oihw), o, i, k, ptr(w_f), ptr(w_d), o_pad, stream_ptr()), "pack_weight")
+
+
+def conv_desc(n, h, w, cin, cout, ksize, stride, x_ld, y_ld, out_fp32=False, has_bias=False, emit_stats=False,
+              force_kc=0):
     d = ConvDesc()
-    d.n, d.h, d.w = n, h, w
-    d.cin = x.shape[3] if cin is None else cin
-    d.cout = cout
+    d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
     d.ksize, d.stride, d.pad = ksize, stride, (1 if ksize == 3 else 0)
-    d.x_ld = x.stride(2)
-    d.y_ld = y_ld
+    d.x_ld, d.y_ld = x_ld, y_ld
     d.out_fp32, d.has_bias, d.emit_stats, d.reserved = int(out_fp32), int(has_bias), int(emit_stats), force_kc
     return d
 
 
+def out_hw(h, w, ksize, stride):
+    pad = 1 if ksize == 3 else 0
+    return (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
+
+
 def conv2d_fwd(x, w_ohwi, bias=None, stride=1, out=None, out_fp32=False, emit_stats=False, force_kc=0,
-               direct=False):
-    """x: [N,H,W,Cin] bf16 view (channel stride 1, pixel pitch x.stride(2)); w_ohwi: [Cout][k*k][Cin] bf16.
-    Returns y [N,Ho,Wo,Cout] (bf16|fp32) and, with emit_stats, the per-CTA partials [grid][2][cout_pad] fp32."""
-    assert x.is_cuda and x.dtype == torch.bfloat16 and x.stride(3) == 1
+               direct=False, out_ld=None):
+    """x: [N,H,W,Cin] bf16; w_ohwi: [Cout][k*k][Cin] bf16. Returns y (and with emit_stats the per-CTA partials
+    [grid][2][cout_pad] fp32)."""
+    assert x.is_cuda and x.dtype == BF16
     cout, taps, cin = w_ohwi.shape
-    assert cin == x.shape[3]
+    assert cin == x.shape[3], (cin, x.shape)
     ksize = 3 if taps == 9 else 1
     n, h, w, _ = x.shape
-    pad = 1 if ksize == 3 else 0
-    ho = (h + 2 * pad - ksize) // stride + 1
-    wo = (w + 2 * pad - ksize) // stride + 1
+    ho, wo = out_hw(h, w, ksize, stride)
     if out is None:
-        out = torch.empty((n, ho, wo, cout), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
-    assert out.stride(3) == 1
-    d = _conv_desc(x, cout, ksize, stride, out.stride(2), out_fp32, bias is not None, emit_stats, force_kc)
+        width = cout if out_ld is None else out_ld
+        buf = torch.empty((n, ho, wo, width), dtype=F32 if out_fp32 else BF16, device=x.device)
+        out = buf[..., :cout] if width != cout else buf
+    d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(out), out_fp32, bias is not None, emit_stats,
+                  force_kc)
     if direct:
         check(lib().b200seg_conv2d_fwd_direct(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out),
                                               stream_ptr()), "conv2d_fwd_direct")
@@ -57,10 +83,243 @@ def conv2d_fwd(x, w_ohwi, bias=None, stride=1, out=None, out_fp32=False, emit_st
     grid = ctypes.c_int32(0)
     if emit_stats:
         nelem = lib().b200seg_conv2d_stats_elems(ctypes.byref(d))
-        stats = torch.empty(nelem, dtype=torch.float32, device=x.device)
+        stats = torch.empty(nelem, dtype=F32, device=x.device)
     check(lib().b200seg_conv2d_fwd(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out), ptr(stats),
                                    ctypes.byref(grid), stream_ptr()), "conv2d_fwd")
     if emit_stats:
         cout_pad = nelem // (148 * 2)
-        return out, stats[: grid.value * 2 * cout_pad].view(grid.value, 2, cout_pad)
+        return out, (stats, grid.value, cout_pad)
     return out
+
+
+def conv2d_dgrad(dy, w_dgrad, x_shape, ksize, stride, addend=None, out=None, force_kc=0):
+    """dy: [N,Ho,Wo,roundup8(Cout)] bf16; w_dgrad: [Cin][k*k][roundup8(Cout)]; x_shape = (N,H,W,Cin)."""
+    n, h, w, cin = x_shape
+    cout_pad = w_dgrad.shape[2]
+    assert dy.shape[3] >= cout_pad or dy.shape[3] == cout_pad, (dy.shape, w_dgrad.shape)
+    if out is None:
+        out = addend if addend is not None else torch.empty((n, h, w, cin), dtype=BF16, device=dy.device)
+    d = conv_desc(n, h, w, cin, cout_pad, ksize, stride, _ld(out), _ld(out), force_kc=force_kc)
+    check(lib().b200seg_conv2d_dgrad(ctypes.byref(d), ptr(dy), _ld(dy), ptr(w_dgrad), ptr(addend),
+                                     _ld(addend) if addend is not None else 0, ptr(out), _ld(out), stream_ptr()),
+          "conv2d_dgrad")
+    return out
+
+
+def conv2d_wgrad(x, dy, dw_oihw, cout, ksize, stride):
+    """dw_oihw (fp32 [Cout,Cin,k,k], contiguous) += sum_pixels dy x shifted(x)."""
+    n, h, w, cin = x.shape
+    assert dw_oihw.is_contiguous() and dw_oihw.dtype == F32
+    d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(dy))
+    check(lib().b200seg_conv2d_wgrad(ctypes.byref(d), ptr(x), ptr(dy), _ld(dy), ptr(dw_oihw), stream_ptr()),
+          "conv2d_wgrad")
+
+
+# ----------------------------------------------------------------------------------------------- batch norm
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, c):
+    buf, grid, cpad = stats
+    out = torch.empty((4, c), dtype=F32, device=buf.device)   # scale, shift, mean, invstd
+    check(lib().b200seg_bn_finalize(ptr(buf), grid, c, cpad, float(count), ptr(gamma), ptr(beta), eps, momentum,
+                                    ptr(running_mean), ptr(running_var), ptr(nbt), ptr(out[0]), ptr(out[1]),
+                                    ptr(out[2]), ptr(out[3]), stream_ptr()), "bn_finalize")
+    return out
+
+
+def bn_eval_params(gamma, beta, eps, running_mean, running_var):
+    c = gamma.shape[0]
+    out = torch.empty((2, c), dtype=F32, device=gamma.device)
+    check(lib().b200seg_bn_eval_params(c, ptr(gamma), ptr(beta), eps, ptr(running_mean), ptr(running_var), ptr(out[0]),
+                                       ptr(out[1]), stream_ptr()), "bn_eval_params")
+    return out
+
+
+def bn_apply(y, scale, shift, res=None, post_scale=None, relu=True, out=None):
+    n, h, w, c = y.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=BF16, device=y.device)
+    check(lib().b200seg_bn_apply(ptr(y), _ld(y), ptr(scale), ptr(shift), ptr(res), _ld(res) if res is not None else 0,
+                                 ptr(post_scale), int(relu), ptr(out), _ld(out), n * h * w, h * w, c, stream_ptr()),
+          "bn_apply")
+    return out
+
+
+def bn_bwd(dz, mask, post_scale, y, mean, invstd, gamma, dgamma, dbeta, g_out=None, g_accumulate=False, dy_out=None):
+    """Returns dy (gradient w.r.t. the BN input). dgamma/dbeta (fp32 views) are accumulated into."""
+    n, h, w, c = y.shape
+    npix = n * h * w
+    L = lib()
+    grid = L.b200seg_bn_bwd_grid(npix, c)
+    partials = torch.empty((grid, 2, c), dtype=F32, device=y.device)
+    check(L.b200seg_bn_bwd_reduce(ptr(dz), _ld(dz), ptr(mask), _ld(mask) if mask is not None else 0, ptr(post_scale),
+                                  ptr(y), _ld(y), ptr(mean), ptr(invstd), npix, h * w, c, ptr(partials),
+                                  stream_ptr()), "bn_bwd_reduce")
+    cc = torch.empty((2, c), dtype=F32, device=y.device)
+    check(L.b200seg_bn_bwd_finalize(ptr(partials), grid, c, float(npix), ptr(dgamma), ptr(dbeta), ptr(cc[0]),
+                                    ptr(cc[1]), stream_ptr()), "bn_bwd_finalize")
+    dy = dy_out if dy_out is not None else torch.empty((n, h, w, c), dtype=BF16, device=y.device)
+    check(L.b200seg_bn_bwd_apply(ptr(dz), _ld(dz), ptr(mask), _ld(mask) if mask is not None else 0, ptr(post_scale),
+                                 ptr(y), _ld(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(cc[0]), ptr(cc[1]), ptr(dy),
+                                 _ld(dy), ptr(g_out), _ld(g_out) if g_out is not None else 0, int(g_accumulate), npix,
+                                 h * w, c, stream_ptr()), "bn_bwd_apply")
+    return dy
+
+
+def masked_accum(src, mask, dst, accumulate):
+    n, h, w, c = src.shape
+    check(lib().b200seg_masked_accum(ptr(src), _ld(src), ptr(mask), _ld(mask) if mask is not None else 0, ptr(dst),
+                                     _ld(dst), int(accumulate), n * h * w, c, stream_ptr()), "masked_accum")
+    return dst
+
+
+# ----------------------------------------------------------------------------------------------- resampling
+def fuse_fwd(terms, n, h, w, c, relu, out=None):
+    """terms: list of (x [N,hj,wj,C], scale or None, shift or None)."""
+    d = FuseDesc()
+    d.nterms = len(terms)
+    d.n, d.h, d.w, d.c, d.relu = n, h, w, c, int(relu)
+    for i, (x, sc, sh) in enumerate(terms):
+        t = d.term[i]
+        t.x, t.scale, t.shift = ptr(x), ptr(sc), ptr(sh)
+        t.ld, t.h, t.w = _ld(x), x.shape[1], x.shape[2]
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=BF16, device=terms[0][0].device)
+    check(lib().b200seg_fuse_fwd(ctypes.byref(d), ptr(out), _ld(out), stream_ptr()), "fuse_fwd")
+    return out
+
+
+def upsample_adjoint(g, mask, h, w, out=None, accumulate=False):
+    n, H, W, c = g.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=BF16, device=g.device)
+    check(lib().b200seg_upsample_adjoint(ptr(g), _ld(g), ptr(mask), _ld(mask) if mask is not None else 0, n, H, W, c,
+                                         ptr(out), _ld(out), h, w, int(accumulate), stream_ptr()), "upsample_adjoint")
+    return out
+
+
+def image_prep(images_nchw, h, w):
+    n, three, H, W = images_nchw.shape
+    assert three == 3 and images_nchw.dtype == F32 and images_nchw.is_contiguous()
+    out = torch.empty((n, h, w, 16), dtype=BF16, device=images_nchw.device)
+    check(lib().b200seg_image_prep(ptr(images_nchw), n, H, W, ptr(out), h, w, stream_ptr()), "image_prep")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- OCR glue
+def spatial_softmax_fwd(logits, K):
+    """logits fp32 [N,P,ld] -> probs bf16 [N,P,32] (softmax over P)."""
+    n, P, ld = logits.shape
+    L = lib()
+    B = L.b200seg_spatial_softmax_blocks(P)
+    ws = torch.empty((n * B * 32 * 2,), dtype=F32, device=logits.device)
+    probs = torch.empty((n, P, 32), dtype=BF16, device=logits.device)
+    check(L.b200seg_spatial_softmax_fwd(ptr(logits), ld, n, P, K, ptr(ws), ptr(probs), None, stream_ptr()),
+          "spatial_softmax_fwd")
+    return probs
+
+
+def spatial_softmax_bwd(dprobs, probs, K, dlogit, accumulate):
+    n, P, ldd = dprobs.shape
+    L = lib()
+    B = L.b200seg_spatial_softmax_blocks(P)
+    ws = torch.empty((n * B * 32,), dtype=F32, device=dprobs.device)
+    check(L.b200seg_spatial_softmax_bwd(ptr(dprobs), ldd, ptr(probs), n, P, K, ptr(ws), ptr(dlogit), int(accumulate),
+                                        stream_ptr()), "spatial_softmax_bwd")
+    return dlogit
+
+
+def class_softmax_fwd(x, K, scale):
+    P, ld = x.shape
+    sim = torch.empty((P, 32), dtype=BF16, device=x.device)
+    check(lib().b200seg_class_softmax_fwd(ptr(x), ld, P, K, scale, ptr(sim), stream_ptr()), "class_softmax_fwd")
+    return sim
+
+
+def class_softmax_bwd(dsim, sim, K, scale):
+    P, ld = dsim.shape
+    ds = torch.empty((P, 32), dtype=BF16, device=dsim.device)
+    check(lib().b200seg_class_softmax_bwd(ptr(dsim), ld, ptr(sim), P, K, scale, ptr(ds), stream_ptr()),
+          "class_softmax_bwd")
+    return ds
+
+
+def transpose_pad(src, rpad):
+    """src [R][C] (bf16 or fp32, row pitch = stride(0)) -> bf16 [C][rpad] zero padded."""
+    R, C = src.shape
+    dst = torch.empty((C, rpad), dtype=BF16, device=src.device)
+    check(lib().b200seg_transpose_pad(ptr(src), int(src.dtype == F32), R, C, src.stride(0), ptr(dst), rpad,
+                                      stream_ptr()), "transpose_pad")
+    return dst
+
+
+def cast_rows(src, dst, C, accumulate=False):
+    rows = src.shape[0]
+    check(lib().b200seg_cast_rows(ptr(src), src.stride(0), ptr(dst), dst.stride(0), rows, C, int(accumulate),
+                                  stream_ptr()), "cast_rows")
+    return dst
+
+
+def bias_grad(dy, C, db):
+    rows = dy.numel() // dy.shape[-1]
+    check(lib().b200seg_bias_grad(ptr(dy), _ld(dy), rows, C, ptr(db), stream_ptr()), "bias_grad")
+
+
+# ----------------------------------------------------------------------------------------------- mscale + loss
+def mscale_desc(n, h, w, hq, wq, hm=0, wm=0, hl=0, wl=0, nheads=2, w0=1.0, w1=0.4, sup_wt=0.0, ignore_index=255):
+    d = MscaleDesc()
+    d.n, d.h, d.w, d.hq, d.wq, d.hm, d.wm, d.hl, d.wl = n, h, w, hq, wq, hm, wm, hl, wl
+    d.nheads, d.w_head0, d.w_head1, d.sup_wt, d.ignore_index = nheads, w0, w1, sup_wt, ignore_index
+    return d
+
+
+def count_valid(labels, ignore_index=255):
+    ws = torch.empty((1,), dtype=torch.int64, device=labels.device)
+    inv = torch.empty((1,), dtype=F32, device=labels.device)
+    check(lib().b200seg_count_valid(ptr(labels), labels.numel(), ignore_index, ptr(ws), ptr(inv), stream_ptr()),
+          "count_valid")
+    return inv
+
+
+def mscale_mid_fwd(d, lo_cls, lo_aux, lo_attn):
+    dev = lo_cls.device
+    mid = torch.empty((d.n, d.hm, d.wm, 40), dtype=F32, device=dev)
+    mid_sup = torch.empty((d.n, d.hm, d.wm, 20), dtype=F32, device=dev) if d.sup_wt != 0.0 else None
+    check(lib().b200seg_mscale_mid_fwd(ctypes.byref(d), ptr(lo_cls), ptr(lo_aux), ptr(lo_attn), ptr(mid), ptr(mid_sup),
+                                       stream_ptr()), "mscale_mid_fwd")
+    return mid, mid_sup
+
+
+def mscale_loss_fwd(d, labels, inv_count, hi_cls, hi_aux, mid, mid_sup):
+    dev = hi_cls.device
+    L = lib()
+    nb = L.b200seg_mscale_loss_blocks(ctypes.byref(d))
+    npix = d.n * d.h * d.w
+    g_hi = torch.empty((npix, 40), dtype=BF16, device=dev)
+    g_lo = torch.empty((npix, 40), dtype=BF16, device=dev) if d.hm > 0 else None
+    g_sup = torch.empty((npix, 40), dtype=BF16, device=dev) if (d.hm > 0 and d.sup_wt != 0.0) else None
+    ws = torch.empty((nb * 4,), dtype=F32, device=dev)
+    loss = torch.empty((5,), dtype=F32, device=dev)
+    check(L.b200seg_mscale_loss_fwd(ctypes.byref(d), ptr(labels), ptr(inv_count), ptr(hi_cls), ptr(hi_aux), ptr(mid),
+                                    ptr(mid_sup), ptr(g_hi), ptr(g_lo), ptr(g_sup), ptr(ws), ptr(loss), stream_ptr()),
+          "mscale_loss_fwd")
+    return loss, g_hi, g_lo, g_sup
+
+
+def mscale_hi_bwd(d, g_hi):
+    dev = g_hi.device
+    d_cls = torch.empty((d.n, d.hq, d.wq, 32), dtype=BF16, device=dev)
+    d_aux = torch.empty((d.n, d.hq, d.wq, 32), dtype=BF16, device=dev) if d.nheads > 1 else None
+    check(lib().b200seg_mscale_hi_bwd(ctypes.byref(d), ptr(g_hi), ptr(d_cls), ptr(d_aux), stream_ptr()),
+          "mscale_hi_bwd")
+    return d_cls, d_aux
+
+
+def mscale_lo_bwd(d, g_lo, g_sup, lo_cls, lo_aux, lo_attn, mid):
+    dev = g_lo.device
+    ws = torch.empty((d.n, d.hm, d.wm, 40), dtype=F32, device=dev)
+    d_cls = torch.empty((d.n, d.hl, d.wl, 32), dtype=BF16, device=dev)
+    d_aux = torch.empty((d.n, d.hl, d.wl, 32), dtype=BF16, device=dev) if d.nheads > 1 else None
+    d_attn = torch.empty((d.n, d.hl, d.wl, 8), dtype=BF16, device=dev)
+    check(lib().b200seg_mscale_lo_bwd(ctypes.byref(d), ptr(g_lo), ptr(g_sup), ptr(lo_cls), ptr(lo_aux), ptr(lo_attn),
+                                      ptr(mid), ptr(ws), ptr(d_cls), ptr(d_aux), ptr(d_attn), stream_ptr()),
+          "mscale_lo_bwd")
+    return d_cls, d_aux, d_attn

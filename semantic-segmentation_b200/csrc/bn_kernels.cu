@@ -1,0 +1,348 @@
+// Training-mode BatchNorm around the tcgen05 convolutions (reference: Norm2d -> torch.nn.BatchNorm2d /
+// apex SyncBatchNorm, network/mynn.py:18-24; eps 1e-5, momentum 0.1, biased variance to normalise, unbiased for the
+// running estimate). All kernels are HBM-bound streaming passes over NHWC bf16 with 16-byte vector accesses.
+//
+//   forward : conv epilogue partials -> bn_finalize (scale/shift/mean/invstd + running stats) -> bn_apply
+//             z = relu?( (y*scale + shift [+ residual]) ) [* post_scale[n][c]]          (Dropout2d folded in post_scale)
+//   backward: bn_bwd_reduce (sum g, sum g*xhat per channel; g = dz * (mask>0)) -> bn_bwd_finalize (dgamma, dbeta, c1, c2)
+//             -> bn_bwd_apply  dy = gamma*invstd*(g - c1 - xhat*c2)  [and g written out for the residual branch]
+#include "ptx.cuh"
+#include "../../include/b200seg.h"
+#include "vec.cuh"
+
+namespace b200seg {
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int Cpad, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int g = 0; g < G; ++g) {
+    s1 += (double)partials[(size_t)g * 2 * Cpad + c];
+    s2 += (double)partials[(size_t)g * 2 * Cpad + Cpad + c];
+  }
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g_ = gamma ? gamma[c] : 1.f, b_ = beta ? beta[c] : 0.f;
+  scale[c] = g_ * invstd;
+  shift[c] = b_ - (float)mean * g_ * invstd;
+  mean_out[c] = (float)mean;
+  invstd_out[c] = invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.f ? var * (double)count / ((double)count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// Eval-mode: scale/shift from the running statistics.
+__global__ void bn_eval_params_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = rsqrtf(running_var[c] + eps);
+  const float g_ = gamma[c];
+  scale[c] = g_ * invstd;
+  shift[c] = beta[c] - running_mean[c] * g_ * invstd;
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const float* __restrict__ scale,
+                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_ld,
+                const float* __restrict__ post_scale, int relu, __nv_bfloat16* __restrict__ z, int z_ld,
+                long long npix, int hw, int C) {
+  extern __shared__ float s_par[];   // [2][C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = scale[i]; s_par[C + i] = shift[i]; }
+  __syncthreads();
+  const int groups = C >> 3;
+  const long long total = npix * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long pix = idx / groups;
+    const int c0 = (int)(idx - pix * groups) << 3;
+    float v[8];
+    load8(y + pix * y_ld + c0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * s_par[c0 + j] + s_par[C + c0 + j];
+    if (res) {
+      float r[8];
+      load8(res + pix * res_ld + c0, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (post_scale) {
+      const float* ps = post_scale + (pix / hw) * C + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= ps[j];
+    }
+    store8(z + pix * z_ld + c0, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// Thread (r, cg): r-th pixel row of the block, 8-channel group cg. blockDim.x = groups * rows.
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv_bfloat16* __restrict__ mask,
+                     int mask_ld, const float* __restrict__ post_scale, const __nv_bfloat16* __restrict__ y, int y_ld,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, long long npix, int hw, int C,
+                     int rows, float* __restrict__ partials) {
+  extern __shared__ float s_red[];   // [rows][groups][16]
+  const int groups = C >> 3;
+  const int cg = threadIdx.x % groups, r = threadIdx.x / groups;
+  const int c0 = cg << 3;
+  float m[8], is[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { m[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; s1[j] = 0.f; s2[j] = 0.f; }
+  if (r < rows) {
+    for (long long pix = (long long)blockIdx.x * rows + r; pix < npix; pix += (long long)gridDim.x * rows) {
+      float g[8], yv[8];
+      load8(dz + pix * dz_ld + c0, g);
+      if (post_scale) {
+        const float* ps = post_scale + (pix / hw) * C + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] *= ps[j];
+      }
+      if (mask) {
+        float mk[8];
+        load8(mask + pix * mask_ld + c0, mk);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = mk[j] > 0.f ? g[j] : 0.f;
+      }
+      load8(y + pix * y_ld + c0, yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += g[j];
+        s2[j] += g[j] * (yv[j] - m[j]) * is[j];
+      }
+    }
+    float* dst = s_red + ((size_t)r * groups + cg) * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dst[j] = s1[j]; dst[8 + j] = s2[j]; }
+  }
+  __syncthreads();
+  // deterministic in-block reduction over rows
+  for (int i = threadIdx.x; i < groups * 16; i += blockDim.x) {
+    const int g_ = i / 16, k = i % 16;
+    float acc = 0.f;
+    for (int rr = 0; rr < rows; ++rr) acc += s_red[((size_t)rr * groups + g_) * 16 + k];
+    const int c = g_ * 8 + (k & 7);
+    partials[(size_t)blockIdx.x * 2 * C + (k >> 3) * C + c] = acc;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, float count,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
+                                       float* __restrict__ c2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int g = 0; g < G; ++g) {
+    s1 += (double)partials[(size_t)g * 2 * C + c];
+    s2 += (double)partials[(size_t)g * 2 * C + C + c];
+  }
+  if (dbeta) dbeta[c] += (float)s1;     // parameter gradients accumulate (two scale passes share the weights)
+  if (dgamma) dgamma[c] += (float)s2;
+  c1[c] = (float)(s1 / count);
+  c2[c] = (float)(s2 / count);
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv_bfloat16* __restrict__ mask,
+                    int mask_ld, const float* __restrict__ post_scale, const __nv_bfloat16* __restrict__ y, int y_ld,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ c1, const float* __restrict__ c2, __nv_bfloat16* __restrict__ dy, int dy_ld,
+                    __nv_bfloat16* __restrict__ g_out, int g_ld, int g_accumulate, long long npix, int hw, int C) {
+  extern __shared__ float s_par[];   // [5][C]: mean, invstd, gamma*invstd, c1, c2
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_par[i] = mean[i];
+    s_par[C + i] = invstd[i];
+    s_par[2 * C + i] = (gamma ? gamma[i] : 1.f) * invstd[i];
+    s_par[3 * C + i] = c1[i];
+    s_par[4 * C + i] = c2[i];
+  }
+  __syncthreads();
+  const int groups = C >> 3;
+  const long long total = npix * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long pix = idx / groups;
+    const int c0 = (int)(idx - pix * groups) << 3;
+    float g[8], yv[8], o[8];
+    load8(dz + pix * dz_ld + c0, g);
+    if (post_scale) {
+      const float* ps = post_scale + (pix / hw) * C + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= ps[j];
+    }
+    if (mask) {
+      float mk[8];
+      load8(mask + pix * mask_ld + c0, mk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = mk[j] > 0.f ? g[j] : 0.f;
+    }
+    load8(y + pix * y_ld + c0, yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xhat = (yv[j] - s_par[c0 + j]) * s_par[C + c0 + j];
+      o[j] = s_par[2 * C + c0 + j] * (g[j] - s_par[3 * C + c0 + j] - xhat * s_par[4 * C + c0 + j]);
+    }
+    store8(dy + pix * dy_ld + c0, o);
+    if (g_out) {
+      if (g_accumulate) {
+        float old[8];
+        load8(g_out + pix * g_ld + c0, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += old[j];
+      }
+      store8(g_out + pix * g_ld + c0, g);
+    }
+  }
+}
+
+// dst = (accumulate ? dst : 0) + src * (mask > 0)    (ReLU backward into a fan-out gradient)
+__global__ void __launch_bounds__(256)
+masked_accum_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, const __nv_bfloat16* __restrict__ mask,
+                    int mask_ld, __nv_bfloat16* __restrict__ dst, int dst_ld, int accumulate, long long npix, int C) {
+  const int groups = C >> 3;
+  const long long total = npix * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long pix = idx / groups;
+    const int c0 = (int)(idx - pix * groups) << 3;
+    float g[8];
+    load8(src + pix * src_ld + c0, g);
+    if (mask) {
+      float mk[8];
+      load8(mask + pix * mask_ld + c0, mk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = mk[j] > 0.f ? g[j] : 0.f;
+    }
+    if (accumulate) {
+      float old[8];
+      load8(dst + pix * dst_ld + c0, old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += old[j];
+    }
+    store8(dst + pix * dst_ld + c0, g);
+  }
+}
+
+static inline int ew_grid(long long total_threads) {
+  long long b = (total_threads + 255) / 256;
+  const long long cap = 148LL * 8;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace b200seg
+
+using namespace b200seg;
+
+#define CHECK_LAUNCH()                      \
+  do {                                      \
+    cudaError_t e_ = cudaGetLastError();    \
+    return e_ == cudaSuccess ? 0 : (int)e_; \
+  } while (0)
+
+extern "C" int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t c, int32_t cpad, float count,
+                                   const float* gamma, const float* beta, float eps, float momentum,
+                                   float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
+                                   float* shift, float* mean, float* invstd, void* stream) {
+  if (!partials || !scale || !shift || !mean || !invstd || c <= 0 || grid <= 0) return B200SEG_E_BADARG;
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      partials, grid, c, cpad, count, gamma, beta, eps, momentum, running_mean, running_var,
+      (long long*)num_batches_tracked, scale, shift, mean, invstd);
+  CHECK_LAUNCH();
+}
+
+extern "C" int b200seg_bn_eval_params(int32_t c, const float* gamma, const float* beta, float eps,
+                                      const float* running_mean, const float* running_var, float* scale, float* shift,
+                                      void* stream) {
+  if (!gamma || !beta || !running_mean || !running_var || !scale || !shift) return B200SEG_E_BADARG;
+  bn_eval_params_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c, gamma, beta, eps, running_mean,
+                                                                          running_var, scale, shift);
+  CHECK_LAUNCH();
+}
+
+extern "C" int b200seg_bn_apply(const void* y, int32_t y_ld, const float* scale, const float* shift, const void* res,
+                                int32_t res_ld, const float* post_scale, int32_t relu, void* z, int32_t z_ld,
+                                int64_t npix, int32_t hw, int32_t c, void* stream) {
+  if (!y || !z || !scale || !shift || c % 8 || y_ld % 8 || z_ld % 8 || (res && res_ld % 8)) return B200SEG_E_BADARG;
+  bn_apply_kernel<<<ew_grid(npix * (c / 8)), 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, post_scale, relu,
+      (__nv_bfloat16*)z, z_ld, npix, hw, c);
+  CHECK_LAUNCH();
+}
+
+static inline void reduce_shape(int c, int* rows, int* threads) {
+  const int groups = c / 8;
+  int r = 256 / groups;
+  if (r < 1) r = 1;
+  *rows = r;
+  *threads = groups * r;
+}
+
+extern "C" int32_t b200seg_bn_bwd_grid(int64_t npix, int32_t c) {
+  int rows, threads;
+  reduce_shape(c, &rows, &threads);
+  long long b = (npix + rows - 1) / rows;
+  const long long cap = 148LL * 4;
+  return (int32_t)(b < cap ? b : cap);
+}
+
+extern "C" int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld,
+                                     const float* post_scale, const void* y, int32_t y_ld, const float* mean,
+                                     const float* invstd, int64_t npix, int32_t hw, int32_t c, float* partials,
+                                     void* stream) {
+  if (!dz || !y || !mean || !invstd || !partials || c % 8 || c > 2048) return B200SEG_E_BADARG;
+  int rows, threads;
+  reduce_shape(c, &rows, &threads);
+  if (threads > 256) return B200SEG_E_BADARG;
+  const int grid = b200seg_bn_bwd_grid(npix, c);
+  const size_t smem = (size_t)rows * (c / 8) * 16 * sizeof(float);
+  bn_bwd_reduce_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y, y_ld,
+      mean, invstd, npix, hw, c, rows, partials);
+  CHECK_LAUNCH();
+}
+
+extern "C" int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int32_t c, float count, float* dgamma,
+                                       float* dbeta, float* c1, float* c2, void* stream) {
+  if (!partials || !c1 || !c2) return B200SEG_E_BADARG;
+  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, grid, c, count, dgamma, dbeta,
+                                                                           c1, c2);
+  CHECK_LAUNCH();
+}
+
+extern "C" int b200seg_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld,
+                                    const float* post_scale, const void* y, int32_t y_ld, const float* mean,
+                                    const float* invstd, const float* gamma, const float* c1, const float* c2, void* dy,
+                                    int32_t dy_ld, void* g_out, int32_t g_ld, int32_t g_accumulate, int64_t npix,
+                                    int32_t hw, int32_t c, void* stream) {
+  if (!dz || !y || !dy || !mean || !invstd || !c1 || !c2 || c % 8) return B200SEG_E_BADARG;
+  bn_bwd_apply_kernel<<<ew_grid(npix * (c / 8)), 256, 5 * c * sizeof(float), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y, y_ld,
+      mean, invstd, gamma, c1, c2, (__nv_bfloat16*)dy, dy_ld, (__nv_bfloat16*)g_out, g_ld, g_accumulate, npix, hw, c);
+  CHECK_LAUNCH();
+}
+
+extern "C" int b200seg_masked_accum(const void* src, int32_t src_ld, const void* mask, int32_t mask_ld, void* dst,
+                                    int32_t dst_ld, int32_t accumulate, int64_t npix, int32_t c, void* stream) {
+  if (!src || !dst || c % 8) return B200SEG_E_BADARG;
+  masked_accum_kernel<<<ew_grid(npix * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)src, src_ld, (const __nv_bfloat16*)mask, mask_ld, (__nv_bfloat16*)dst, dst_ld, accumulate,
+      npix, c);
+  CHECK_LAUNCH();
+}

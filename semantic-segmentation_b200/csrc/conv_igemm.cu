@@ -16,15 +16,20 @@
 #include "tma_host.h"
 #include "../../include/b200seg.h"
 #include "conv_common.h"
+#include "vec.cuh"
 
 namespace b200seg {
 
 struct ConvKParams {
-  int N, Ho, Wo, Cout;
-  int ksize, stride, pad;
+  int N, Ho, Wo, Cout;          // Ho/Wo: full output extent (addressing)
+  int sub_H, sub_W;             // extent of the output sub-lattice this launch covers (== Ho/Wo unless strided dgrad)
+  int in_stride;                // input sampling stride (forward conv stride; 1 for data gradients)
+  int out_stride, out_off_h, out_off_w;   // output lattice: row = r*out_stride + out_off_h
+  int ntaps;
+  int tap_dh[9], tap_dw[9], tap_w[9];     // input offset and weight-tap index per filter tap
   int cchunks, KC, BN, n_tiles;
   int TH, TW, tiles_h, tiles_w, total_tiles;
-  int y_ld, out_fp32, has_bias, emit_stats, cout_pad;
+  int y_ld, out_fp32, has_bias, emit_stats, cout_pad, addend_ld;
   int layout_type, sbo;
   int a_bytes, b_bytes, stage_bytes, nstages;
 };
@@ -62,7 +67,7 @@ __device__ __forceinline__ void butterfly16(float (&v)[16], uint32_t lane) {
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ConvKParams p, void* __restrict__ y, const float* __restrict__ bias,
-                  float* __restrict__ stats_partials) {
+                  float* __restrict__ stats_partials, const __nv_bfloat16* __restrict__ addend) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A|B] (1024-aligned) | barriers | tmem ptr | stats[4][2][cout_pad]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -99,7 +104,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int kblocks = p.ksize * p.ksize * p.cchunks;
+  const int kblocks = p.ntaps * p.cchunks;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -111,20 +116,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tw_i = m_tile % p.tiles_w;
         const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
         const int img = m_tile / (p.tiles_w * p.tiles_h);
-        const int h0 = th_i * p.TH * p.stride - p.pad;
-        const int w0 = tw_i * p.TW * p.stride - p.pad;
+        const int h0 = th_i * p.TH * p.in_stride;
+        const int w0 = tw_i * p.TW * p.in_stride;
         const int n0 = n_tile * p.BN;
-        for (int kh = 0; kh < p.ksize; ++kh)
-          for (int kw = 0; kw < p.ksize; ++kw)
-            for (int cc = 0; cc < p.cchunks; ++cc) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sa = stage_base + (size_t)stage * p.stage_bytes;
-              uint8_t* sb = sa + p.a_bytes;
-              mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-              tma_load_4d(&tmA, &full_bar[stage], sa, cc * p.KC, w0 + kw, h0 + kh, img);
-              tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.KC, kh * p.ksize + kw, n0);
-              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
-            }
+        for (int t = 0; t < p.ntaps; ++t)
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = stage_base + (size_t)stage * p.stage_bytes;
+            uint8_t* sb = sa + p.a_bytes;
+            mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+            tma_load_4d(&tmA, &full_bar[stage], sa, cc * p.KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], img);
+            tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.KC, p.tap_w[t], n0);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          }
       }
     }
     __syncwarp();
@@ -174,8 +178,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int tw_i = m_tile % p.tiles_w;
       const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
       const int img = m_tile / (p.tiles_w * p.tiles_h);
-      const int ho = th_i * p.TH + th, wo = tw_i * p.TW + tw;
-      const bool valid = (ho < p.Ho) && (wo < p.Wo);
+      const int hs = th_i * p.TH + th, ws = tw_i * p.TW + tw;
+      const bool valid = (hs < p.sub_H) && (ws < p.sub_W);
+      const int ho = hs * p.out_stride + p.out_off_h, wo = ws * p.out_stride + p.out_off_w;
       const int n0 = n_tile * p.BN;
       const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
 
@@ -195,6 +200,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.has_bias) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.Cout) ? __ldg(bias + c0 + j) : 0.f;
+        }
+        if (addend != nullptr && valid && c0 + 16 <= p.Cout) {
+          const __nv_bfloat16* ap = addend + pix * p.addend_ld + c0;
+          float a0[8], a1[8];
+          load8(ap, a0);
+          load8(ap + 8, a1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
         }
         if (p.out_fp32) {
           if (valid) {
@@ -252,40 +265,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------- host side
-int conv_plan(const b200seg_conv_desc* d, ConvPlan* pl) {
-  if (!d || d->n <= 0 || d->h <= 0 || d->w <= 0) return B200SEG_E_BADARG;
-  if (!((d->ksize == 1 && d->pad == 0) || (d->ksize == 3 && d->pad == 1))) return B200SEG_E_BADARG;
-  if (d->stride != 1 && d->stride != 2) return B200SEG_E_BADARG;
-  if (d->cin % 8 || d->x_ld % 8 || d->x_ld < d->cin) return B200SEG_E_BADARG;
-  if (d->cout <= 0 || d->y_ld < d->cout) return B200SEG_E_BADARG;
-  if (!d->out_fp32 && (d->y_ld % 8)) return B200SEG_E_BADARG;
-  pl->Ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
-  pl->Wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
-  // channel chunk / swizzle width: the widest of {64, 32, 16} that tiles cin without waste (zero-fill covers 720).
+// Geometry of one launch: an implicit GEMM over an output lattice of sub_h x sub_w pixels per image.
+struct LaunchGeom {
+  int n, in_h, in_w, in_c, in_ld;       // operand A tensor
+  int out_h, out_w, out_c, out_ld;      // full output tensor
+  int sub_h, sub_w, in_stride, out_stride, out_off_h, out_off_w;
+  int ntaps, tap_dh[9], tap_dw[9], tap_w[9], wtaps;   // wtaps = taps dimension of the weight tensor
+  int out_fp32, has_bias, emit_stats, force_kc;
+};
+
+static int plan_geom(const LaunchGeom& g, ConvPlan* pl) {
+  if (g.n <= 0 || g.sub_h <= 0 || g.sub_w <= 0) return B200SEG_E_BADARG;
+  if (g.in_c % 8 || g.in_ld % 8 || g.in_ld < g.in_c) return B200SEG_E_BADARG;
+  if (g.out_c <= 0 || g.out_ld < g.out_c) return B200SEG_E_BADARG;
+  if (!g.out_fp32 && (g.out_ld % 8)) return B200SEG_E_BADARG;
+  pl->Ho = g.sub_h; pl->Wo = g.sub_w;
+  // channel chunk / swizzle width: the widest of {64, 32, 16} that tiles cin without waste (zero-fill covers 720 and 48).
   int KC = 64;
-  if (d->cin % 64 != 0) {
-    if (d->cin % 32 == 0 && d->cin < 256) KC = 32;
-    else if (d->cin % 16 == 0 && d->cin < 128) KC = 16;
+  if (g.in_c % 64 != 0) {
+    if (g.in_c % 32 == 0 && g.in_c < 256) KC = 32;
+    else if (g.in_c == 16) KC = 16;
     else KC = 64;   // remainder chunk is zero-filled by TMA on both operands
   }
-  if (d->reserved == 16 || d->reserved == 32 || d->reserved == 64) KC = d->reserved;   // test hook: force the chunk width
+  if (g.force_kc == 16 || g.force_kc == 32 || g.force_kc == 64) KC = g.force_kc;   // test hook
   pl->KC = KC;
-  pl->cchunks = (d->cin + KC - 1) / KC;
+  pl->cchunks = (g.in_c + KC - 1) / KC;
   // N tile: whole cout when it fits one accumulator stage, else the smallest even split into <= 256-wide multiples of 16
-  int cout16 = (d->cout + 15) / 16 * 16;
+  int cout16 = (g.out_c + 15) / 16 * 16;
   int n_tiles = (cout16 + 255) / 256;
   int BN = ((cout16 / 16 + n_tiles - 1) / n_tiles) * 16;
   if (BN < 16) BN = 16;
   pl->BN = BN;
   pl->n_tiles = (cout16 + BN - 1) / BN;
   pl->cout_pad = pl->n_tiles * BN;
-  // spatial patch of 128 output pixels
   int TW = 16, TH = 8;
-  if (pl->Wo <= 8) { TW = 8; TH = 16; }
+  if (g.sub_w <= 8) { TW = 8; TH = 16; }
   pl->TW = TW; pl->TH = TH;
-  pl->tiles_w = (pl->Wo + TW - 1) / TW;
-  pl->tiles_h = (pl->Ho + TH - 1) / TH;
-  pl->total_tiles = d->n * pl->tiles_h * pl->tiles_w * pl->n_tiles;
+  pl->tiles_w = (g.sub_w + TW - 1) / TW;
+  pl->tiles_h = (g.sub_h + TH - 1) / TH;
+  pl->total_tiles = g.n * pl->tiles_h * pl->tiles_w * pl->n_tiles;
   pl->grid = pl->total_tiles < B200SEG_MAX_CTAS ? pl->total_tiles : B200SEG_MAX_CTAS;
   pl->a_bytes = 128 * KC * 2;
   pl->b_bytes = BN * KC * 2;
@@ -300,6 +318,94 @@ int conv_plan(const b200seg_conv_desc* d, ConvPlan* pl) {
   return 0;
 }
 
+static LaunchGeom fwd_geom(const b200seg_conv_desc* d) {
+  LaunchGeom g{};
+  g.n = d->n; g.in_h = d->h; g.in_w = d->w; g.in_c = d->cin; g.in_ld = d->x_ld;
+  g.out_h = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
+  g.out_w = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
+  g.out_c = d->cout; g.out_ld = d->y_ld;
+  g.sub_h = g.out_h; g.sub_w = g.out_w;
+  g.in_stride = d->stride; g.out_stride = 1; g.out_off_h = g.out_off_w = 0;
+  g.ntaps = d->ksize * d->ksize; g.wtaps = g.ntaps;
+  for (int kh = 0; kh < d->ksize; ++kh)
+    for (int kw = 0; kw < d->ksize; ++kw) {
+      const int t = kh * d->ksize + kw;
+      g.tap_dh[t] = kh - d->pad; g.tap_dw[t] = kw - d->pad; g.tap_w[t] = t;
+    }
+  g.out_fp32 = d->out_fp32; g.has_bias = d->has_bias; g.emit_stats = d->emit_stats; g.force_kc = d->reserved;
+  return g;
+}
+
+static bool desc_ok(const b200seg_conv_desc* d) {
+  if (!d || d->n <= 0 || d->h <= 0 || d->w <= 0) return false;
+  if (!((d->ksize == 1 && d->pad == 0) || (d->ksize == 3 && d->pad == 1))) return false;
+  if (d->stride != 1 && d->stride != 2) return false;
+  return true;
+}
+
+int conv_plan(const b200seg_conv_desc* d, ConvPlan* pl) {
+  if (!desc_ok(d)) return B200SEG_E_BADARG;
+  return plan_geom(fwd_geom(d), pl);
+}
+
+static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const float* bias, void* out,
+                       float* stats_partials, int32_t* stats_grid, const void* addend, int addend_ld,
+                       cudaStream_t stream) {
+  ConvPlan pl;
+  int rc = plan_geom(g, &pl);
+  if (rc) return rc;
+  if (!a || !w || !out) return B200SEG_E_BADARG;
+  if (g.has_bias && !bias) return B200SEG_E_BADARG;
+  if (g.emit_stats && (!stats_partials || g.out_fp32)) return B200SEG_E_BADARG;
+  if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15))
+    return B200SEG_E_BADARG;
+  if (addend && (addend_ld % 8)) return B200SEG_E_BADARG;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)g.in_c, (uint64_t)g.in_w, (uint64_t)g.in_h, (uint64_t)g.n};
+    uint64_t strides[3] = {(uint64_t)g.in_ld * 2, (uint64_t)g.in_w * g.in_ld * 2,
+                           (uint64_t)g.in_h * g.in_w * g.in_ld * 2};
+    uint32_t box[4] = {(uint32_t)pl.KC, (uint32_t)(pl.TW * g.in_stride), (uint32_t)(pl.TH * g.in_stride), 1};
+    uint32_t es[4] = {1, (uint32_t)g.in_stride, (uint32_t)g.in_stride, 1};
+    rc = encode_bf16(&tmA, a, 4, dims, strides, box, es, swizzle_for_bytes(pl.KC * 2));
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)g.in_c, (uint64_t)g.wtaps, (uint64_t)g.out_c};
+    uint64_t strides[2] = {(uint64_t)g.in_c * 2, (uint64_t)g.wtaps * g.in_c * 2};
+    uint32_t box[3] = {(uint32_t)pl.KC, 1, (uint32_t)pl.BN};
+    rc = encode_bf16(&tmB, w, 3, dims, strides, box, nullptr, swizzle_for_bytes(pl.KC * 2));
+    if (rc) return rc;
+  }
+  ConvKParams p;
+  p.N = g.n; p.Ho = g.out_h; p.Wo = g.out_w; p.Cout = g.out_c;
+  p.sub_H = g.sub_h; p.sub_W = g.sub_w;
+  p.in_stride = g.in_stride; p.out_stride = g.out_stride; p.out_off_h = g.out_off_h; p.out_off_w = g.out_off_w;
+  p.ntaps = g.ntaps;
+  for (int t = 0; t < 9; ++t) { p.tap_dh[t] = g.tap_dh[t]; p.tap_dw[t] = g.tap_dw[t]; p.tap_w[t] = g.tap_w[t]; }
+  p.cchunks = pl.cchunks; p.KC = pl.KC; p.BN = pl.BN; p.n_tiles = pl.n_tiles;
+  p.TH = pl.TH; p.TW = pl.TW; p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w; p.total_tiles = pl.total_tiles;
+  p.y_ld = g.out_ld; p.out_fp32 = g.out_fp32; p.has_bias = g.has_bias; p.emit_stats = g.emit_stats;
+  p.cout_pad = pl.cout_pad; p.addend_ld = addend_ld;
+  p.layout_type = pl.KC == 64 ? 2 : (pl.KC == 32 ? 4 : 6);
+  p.sbo = 8 * pl.KC * 2;
+  p.a_bytes = pl.a_bytes; p.b_bytes = pl.b_bytes; p.stage_bytes = pl.stage_bytes; p.nstages = pl.nstages;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  conv_igemm_kernel<<<pl.grid, kThreads, pl.smem_bytes, stream>>>(tmA, tmB, p, out, bias, stats_partials,
+                                                                  (const __nv_bfloat16*)addend);
+  if (stats_grid) *stats_grid = pl.grid;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 }  // namespace b200seg
 
 using namespace b200seg;
@@ -312,52 +418,53 @@ extern "C" size_t b200seg_conv2d_stats_elems(const b200seg_conv_desc* d) {
 
 extern "C" int b200seg_conv2d_fwd(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
                                   void* y, float* stats_partials, int32_t* stats_grid, void* stream) {
-  ConvPlan pl;
-  int rc = conv_plan(d, &pl);
-  if (rc) return rc;
-  if (!x || !w_ohwi || !y) return B200SEG_E_BADARG;
-  if (d->has_bias && !bias) return B200SEG_E_BADARG;
-  if (d->emit_stats && (!stats_partials || d->out_fp32)) return B200SEG_E_BADARG;
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w_ohwi) & 15) ||
-      (reinterpret_cast<uintptr_t>(y) & 15))
-    return B200SEG_E_BADARG;
+  if (!desc_ok(d)) return B200SEG_E_BADARG;
+  return launch_geom(fwd_geom(d), x, w_ohwi, bias, y, stats_partials, stats_grid, nullptr, 0, (cudaStream_t)stream);
+}
 
-  CUtensorMap tmA, tmB;
-  {
-    uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
-    uint64_t strides[3] = {(uint64_t)d->x_ld * 2, (uint64_t)d->w * d->x_ld * 2, (uint64_t)d->h * d->w * d->x_ld * 2};
-    uint32_t box[4] = {(uint32_t)pl.KC, (uint32_t)(pl.TW * d->stride), (uint32_t)(pl.TH * d->stride), 1};
-    uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
-    rc = encode_bf16(&tmA, x, 4, dims, strides, box, es, swizzle_for_bytes(pl.KC * 2));
-    if (rc) return rc;
+// Data gradient. d describes the FORWARD convolution. dx[n,h,w,cin] = sum_taps dy[...] * W  (+ addend).
+//   stride 1: one launch, a 3x3 (or 1x1) convolution of dy with the flipped, transposed weights;
+//   stride 2: four launches, one per output parity class (a,b): dx[2u+a, 2v+b] only receives the taps with
+//             kh = a+1 (mod 2), kw = b+1 (mod 2), read from dy[u + (a+1-kh)/2, v + (b+1-kw)/2].
+extern "C" int b200seg_conv2d_dgrad(const b200seg_conv_desc* d, const void* dy, int32_t dy_ld, const void* w_dgrad,
+                                    const void* addend, int32_t addend_ld, void* dx, int32_t dx_ld, void* stream) {
+  if (!desc_ok(d)) return B200SEG_E_BADARG;
+  const int Ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
+  const int Wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
+  const int K = d->ksize, taps = K * K;
+  LaunchGeom g{};
+  g.n = d->n; g.in_h = Ho; g.in_w = Wo; g.in_c = (d->cout + 7) / 8 * 8; g.in_ld = dy_ld;
+  g.out_h = d->h; g.out_w = d->w; g.out_c = d->cin; g.out_ld = dx_ld;
+  g.in_stride = 1; g.wtaps = taps;
+  g.out_fp32 = 0; g.has_bias = 0; g.emit_stats = 0; g.force_kc = d->reserved;
+  if (d->stride == 1) {
+    g.sub_h = d->h; g.sub_w = d->w; g.out_stride = 1; g.out_off_h = g.out_off_w = 0;
+    g.ntaps = taps;
+    for (int kh = 0; kh < K; ++kh)
+      for (int kw = 0; kw < K; ++kw) {
+        const int t = kh * K + kw;
+        g.tap_dh[t] = d->pad - kh; g.tap_dw[t] = d->pad - kw; g.tap_w[t] = taps - 1 - t;
+      }
+    return launch_geom(g, dy, w_dgrad, nullptr, dx, nullptr, nullptr, addend, addend_ld, (cudaStream_t)stream);
   }
-  {
-    const int taps = d->ksize * d->ksize;
-    uint64_t dims[3] = {(uint64_t)d->cin, (uint64_t)taps, (uint64_t)d->cout};
-    uint64_t strides[2] = {(uint64_t)d->cin * 2, (uint64_t)taps * d->cin * 2};
-    uint32_t box[3] = {(uint32_t)pl.KC, 1, (uint32_t)pl.BN};
-    rc = encode_bf16(&tmB, w_ohwi, 3, dims, strides, box, nullptr, swizzle_for_bytes(pl.KC * 2));
-    if (rc) return rc;
-  }
-  ConvKParams p;
-  p.N = d->n; p.Ho = pl.Ho; p.Wo = pl.Wo; p.Cout = d->cout;
-  p.ksize = d->ksize; p.stride = d->stride; p.pad = d->pad;
-  p.cchunks = pl.cchunks; p.KC = pl.KC; p.BN = pl.BN; p.n_tiles = pl.n_tiles;
-  p.TH = pl.TH; p.TW = pl.TW; p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w; p.total_tiles = pl.total_tiles;
-  p.y_ld = d->y_ld; p.out_fp32 = d->out_fp32; p.has_bias = d->has_bias; p.emit_stats = d->emit_stats;
-  p.cout_pad = pl.cout_pad;
-  p.layout_type = pl.KC == 64 ? 2 : (pl.KC == 32 ? 4 : 6);
-  p.sbo = 8 * pl.KC * 2;
-  p.a_bytes = pl.a_bytes; p.b_bytes = pl.b_bytes; p.stage_bytes = pl.stage_bytes; p.nstages = pl.nstages;
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  conv_igemm_kernel<<<pl.grid, kThreads, pl.smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p, y, bias, stats_partials);
-  if (stats_grid) *stats_grid = pl.grid;
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 0 : (int)e;
+  if (K != 3) return B200SEG_E_BADARG;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      g.sub_h = (d->h - a + 1) / 2; g.sub_w = (d->w - b + 1) / 2;
+      if (g.sub_h <= 0 || g.sub_w <= 0) continue;
+      g.out_stride = 2; g.out_off_h = a; g.out_off_w = b;
+      g.ntaps = 0;
+      for (int kh = 0; kh < 3; ++kh) {
+        if (((a + 1 - kh) & 1) != 0) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+          if (((b + 1 - kw) & 1) != 0) continue;
+          g.tap_dh[g.ntaps] = (a + 1 - kh) / 2; g.tap_dw[g.ntaps] = (b + 1 - kw) / 2;
+          g.tap_w[g.ntaps] = taps - 1 - (kh * 3 + kw);
+          ++g.ntaps;
+        }
+      }
+      int rc = launch_geom(g, dy, w_dgrad, nullptr, dx, nullptr, nullptr, addend, addend_ld, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+  return 0;
 }

@@ -36,7 +36,7 @@ __global__ void direct_conv_kernel(const __nv_bfloat16* __restrict__ x, const __
 }
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, int K, __nv_bfloat16* __restrict__ ohwi,
-                                   __nv_bfloat16* __restrict__ dgrad) {
+                                   __nv_bfloat16* __restrict__ dgrad, int Opad) {
   const int taps = K * K;
   const size_t total = (size_t)O * I * taps;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -46,7 +46,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, in
     const int o = idx / ((size_t)taps * I);
     const __nv_bfloat16 v = __float2bfloat16_rn(w[idx]);
     if (ohwi) ohwi[((size_t)o * taps + t) * I + i] = v;
-    if (dgrad) dgrad[((size_t)i * taps + (taps - 1 - t)) * O + o] = v;
+    if (dgrad) dgrad[((size_t)i * taps + (taps - 1 - t)) * Opad + o] = v;   // pad columns stay zero (caller memset)
   }
 }
 
@@ -73,13 +73,14 @@ extern "C" int b200seg_conv2d_fwd_direct(const b200seg_conv_desc* d, const void*
 }
 
 extern "C" int b200seg_pack_weight(const float* w_oihw, int32_t o, int32_t i, int32_t ksize, void* w_ohwi,
-                                   void* w_dgrad, void* stream) {
+                                   void* w_dgrad, int32_t o_pad, void* stream) {
+  if (w_dgrad && o_pad < o) return B200SEG_E_BADARG;
   if (!w_oihw || o <= 0 || i <= 0 || (ksize != 1 && ksize != 3)) return B200SEG_E_BADARG;
   const size_t total = (size_t)o * i * ksize * ksize;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, o, i, ksize, (__nv_bfloat16*)w_ohwi,
-                                                               (__nv_bfloat16*)w_dgrad);
+                                                               (__nv_bfloat16*)w_dgrad, o_pad);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
