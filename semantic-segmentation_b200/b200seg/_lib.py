@@ -121,9 +121,14 @@ def lib():
     return _lib
 
 
-def check(rc, what):
+KERNEL_LAUNCHES = 0   # running count of kernels launched through the ABI by this process (bench.py reports it)
+
+
+def check(rc, what, launches=1):
+    global KERNEL_LAUNCHES
     if rc != 0:
         raise B200SegError("%s failed with status %d" % (what, rc))
+    KERNEL_LAUNCHES += launches
 
 
 def ptr(t):

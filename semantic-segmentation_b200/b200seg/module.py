@@ -167,6 +167,14 @@ class B200SegModule(nn.Module):
 
     # ------------------------------------------------------------------------------------------ training step
     def _step_eager(self, images, gts, drop_mask):
+        from . import _lib
+        launches0 = _lib.KERNEL_LAUNCHES
+        try:
+            return self._step_body(images, gts, drop_mask)
+        finally:
+            self.kernels_per_step = _lib.KERNEL_LAUNCHES - launches0   # same count when the captured graph replays
+
+    def _step_body(self, images, gts, drop_mask):
         self._repack()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
         grads = dict(self._grad_views)

@@ -102,7 +102,7 @@ def conv2d_dgrad(dy, w_dgrad, x_shape, ksize, stride, addend=None, out=None, for
     d = conv_desc(n, h, w, cin, cout_pad, ksize, stride, _ld(out), _ld(out), force_kc=force_kc)
     check(lib().b200seg_conv2d_dgrad(ctypes.byref(d), ptr(dy), _ld(dy), ptr(w_dgrad), ptr(addend),
                                      _ld(addend) if addend is not None else 0, ptr(out), _ld(out), stream_ptr()),
-          "conv2d_dgrad")
+          "conv2d_dgrad", 4 if stride == 2 else 1)
     return out
 
 
@@ -213,7 +213,7 @@ def spatial_softmax_fwd(logits, K):
     ws = torch.empty((n * B * 32 * 2,), dtype=F32, device=logits.device)
     probs = torch.empty((n, P, 32), dtype=BF16, device=logits.device)
     check(L.b200seg_spatial_softmax_fwd(ptr(logits), ld, n, P, K, ptr(ws), ptr(probs), None, stream_ptr()),
-          "spatial_softmax_fwd")
+          "spatial_softmax_fwd", 2)
     return probs
 
 
@@ -223,7 +223,7 @@ def spatial_softmax_bwd(dprobs, probs, K, dlogit, accumulate):
     B = L.b200seg_spatial_softmax_blocks(P)
     ws = torch.empty((n * B * 32,), dtype=F32, device=dprobs.device)
     check(L.b200seg_spatial_softmax_bwd(ptr(dprobs), ldd, ptr(probs), n, P, K, ptr(ws), ptr(dlogit), int(accumulate),
-                                        stream_ptr()), "spatial_softmax_bwd")
+                                        stream_ptr()), "spatial_softmax_bwd", 2)
     return dlogit
 
 
@@ -275,7 +275,7 @@ def count_valid(labels, ignore_index=255):
     ws = torch.empty((1,), dtype=torch.int64, device=labels.device)
     inv = torch.empty((1,), dtype=F32, device=labels.device)
     check(lib().b200seg_count_valid(ptr(labels), labels.numel(), ignore_index, ptr(ws), ptr(inv), stream_ptr()),
-          "count_valid")
+          "count_valid", 2)
     return inv
 
 
@@ -300,7 +300,7 @@ def mscale_loss_fwd(d, labels, inv_count, hi_cls, hi_aux, mid, mid_sup):
     loss = torch.empty((5,), dtype=F32, device=dev)
     check(L.b200seg_mscale_loss_fwd(ctypes.byref(d), ptr(labels), ptr(inv_count), ptr(hi_cls), ptr(hi_aux), ptr(mid),
                                     ptr(mid_sup), ptr(g_hi), ptr(g_lo), ptr(g_sup), ptr(ws), ptr(loss), stream_ptr()),
-          "mscale_loss_fwd")
+          "mscale_loss_fwd", 2)
     return loss, g_hi, g_lo, g_sup
 
 
@@ -321,5 +321,5 @@ def mscale_lo_bwd(d, g_lo, g_sup, lo_cls, lo_aux, lo_attn, mid):
     d_attn = torch.empty((d.n, d.hl, d.wl, 8), dtype=BF16, device=dev)
     check(lib().b200seg_mscale_lo_bwd(ctypes.byref(d), ptr(g_lo), ptr(g_sup), ptr(lo_cls), ptr(lo_aux), ptr(lo_attn),
                                       ptr(mid), ptr(ws), ptr(d_cls), ptr(d_aux), ptr(d_attn), stream_ptr()),
-          "mscale_lo_bwd")
+          "mscale_lo_bwd", 2)
     return d_cls, d_aux, d_attn
