@@ -82,9 +82,11 @@ int b200seg_conv2d_dgrad(const b200seg_conv_desc* d, const void* dy, int32_t dy_
 
 /* Weight gradient: dw_oihw[co][ci][kh][kw] (fp32, the nn.Parameter .grad layout) += sum_pixels dy * x_shifted.
  * d describes the FORWARD convolution (input geometry, stride, pad); dy is bf16 NHWC [n,ho,wo,cout] with pitch dy_ld.
- * cin multiple of 16. Accumulates with red.global (zero the buffer once per optimizer step). */
+ * cin multiple of 16. Two launches: the tcgen05 kernel writes per-work-unit fp32 partial slabs into the caller's
+ * workspace, a reduce kernel adds them into dw in a fixed order (deterministic; dw accumulates across calls). */
+size_t b200seg_conv2d_wgrad_ws_bytes(const b200seg_conv_desc* d);
 int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, int32_t dy_ld, float* dw_oihw,
-                         void* stream);
+                         void* workspace, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training-mode BatchNorm around the convolutions. Replaces cuDNN/Apex BN behind Norm2d (network/mynn.py:18-24),

@@ -111,8 +111,11 @@ def conv2d_wgrad(x, dy, dw_oihw, cout, ksize, stride):
     n, h, w, cin = x.shape
     assert dw_oihw.is_contiguous() and dw_oihw.dtype == F32
     d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(dy))
-    check(lib().b200seg_conv2d_wgrad(ctypes.byref(d), ptr(x), ptr(dy), _ld(dy), ptr(dw_oihw), stream_ptr()),
-          "conv2d_wgrad")
+    L = lib()
+    nbytes = L.b200seg_conv2d_wgrad_ws_bytes(ctypes.byref(d))
+    ws = torch.empty((nbytes // 4,), dtype=F32, device=x.device)
+    check(L.b200seg_conv2d_wgrad(ctypes.byref(d), ptr(x), ptr(dy), _ld(dy), ptr(dw_oihw), ptr(ws), nbytes,
+                                 stream_ptr()), "conv2d_wgrad", 2)
 
 
 # ----------------------------------------------------------------------------------------------- batch norm

@@ -19,14 +19,23 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, in
                                    long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  if (c >= C) return;
+  // block = 32 channels x 8 slices of the G partial rows (coalesced 128-byte reads), then a fixed-order fold
+  __shared__ double sh1[8][32], sh2[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C)
+    for (int g = slice; g < G; g += 8) {
+      a1 += (double)partials[(size_t)g * 2 * Cpad + c];
+      a2 += (double)partials[(size_t)g * 2 * Cpad + Cpad + c];
+    }
+  sh1[slice][lane] = a1;
+  sh2[slice][lane] = a2;
+  __syncthreads();
+  if (slice != 0 || c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int g = 0; g < G; ++g) {
-    s1 += (double)partials[(size_t)g * 2 * Cpad + c];
-    s2 += (double)partials[(size_t)g * 2 * Cpad + Cpad + c];
-  }
+  for (int k = 0; k < 8; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
   const double mean = s1 / count;
   double var = s2 / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -146,13 +155,21 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, float count,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
                                        float* __restrict__ c2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double sh1[8][32], sh2[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C)
+    for (int g = slice; g < G; g += 8) {
+      a1 += (double)partials[(size_t)g * 2 * C + c];
+      a2 += (double)partials[(size_t)g * 2 * C + C + c];
+    }
+  sh1[slice][lane] = a1;
+  sh2[slice][lane] = a2;
+  __syncthreads();
+  if (slice != 0 || c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int g = 0; g < G; ++g) {
-    s1 += (double)partials[(size_t)g * 2 * C + c];
-    s2 += (double)partials[(size_t)g * 2 * C + C + c];
-  }
+  for (int k = 0; k < 8; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
   if (dbeta) dbeta[c] += (float)s1;     // parameter gradients accumulate (two scale passes share the weights)
   if (dgamma) dgamma[c] += (float)s2;
   c1[c] = (float)(s1 / count);
@@ -261,7 +278,7 @@ extern "C" int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t 
                                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
                                    float* shift, float* mean, float* invstd, void* stream) {
   if (!partials || !scale || !shift || !mean || !invstd || c <= 0 || grid <= 0) return B200SEG_E_BADARG;
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  bn_finalize_kernel<<<(c + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
       partials, grid, c, cpad, count, gamma, beta, eps, momentum, running_mean, running_var,
       (long long*)num_batches_tracked, scale, shift, mean, invstd);
   CHECK_LAUNCH();
@@ -298,7 +315,7 @@ extern "C" int32_t b200seg_bn_bwd_grid(int64_t npix, int32_t c) {
   int rows, threads;
   reduce_shape(c, &rows, &threads);
   long long b = (npix + rows - 1) / rows;
-  const long long cap = 148LL * 4;
+  const long long cap = 148LL * 2;
   return (int32_t)(b < cap ? b : cap);
 }
 
@@ -321,7 +338,7 @@ extern "C" int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* 
 extern "C" int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int32_t c, float count, float* dgamma,
                                        float* dbeta, float* c1, float* c2, void* stream) {
   if (!partials || !c1 || !c2) return B200SEG_E_BADARG;
-  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, grid, c, count, dgamma, dbeta,
+  bn_bwd_finalize_kernel<<<(c + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, grid, c, count, dgamma, dbeta,
                                                                            c1, c2);
   CHECK_LAUNCH();
 }

@@ -22,6 +22,8 @@ struct WgradParams {
   int TH, TW, tiles_h, tiles_w, pix_tiles;
   int m_tiles, n_tiles, tap_groups, taps_per_group, splits, total_units;
   int nblocksB_max;
+  int unit_n;            // accumulator row pitch of a unit slab (= min(256, Cin))
+  long long unit_stride; // floats per unit slab
   int a_slot_bytes, b_slot_bytes, b_slots;
 };
 
@@ -31,7 +33,7 @@ constexpr int kMaxBSlots = 6;
 
 __global__ void __launch_bounds__(kWThreads, 1)
 wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
-                   const WgradParams p, float* __restrict__ dw) {
+                   const WgradParams p, float* __restrict__ ws) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_base = smem;                               // 2 slots
@@ -169,9 +171,13 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
             tmem_ld16(tmem_base + ((q * 32u) << 16) + (tap - tap0) * Nn + ch * 16, r);
             tmem_ld_wait();
             if (co < p.Cout) {
-              float* dst = dw + ((size_t)co * p.Cin + n0 + ch * 16) * p.taps + tap;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) atomicAdd(dst + (size_t)j * p.taps, __uint_as_float(r[j]));
+              // per-unit slab [tap_local][128 rows][unit_n] fp32: plain 16-byte stores, summed by wgrad_reduce_kernel
+              float4* dst = reinterpret_cast<float4*>(ws + (size_t)unit * p.unit_stride +
+                                                      ((size_t)(tap - tap0) * 128 + q * 32 + lane) * p.unit_n + ch * 16);
+              dst[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+              dst[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+              dst[2] = make_float4(__uint_as_float(r[8]), __uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
+              dst[3] = make_float4(__uint_as_float(r[12]), __uint_as_float(r[13]), __uint_as_float(r[14]), __uint_as_float(r[15]));
             }
           }
         }
@@ -186,17 +192,36 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+
+// dw[co][ci][tap] += sum over the pixel splits of the unit slabs (fixed order -> deterministic)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const WgradParams p, const float* __restrict__ ws, float* __restrict__ dw) {
+  const long long total = (long long)p.Cout * p.taps * p.Cin;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % p.Cin);
+    const int tap = (int)((idx / p.Cin) % p.taps);
+    const int co = (int)(idx / ((long long)p.Cin * p.taps));
+    const int m_tile = co >> 7, row = co & 127;
+    const int n_tile = ci >> 8, col = ci & 255;
+    const int tg = tap / p.taps_per_group, tl = tap - tg * p.taps_per_group;
+    const int item = (m_tile * p.n_tiles + n_tile) * p.tap_groups + tg;
+    const float* src = ws + (size_t)item * p.splits * p.unit_stride + ((size_t)tl * 128 + row) * p.unit_n + col;
+    float acc = 0.f;
+    for (int s_ = 0; s_ < p.splits; ++s_) acc += src[(size_t)s_ * p.unit_stride];
+    dw[((size_t)co * p.Cin + ci) * p.taps + tap] += acc;
+  }
+}
+
 }  // namespace b200seg
 
 using namespace b200seg;
 
-extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, int32_t dy_ld,
-                                    float* dw_oihw, void* stream) {
-  if (!d || !x || !dy || !dw_oihw) return B200SEG_E_BADARG;
+static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
+  if (!d) return B200SEG_E_BADARG;
   if (!((d->ksize == 1 && d->pad == 0) || (d->ksize == 3 && d->pad == 1))) return B200SEG_E_BADARG;
   if (d->stride != 1 && d->stride != 2) return B200SEG_E_BADARG;
-  if (d->cin % 16 || d->x_ld % 8 || dy_ld % 8 || dy_ld < 8) return B200SEG_E_BADARG;
-  WgradParams p;
+  if (d->cin % 16 || d->x_ld % 8) return B200SEG_E_BADARG;
   p.N = d->n; p.Cout = d->cout; p.Cin = d->cin;
   p.ksize = d->ksize; p.stride = d->stride; p.pad = d->pad; p.taps = d->ksize * d->ksize;
   p.Ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
@@ -214,14 +239,34 @@ extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, c
   p.tap_groups = (p.taps + tpg - 1) / tpg;
   p.taps_per_group = (p.taps + p.tap_groups - 1) / p.tap_groups;   // balanced groups
   const int items = p.m_tiles * p.n_tiles * p.tap_groups;
-  int splits = (2 * B200SEG_MAX_CTAS + items - 1) / items;          // ~2 units per CTA
+  int splits = (B200SEG_MAX_CTAS + items - 1) / items;              // ~1 unit per SM
   if (splits > p.pix_tiles) splits = p.pix_tiles;
   if (splits < 1) splits = 1;
   p.splits = splits;
   p.total_units = items * splits;
   p.nblocksB_max = (Nmax + 63) / 64;
+  p.unit_n = Nmax;
+  p.unit_stride = (long long)p.taps_per_group * 128 * Nmax;
   p.a_slot_bytes = 2 * kABlock;
   p.b_slot_bytes = p.nblocksB_max * kABlock;
+  return 0;
+}
+
+extern "C" size_t b200seg_conv2d_wgrad_ws_bytes(const b200seg_conv_desc* d) {
+  WgradParams p;
+  if (wgrad_plan(d, p) != 0) return 0;
+  return (size_t)p.total_units * p.unit_stride * sizeof(float);
+}
+
+extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, int32_t dy_ld,
+                                    float* dw_oihw, void* workspace, size_t ws_bytes, void* stream) {
+  if (!d || !x || !dy || !dw_oihw || !workspace) return B200SEG_E_BADARG;
+  if (dy_ld % 8 || dy_ld < 8) return B200SEG_E_BADARG;
+  WgradParams p;
+  int rc0 = wgrad_plan(d, p);
+  if (rc0) return rc0;
+  if (ws_bytes < (size_t)p.total_units * p.unit_stride * sizeof(float)) return B200SEG_E_BADARG;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return B200SEG_E_BADARG;
   const size_t fixed = 1024 + 2 * (size_t)p.a_slot_bytes + (4 + 2 * kMaxBSlots + 2) * 8 + 16;
   int bs = (int)((227 * 1024 - fixed) / p.b_slot_bytes);
   if (bs > kMaxBSlots) bs = kMaxBSlots;
@@ -253,7 +298,11 @@ extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, c
     attr_set = true;
   }
   const int grid = p.total_units < B200SEG_MAX_CTAS ? p.total_units : B200SEG_MAX_CTAS;
-  wgrad_igemm_kernel<<<grid, kWThreads, smem_bytes, (cudaStream_t)stream>>>(tmDy, tmX, p, dw_oihw);
+  wgrad_igemm_kernel<<<grid, kWThreads, smem_bytes, (cudaStream_t)stream>>>(tmDy, tmX, p, (float*)workspace);
+  const long long total = (long long)p.Cout * p.taps * p.Cin;
+  long long rb = (total + 255) / 256;
+  if (rb > 148 * 8) rb = 148 * 8;
+  wgrad_reduce_kernel<<<(int)rb, 256, 0, (cudaStream_t)stream>>>(p, (const float*)workspace, dw_oihw);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
