@@ -37,6 +37,19 @@ def _criterion_kind(criterion):
     raise NotImplementedError("criterion %s is outside the B200 hot path (CE and RMI are covered)" % name)
 
 
+def allreduce_mean_(flat):
+    """Gradient all-reduce-average of the data-parallel step (collective C1): ONE collective over the flat
+    fp32 gradient buffer (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests). No-op without a process
+    group or with a single rank."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return flat
+    ws = torch.distributed.get_world_size()
+    if ws > 1:
+        torch.distributed.all_reduce(flat)
+        flat.mul_(1.0 / ws)
+    return flat
+
+
 class _PublishGrads(torch.autograd.Function):
     """Bridges the engine's eagerly computed gradients into autograd: forward returns the loss, backward hands every
     parameter its slice of the flat gradient buffer."""
@@ -239,11 +252,8 @@ class B200SegModule(nn.Module):
     def _publish(self):
         """Called from loss.backward(): aliases every ``param.grad`` to its slice of the flat gradient buffer (or adds
         into a foreign .grad tensor) and, under the data-parallel shim, averages the buffer across ranks (C1)."""
-        if self._ddp_allreduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            ws = torch.distributed.get_world_size()
-            if ws > 1:
-                torch.distributed.all_reduce(self._flat_grad)
-                self._flat_grad.mul_(1.0 / ws)
+        if self._ddp_allreduce:
+            allreduce_mean_(self._flat_grad)
         for n, p in self.named_parameters():
             g = self._grad_views[n]
             if p.grad is None:

@@ -1,0 +1,87 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/b200seg.h declares, the Python binding
+table covers the header, the module reproduces the reference's state_dict naming/registration order, and the
+reference-facing factory (network.get_model) returns it. No kernel is launched here."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "b200seg.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200seg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from b200seg import _lib
+    L = _lib.lib()
+    assert L.b200seg_abi_version() == 1
+    assert b"sm_100a" in L.b200seg_build_info()
+    syms = header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(L, s), "libb200seg.so does not export %s" % s
+        assert s in _lib.SIGNATURES, "ctypes table lacks %s" % s
+    for s in _lib.SIGNATURES:
+        assert s in syms, "%s is bound but not declared in include/b200seg.h" % s
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(os.path.join(ROOT, "include", "b200seg.h")).read()
+    assert "torch" not in src.lower() and "at::" not in src and "#include <cuda" not in src
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "semantic-segmentation_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("# oracle", ""), "%s references the oracle" % os.path.join(dp, f)
+
+
+@pytest.mark.parametrize("arch", ["ocrnet.HRNet_Mscale", "ocrnet.HRNet", "basic.HRNet"])
+def test_state_dict_names_and_order_match_reference(golden, arch):
+    from b200seg.module import B200SegModule
+    from oracle import seg_oracle as O
+    net = B200SegModule(arch, 19)
+    keys = list(net.state_dict().keys())
+    assert keys == golden["state_dict_keys_w48"][arch]
+    sd = O.synth_state_dict(arch, O.HRNET_W48)
+    for k, v in net.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    if arch == "ocrnet.HRNet_Mscale":
+        assert [n for n, _ in net.named_parameters()] == golden["param_order_w48"][arch]   # optimizer state order
+        assert len(keys) == 1903 and sum(p.numel() for p in net.parameters()) == 72143430
+
+
+def test_factory_contract_and_cpu_refusal():
+    import network
+    net = network.get_model("network.ocrnet.HRNet_Mscale", 19, None)
+    assert type(net).__name__ == "B200SegModule" and net.arch == "ocrnet.HRNet_Mscale"
+    assert network.get_model("network.basic.HRNet", 19, None).arch == "basic.HRNet"
+    with pytest.raises((ImportError, ModuleNotFoundError, AttributeError)):
+        network.get_model("network.deepv3.DeepV3PlusW38", 19, None)     # outside the hot path: not provided
+    net.train()
+    with pytest.raises(RuntimeError, match="CUDA only"):                 # no CPU fallback
+        net({"images": torch.zeros(1, 3, 64, 64), "gts": torch.zeros(1, 64, 64, dtype=torch.long)})
+
+
+def test_conv_planner_rejects_bad_shapes():
+    import ctypes
+    from b200seg import _lib
+    L = _lib.lib()
+    d = _lib.ConvDesc()
+    d.n, d.h, d.w, d.cin, d.cout, d.ksize, d.stride, d.pad, d.x_ld, d.y_ld = 1, 32, 32, 48, 48, 3, 1, 1, 48, 48
+    d.emit_stats = 1
+    assert L.b200seg_conv2d_stats_elems(ctypes.byref(d)) == 148 * 2 * 48
+    assert L.b200seg_conv2d_wgrad_ws_bytes(ctypes.byref(d)) > 0
+    d.cin = 50                                                          # not a multiple of 8
+    assert L.b200seg_conv2d_stats_elems(ctypes.byref(d)) == 0
+    d.cin, d.ksize = 48, 5
+    assert L.b200seg_conv2d_stats_elems(ctypes.byref(d)) == 0
+    assert L.b200seg_conv2d_fwd(ctypes.byref(d), None, None, None, None, None, None, None) == -1
