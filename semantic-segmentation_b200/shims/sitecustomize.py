@@ -1,0 +1,26 @@
+"""Launcher glue for the unmodified reference train.py on torch >= 2.0 (SURVEY.md §7 hard part 8).
+
+torch.distributed.launch / torchrun export LOCAL_RANK (and pass the dashed ``--local-rank``), while train.py:112 only
+declares ``--local_rank`` and train.py:298 reads it from argv. When this directory is on PYTHONPATH, Python imports
+this module at start-up and the two spellings are reconciled without touching the reference file."""
+import os
+import sys
+
+if sys.argv and os.path.basename(sys.argv[0]) == "train.py":
+    argv = []
+    have = False
+    for a in sys.argv[1:]:
+        if a.startswith("--local-rank"):
+            a = a.replace("--local-rank", "--local_rank", 1)
+        if a.startswith("--local_rank"):
+            have = True
+        argv.append(a)
+    if not have and "LOCAL_RANK" in os.environ:
+        argv += ["--local_rank", os.environ["LOCAL_RANK"]]
+    sys.argv[1:] = argv
+    try:
+        import numpy as _np
+        if not hasattr(_np, "int"):
+            _np.int = int          # network/hrnetv2.py:315 uses the alias NumPy 2 removed
+    except Exception:
+        pass
