@@ -1,0 +1,353 @@
+// 3x3 / stride-1 / pad-1 convolution (forward and data gradient) with ONE halo tile per (pixel tile, channel chunk).
+//
+// The generic kernel (conv_igemm.cu) fetches a shifted 128-pixel box per filter tap, i.e. it reads the input 9 times
+// from L2 — the limiter of HRNet's 48/96-channel high-resolution branch, which is HBM-bound on paper. Here the TMA unit
+// brings a (16+2) x (8+2) pixel halo tile (64-channel chunk, SWIZZLE_128B, 128 bytes per pixel row) into shared memory
+// ONCE, and the nine taps are nine tcgen05 shared-memory descriptors into that same tile:
+//     start = tile + (kh*10 + kw) * 128 B,   stride-byte-offset = 10 * 128 B (one 8-pixel tile row per 8-row group)
+// which works because the tensor core applies the 128B swizzle to absolute shared-memory addresses (pinned on silicon,
+// profiles/r1_umma_probe.txt: row-shifted starts and arbitrary SBO read exactly the rows TMA wrote).
+// Weights: resident in shared memory for the whole persistent CTA when they fit (C <= 96: the HBM-bound layers), else
+// streamed per (chunk, tap) through an mbarrier ring. Everything else (TMEM double buffering, warp roles, BN-statistics
+// epilogue, gradient-accumulating addend) matches conv_igemm.cu.
+// Replaces cuDNN fwd/dgrad behind the 3x3 stride-1 convolutions of network/hrnetv2.py:31-34 (BasicBlock), :76
+// (Bottleneck), network/ocrnet.py:54-57 (conv3x3_ocr) and network/utils.py:348-356 (attention head).
+#include "ptx.cuh"
+#include "tma_host.h"
+#include "../../include/b200seg.h"
+#include "vec.cuh"
+#include <cstdlib>
+
+namespace b200seg {
+
+struct HaloParams {
+  int N, H, W, Cin, Cout;      // H, W: spatial size (same for input and output)
+  int cchunks;                 // ceil(Cin / 64)
+  int ksteps_last;             // K=16 steps in the last chunk
+  int BN, n_tiles, cout_pad;
+  int tiles_h, tiles_w, total_tiles;
+  int y_ld, has_bias, emit_stats, addend_ld;
+  int resident;                // weights stay in smem for the CTA lifetime
+  int a_slots, b_slots;        // ring depths (b_slots unused when resident)
+  int b_tile_bytes;            // BN * 128 rounded to 1024
+  int dbg;                     // bench-only switches (env B200SEG_DBG): 1 no stats, 2 no stores, 4 no tmem loads
+  int n_tile_fixed;            // resident mode: the single Cout tile this launch covers per CTA (n_tiles == 1)
+};
+
+constexpr int kHThreads = 256;
+constexpr int kASlotBytes = 24576;     // 180 halo rows x 128 B = 23040, padded to a 1024 multiple
+constexpr int kHaloW = 10, kHaloH = 18, kTW = 8, kTH = 16;
+constexpr int kMaxASlots = 4, kMaxBSlots2 = 8;
+
+__device__ __forceinline__ void h_store16(void* dst, const float (&v)[16]) {
+  uint4 a, b;
+  a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);
+  a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
+  b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]);
+  b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+  uint4* p = reinterpret_cast<uint4*>(dst);
+  p[0] = a;
+  p[1] = b;
+}
+__device__ __forceinline__ void h_butterfly16(float (&v)[16], uint32_t lane) {
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+__global__ void __launch_bounds__(kHThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const HaloParams p, __nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
+                    float* __restrict__ stats_partials, const __nv_bfloat16* __restrict__ addend) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + (size_t)p.a_slots * kASlotBytes;
+  const int b_tiles_total = p.resident ? 9 * p.cchunks : p.b_slots;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)b_tiles_total * p.b_tile_bytes);
+  uint64_t* a_full = bars;                         // [kMaxASlots]
+  uint64_t* a_empty = bars + kMaxASlots;
+  uint64_t* b_full = bars + 2 * kMaxASlots;        // [kMaxBSlots2] (resident: only [0])
+  uint64_t* b_empty = b_full + kMaxBSlots2;
+  uint64_t* tfull = b_empty + kMaxBSlots2;         // [2]
+  uint64_t* tempty = tfull + 2;                    // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [4][2][cout_pad]
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kMaxBSlots2; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  if (p.emit_stats)
+    for (int i = threadIdx.x; i < 4 * 2 * p.cout_pad; i += kHThreads) s_stats[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    // Warp-uniform control flow; the single issuing lane is chosen with elect.sync so ptxas keeps the TMA operands in
+    // uniform registers (a `lane == 0` branch makes it emit an R2UR.BROADCAST waterfall loop around every instruction).
+    if (p.resident) {   // all weight tiles of this CTA's Cout tile, once
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&b_full[0], 9 * p.cchunks * p.b_tile_bytes);
+        for (int cc = 0; cc < p.cchunks; ++cc)
+          for (int t = 0; t < 9; ++t)
+            tma_load_3d(&tmB, &b_full[0], b_base + (size_t)(cc * 9 + t) * p.b_tile_bytes, cc * 64, t,
+                        p.n_tile_fixed * p.BN);
+      }
+      __syncwarp();
+    }
+    int a_slot = 0, b_slot = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int tw_i = m_tile % p.tiles_w;
+      const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
+      const int img = m_tile / (p.tiles_w * p.tiles_h);
+      for (int cc = 0; cc < p.cchunks; ++cc) {
+        mbar_wait(&a_empty[a_slot], a_phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&a_full[a_slot], kHaloH * kHaloW * 128);
+          tma_load_4d(&tmA, &a_full[a_slot], a_base + (size_t)a_slot * kASlotBytes, cc * 64, tw_i * kTW - 1,
+                      th_i * kTH - 1, img);
+        }
+        __syncwarp();
+        if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
+        if (!p.resident) {
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&b_empty[b_slot], b_phase ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&b_full[b_slot], p.b_tile_bytes);
+              tma_load_3d(&tmB, &b_full[b_slot], b_base + (size_t)b_slot * p.b_tile_bytes, cc * 64, t, n_tile * p.BN);
+            }
+            __syncwarp();
+            if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    int a_slot = 0, b_slot = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    int it = 0;
+    if (p.resident) mbar_wait(&b_full[0], 0);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 256;
+      for (int cc = 0; cc < p.cchunks; ++cc) {
+        mbar_wait(&a_full[a_slot], a_phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(a_base + (size_t)a_slot * kASlotBytes);
+        const int ksteps = (cc == p.cchunks - 1) ? p.ksteps_last : 4;
+        for (int t = 0; t < 9; ++t) {
+          uint32_t sb;
+          if (p.resident) {
+            sb = smem_u32(b_base + (size_t)(cc * 9 + t) * p.b_tile_bytes);
+          } else {
+            mbar_wait(&b_full[b_slot], b_phase);
+            tc_fence_after();
+            sb = smem_u32(b_base + (size_t)b_slot * p.b_tile_bytes);
+          }
+          const int kh = t / 3, kw = t - kh * 3;
+          const uint64_t adesc = make_smem_desc(sa + (kh * kHaloW + kw) * 128, 16, kHaloW * 128, 2);
+          const uint64_t bdesc = make_smem_desc(sb, 16, 1024, 2);
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k)
+              umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cc | t | k) != 0);
+            if (!p.resident) umma_commit(&b_empty[b_slot]);
+          }
+          __syncwarp();
+          if (!p.resident) { if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; } }
+        }
+        if (elect_one()) {
+          umma_commit(&a_empty[a_slot]);
+          if (cc == p.cchunks - 1) umma_commit(&tfull[as]);
+        }
+        __syncwarp();
+        if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (thread == output pixel)
+    const uint32_t q = warp - 4;
+    const int m = q * 32 + lane;
+    const int th = m >> 3, tw = m & 7;
+    float* my_stats = s_stats + (size_t)q * 2 * p.cout_pad;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int tw_i = m_tile % p.tiles_w;
+      const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
+      const int img = m_tile / (p.tiles_w * p.tiles_h);
+      const int ho = th_i * kTH + th, wo = tw_i * kTW + tw;
+      const bool valid = (ho < p.H) && (wo < p.W);
+      const int n0 = n_tile * p.BN;
+      const size_t pix = ((size_t)img * p.H + ho) * p.W + wo;
+      mbar_wait(&tfull[as], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * 256;
+      const int nchunks = p.BN >> 4;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = n0 + ch * 16;
+        if (c0 >= p.Cout) break;
+        if (p.dbg & 4) break;
+        uint32_t r[16];
+        tmem_ld16(taddr + ch * 16, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.has_bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.Cout) ? __ldg(bias + c0 + j) : 0.f;
+        }
+        if (addend != nullptr && valid && c0 + 16 <= p.Cout) {
+          const __nv_bfloat16* ap = addend + pix * p.addend_ld + c0;
+          float a0[8], a1[8];
+          load8(ap, a0);
+          load8(ap + 8, a1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
+        }
+        if (valid && !(p.dbg & 2)) {
+          __nv_bfloat16* dst = y + pix * p.y_ld + c0;
+          if (c0 + 16 <= p.Cout) {
+            h_store16(dst, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.Cout) dst[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+        if (p.emit_stats && !(p.dbg & 1)) {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float rv = valid ? bf16_round(v[j]) : 0.f;
+            s1[j] = rv;
+            s2[j] = rv * rv;
+          }
+          h_butterfly16(s1, lane);
+          h_butterfly16(s2, lane);
+          if (lane < 16) {
+            my_stats[c0 + lane] += s1[0];
+            my_stats[p.cout_pad + c0 + lane] += s2[0];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (p.emit_stats) {
+    float* out = stats_partials + (size_t)blockIdx.x * 2 * p.cout_pad;
+    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += kHThreads)
+      out[i] = (s_stats[i] + s_stats[2 * p.cout_pad + i]) + (s_stats[4 * p.cout_pad + i] + s_stats[6 * p.cout_pad + i]);
+  }
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// Host launcher shared by forward and stride-1 data gradient. `in` is the A-operand tensor [n,h,w,cin_ext] (pitch in_ld),
+// w is [cout][9][cin_ext] bf16. Returns B200SEG_E_BADARG when the shape is not eligible (caller falls back to the
+// generic per-tap kernel).
+int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
+                        const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
+                        int* cout_pad_out, const void* addend, int addend_ld, int emit_stats, cudaStream_t stream,
+                        bool plan_only) {
+  if (cin % 8 || in_ld % 8 || out_ld % 8 || cout % 16) return B200SEG_E_BADARG;
+  HaloParams p;
+  p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
+  p.cchunks = (cin + 63) / 64;
+  const int rem = cin - (p.cchunks - 1) * 64;
+  p.ksteps_last = (rem + 15) / 16;
+  const int n_tiles0 = (cout + 255) / 256;
+  int BN = ((cout / 16 + n_tiles0 - 1) / n_tiles0) * 16;
+  p.BN = BN;
+  p.n_tiles = (cout + BN - 1) / BN;
+  p.cout_pad = p.n_tiles * BN;
+  if (cout_pad_out) *cout_pad_out = p.cout_pad;
+  p.tiles_w = (w + kTW - 1) / kTW;
+  p.tiles_h = (h + kTH - 1) / kTH;
+  p.total_tiles = n * p.tiles_h * p.tiles_w * p.n_tiles;
+  p.y_ld = out_ld; p.has_bias = bias != nullptr; p.emit_stats = emit_stats; p.addend_ld = addend_ld;
+  p.b_tile_bytes = (BN * 128 + 1023) / 1024 * 1024;
+  const size_t fixed = 1024 + (2 * kMaxASlots + 2 * kMaxBSlots2 + 4) * 8 + 16 + (size_t)4 * 2 * p.cout_pad * 4;
+  const size_t budget = 227 * 1024 - fixed;
+  const size_t resident_bytes = (size_t)9 * p.cchunks * p.b_tile_bytes;
+  p.resident = (p.n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) ? 1 : 0;
+  p.n_tile_fixed = 0;
+  { const char* e = getenv("B200SEG_DBG"); p.dbg = e ? atoi(e) : 0; }
+  size_t smem_bytes;
+  if (p.resident) {
+    int as_ = (int)((budget - resident_bytes) / kASlotBytes);
+    p.a_slots = as_ > kMaxASlots ? kMaxASlots : as_;
+    p.b_slots = 0;
+    smem_bytes = fixed + resident_bytes + (size_t)p.a_slots * kASlotBytes;
+  } else {
+    p.a_slots = 2;
+    int bs = (int)((budget - 2 * (size_t)kASlotBytes) / p.b_tile_bytes);
+    if (bs > kMaxBSlots2) bs = kMaxBSlots2;
+    if (bs < 2) return B200SEG_E_BADARG;
+    p.b_slots = bs;
+    smem_bytes = fixed + 2 * (size_t)kASlotBytes + (size_t)bs * p.b_tile_bytes;
+  }
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
+  const int grid = p.total_tiles < B200SEG_MAX_CTAS ? p.total_tiles : B200SEG_MAX_CTAS;
+  if (stats_grid) *stats_grid = grid;
+  if (plan_only) return 0;
+  if (!in || !wts || !out) return B200SEG_E_BADARG;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(wts) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15) || (addend && addend_ld % 8))
+    return B200SEG_E_BADARG;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    uint64_t strides[3] = {(uint64_t)in_ld * 2, (uint64_t)w * in_ld * 2, (uint64_t)h * w * in_ld * 2};
+    uint32_t box[4] = {64, (uint32_t)kHaloW, (uint32_t)kHaloH, 1};
+    int rc = encode_bf16(&tmA, in, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)cin, 9, (uint64_t)cout};
+    uint64_t strides[2] = {(uint64_t)cin * 2, (uint64_t)9 * cin * 2};
+    uint32_t box[3] = {64, 1, (uint32_t)BN};
+    int rc = encode_bf16(&tmB, wts, 3, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  conv3x3_halo_kernel<<<grid, kHThreads, smem_bytes, stream>>>(tmA, tmB, p, (__nv_bfloat16*)out, bias, stats_partials,
+                                                               (const __nv_bfloat16*)addend);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace b200seg

@@ -108,7 +108,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -124,9 +124,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = stage_base + (size_t)stage * p.stage_bytes;
             uint8_t* sb = sa + p.a_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-            tma_load_4d(&tmA, &full_bar[stage], sa, cc * p.KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], img);
-            tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.KC, p.tap_w[t], n0);
+            if (elect_one()) {   // elect.sync (not lane == 0): keeps the TMA operands in uniform registers
+              mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+              tma_load_4d(&tmA, &full_bar[stage], sa, cc * p.KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], img);
+              tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.KC, p.tap_w[t], n0);
+            }
+            __syncwarp();
             if (++stage == p.nstages) { stage = 0; phase ^= 1; }
           }
       }
@@ -140,20 +143,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
-      if (lane == 0) mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
-      __syncwarp();
+      mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kAccCols;
       for (int kb = 0; kb < kblocks; ++kb) {
-        if (lane == 0) mbar_wait(&full_bar[stage], phase);
-        __syncwarp();
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + p.a_bytes;
-          const uint64_t adesc = make_smem_desc(sa, 16, p.sbo, p.layout_type);
-          const uint64_t bdesc = make_smem_desc(sb, 16, p.sbo, p.layout_type);
-          const int ksteps = p.KC >> 4;
+        const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
+        const uint32_t sb = sa + p.a_bytes;
+        const uint64_t adesc = make_smem_desc(sa, 16, p.sbo, p.layout_type);
+        const uint64_t bdesc = make_smem_desc(sb, 16, p.sbo, p.layout_type);
+        const int ksteps = p.KC >> 4;
+        if (elect_one()) {
           for (int k = 0; k < ksteps; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the 16-byte-unit address field
             umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
@@ -406,6 +407,11 @@ static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const 
   return e == cudaSuccess ? 0 : (int)e;
 }
 
+int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
+                        const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
+                        int* cout_pad_out, const void* addend, int addend_ld, int emit_stats, cudaStream_t stream,
+                        bool plan_only);
+
 }  // namespace b200seg
 
 using namespace b200seg;
@@ -419,6 +425,13 @@ extern "C" size_t b200seg_conv2d_stats_elems(const b200seg_conv_desc* d) {
 extern "C" int b200seg_conv2d_fwd(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
                                   void* y, float* stats_partials, int32_t* stats_grid, void* stream) {
   if (!desc_ok(d)) return B200SEG_E_BADARG;
+  if (d->ksize == 3 && d->stride == 1 && !d->out_fp32 && d->cout % 16 == 0 && d->reserved == 0) {
+    if (d->emit_stats && !stats_partials) return B200SEG_E_BADARG;
+    // halo-tile kernel: the input is read once per tile instead of once per filter tap (conv3x3_halo.cu)
+    return conv3x3_halo_launch(d->n, d->h, d->w, d->cin, d->x_ld, x, d->cout, w_ohwi, d->has_bias ? bias : nullptr, y,
+                               d->y_ld, stats_partials, stats_grid, nullptr, nullptr, 0, d->emit_stats,
+                               (cudaStream_t)stream, false);
+  }
   return launch_geom(fwd_geom(d), x, w_ohwi, bias, y, stats_partials, stats_grid, nullptr, 0, (cudaStream_t)stream);
 }
 
@@ -437,6 +450,9 @@ extern "C" int b200seg_conv2d_dgrad(const b200seg_conv_desc* d, const void* dy, 
   g.out_h = d->h; g.out_w = d->w; g.out_c = d->cin; g.out_ld = dx_ld;
   g.in_stride = 1; g.wtaps = taps;
   g.out_fp32 = 0; g.has_bias = 0; g.emit_stats = 0; g.force_kc = d->reserved;
+  if (d->stride == 1 && K == 3 && d->cin % 16 == 0 && d->reserved == 0)
+    return conv3x3_halo_launch(d->n, d->h, d->w, g.in_c, dy_ld, dy, d->cin, w_dgrad, nullptr, dx, dx_ld, nullptr, nullptr,
+                               nullptr, addend, addend_ld, 0, (cudaStream_t)stream, false);
   if (d->stride == 1) {
     g.sub_h = d->h; g.sub_w = d->w; g.out_stride = 1; g.out_off_h = g.out_off_w = 0;
     g.ntaps = taps;

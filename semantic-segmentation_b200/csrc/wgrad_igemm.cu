@@ -22,6 +22,9 @@ struct WgradParams {
   int TH, TW, tiles_h, tiles_w, pix_tiles;
   int m_tiles, n_tiles, tap_groups, taps_per_group, splits, total_units;
   int nblocksB_max;
+  int halo;              // 3x3 stride-1: one x halo tile per pixel tile, taps are row-shifted descriptors
+  int ntile_w;           // N tile width in channels (256, or 128 in halo mode)
+  int b_block_bytes;     // bytes of one 64-channel B block (16384 dense, 24576 halo)
   int unit_n;            // accumulator row pitch of a unit slab (= min(256, Cin))
   long long unit_stride; // floats per unit slab
   int a_slot_bytes, b_slot_bytes, b_slots;
@@ -72,33 +75,54 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // warp-uniform control flow; issuing lane chosen by elect.sync (keeps TMA operands in uniform registers)
       int a_slot = 0, b_slot = 0;
       uint32_t a_phase = 0, b_phase = 0;
       for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
         int m_tile, n_tile, tg, split;
         decode(unit, m_tile, n_tile, tg, split);
-        const int n0 = n_tile * 256;
-        const int nblk = min(4, (p.Cin - n0 + 63) / 64);
+        const int n0 = n_tile * p.ntile_w;
+        const int nblk = min(p.ntile_w / 64, (p.Cin - n0 + 63) / 64);
         const int tap0 = tg * p.taps_per_group, tap1 = min(p.taps, tap0 + p.taps_per_group);
+        const bool a_two = (p.Cout - m_tile * 128) > 64;      // second 64-channel dy block holds real channels
         for (int t = split; t < p.pix_tiles; t += p.splits) {
           const int tw_i = t % p.tiles_w;
           const int th_i = (t / p.tiles_w) % p.tiles_h;
           const int img = t / (p.tiles_w * p.tiles_h);
           mbar_wait(&a_empty[a_slot], a_phase ^ 1);
           uint8_t* sa = a_base + (size_t)a_slot * p.a_slot_bytes;
-          mbar_arrive_expect_tx(&a_full[a_slot], 2 * kABlock);
-          tma_load_4d(&tmDy, &a_full[a_slot], sa, m_tile * 128, tw_i * p.TW, th_i * p.TH, img);
-          tma_load_4d(&tmDy, &a_full[a_slot], sa + kABlock, m_tile * 128 + 64, tw_i * p.TW, th_i * p.TH, img);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[a_slot], (a_two ? 2 : 1) * kABlock);
+            tma_load_4d(&tmDy, &a_full[a_slot], sa, m_tile * 128, tw_i * p.TW, th_i * p.TH, img);
+            if (a_two)
+              tma_load_4d(&tmDy, &a_full[a_slot], sa + kABlock, m_tile * 128 + 64, tw_i * p.TW, th_i * p.TH, img);
+          }
+          __syncwarp();
           if (++a_slot == 2) { a_slot = 0; a_phase ^= 1; }
+          if (p.halo) {
+            mbar_wait(&b_empty[b_slot], b_phase ^ 1);
+            uint8_t* sb = b_base + (size_t)b_slot * p.b_slot_bytes;
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&b_full[b_slot], nblk * 18 * 10 * 128);
+              for (int b = 0; b < nblk; ++b)
+                tma_load_4d(&tmX, &b_full[b_slot], sb + (size_t)b * p.b_block_bytes, n0 + b * 64, tw_i * p.TW - 1,
+                            th_i * p.TH - 1, img);
+            }
+            __syncwarp();
+            if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
+            continue;
+          }
           for (int tap = tap0; tap < tap1; ++tap) {
             const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
             mbar_wait(&b_empty[b_slot], b_phase ^ 1);
             uint8_t* sb = b_base + (size_t)b_slot * p.b_slot_bytes;
-            mbar_arrive_expect_tx(&b_full[b_slot], nblk * kABlock);
-            for (int b = 0; b < nblk; ++b)
-              tma_load_4d(&tmX, &b_full[b_slot], sb + (size_t)b * kABlock, n0 + b * 64,
-                          tw_i * p.TW * p.stride + kw - p.pad, th_i * p.TH * p.stride + kh - p.pad, img);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&b_full[b_slot], nblk * kABlock);
+              for (int b = 0; b < nblk; ++b)
+                tma_load_4d(&tmX, &b_full[b_slot], sb + (size_t)b * kABlock, n0 + b * 64,
+                            tw_i * p.TW * p.stride + kw - p.pad, th_i * p.TH * p.stride + kh - p.pad, img);
+            }
+            __syncwarp();
             if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
           }
         }
@@ -112,26 +136,47 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++uit) {
       int m_tile, n_tile, tg, split;
       decode(unit, m_tile, n_tile, tg, split);
-      const int n0 = n_tile * 256;
-      const int Nn = min(256, p.Cin - n0);               // multiple of 16
+      const int n0 = n_tile * p.ntile_w;
+      const int Nn = min(p.ntile_w, p.Cin - n0);         // multiple of 16
       const uint32_t idesc = make_idesc_bf16(128, Nn, 1, 1);
       const int tap0 = tg * p.taps_per_group, tap1 = min(p.taps, tap0 + p.taps_per_group);
-      if (lane == 0) mbar_wait(acc_empty, (uit & 1) ^ 1);
-      __syncwarp();
+      mbar_wait(acc_empty, (uit & 1) ^ 1);
       tc_fence_after();
       bool first = true;
       for (int t = split; t < p.pix_tiles; t += p.splits) {
-        if (lane == 0) mbar_wait(&a_full[a_slot], a_phase);
-        __syncwarp();
+        mbar_wait(&a_full[a_slot], a_phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(a_base + (size_t)a_slot * p.a_slot_bytes);
-        for (int tap = tap0; tap < tap1; ++tap) {
-          if (lane == 0) mbar_wait(&b_full[b_slot], b_phase);
-          __syncwarp();
+        if (p.halo) {
+          mbar_wait(&b_full[b_slot], b_phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sb = smem_u32(b_base + (size_t)b_slot * p.b_slot_bytes);
-            const uint32_t d_tmem = tmem_base + (tap - tap0) * Nn;
+          const uint32_t sb = smem_u32(b_base + (size_t)b_slot * p.b_slot_bytes);
+          if (elect_one()) {
+            for (int tap = tap0; tap < tap1; ++tap) {
+              const int kh = tap / 3, kw = tap - kh * 3;
+              const uint32_t d_tmem = tmem_base + (tap - tap0) * Nn;
+#pragma unroll 1
+              for (int k = 0; k < 8; ++k) {   // 16 pixels = two 8-pixel tile rows: dy rows are dense, x rows sit 10 apart
+                const uint64_t ad = make_smem_desc(sa + k * 2048, kABlock, 1024, 2);
+                const uint64_t bd = make_smem_desc(sb + (kh * 10 + kw) * 128 + k * 2560, p.b_block_bytes, 1280, 2);
+                umma_f16(d_tmem, ad, bd, idesc, (!first || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&b_empty[b_slot]);
+            umma_commit(&a_empty[a_slot]);
+          }
+          __syncwarp();
+          if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
+          if (++a_slot == 2) { a_slot = 0; a_phase ^= 1; }
+          first = false;
+          continue;
+        }
+        for (int tap = tap0; tap < tap1; ++tap) {
+          mbar_wait(&b_full[b_slot], b_phase);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(b_base + (size_t)b_slot * p.b_slot_bytes);
+          const uint32_t d_tmem = tmem_base + (tap - tap0) * Nn;
+          if (elect_one()) {
 #pragma unroll 1
             for (int k = 0; k < 8; ++k) {   // 16 pixel rows (2 groups of 8 rows x 128 B) per MMA
               const uint64_t ad = make_smem_desc(sa + k * 2048, kABlock, 1024, 2);
@@ -143,12 +188,12 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
           __syncwarp();
           if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
         }
-        if (lane == 0) umma_commit(&a_empty[a_slot]);
+        if (elect_one()) umma_commit(&a_empty[a_slot]);
         __syncwarp();
         if (++a_slot == 2) { a_slot = 0; a_phase ^= 1; }
         first = false;
       }
-      if (lane == 0) umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -157,8 +202,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++uit) {
       int m_tile, n_tile, tg, split;
       decode(unit, m_tile, n_tile, tg, split);
-      const int n0 = n_tile * 256;
-      const int Nn = min(256, p.Cin - n0);
+      const int n0 = n_tile * p.ntile_w;
+      const int Nn = min(p.ntile_w, p.Cin - n0);
       const int tap0 = tg * p.taps_per_group, tap1 = min(p.taps, tap0 + p.taps_per_group);
       const bool has_tiles = split < p.pix_tiles;
       mbar_wait(acc_full, uit & 1);
@@ -203,7 +248,7 @@ wgrad_reduce_kernel(const WgradParams p, const float* __restrict__ ws, float* __
     const int tap = (int)((idx / p.Cin) % p.taps);
     const int co = (int)(idx / ((long long)p.Cin * p.taps));
     const int m_tile = co >> 7, row = co & 127;
-    const int n_tile = ci >> 8, col = ci & 255;
+    const int n_tile = ci / p.ntile_w, col = ci - n_tile * p.ntile_w;
     const int tg = tap / p.taps_per_group, tl = tap - tg * p.taps_per_group;
     const int item = (m_tile * p.n_tiles + n_tile) * p.tap_groups + tg;
     const float* src = ws + (size_t)item * p.splits * p.unit_stride + ((size_t)tl * 128 + row) * p.unit_n + col;
@@ -226,14 +271,17 @@ static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
   p.ksize = d->ksize; p.stride = d->stride; p.pad = d->pad; p.taps = d->ksize * d->ksize;
   p.Ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
   p.Wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
+  p.halo = (d->ksize == 3 && d->stride == 1 && d->reserved == 0) ? 1 : 0;
+  p.ntile_w = p.halo ? 128 : 256;
+  p.b_block_bytes = p.halo ? 24576 : kABlock;
   p.TW = 16; p.TH = 8;
-  if (p.Wo <= 8) { p.TW = 8; p.TH = 16; }
+  if (p.Wo <= 8 || p.halo) { p.TW = 8; p.TH = 16; }
   p.tiles_w = (p.Wo + p.TW - 1) / p.TW;
   p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
   p.pix_tiles = d->n * p.tiles_h * p.tiles_w;
   p.m_tiles = (d->cout + 127) / 128;
-  p.n_tiles = (d->cin + 255) / 256;
-  const int Nmax = d->cin < 256 ? d->cin : 256;
+  p.n_tiles = (d->cin + p.ntile_w - 1) / p.ntile_w;
+  const int Nmax = d->cin < p.ntile_w ? d->cin : p.ntile_w;
   int tpg = 512 / Nmax;
   if (tpg > p.taps) tpg = p.taps;
   p.tap_groups = (p.taps + tpg - 1) / tpg;
@@ -248,7 +296,7 @@ static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
   p.unit_n = Nmax;
   p.unit_stride = (long long)p.taps_per_group * 128 * Nmax;
   p.a_slot_bytes = 2 * kABlock;
-  p.b_slot_bytes = p.nblocksB_max * kABlock;
+  p.b_slot_bytes = p.nblocksB_max * p.b_block_bytes;
   return 0;
 }
 
@@ -287,6 +335,7 @@ extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, c
     uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
     uint64_t strides[3] = {(uint64_t)d->x_ld * 2, (uint64_t)d->w * d->x_ld * 2, (uint64_t)d->h * d->w * d->x_ld * 2};
     uint32_t box[4] = {64, (uint32_t)(p.TW * d->stride), (uint32_t)(p.TH * d->stride), 1};
+    if (p.halo) { box[1] = 10; box[2] = 18; }
     uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
     int rc = encode_bf16(&tmX, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
