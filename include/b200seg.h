@@ -211,6 +211,20 @@ int b200seg_mscale_lo_bwd(const b200seg_mscale_desc* d, const void* g_lo, const 
                           const float* lo_aux, const float* lo_attn_logit, const float* mid, float* dmid_ws, void* d_cls,
                           void* d_aux, void* d_attn, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Eval-mode output assembly: full-resolution fp32 NCHW maps and the hierarchical blend of
+ * MscaleOCR.nscale_forward / two_scale_forward (network/ocrnet.py:185-262,289-327), mynn.Upsample / scale_as.
+ * ------------------------------------------------------------------------------------------------ */
+/* NHWC fp32 [n,h,w,ld] (first c channels) -> NCHW fp32 [n,c,H,W], bilinear align_corners=False; optional sigmoid first */
+int b200seg_resize_to_nchw(const float* src_nhwc, int32_t ld, int32_t n, int32_t h, int32_t w, int32_t c,
+                           int32_t apply_sigmoid, float* dst_nchw, int32_t H, int32_t W, void* stream);
+/* NCHW fp32 [planes,h,w] -> [planes,H,W] bilinear */
+int b200seg_resize_nchw(const float* src, int32_t planes, int32_t h, int32_t w, float* dst, int32_t H, int32_t W,
+                        void* stream);
+/* a: [n,1,hw]; mode 0: out = a*x + (1-a)*y; 1: out = x + (1-a)*y; 2: out = a*x   (x, y, out: [n,c,hw]) */
+int b200seg_blend(const float* a, const float* x, const float* y, float* out, int32_t n, int32_t c, int64_t hw,
+                  int32_t mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,9 @@ SIGNATURES = {
     "b200seg_mscale_loss_fwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V, V, V, V, V, V, V, V, V]),
     "b200seg_mscale_hi_bwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V]),
     "b200seg_mscale_lo_bwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V, V, V, V, V, V, V, V]),
+    "b200seg_resize_to_nchw": (ctypes.c_int, [V, I32, I32, I32, I32, I32, I32, V, I32, I32, V]),
+    "b200seg_resize_nchw": (ctypes.c_int, [V, I32, I32, I32, V, I32, I32, V]),
+    "b200seg_blend": (ctypes.c_int, [V, V, V, V, I32, I32, I64, I32, V]),
 }
 # test-only probe entry point (csrc/probe.h), not part of include/b200seg.h
 PROBE_SIGNATURES = {

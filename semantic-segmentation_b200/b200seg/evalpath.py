@@ -1,5 +1,79 @@
-"""Eval-mode forward (placeholder until the device-side blend/argmax kernels land)."""
+"""Eval-mode forward: per-scale passes on the sm_100a kernels (BatchNorm from running statistics, no tape), then the
+reference's output assembly in fp32 NCHW on the device.
+
+  ocrnet.HRNet_Mscale : MscaleOCR.nscale_forward when cfg.MODEL.N_SCALES is set (network/ocrnet.py:185-262), else the
+                        eval branch of two_scale_forward (:264-327)
+  ocrnet.HRNet        : OCRNet.forward eval branch (:104-122)
+  basic.HRNet         : Basic.forward eval branch (network/basic.py:50-64)
+"""
+import torch
+
+from . import model as M
+from . import raw
+from .engine import Engine
 
 
+def _fmt_scale(prefix, scale):
+    """utils/misc.fmt_scale (utils/misc.py:503-513): keeps the dot ('pred_0.5x')."""
+    return "%s_%sx" % (prefix, str(float(scale)))
+
+
+def _pass(module, E, images, size_hw):
+    """One scale pass -> full-resolution (= pass input size) fp32 NCHW cls / aux / attn maps (MscaleOCR._fwd)."""
+    out = M.scale_pass(E, images, size_hw, module.arch, module.hcfg, module.ocfg)
+    H, W = size_hw
+    res = dict(cls_out=raw.resize_to_nchw(out["cls"].logits, 19, H, W))
+    if out["aux"] is not None:
+        res["aux_out"] = raw.resize_to_nchw(out["aux"].logits, 19, H, W)
+    if out["attn"] is not None:
+        res["logit_attn"] = raw.resize_to_nchw(out["attn"].logits, 1, H, W, apply_sigmoid=True)
+    return res
+
+
+@torch.no_grad()
 def eval_forward(module, images):
-    raise NotImplementedError("eval-mode forward of the B200 path is not implemented yet")
+    module._ensure_device_state()
+    module._repack()
+    images = images.contiguous().float()
+    n, _, H, W = images.shape
+    tensors = {k: v.detach() for k, v in module._tensors().items()}
+    E = Engine(tensors, {}, module._packed, False, None)
+    arch = module.arch
+    if arch != "ocrnet.HRNet_Mscale":
+        return {"pred": _pass(module, E, images, (H, W))["cls_out"]}
+
+    if module.n_scales:
+        scales = sorted([float(s) for s in module.n_scales], reverse=True)
+        assert 1.0 in scales, "expected 1.0 to be the target scale"
+        pred = aux = None
+        out = {}
+        for s in scales:
+            hs, ws = int(H * s), int(W * s)             # ResizeX: floor(in * scale)
+            o = _pass(module, E, images, (hs, ws))
+            cls, attn, auxo = o["cls_out"], o["logit_attn"], o["aux_out"]
+            out[_fmt_scale("pred", s)] = cls
+            if s != 2.0:
+                out[_fmt_scale("attn", s)] = attn
+            if pred is None:
+                pred, aux = cls, auxo
+            elif s >= 1.0:
+                pred = raw.blend(attn, cls, raw.resize_nchw(pred, hs, ws), 0)
+                aux = raw.blend(attn, auxo, raw.resize_nchw(aux, hs, ws), 0)
+            else:
+                ph, pw = pred.shape[2:]
+                cls_s = raw.resize_nchw(raw.blend(attn, cls, None, 2), ph, pw)
+                aux_s = raw.resize_nchw(raw.blend(attn, auxo, None, 2), ph, pw)
+                attn_s = raw.resize_nchw(attn, ph, pw)
+                pred = raw.blend(attn_s, cls_s, pred, 1)
+                aux = raw.blend(attn_s, aux_s, aux, 1)
+        out["pred"] = pred
+        return out
+
+    hm, wm = int(H * module.lo_scale), int(W * module.lo_scale)
+    lo = _pass(module, E, images, (hm, wm))
+    hi = _pass(module, E, images, (H, W))
+    attn = lo["logit_attn"]
+    p_lo = raw.resize_nchw(raw.blend(attn, lo["cls_out"], None, 2), H, W)
+    attn_up = raw.resize_nchw(attn, H, W)
+    joint = raw.blend(attn_up, p_lo, hi["cls_out"], 1)
+    return {"pred": joint, "pred_05x": lo["cls_out"], "pred_10x": hi["cls_out"], "attn_05x": attn}

@@ -326,3 +326,30 @@ def mscale_lo_bwd(d, g_lo, g_sup, lo_cls, lo_aux, lo_attn, mid):
                                       ptr(mid), ptr(ws), ptr(d_cls), ptr(d_aux), ptr(d_attn), stream_ptr()),
           "mscale_lo_bwd", 2)
     return d_cls, d_aux, d_attn
+
+
+# ----------------------------------------------------------------------------------------------- eval-mode assembly
+def resize_to_nchw(src_nhwc, C, H, W, apply_sigmoid=False):
+    """fp32 NHWC [n,h,w,ld] -> fp32 NCHW [n,C,H,W] (bilinear, align_corners=False)."""
+    n, h, w, _ = src_nhwc.shape
+    dst = torch.empty((n, C, H, W), dtype=F32, device=src_nhwc.device)
+    check(lib().b200seg_resize_to_nchw(ptr(src_nhwc), _ld(src_nhwc), n, h, w, C, int(apply_sigmoid), ptr(dst), H, W,
+                                       stream_ptr()), "resize_to_nchw")
+    return dst
+
+
+def resize_nchw(src, H, W):
+    n, c, h, w = src.shape
+    if (h, w) == (H, W):
+        return src
+    dst = torch.empty((n, c, H, W), dtype=F32, device=src.device)
+    check(lib().b200seg_resize_nchw(ptr(src), n * c, h, w, ptr(dst), H, W, stream_ptr()), "resize_nchw")
+    return dst
+
+
+def blend(a, x, y, mode):
+    """mode 0: a*x + (1-a)*y; 1: x + (1-a)*y; 2: a*x   (a [n,1,H,W]; x,y [n,C,H,W])."""
+    n, c, h, w = x.shape
+    out = torch.empty_like(x)
+    check(lib().b200seg_blend(ptr(a), ptr(x), ptr(y), ptr(out), n, c, h * w, mode, stream_ptr()), "blend")
+    return out

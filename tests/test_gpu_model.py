@@ -139,3 +139,45 @@ def test_cuda_graph_replay_equals_eager():
             opt.step()
             losses.append(float(loss))
         assert abs(losses[0] - losses[1]) <= 2e-3 * abs(losses[0]), (step, losses)
+
+
+@pytest.mark.parametrize("arch,n_scales", [("ocrnet.HRNet_Mscale", None), ("ocrnet.HRNet_Mscale", [0.5, 1.0, 2.0]),
+                                           ("ocrnet.HRNet", None), ("basic.HRNet", None)])
+def test_eval_forward_matches_oracle(arch, n_scales):
+    """Eval mode (running-stat BN: no batch-statistics chaos) against the oracle with bf16-storage emulation: same dict
+    keys as the reference (network/ocrnet.py:234-262,319-327), fp32 NCHW maps, argmax agreement."""
+    O, B200SegModule = _mods()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    hcfg = O.HRNET_W16_TEST
+    sd0 = O.synth_state_dict(arch, hcfg, seed=3)
+    # non-trivial running statistics
+    g = torch.Generator().manual_seed(9)
+    for k in sd0:
+        if k.endswith("running_mean"):
+            sd0[k] = 0.1 * torch.randn(sd0[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            sd0[k] = 0.5 + torch.rand(sd0[k].shape, generator=g)
+    images, _ = O.synth_batch(2, 64, 128, seed=5)
+    sd = {k: v.clone().cuda() for k, v in sd0.items()}
+    ctx = O.Ctx(sd, training=False, emulate_bf16=True)
+    with torch.no_grad():
+        if arch == "ocrnet.HRNet_Mscale":
+            ref = O.mscale_nscale(ctx, images.cuda(), n_scales, hcfg=hcfg) if n_scales else \
+                O.mscale_two_scale(ctx, images.cuda(), hcfg=hcfg)
+        elif arch == "ocrnet.HRNet":
+            ref = O.ocrnet_forward(ctx, images.cuda(), hcfg=hcfg)
+        else:
+            ref = O.basic_forward(ctx, images.cuda(), hcfg=hcfg)
+    net = B200SegModule(arch, 19, hcfg=hcfg, n_scales=n_scales)
+    net.load_state_dict(sd0)
+    net = net.cuda().eval()
+    out = net({"images": images.cuda()})
+    assert sorted(out.keys()) == sorted(ref.keys())
+    for k in ref:
+        a, b = out[k].double(), ref[k].double()
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        rel = float((a - b).norm() / (b.norm() + 1e-30))
+        assert rel < 0.03, (k, rel)
+    agree = float((out["pred"].argmax(1) == ref["pred"].argmax(1)).float().mean())
+    assert agree > 0.97, agree
