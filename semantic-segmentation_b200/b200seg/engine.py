@@ -41,7 +41,7 @@ class HeadRec:
 
 
 class Engine:
-    def __init__(self, params, grads, packed, training, drop_mask=None):
+    def __init__(self, params, grads, packed, training, drop_mask=None, side_stream=None):
         """params: name -> tensor (weights, BN buffers); grads: name -> fp32 tensor accumulated into (training);
         packed: name -> (w_fwd, w_dgrad) bf16 operand caches; drop_mask: fp32 [N, mid] post-ReLU multiplier."""
         self.p = params
@@ -50,6 +50,11 @@ class Engine:
         self.training = training
         self.drop_mask = drop_mask
         self.tape = []
+        # Weight gradients do not feed the rest of the backward chain: they run on a side stream (a parallel branch of
+        # the captured CUDA graph) and overlap with the BN / data-gradient kernels of the main chain.
+        self.side = side_stream if side_stream is not None else (
+            torch.cuda.Stream() if (training and torch.cuda.is_available()) else None)
+        self._keepalive = []
 
     # ------------------------------------------------------------------------------------------ tape
     def run_backward(self):
@@ -57,6 +62,21 @@ class Engine:
         while tape:
             fn = tape.pop()
             fn()
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self._keepalive.clear()
+
+    def wgrad(self, x_t, dy, dw, cout, ksize, stride):
+        """dw += wgrad(x, dy) on the side stream. Operands are kept alive until the streams are joined (the caching
+        allocator must not hand their memory to main-stream allocations while the side stream still reads them)."""
+        if self.side is None:
+            raw.conv2d_wgrad(x_t, dy, dw, cout, ksize, stride)
+            return
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            ws = raw.conv2d_wgrad(x_t, dy, dw, cout, ksize, stride)
+        self._keepalive.append((x_t, dy, ws))
 
     def _push(self, fn):
         if self.training:
@@ -98,7 +118,7 @@ class Engine:
                         self.g[rec.bname + ".weight"], self.g[rec.bname + ".bias"], g_out=g_out,
                         g_accumulate=g_accumulate)
         x = rec.x
-        raw.conv2d_wgrad(x.t, dy, self.g[rec.cname + ".weight"], rec.cout, rec.ksize, rec.stride)
+        self.wgrad(x.t, dy, self.g[rec.cname + ".weight"], rec.cout, rec.ksize, rec.stride)
         # a conv bias in front of a training-mode BN has an exactly zero gradient (BN removes the mean): left at 0
         if x.needs_grad:
             _, w_d = self.packed[rec.cname]
@@ -205,7 +225,7 @@ class Engine:
             dl = rec.dlogits
             if dl is None:
                 return   # dead head (e.g. the 1x pass' attention, network/ocrnet.py:284-287)
-            raw.conv2d_wgrad(x.t, dl, self.g[cname + ".weight"], cout, 1, 1)
+            self.wgrad(x.t, dl, self.g[cname + ".weight"], cout, 1, 1)
             if bias:
                 raw.bias_grad(dl, cout, self.g[cname + ".bias"])
             _, w_d = self.packed[cname]

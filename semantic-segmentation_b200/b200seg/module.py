@@ -194,7 +194,9 @@ class B200SegModule(nn.Module):
         stem = "backbone.conv1.weight"
         stem_pad_grad = torch.zeros((grads[stem].shape[0], 16, 3, 3), dtype=F32, device=images.device)
         grads[stem] = stem_pad_grad          # the stem runs on the 16-channel padded image
-        E = Engine(tensors, grads, self._packed, True, drop_mask)
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream()
+        E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream)
         if self.loss_kind != "ce":
             raise NotImplementedError("RMI loss kernels are not wired into the fused step yet")
         loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,

@@ -116,6 +116,7 @@ def conv2d_wgrad(x, dy, dw_oihw, cout, ksize, stride):
     ws = torch.empty((nbytes // 4,), dtype=F32, device=x.device)
     check(L.b200seg_conv2d_wgrad(ctypes.byref(d), ptr(x), ptr(dy), _ld(dy), ptr(dw_oihw), ptr(ws), nbytes,
                                  stream_ptr()), "conv2d_wgrad", 2)
+    return ws
 
 
 # ----------------------------------------------------------------------------------------------- batch norm

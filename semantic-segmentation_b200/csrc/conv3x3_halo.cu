@@ -63,6 +63,18 @@ __device__ __forceinline__ void h_butterfly16(float (&v)[16], uint32_t lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// bench-only timeline (B200SEG_DBG & 8): block 0 records ns timestamps per role and tile behind the stats partials
+#define DBG_TS(role, it)                                                                                     \
+  do {                                                                                                       \
+    if ((p.dbg & 8) && blockIdx.x == 0 && (it) < 16)                                                         \
+      reinterpret_cast<unsigned long long*>(stats_partials + 148 * 2 * 1024)[(role) * 16 + (it)] = gtime(); \
+  } while (0)
+
 __global__ void __launch_bounds__(kHThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const HaloParams p, __nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
@@ -97,6 +109,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) DBG_TS(5, 2);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -125,6 +138,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_arrive_expect_tx(&a_full[a_slot], kHaloH * kHaloW * 128);
           tma_load_4d(&tmA, &a_full[a_slot], a_base + (size_t)a_slot * kASlotBytes, cc * 64, tw_i * kTW - 1,
                       th_i * kTH - 1, img);
+          DBG_TS(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
         }
         __syncwarp();
         if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
@@ -156,6 +170,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int cc = 0; cc < p.cchunks; ++cc) {
         mbar_wait(&a_full[a_slot], a_phase);
         tc_fence_after();
+        if (lane == 0) DBG_TS(1, it);
         const uint32_t sa = smem_u32(a_base + (size_t)a_slot * kASlotBytes);
         const int ksteps = (cc == p.cchunks - 1) ? p.ksteps_last : 4;
         for (int t = 0; t < 9; ++t) {
@@ -181,6 +196,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (elect_one()) {
           umma_commit(&a_empty[a_slot]);
           if (cc == p.cchunks - 1) umma_commit(&tfull[as]);
+          DBG_TS(2, it);
         }
         __syncwarp();
         if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
@@ -205,6 +221,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const size_t pix = ((size_t)img * p.H + ho) * p.W + wo;
       mbar_wait(&tfull[as], (it >> 1) & 1);
       tc_fence_after();
+      if (warp == 4 && lane == 0) DBG_TS(3, it);
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * 256;
       const int nchunks = p.BN >> 4;
       for (int ch = 0; ch < nchunks; ++ch) {
@@ -258,11 +275,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
+      if (warp == 4 && lane == 0) DBG_TS(4, it);
     }
   }
+  if (threadIdx.x == 0) DBG_TS(5, 0);
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DBG_TS(5, 1);
   if (p.emit_stats) {
     float* out = stats_partials + (size_t)blockIdx.x * 2 * p.cout_pad;
     for (int i = threadIdx.x; i < 2 * p.cout_pad; i += kHThreads)

@@ -238,23 +238,44 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
 }
 
 
-// dw[co][ci][tap] += sum over the pixel splits of the unit slabs (fixed order -> deterministic)
+// dw[co][ci][tap] += sum over the pixel splits of the unit slabs (fixed order -> deterministic).
+// Block = 32 consecutive ci (coalesced slab reads) x 8 split-slices; one (co, tap) row per blockIdx.y iteration.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const WgradParams p, const float* __restrict__ ws, float* __restrict__ dw) {
-  const long long total = (long long)p.Cout * p.taps * p.Cin;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(idx % p.Cin);
-    const int tap = (int)((idx / p.Cin) % p.taps);
-    const int co = (int)(idx / ((long long)p.Cin * p.taps));
-    const int m_tile = co >> 7, row = co & 127;
-    const int n_tile = ci / p.ntile_w, col = ci - n_tile * p.ntile_w;
-    const int tg = tap / p.taps_per_group, tl = tap - tg * p.taps_per_group;
-    const int item = (m_tile * p.n_tiles + n_tile) * p.tap_groups + tg;
-    const float* src = ws + (size_t)item * p.splits * p.unit_stride + ((size_t)tl * 128 + row) * p.unit_n + col;
+  __shared__ float sh[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int ci_blocks = (p.Cin + 31) / 32;
+  const long long rows = (long long)p.Cout * p.taps * ci_blocks;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int cb = (int)(r % ci_blocks);
+    const int tap = (int)((r / ci_blocks) % p.taps);
+    const int co = (int)(r / ((long long)ci_blocks * p.taps));
+    const int ci = cb * 32 + lane;
     float acc = 0.f;
-    for (int s_ = 0; s_ < p.splits; ++s_) acc += src[(size_t)s_ * p.unit_stride];
-    dw[((size_t)co * p.Cin + ci) * p.taps + tap] += acc;
+    if (ci < p.Cin) {
+      const int m_tile = co >> 7, row = co & 127;
+      const int n_tile = ci / p.ntile_w, col = ci - n_tile * p.ntile_w;
+      const int tg = tap / p.taps_per_group, tl = tap - tg * p.taps_per_group;
+      const int item = (m_tile * p.n_tiles + n_tile) * p.tap_groups + tg;
+      const float* src = ws + (size_t)item * p.splits * p.unit_stride + ((size_t)tl * 128 + row) * p.unit_n + col;
+      float a0 = 0.f, a1 = 0.f;
+      int s_ = slice;
+      for (; s_ + 8 < p.splits; s_ += 16) {
+        a0 += src[(size_t)s_ * p.unit_stride];
+        a1 += src[(size_t)(s_ + 8) * p.unit_stride];
+      }
+      if (s_ < p.splits) a0 += src[(size_t)s_ * p.unit_stride];
+      acc = a0 + a1;
+    }
+    sh[slice][lane] = acc;
+    __syncthreads();
+    if (slice == 0 && ci < p.Cin) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sh[k][lane];
+      dw[((size_t)co * p.Cin + ci) * p.taps + tap] += t;
+    }
+    __syncthreads();
   }
 }
 
@@ -348,8 +369,7 @@ extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, c
   }
   const int grid = p.total_units < B200SEG_MAX_CTAS ? p.total_units : B200SEG_MAX_CTAS;
   wgrad_igemm_kernel<<<grid, kWThreads, smem_bytes, (cudaStream_t)stream>>>(tmDy, tmX, p, (float*)workspace);
-  const long long total = (long long)p.Cout * p.taps * p.Cin;
-  long long rb = (total + 255) / 256;
+  long long rb = (long long)p.Cout * p.taps * ((p.Cin + 31) / 32);
   if (rb > 148 * 8) rb = 148 * 8;
   wgrad_reduce_kernel<<<(int)rb, 256, 0, (cudaStream_t)stream>>>(p, (const float*)workspace, dw_oihw);
   cudaError_t e = cudaGetLastError();
