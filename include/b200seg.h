@@ -93,11 +93,22 @@ int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, const void* 
  * in-place ReLU (network/hrnetv2.py:28,44) and the residual add (network/hrnetv2.py:63-64,103-104).
  * ------------------------------------------------------------------------------------------------ */
 /* partials[grid][2][cpad] (conv epilogue) -> scale = gamma*invstd, shift = beta - mean*scale, saved mean/invstd;
- * running stats updated with `momentum` (unbiased variance), num_batches_tracked += 1 (all optional). */
+ * running stats updated with `momentum` (unbiased variance), num_batches_tracked += 1 (all optional);
+ * batch_stats_out (optional) receives [mean c | unbiased var c] for a deferred b200seg_bn_running_update. */
 int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t c, int32_t cpad, float count, const float* gamma,
                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                         int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
-                        void* stream);
+                        float* batch_stats_out, void* stream);
+/* Momentum update of every BatchNorm layer's running statistics in one launch: running / batch_pass* are flat fp32
+ * buffers of n elements with one layout ([mean c | var c] per layer); pass 0 is applied before pass 1 (the order of
+ * the two _fwd calls in network/ocrnet.py:278-281); batch_pass1 may be NULL. num_batches_tracked[n_layers] += n_passes
+ * (the BatchNorm2d bookkeeping behind Norm2d, network/mynn.py:18-24). */
+int b200seg_bn_running_update(float* running, const float* batch_pass0, const float* batch_pass1, int64_t n,
+                              float momentum, int64_t* num_batches_tracked, int32_t n_layers, int32_t n_passes,
+                              void* stream);
+/* dst[n] += src[n] (fp32, n multiple of 4, 16-byte aligned): folds a scale pass' private parameter-gradient buffer
+ * into the step gradient (the passes run concurrently; autograd's accumulation order lo -> hi is kept). */
+int b200seg_accum_f32(float* dst, const float* src, int64_t n, void* stream);
 /* eval mode: scale/shift from running statistics */
 int b200seg_bn_eval_params(int32_t c, const float* gamma, const float* beta, float eps, const float* running_mean,
                            const float* running_var, float* scale, float* shift, void* stream);

@@ -41,15 +41,23 @@ class HeadRec:
 
 
 class Engine:
-    def __init__(self, params, grads, packed, training, drop_mask=None, side_stream=None):
+    def __init__(self, params, grads, packed, training, drop_mask=None, side_stream=None, bstat=None, stream=None):
         """params: name -> tensor (weights, BN buffers); grads: name -> fp32 tensor accumulated into (training);
-        packed: name -> (w_fwd, w_dgrad) bf16 operand caches; drop_mask: fp32 [N, mid] post-ReLU multiplier."""
+        packed: name -> (w_fwd, w_dgrad) bf16 operand caches; drop_mask: fp32 [N, mid] post-ReLU multiplier;
+        bstat: BN layer name -> fp32 [2*C] slot receiving the batch [mean | unbiased var] (the running statistics are
+        then updated once per step by bn_running_update; without it bn_finalize updates them in place);
+        stream: the stream this engine's program is enqueued on when it runs concurrently with another engine (the
+        low-resolution pass of the two-scale step), None = the caller's current stream."""
         self.p = params
         self.g = grads
         self.packed = packed
         self.training = training
         self.drop_mask = drop_mask
+        self.bstat = bstat
+        self.stream = stream
         self.tape = []
+        self.bn_seen = set()
+        self.hold = []      # tensors handed across streams: kept alive until the step's final join
         # Weight gradients do not feed the rest of the backward chain: they run on a side stream (a parallel branch of
         # the captured CUDA graph) and overlap with the BN / data-gradient kernels of the main chain.
         self.side = side_stream if side_stream is not None else (
@@ -65,6 +73,10 @@ class Engine:
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
         self._keepalive.clear()
+
+    def finish(self):
+        """After every stream of the step has been joined: drop the cross-stream keep-alive references."""
+        self.hold.clear()
 
     def wgrad(self, x_t, dy, dw, cout, ksize, stride):
         """dw += wgrad(x, dy) on the side stream. Operands are kept alive until the streams are joined (the caching
@@ -100,9 +112,14 @@ class Engine:
         if self.training:
             y, stats = raw.conv2d_fwd(x.t, w_f, b, stride=stride, emit_stats=True)
             n, ho, wo, _ = y.shape
-            par = raw.bn_finalize(stats, n * ho * wo, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
-                                  BN_MOMENTUM, self.p[bname + ".running_mean"], self.p[bname + ".running_var"],
-                                  self.p[bname + ".num_batches_tracked"], rec.cout)
+            if self.bstat is not None:
+                self.bn_seen.add(bname)
+                par = raw.bn_finalize(stats, n * ho * wo, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
+                                      BN_MOMENTUM, None, None, None, rec.cout, batch_out=self.bstat[bname])
+            else:
+                par = raw.bn_finalize(stats, n * ho * wo, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
+                                      BN_MOMENTUM, self.p[bname + ".running_mean"], self.p[bname + ".running_var"],
+                                      self.p[bname + ".num_batches_tracked"], rec.cout)
             rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], par[2], par[3]
         else:
             y = raw.conv2d_fwd(x.t, w_f, b, stride=stride)

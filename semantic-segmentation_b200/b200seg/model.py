@@ -242,17 +242,33 @@ def scale_pass(E, images, size_hw, arch, hcfg, ocfg):
     return dict(cls=cls, aux=aux, attn=attn)
 
 
-def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, sup_wt=0.0, ignore_index=255):
+def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, sup_wt=0.0, ignore_index=255, E_lo=None):
     """Training forward + loss. ocrnet.HRNet_Mscale: MscaleOCR.two_scale_forward (network/ocrnet.py:264-319);
     ocrnet.HRNet: OCRNet.forward (:104-122); basic.HRNet: Basic.forward (network/basic.py:50-64).
-    Returns the fp32 loss vector [total, cls, aux, sup_lo, sup_hi]; pushes the loss backward on the tape."""
+    Returns the fp32 loss vector [total, cls, aux, sup_lo, sup_hi]; pushes the loss backward on the tape.
+
+    E_lo (optional, two-scale only): a second engine with its own stream, gradient buffer and BN batch-statistics
+    slots. The 0.5x and 1.0x passes are independent until the blend, so the low-resolution program is enqueued on
+    E_lo.stream (a parallel branch of the captured CUDA graph) in forward and in backward; its small kernels fill the
+    SMs the full-resolution pass leaves idle."""
     n, _, H, W = images.shape
     two_scale = arch == "ocrnet.HRNet_Mscale"
     lo = None
+    main = torch.cuda.current_stream() if images.is_cuda else None
+    par = two_scale and E_lo is not None and E_lo.stream is not None
+    if not par:
+        E_lo = E
     if two_scale:
         hm, wm = int(H * lo_scale), int(W * lo_scale)      # ResizeX: floor(in * scale)
-        lo = scale_pass(E, images, (hm, wm), arch, hcfg, ocfg)
+        if par:
+            E_lo.stream.wait_stream(main)
+            with torch.cuda.stream(E_lo.stream):
+                lo = scale_pass(E_lo, images, (hm, wm), arch, hcfg, ocfg)
+        else:
+            lo = scale_pass(E, images, (hm, wm), arch, hcfg, ocfg)
     hi = scale_pass(E, images, (H, W), arch, hcfg, ocfg)
+    if par:
+        main.wait_stream(E_lo.stream)
     nheads = 1 if arch == "basic.HRNet" else 2
     hq, wq = hi["cls"].logits.shape[1:3]
     if two_scale:
@@ -276,5 +292,21 @@ def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, su
             dl_cls, dl_aux, dl_attn = raw.mscale_lo_bwd(d, g_lo, g_sup, lo["cls"].logits, lo["aux"].logits, lo_attn,
                                                         mid)
             lo["cls"].dlogits, lo["aux"].dlogits, lo["attn"].dlogits = dl_cls, dl_aux, dl_attn
+            if par:
+                # allocated on the main stream, consumed on the low-resolution stream: keep them until the final join
+                E.hold.extend((dl_cls, dl_aux, dl_attn))
+                E_lo.stream.wait_stream(main)
+                with torch.cuda.stream(E_lo.stream):
+                    E_lo.run_backward()        # whole 0.5x backward, concurrent with the 1.0x tape below
     E._push(loss_bwd)
     return loss
+
+
+def run_backward(E, E_lo=None):
+    """Backward of a step built by train_loss: E's tape on the current stream (its first entry forks E_lo's tape onto
+    E_lo.stream), then the join."""
+    E.run_backward()
+    if E_lo is not None and E_lo.stream is not None:
+        torch.cuda.current_stream().wait_stream(E_lo.stream)
+        E_lo.finish()
+    E.finish()

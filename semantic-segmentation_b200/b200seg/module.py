@@ -20,7 +20,7 @@ from torch import nn
 from . import arch as A
 from . import model as M
 from . import raw
-from .engine import Engine
+from .engine import BN_MOMENTUM, Engine
 
 F32 = torch.float32
 
@@ -69,7 +69,8 @@ class _PublishGrads(torch.autograd.Function):
 
 class B200SegModule(nn.Module):
     def __init__(self, arch, num_classes=19, criterion=None, hcfg=None, ocfg=None, lo_scale=0.5, ocr_alpha=0.4,
-                 supervised_mscale_wt=0.0, ignore_index=255, n_scales=None, use_cuda_graph=True):
+                 supervised_mscale_wt=0.0, ignore_index=255, n_scales=None, use_cuda_graph=True,
+                 parallel_scales=True):
         super().__init__()
         self.arch = arch
         self.criterion = criterion
@@ -81,6 +82,8 @@ class B200SegModule(nn.Module):
         self.lo_scale, self.ocr_alpha, self.sup_wt, self.ignore_index = lo_scale, ocr_alpha, supervised_mscale_wt, ignore_index
         self.n_scales = n_scales
         self.use_cuda_graph = use_cuda_graph
+        self.parallel_scales = parallel_scales     # run the 0.5x and 1.0x passes of the two-scale step concurrently
+        self._run_flat = None
         self._specs = A.tensor_specs(arch, self.hcfg, self.ocfg)
         self._build_parameters()
         self._flat_grad = None
@@ -163,6 +166,49 @@ class B200SegModule(nn.Module):
                     self._packed[n[: -len(".weight")]] = (w_f, w_d)
             self._stem_pad = None
             self._graphs = {}
+            # private gradient buffer of the concurrently executed low-resolution pass (folded in at the end of a step)
+            self._flat_grad_lo = torch.zeros_like(self._flat_grad)
+            self._grad_views_lo = {}
+            off = 0
+            for n, p in params:
+                self._grad_views_lo[n] = self._flat_grad_lo[off:off + p.numel()].view(p.shape)
+                off += (p.numel() + 63) // 64 * 64
+        self._ensure_flat_running(dev)
+
+    def _ensure_flat_running(self, dev):
+        """BatchNorm running statistics live in ONE flat fp32 buffer ([mean C | var C] per layer) and the module's
+        registered buffers are views of it (state_dict / load_state_dict / checkpoints unchanged). That lets a step
+        update every layer's running statistics with a single kernel after its concurrent scale passes have joined."""
+        bn_names = [n[: -len(".running_mean")] for n, _s, k in self._specs if k == "bn_rm"]
+        owners = [self._container(b.split(".")) for b in bn_names]
+        ok = (self._run_flat is not None and self._run_flat.device == dev and
+              all(o._buffers["running_mean"].device == dev for o in owners[:1]) and
+              owners[0]._buffers["running_mean"].data_ptr() == self._run_flat.data_ptr() and
+              owners[-1]._buffers["num_batches_tracked"].data_ptr() ==
+              self._nbt_flat.data_ptr() + 8 * (len(owners) - 1))
+        if ok:
+            return
+        total = sum(2 * o._buffers["running_mean"].numel() for o in owners)
+        total = (total + 3) // 4 * 4
+        flat = torch.zeros(total, dtype=F32, device=dev)
+        nbt_flat = torch.zeros(len(owners), dtype=torch.long, device=dev)
+        self._bn_slots = {}
+        off = 0
+        with torch.no_grad():
+            for li, (b, o) in enumerate(zip(bn_names, owners)):
+                c = o._buffers["running_mean"].numel()
+                flat[off:off + c].copy_(o._buffers["running_mean"])
+                flat[off + c:off + 2 * c].copy_(o._buffers["running_var"])
+                nbt_flat[li].copy_(o._buffers["num_batches_tracked"])
+                o._buffers["running_mean"] = flat[off:off + c]
+                o._buffers["running_var"] = flat[off + c:off + 2 * c]
+                o._buffers["num_batches_tracked"] = nbt_flat[li]
+                self._bn_slots[b] = (off, c)
+                off += 2 * c
+        self._run_flat, self._nbt_flat = flat, nbt_flat
+        self._bstat = [torch.zeros(total, dtype=F32, device=dev) for _ in range(2)]
+        self._bstat_views = [{b: t[o_:o_ + 2 * c_] for b, (o_, c_) in self._bn_slots.items()} for t in self._bstat]
+        self._graphs = {}
 
     def _repack(self):
         """fp32 OIHW master weights -> bf16 kernel layouts (inside the captured step: weights change every step)."""
@@ -190,19 +236,39 @@ class B200SegModule(nn.Module):
     def _step_body(self, images, gts, drop_mask):
         self._repack()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
-        grads = dict(self._grad_views)
         stem = "backbone.conv1.weight"
-        stem_pad_grad = torch.zeros((grads[stem].shape[0], 16, 3, 3), dtype=F32, device=images.device)
-        grads[stem] = stem_pad_grad          # the stem runs on the 16-channel padded image
-        if getattr(self, "_side_stream", None) is None:
-            self._side_stream = torch.cuda.Stream()
-        E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream)
+
+        def grad_table(views):
+            g = dict(views)
+            pad = torch.zeros((g[stem].shape[0], 16, 3, 3), dtype=F32, device=images.device)
+            g[stem] = pad                    # the stem runs on the 16-channel padded image
+            return g, pad
+
         if self.loss_kind != "ce":
             raise NotImplementedError("RMI loss kernels are not wired into the fused step yet")
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream()
+        grads, stem_pad_grad = grad_table(self._grad_views)
+        par = self.parallel_scales and self.arch == "ocrnet.HRNet_Mscale"
+        E_lo = None
+        if par:
+            if getattr(self, "_lo_stream", None) is None:
+                self._lo_stream, self._side_stream_lo = torch.cuda.Stream(), torch.cuda.Stream()
+            self._flat_grad_lo.zero_()
+            grads_lo, stem_pad_grad_lo = grad_table(self._grad_views_lo)
+            E_lo = Engine(tensors, grads_lo, self._packed, True, drop_mask, side_stream=self._side_stream_lo,
+                          bstat=self._bstat_views[0], stream=self._lo_stream)
+        E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream,
+                   bstat=self._bstat_views[1] if par else None)
         loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,
-                            self.ignore_index)
-        E.run_backward()
+                            self.ignore_index, E_lo=E_lo)
+        M.run_backward(E, E_lo)
         self._grad_views[stem].add_(stem_pad_grad[:, :3])
+        if par:
+            assert E.bn_seen == E_lo.bn_seen and len(E.bn_seen) == len(self._bn_slots), "BN bookkeeping out of sync"
+            self._grad_views_lo[stem].add_(stem_pad_grad_lo[:, :3])
+            raw.accum_f32(self._flat_grad, self._flat_grad_lo)
+            raw.bn_running_update(self._run_flat, self._bstat[0], self._bstat[1], BN_MOMENTUM, self._nbt_flat, 2)
         return loss
 
     def _drop_mask(self, n, device):

@@ -120,13 +120,26 @@ def conv2d_wgrad(x, dy, dw_oihw, cout, ksize, stride):
 
 
 # ----------------------------------------------------------------------------------------------- batch norm
-def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, c):
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, c, batch_out=None):
+    """batch_out (fp32 [2*c], optional): receives [mean | unbiased var] for a deferred bn_running_update; pass
+    running_mean = running_var = nbt = None with it."""
     buf, grid, cpad = stats
     out = torch.empty((4, c), dtype=F32, device=buf.device)   # scale, shift, mean, invstd
     check(lib().b200seg_bn_finalize(ptr(buf), grid, c, cpad, float(count), ptr(gamma), ptr(beta), eps, momentum,
                                     ptr(running_mean), ptr(running_var), ptr(nbt), ptr(out[0]), ptr(out[1]),
-                                    ptr(out[2]), ptr(out[3]), stream_ptr()), "bn_finalize")
+                                    ptr(out[2]), ptr(out[3]), ptr(batch_out), stream_ptr()), "bn_finalize")
     return out
+
+
+def bn_running_update(running, batch0, batch1, momentum, nbt, n_passes):
+    check(lib().b200seg_bn_running_update(ptr(running), ptr(batch0), ptr(batch1), running.numel(), momentum, ptr(nbt),
+                                          nbt.numel() if nbt is not None else 0, n_passes, stream_ptr()),
+          "bn_running_update")
+
+
+def accum_f32(dst, src):
+    assert dst.numel() == src.numel() and dst.dtype == F32 and src.dtype == F32
+    check(lib().b200seg_accum_f32(ptr(dst), ptr(src), dst.numel(), stream_ptr()), "accum_f32")
 
 
 def bn_eval_params(gamma, beta, eps, running_mean, running_var):

@@ -7,6 +7,7 @@
 //   backward: bn_bwd_reduce (sum g, sum g*xhat per channel; g = dz * (mask>0)) -> bn_bwd_finalize (dgamma, dbeta, c1, c2)
 //             -> bn_bwd_apply  dy = gamma*invstd*(g - c1 - xhat*c2)  [and g written out for the residual branch]
 #include "ptx.cuh"
+#include "launch.h"
 #include "../../include/b200seg.h"
 #include "vec.cuh"
 
@@ -18,7 +19,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, in
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out) {
+                                   float* __restrict__ invstd_out, float* __restrict__ batch_stats_out) {
+  pdl_sync();
   // block = 32 channels x 8 slices of the G partial rows (coalesced 128-byte reads), then a fixed-order fold
   __shared__ double sh1[8][32], sh2[8][32];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -45,10 +47,43 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, in
   shift[c] = b_ - (float)mean * g_ * invstd;
   mean_out[c] = (float)mean;
   invstd_out[c] = invstd;
+  const double unbiased = count > 1.f ? var * (double)count / ((double)count - 1.0) : var;
   if (running_mean) {
-    const double unbiased = count > 1.f ? var * (double)count / ((double)count - 1.0) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+  if (batch_stats_out) {   // deferred running-stat update (bn_running_update_kernel): [mean C | unbiased var C]
+    batch_stats_out[c] = (float)mean;
+    batch_stats_out[C + c] = (float)unbiased;
+  }
+}
+
+// Running-statistics update of ALL BatchNorm layers of a step in one pass. The scale passes of the multi-scale step run
+// concurrently on different streams, so their finalisers only store the batch statistics; this kernel then applies the
+// momentum updates in the reference's order (low-resolution pass first, network/ocrnet.py:278-281):
+//   r <- (1-m) r + m b_pass0 ;  r <- (1-m) r + m b_pass1.   running / batch buffers share one flat layout.
+__global__ void bn_running_update_kernel(float* __restrict__ running, const float* __restrict__ b0,
+                                         const float* __restrict__ b1, long long n, float momentum,
+                                         long long* __restrict__ nbt, int n_layers, int n_passes) {
+  pdl_sync();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float r = running[i];
+    r = (1.f - momentum) * r + momentum * b0[i];
+    if (b1) r = (1.f - momentum) * r + momentum * b1[i];
+    running[i] = r;
+  }
+  if (nbt && i < n_layers) nbt[i] += n_passes;
+}
+
+// dst += src (fp32): folds the low-resolution pass' private parameter-gradient buffer into the step's gradient.
+__global__ void accum_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4) {
+  pdl_sync();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
   }
 }
 
@@ -56,6 +91,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, in
 __global__ void bn_eval_params_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                       float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = rsqrtf(running_var[c] + eps);
@@ -69,6 +105,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const float* __re
                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_ld,
                 const float* __restrict__ post_scale, int relu, __nv_bfloat16* __restrict__ z, int z_ld,
                 long long npix, int hw, int C) {
+  pdl_sync();
   extern __shared__ float s_par[];   // [2][C]
   for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = scale[i]; s_par[C + i] = shift[i]; }
   __syncthreads();
@@ -108,6 +145,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv
                      int mask_ld, const float* __restrict__ post_scale, const __nv_bfloat16* __restrict__ y, int y_ld,
                      const float* __restrict__ mean, const float* __restrict__ invstd, long long npix, int hw, int C,
                      int rows, float* __restrict__ partials) {
+  pdl_sync();
   extern __shared__ float s_red[];   // [rows][groups][16]
   const int groups = C >> 3;
   const int cg = threadIdx.x % groups, r = threadIdx.x / groups;
@@ -155,6 +193,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, float count,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
                                        float* __restrict__ c2) {
+  pdl_sync();
   __shared__ double sh1[8][32], sh2[8][32];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -182,6 +221,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv_
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ c1, const float* __restrict__ c2, __nv_bfloat16* __restrict__ dy, int dy_ld,
                     __nv_bfloat16* __restrict__ g_out, int g_ld, int g_accumulate, long long npix, int hw, int C) {
+  pdl_sync();
   extern __shared__ float s_par[];   // [5][C]: mean, invstd, gamma*invstd, c1, c2
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     s_par[i] = mean[i];
@@ -233,6 +273,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv_
 __global__ void __launch_bounds__(256)
 masked_accum_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, const __nv_bfloat16* __restrict__ mask,
                     int mask_ld, __nv_bfloat16* __restrict__ dst, int dst_ld, int accumulate, long long npix, int C) {
+  pdl_sync();
   const int groups = C >> 3;
   const long long total = npix * groups;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -276,11 +317,27 @@ using namespace b200seg;
 extern "C" int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t c, int32_t cpad, float count,
                                    const float* gamma, const float* beta, float eps, float momentum,
                                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
-                                   float* shift, float* mean, float* invstd, void* stream) {
+                                   float* shift, float* mean, float* invstd, float* batch_stats_out, void* stream) {
   if (!partials || !scale || !shift || !mean || !invstd || c <= 0 || grid <= 0) return B200SEG_E_BADARG;
-  bn_finalize_kernel<<<(c + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
-      partials, grid, c, cpad, count, gamma, beta, eps, momentum, running_mean, running_var,
-      (long long*)num_batches_tracked, scale, shift, mean, invstd);
+  launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(256), 0, (cudaStream_t)stream, partials, grid, c, cpad, count, gamma, beta, eps, momentum, running_mean, running_var,
+      (long long*)num_batches_tracked, scale, shift, mean, invstd, batch_stats_out);
+  CHECK_LAUNCH();
+}
+
+extern "C" int b200seg_bn_running_update(float* running, const float* batch_pass0, const float* batch_pass1,
+                                         int64_t n, float momentum, int64_t* num_batches_tracked, int32_t n_layers,
+                                         int32_t n_passes, void* stream) {
+  if (!running || !batch_pass0 || n <= 0 || n_layers > n) return B200SEG_E_BADARG;
+  launch_k(bn_running_update_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, running,
+           batch_pass0, batch_pass1, (long long)n, momentum, (long long*)num_batches_tracked, n_layers, n_passes);
+  CHECK_LAUNCH();
+}
+
+extern "C" int b200seg_accum_f32(float* dst, const float* src, int64_t n, void* stream) {
+  if (!dst || !src || n <= 0 || (n & 3) || (reinterpret_cast<uintptr_t>(dst) & 15) ||
+      (reinterpret_cast<uintptr_t>(src) & 15))
+    return B200SEG_E_BADARG;
+  launch_k(accum_f32_kernel, dim3(148 * 8), dim3(256), 0, (cudaStream_t)stream, dst, src, (long long)(n / 4));
   CHECK_LAUNCH();
 }
 
@@ -288,7 +345,7 @@ extern "C" int b200seg_bn_eval_params(int32_t c, const float* gamma, const float
                                       const float* running_mean, const float* running_var, float* scale, float* shift,
                                       void* stream) {
   if (!gamma || !beta || !running_mean || !running_var || !scale || !shift) return B200SEG_E_BADARG;
-  bn_eval_params_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c, gamma, beta, eps, running_mean,
+  launch_k(bn_eval_params_kernel, dim3((c + 127) / 128), dim3(128), 0, (cudaStream_t)stream, c, gamma, beta, eps, running_mean,
                                                                           running_var, scale, shift);
   CHECK_LAUNCH();
 }
@@ -297,8 +354,7 @@ extern "C" int b200seg_bn_apply(const void* y, int32_t y_ld, const float* scale,
                                 int32_t res_ld, const float* post_scale, int32_t relu, void* z, int32_t z_ld,
                                 int64_t npix, int32_t hw, int32_t c, void* stream) {
   if (!y || !z || !scale || !shift || c % 8 || y_ld % 8 || z_ld % 8 || (res && res_ld % 8)) return B200SEG_E_BADARG;
-  bn_apply_kernel<<<ew_grid(npix * (c / 8)), 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, post_scale, relu,
+  launch_k(bn_apply_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 2 * c * sizeof(float), (cudaStream_t)stream, (const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, post_scale, relu,
       (__nv_bfloat16*)z, z_ld, npix, hw, c);
   CHECK_LAUNCH();
 }
@@ -329,8 +385,7 @@ extern "C" int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* 
   if (threads > 256) return B200SEG_E_BADARG;
   const int grid = b200seg_bn_bwd_grid(npix, c);
   const size_t smem = (size_t)rows * (c / 8) * 16 * sizeof(float);
-  bn_bwd_reduce_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y, y_ld,
+  launch_k(bn_bwd_reduce_kernel, dim3(grid), dim3(threads), smem, (cudaStream_t)stream, (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y, y_ld,
       mean, invstd, npix, hw, c, rows, partials);
   CHECK_LAUNCH();
 }
@@ -338,7 +393,7 @@ extern "C" int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* 
 extern "C" int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int32_t c, float count, float* dgamma,
                                        float* dbeta, float* c1, float* c2, void* stream) {
   if (!partials || !c1 || !c2) return B200SEG_E_BADARG;
-  bn_bwd_finalize_kernel<<<(c + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, grid, c, count, dgamma, dbeta,
+  launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(256), 0, (cudaStream_t)stream, partials, grid, c, count, dgamma, dbeta,
                                                                            c1, c2);
   CHECK_LAUNCH();
 }
@@ -349,8 +404,7 @@ extern "C" int b200seg_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* m
                                     int32_t dy_ld, void* g_out, int32_t g_ld, int32_t g_accumulate, int64_t npix,
                                     int32_t hw, int32_t c, void* stream) {
   if (!dz || !y || !dy || !mean || !invstd || !c1 || !c2 || c % 8) return B200SEG_E_BADARG;
-  bn_bwd_apply_kernel<<<ew_grid(npix * (c / 8)), 256, 5 * c * sizeof(float), (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y, y_ld,
+  launch_k(bn_bwd_apply_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 5 * c * sizeof(float), (cudaStream_t)stream, (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y, y_ld,
       mean, invstd, gamma, c1, c2, (__nv_bfloat16*)dy, dy_ld, (__nv_bfloat16*)g_out, g_ld, g_accumulate, npix, hw, c);
   CHECK_LAUNCH();
 }
@@ -358,8 +412,7 @@ extern "C" int b200seg_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* m
 extern "C" int b200seg_masked_accum(const void* src, int32_t src_ld, const void* mask, int32_t mask_ld, void* dst,
                                     int32_t dst_ld, int32_t accumulate, int64_t npix, int32_t c, void* stream) {
   if (!src || !dst || c % 8) return B200SEG_E_BADARG;
-  masked_accum_kernel<<<ew_grid(npix * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)src, src_ld, (const __nv_bfloat16*)mask, mask_ld, (__nv_bfloat16*)dst, dst_ld, accumulate,
+  launch_k(masked_accum_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, src_ld, (const __nv_bfloat16*)mask, mask_ld, (__nv_bfloat16*)dst, dst_ld, accumulate,
       npix, c);
   CHECK_LAUNCH();
 }

@@ -7,13 +7,19 @@
 //     start = tile + (kh*10 + kw) * 128 B,   stride-byte-offset = 10 * 128 B (one 8-pixel tile row per 8-row group)
 // which works because the tensor core applies the 128B swizzle to absolute shared-memory addresses (pinned on silicon,
 // profiles/r1_umma_probe.txt: row-shifted starts and arbitrary SBO read exactly the rows TMA wrote).
+//
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = ONE elected thread that waits on the barriers and issues every
+// tcgen05.mma of the CTA from fully unrolled code (a narrow layer's MMA lasts ~32 clocks, so the issue path must be a
+// handful of uniform-datapath instructions per MMA), warp 2 = TMEM allocator, warps 4-11 = epilogue: two warps per TMEM
+// lane quarter, each taking half of the accumulator columns.
 // Weights: resident in shared memory for the whole persistent CTA when they fit (C <= 96: the HBM-bound layers), else
-// streamed per (chunk, tap) through an mbarrier ring. Everything else (TMEM double buffering, warp roles, BN-statistics
-// epilogue, gradient-accumulating addend) matches conv_igemm.cu.
+// streamed per (chunk, tap) through an mbarrier ring. The Cout tile (BN) is chosen per launch by a small cost model so
+// that low-resolution layers still spread over the SMs (a 16x32x384 layer has 4 pixel tiles but 6 x 64-wide Cout tiles).
 // Replaces cuDNN fwd/dgrad behind the 3x3 stride-1 convolutions of network/hrnetv2.py:31-34 (BasicBlock), :76
 // (Bottleneck), network/ocrnet.py:54-57 (conv3x3_ocr) and network/utils.py:348-356 (attention head).
 #include "ptx.cuh"
 #include "tma_host.h"
+#include "launch.h"
 #include "../../include/b200seg.h"
 #include "vec.cuh"
 #include <cstdlib>
@@ -24,31 +30,20 @@ struct HaloParams {
   int N, H, W, Cin, Cout;      // H, W: spatial size (same for input and output)
   int cchunks;                 // ceil(Cin / 64)
   int ksteps_last;             // K=16 steps in the last chunk
-  int BN, n_tiles, cout_pad;
+  int BN, n_tiles, cout_pad;   // cout_pad = roundup16(Cout): row pitch of the statistics partials
   int tiles_h, tiles_w, total_tiles;
   int y_ld, has_bias, emit_stats, addend_ld;
   int resident;                // weights stay in smem for the CTA lifetime
   int a_slots, b_slots;        // ring depths (b_slots unused when resident)
   int b_tile_bytes;            // BN * 128 rounded to 1024
-  int dbg;                     // bench-only switches (env B200SEG_DBG): 1 no stats, 2 no stores, 4 no tmem loads
-  int n_tile_fixed;            // resident mode: the single Cout tile this launch covers per CTA (n_tiles == 1)
 };
 
-constexpr int kHThreads = 256;
+constexpr int kHThreads = 384;
 constexpr int kASlotBytes = 24576;     // 180 halo rows x 128 B = 23040, padded to a 1024 multiple
 constexpr int kHaloW = 10, kHaloH = 18, kTW = 8, kTH = 16;
 constexpr int kMaxASlots = 4, kMaxBSlots2 = 8;
 
-__device__ __forceinline__ void h_store16(void* dst, const float (&v)[16]) {
-  uint4 a, b;
-  a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);
-  a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
-  b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]);
-  b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
-  uint4* p = reinterpret_cast<uint4*>(dst);
-  p[0] = a;
-  p[1] = b;
-}
+// Sum v[0..15] over the 32 lanes of the warp: afterwards v[0] holds the total for channel (lane & 15).
 __device__ __forceinline__ void h_butterfly16(float (&v)[16], uint32_t lane) {
 #pragma unroll
   for (int off = 8; off >= 1; off >>= 1) {
@@ -63,17 +58,20 @@ __device__ __forceinline__ void h_butterfly16(float (&v)[16], uint32_t lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
+// All nine taps of one resident 64-channel chunk: 9 x KS MMAs, compile-time offsets only.
+template <int KS>
+__device__ __forceinline__ void halo_issue9(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t btile16,
+                                            uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int kh = t / 3, kw = t - kh * 3;
+    const uint64_t ad = adesc + (uint64_t)((kh * kHaloW + kw) * 8);   // (kh*10 + kw) rows of 128 B, in 16-byte units
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+      umma_f16(d_tmem, ad + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (t | k) ? 1u : acc_first);
+    bdesc += btile16;
+  }
 }
-// bench-only timeline (B200SEG_DBG & 8): block 0 records ns timestamps per role and tile behind the stats partials
-#define DBG_TS(role, it)                                                                                     \
-  do {                                                                                                       \
-    if ((p.dbg & 8) && blockIdx.x == 0 && (it) < 16)                                                         \
-      reinterpret_cast<unsigned long long*>(stats_partials + 148 * 2 * 1024)[(role) * 16 + (it)] = gtime(); \
-  } while (0)
 
 __global__ void __launch_bounds__(kHThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -92,14 +90,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull = b_empty + kMaxBSlots2;         // [2]
   uint64_t* tempty = tfull + 2;                    // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [4][2][cout_pad]
+  float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [4 lane quarters][2][cout_pad]
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kMaxBSlots2; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
@@ -109,105 +107,107 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  if (threadIdx.x == 0) DBG_TS(5, 2);
+  pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    // Warp-uniform control flow; the single issuing lane is chosen with elect.sync so ptxas keeps the TMA operands in
-    // uniform registers (a `lane == 0` branch makes it emit an R2UR.BROADCAST waterfall loop around every instruction).
-    if (p.resident) {   // all weight tiles of this CTA's Cout tile, once
-      if (elect_one()) {
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
+    if (elect_one()) {
+      if (p.resident) {   // all weight tiles of this CTA's (single) Cout tile, once
         mbar_arrive_expect_tx(&b_full[0], 9 * p.cchunks * p.b_tile_bytes);
         for (int cc = 0; cc < p.cchunks; ++cc)
           for (int t = 0; t < 9; ++t)
-            tma_load_3d(&tmB, &b_full[0], b_base + (size_t)(cc * 9 + t) * p.b_tile_bytes, cc * 64, t,
-                        p.n_tile_fixed * p.BN);
+            tma_load_3d(&tmB, &b_full[0], b_base + (size_t)(cc * 9 + t) * p.b_tile_bytes, cc * 64, t, 0);
       }
-      __syncwarp();
-    }
-    int a_slot = 0, b_slot = 0;
-    uint32_t a_phase = 0, b_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-      const int tw_i = m_tile % p.tiles_w;
-      const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
-      const int img = m_tile / (p.tiles_w * p.tiles_h);
-      for (int cc = 0; cc < p.cchunks; ++cc) {
-        mbar_wait(&a_empty[a_slot], a_phase ^ 1);
-        if (elect_one()) {
+      int a_slot = 0, b_slot = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const int tw_i = m_tile % p.tiles_w;
+        const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
+        const int img = m_tile / (p.tiles_w * p.tiles_h);
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          mbar_wait(&a_empty[a_slot], a_phase ^ 1);
           mbar_arrive_expect_tx(&a_full[a_slot], kHaloH * kHaloW * 128);
           tma_load_4d(&tmA, &a_full[a_slot], a_base + (size_t)a_slot * kASlotBytes, cc * 64, tw_i * kTW - 1,
                       th_i * kTH - 1, img);
-          DBG_TS(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
-        }
-        __syncwarp();
-        if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
-        if (!p.resident) {
-          for (int t = 0; t < 9; ++t) {
-            mbar_wait(&b_empty[b_slot], b_phase ^ 1);
-            if (elect_one()) {
+          if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
+          if (!p.resident) {
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(&b_empty[b_slot], b_phase ^ 1);
               mbar_arrive_expect_tx(&b_full[b_slot], p.b_tile_bytes);
               tma_load_3d(&tmB, &b_full[b_slot], b_base + (size_t)b_slot * p.b_tile_bytes, cc * 64, t, n_tile * p.BN);
+              if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
             }
-            __syncwarp();
-            if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
           }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
-    int a_slot = 0, b_slot = 0;
-    uint32_t a_phase = 0, b_phase = 0;
-    int it = 0;
-    if (p.resident) mbar_wait(&b_full[0], 0);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * 256;
-      for (int cc = 0; cc < p.cchunks; ++cc) {
-        mbar_wait(&a_full[a_slot], a_phase);
+    // ------------------------------------------------------------------ MMA issuer (one elected thread, whole loop)
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+      const uint64_t a_tmpl = make_smem_desc(0, 16, kHaloW * 128, 2);
+      const uint64_t b_tmpl = make_smem_desc(0, 16, 1024, 2);
+      const uint32_t a0 = smem_u32(a_base) >> 4, b0 = smem_u32(b_base) >> 4;
+      const uint32_t btile16 = (uint32_t)p.b_tile_bytes >> 4;
+      const int last = p.cchunks - 1;
+      int a_slot = 0, b_slot = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      int it = 0;
+      if (p.resident) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (lane == 0) DBG_TS(1, it);
-        const uint32_t sa = smem_u32(a_base + (size_t)a_slot * kASlotBytes);
-        const int ksteps = (cc == p.cchunks - 1) ? p.ksteps_last : 4;
-        for (int t = 0; t < 9; ++t) {
-          uint32_t sb;
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int cc = 0; cc <= last; ++cc) {
+          mbar_wait(&a_full[a_slot], a_phase);
+          tc_fence_after();
+          const uint64_t ad = a_tmpl + (uint64_t)(a0 + (uint32_t)a_slot * (kASlotBytes >> 4));
+          const int ks = (cc == last) ? p.ksteps_last : 4;
+          const uint32_t acc_first = cc != 0 ? 1u : 0u;
           if (p.resident) {
-            sb = smem_u32(b_base + (size_t)(cc * 9 + t) * p.b_tile_bytes);
+            const uint64_t bd = b_tmpl + (uint64_t)(b0 + (uint32_t)(cc * 9) * btile16);
+            switch (ks) {
+              case 4: halo_issue9<4>(d_tmem, ad, bd, btile16, idesc, acc_first); break;
+              case 3: halo_issue9<3>(d_tmem, ad, bd, btile16, idesc, acc_first); break;
+              case 2: halo_issue9<2>(d_tmem, ad, bd, btile16, idesc, acc_first); break;
+              default: halo_issue9<1>(d_tmem, ad, bd, btile16, idesc, acc_first); break;
+            }
           } else {
-            mbar_wait(&b_full[b_slot], b_phase);
-            tc_fence_after();
-            sb = smem_u32(b_base + (size_t)b_slot * p.b_tile_bytes);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const int kh = t / 3, kw = t - kh * 3;
+              mbar_wait(&b_full[b_slot], b_phase);
+              tc_fence_after();
+              const uint64_t at = ad + (uint64_t)((kh * kHaloW + kw) * 8);
+              const uint64_t bd = b_tmpl + (uint64_t)(b0 + (uint32_t)b_slot * btile16);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < ks) umma_f16(d_tmem, at + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (t | k) ? 1u : acc_first);
+              umma_commit(&b_empty[b_slot]);
+              if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
+            }
           }
-          const int kh = t / 3, kw = t - kh * 3;
-          const uint64_t adesc = make_smem_desc(sa + (kh * kHaloW + kw) * 128, 16, kHaloW * 128, 2);
-          const uint64_t bdesc = make_smem_desc(sb, 16, 1024, 2);
-          if (elect_one()) {
-            for (int k = 0; k < ksteps; ++k)
-              umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cc | t | k) != 0);
-            if (!p.resident) umma_commit(&b_empty[b_slot]);
-          }
-          __syncwarp();
-          if (!p.resident) { if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; } }
-        }
-        if (elect_one()) {
           umma_commit(&a_empty[a_slot]);
-          if (cc == p.cchunks - 1) umma_commit(&tfull[as]);
-          DBG_TS(2, it);
+          if (cc == last) umma_commit(&tfull[as]);
+          if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
         }
-        __syncwarp();
-        if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (thread == output pixel)
-    const uint32_t q = warp - 4;
+    const uint32_t ew = warp - 4;
+    const uint32_t q = ew & 3;                  // TMEM lane quarter == warp % 4
+    const uint32_t half = ew >> 2;              // which half of the accumulator columns
     const int m = q * 32 + lane;
     const int th = m >> 3, tw = m & 7;
     float* my_stats = s_stats + (size_t)q * 2 * p.cout_pad;
+    const int nchunks = p.BN >> 4;
+    const int ch_begin = half ? (nchunks + 1) / 2 : 0;
+    const int ch_end = half ? nchunks : (nchunks + 1) / 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -221,16 +221,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const size_t pix = ((size_t)img * p.H + ho) * p.W + wo;
       mbar_wait(&tfull[as], (it >> 1) & 1);
       tc_fence_after();
-      if (warp == 4 && lane == 0) DBG_TS(3, it);
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * 256;
-      const int nchunks = p.BN >> 4;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int c0 = n0 + ch * 16;
-        if (c0 >= p.Cout) break;
-        if (p.dbg & 4) break;
-        uint32_t r[16];
-        tmem_ld16(taddr + ch * 16, r);
-        tmem_ld_wait();
+
+      // one 16-column group: bias, gradient addend, bf16 store, batch statistics of the stored values
+      auto epi16 = [&](const uint32_t* r, int c0) {
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -246,23 +240,28 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
         }
-        if (valid && !(p.dbg & 2)) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        if (valid) {
           __nv_bfloat16* dst = y + pix * p.y_ld + c0;
           if (c0 + 16 <= p.Cout) {
-            h_store16(dst, v);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (c0 + j < p.Cout) dst[j] = __float2bfloat16_rn(v[j]);
           }
         }
-        if (p.emit_stats && !(p.dbg & 1)) {
+        if (p.emit_stats) {
           float s1[16], s2[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float rv = valid ? bf16_round(v[j]) : 0.f;
-            s1[j] = rv;
-            s2[j] = rv * rv;
+          for (int j = 0; j < 8; ++j) {
+            const float lo = valid ? bf16_lo(pk[j]) : 0.f, hi = valid ? bf16_hi(pk[j]) : 0.f;
+            s1[2 * j] = lo;      s1[2 * j + 1] = hi;
+            s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
           }
           h_butterfly16(s1, lane);
           h_butterfly16(s2, lane);
@@ -271,18 +270,31 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             my_stats[p.cout_pad + c0 + lane] += s2[0];
           }
         }
+      };
+
+      int ch = ch_begin;
+      for (; ch + 2 <= ch_end; ch += 2) {
+        if (n0 + ch * 16 >= p.Cout) break;      // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 16, r);
+        tmem_ld_wait();
+        epi16(r, n0 + ch * 16);
+        if (n0 + ch * 16 + 16 < p.Cout) epi16(r + 16, n0 + ch * 16 + 16);
+      }
+      if (ch < ch_end && n0 + ch * 16 < p.Cout) {
+        uint32_t r[16];
+        tmem_ld16(taddr + ch * 16, r);
+        tmem_ld_wait();
+        epi16(r, n0 + ch * 16);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
-      if (warp == 4 && lane == 0) DBG_TS(4, it);
     }
   }
-  if (threadIdx.x == 0) DBG_TS(5, 0);
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) DBG_TS(5, 1);
   if (p.emit_stats) {
     float* out = stats_partials + (size_t)blockIdx.x * 2 * p.cout_pad;
     for (int i = threadIdx.x; i < 2 * p.cout_pad; i += kHThreads)
@@ -291,36 +303,52 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// Cout tile width: minimise (waves x per-tile clocks) with per-tile clocks = max(tensor issue, L2->smem fill).
+// A narrow tile costs ~32 clocks per MMA regardless of N (the A operand read from shared memory bounds it).
+static int halo_pick_ntiles(int m_tiles, int cout, int cchunks, int k16) {
+  int best_nt = 0;
+  double best = 0;
+  for (int nt = 1; nt <= 16; ++nt) {
+    const int BN = ((cout + nt - 1) / nt + 15) / 16 * 16;
+    if (BN > 256) continue;
+    if ((cout + BN - 1) / BN != nt) continue;          // same split as a smaller nt
+    const long long tiles = (long long)m_tiles * nt;
+    const double waves = (double)((tiles + B200SEG_MAX_CTAS - 1) / B200SEG_MAX_CTAS);
+    const double mma = (double)k16 * (BN / 2 > 32 ? BN / 2 : 32);
+    const double fill = ((double)cchunks * kHaloH * kHaloW * 128 + (double)k16 * 32.0 * BN) / 64.0;
+    const double cost = waves * (mma > fill ? mma : fill) + 8.0 * BN + 2000.0 + 64.0 * nt;
+    if (best_nt == 0 || cost < best) { best = cost; best_nt = nt; }
+    if (BN <= 16) break;
+  }
+  return best_nt ? best_nt : 1;
+}
+
 // Host launcher shared by forward and stride-1 data gradient. `in` is the A-operand tensor [n,h,w,cin_ext] (pitch in_ld),
 // w is [cout][9][cin_ext] bf16. Returns B200SEG_E_BADARG when the shape is not eligible (caller falls back to the
-// generic per-tap kernel).
+// generic per-tap kernel). The statistics partials are [grid][2][roundup16(cout)].
 int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
                         const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
-                        int* cout_pad_out, const void* addend, int addend_ld, int emit_stats, cudaStream_t stream,
-                        bool plan_only) {
+                        const void* addend, int addend_ld, int emit_stats, cudaStream_t stream) {
   if (cin % 8 || in_ld % 8 || out_ld % 8 || cout % 16) return B200SEG_E_BADARG;
   HaloParams p;
   p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
   p.cchunks = (cin + 63) / 64;
   const int rem = cin - (p.cchunks - 1) * 64;
   p.ksteps_last = (rem + 15) / 16;
-  const int n_tiles0 = (cout + 255) / 256;
-  int BN = ((cout / 16 + n_tiles0 - 1) / n_tiles0) * 16;
-  p.BN = BN;
-  p.n_tiles = (cout + BN - 1) / BN;
-  p.cout_pad = p.n_tiles * BN;
-  if (cout_pad_out) *cout_pad_out = p.cout_pad;
   p.tiles_w = (w + kTW - 1) / kTW;
   p.tiles_h = (h + kTH - 1) / kTH;
-  p.total_tiles = n * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int m_tiles = n * p.tiles_h * p.tiles_w;
+  const int k16 = 9 * ((p.cchunks - 1) * 4 + p.ksteps_last);
+  p.n_tiles = halo_pick_ntiles(m_tiles, cout, p.cchunks, k16);
+  p.BN = ((cout + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;
+  p.cout_pad = (cout + 15) / 16 * 16;
+  p.total_tiles = m_tiles * p.n_tiles;
   p.y_ld = out_ld; p.has_bias = bias != nullptr; p.emit_stats = emit_stats; p.addend_ld = addend_ld;
-  p.b_tile_bytes = (BN * 128 + 1023) / 1024 * 1024;
+  p.b_tile_bytes = (p.BN * 128 + 1023) / 1024 * 1024;
   const size_t fixed = 1024 + (2 * kMaxASlots + 2 * kMaxBSlots2 + 4) * 8 + 16 + (size_t)4 * 2 * p.cout_pad * 4;
   const size_t budget = 227 * 1024 - fixed;
   const size_t resident_bytes = (size_t)9 * p.cchunks * p.b_tile_bytes;
   p.resident = (p.n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) ? 1 : 0;
-  p.n_tile_fixed = 0;
-  { const char* e = getenv("B200SEG_DBG"); p.dbg = e ? atoi(e) : 0; }
   size_t smem_bytes;
   if (p.resident) {
     int as_ = (int)((budget - resident_bytes) / kASlotBytes);
@@ -335,10 +363,9 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
     p.b_slots = bs;
     smem_bytes = fixed + 2 * (size_t)kASlotBytes + (size_t)bs * p.b_tile_bytes;
   }
-  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM: each allocates all 512 TMEM columns
   const int grid = p.total_tiles < B200SEG_MAX_CTAS ? p.total_tiles : B200SEG_MAX_CTAS;
   if (stats_grid) *stats_grid = grid;
-  if (plan_only) return 0;
   if (!in || !wts || !out) return B200SEG_E_BADARG;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(wts) & 15) ||
       (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15) || (addend && addend_ld % 8))
@@ -354,7 +381,7 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   {
     uint64_t dims[3] = {(uint64_t)cin, 9, (uint64_t)cout};
     uint64_t strides[2] = {(uint64_t)cin * 2, (uint64_t)9 * cin * 2};
-    uint32_t box[3] = {64, 1, (uint32_t)BN};
+    uint32_t box[3] = {64, 1, (uint32_t)p.BN};
     int rc = encode_bf16(&tmB, wts, 3, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -364,9 +391,8 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  conv3x3_halo_kernel<<<grid, kHThreads, smem_bytes, stream>>>(tmA, tmB, p, (__nv_bfloat16*)out, bias, stats_partials,
-                                                               (const __nv_bfloat16*)addend);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(conv3x3_halo_kernel, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, p,
+                           (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend);
   return e == cudaSuccess ? 0 : (int)e;
 }
 

@@ -10,10 +10,14 @@
 //   Epilogue:   4 warps, thread == pixel: tcgen05.ld -> (+bias) -> round to bf16 -> 16-byte stores; per-channel
 //               sum / sum-of-squares of the *stored* values for training-mode BatchNorm (network/mynn.py:18-24)
 //               reduced with a shuffle butterfly and kept per-warp in shared memory (deterministic order).
-//   Schedule:   persistent CTAs (<= 1 per SM), static round-robin tile order, warp-specialised:
-//               warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
+//   Schedule:   persistent CTAs (<= 1 per SM), static round-robin tile order, warp-specialised (384 threads):
+//               warp 0 TMA producer (one elected lane), warp 1 MMA issuer (one elected thread runs the whole loop:
+//               barrier waits + unrolled tcgen05.mma issue), warp 2 TMEM allocator, warps 4-11 epilogue (two warps
+//               per TMEM lane quarter, half of the accumulator columns each).
+//   Launch:     programmatic dependent launch (launch.h): the prologue overlaps the previous kernel's tail.
 #include "ptx.cuh"
 #include "tma_host.h"
+#include "launch.h"
 #include "../../include/b200seg.h"
 #include "conv_common.h"
 #include "vec.cuh"
@@ -34,20 +38,9 @@ struct ConvKParams {
   int a_bytes, b_bytes, stage_bytes, nstages;
 };
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr int kMaxStages = 8;
 constexpr int kAccCols = 256;   // TMEM columns per accumulator stage
-
-__device__ __forceinline__ void store16_bf16(void* dst, const float (&v)[16]) {
-  uint4 a, b;
-  a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);
-  a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
-  b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]);
-  b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
-  uint4* p = reinterpret_cast<uint4*>(dst);
-  p[0] = a;
-  p[1] = b;
-}
 
 // Sum v[0..15] over the 32 lanes of the warp: afterwards v[0] holds the total for channel (lane & 15).
 __device__ __forceinline__ void butterfly16(float (&v)[16], uint32_t lane) {
@@ -89,7 +82,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -103,12 +96,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();   // the prologue above overlapped the previous kernel; global memory is touched only below
 
   const int kblocks = p.ntaps * p.cchunks;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    {
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -124,54 +118,56 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = stage_base + (size_t)stage * p.stage_bytes;
             uint8_t* sb = sa + p.a_bytes;
-            if (elect_one()) {   // elect.sync (not lane == 0): keeps the TMA operands in uniform registers
-              mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-              tma_load_4d(&tmA, &full_bar[stage], sa, cc * p.KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], img);
-              tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.KC, p.tap_w[t], n0);
-            }
-            __syncwarp();
+            mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+            tma_load_4d(&tmA, &full_bar[stage], sa, cc * p.KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], img);
+            tma_load_3d(&tmB, &full_bar[stage], sb, cc * p.KC, p.tap_w[t], n0);
             if (++stage == p.nstages) { stage = 0; phase ^= 1; }
           }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * kAccCols;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ------------------------------------------------------------------ MMA issuer (one elected thread, whole loop)
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+      const uint64_t tmpl = make_smem_desc(0, 16, p.sbo, p.layout_type);
+      const uint32_t s0 = smem_u32(stage_base) >> 4, stage16 = (uint32_t)p.stage_bytes >> 4, a16 = (uint32_t)p.a_bytes >> 4;
+      const int ksteps = p.KC >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
-        const uint32_t sb = sa + p.a_bytes;
-        const uint64_t adesc = make_smem_desc(sa, 16, p.sbo, p.layout_type);
-        const uint64_t bdesc = make_smem_desc(sb, 16, p.sbo, p.layout_type);
-        const int ksteps = p.KC >> 4;
-        if (elect_one()) {
-          for (int k = 0; k < ksteps; ++k) {
-            // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the 16-byte-unit address field
-            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          }
+        const uint32_t d_tmem = tmem_base + as * kAccCols;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = tmpl + (uint64_t)(s0 + (uint32_t)stage * stage16);
+          const uint64_t bdesc = adesc + (uint64_t)a16;
+          // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the 16-byte-unit address field
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < ksteps) umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           umma_commit(&empty_bar[stage]);
           if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const uint32_t q = warp - 4;               // TMEM sub-partition == warp % 4
+    const uint32_t ew = warp - 4;
+    const uint32_t q = ew & 3;                 // TMEM sub-partition == warp % 4
+    const uint32_t half = ew >> 2;             // which half of the accumulator columns
     const int m = q * 32 + lane;               // accumulator row == pixel within the tile
     const int th = m / p.TW, tw = m - th * p.TW;
     float* my_stats = s_stats + (size_t)q * 2 * p.cout_pad;
+    const int nchunks = p.BN >> 4;
+    const int ch_begin = half ? (nchunks + 1) / 2 : 0;
+    const int ch_end = half ? nchunks : (nchunks + 1) / 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -188,13 +184,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * kAccCols;
-      const int nchunks = p.BN >> 4;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int c0 = n0 + ch * 16;
-        if (c0 >= p.Cout) break;               // warp-uniform
-        uint32_t r[16];
-        tmem_ld16(taddr + ch * 16, r);
-        tmem_ld_wait();
+
+      auto epi16 = [&](const uint32_t* r, int c0) {
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -217,33 +208,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 16; ++j)
               if (c0 + j < p.Cout) dst[j] = v[j];
           }
-        } else {
-          if (valid) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + pix * p.y_ld + c0;
-            if (c0 + 16 <= p.Cout) {
-              store16_bf16(dst, v);
-            } else {
+          return;
+        }
+        uint32_t pk[8];
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.Cout) dst[j] = __float2bfloat16_rn(v[j]);
-            }
-          }
-          if (p.emit_stats) {
-            float s1[16], s2[16];
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        if (valid) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(y) + pix * p.y_ld + c0;
+          if (c0 + 16 <= p.Cout) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float rv = valid ? bf16_round(v[j]) : 0.f;
-              s1[j] = rv;
-              s2[j] = rv * rv;
-            }
-            butterfly16(s1, lane);
-            butterfly16(s2, lane);
-            if (lane < 16) {
-              my_stats[c0 + lane] += s1[0];
-              my_stats[p.cout_pad + c0 + lane] += s2[0];
-            }
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.Cout) dst[j] = __float2bfloat16_rn(v[j]);
           }
         }
+        if (p.emit_stats) {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float lo = valid ? bf16_lo(pk[j]) : 0.f, hi = valid ? bf16_hi(pk[j]) : 0.f;
+            s1[2 * j] = lo;      s1[2 * j + 1] = hi;
+            s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
+          }
+          butterfly16(s1, lane);
+          butterfly16(s2, lane);
+          if (lane < 16) {
+            my_stats[c0 + lane] += s1[0];
+            my_stats[p.cout_pad + c0 + lane] += s2[0];
+          }
+        }
+      };
+
+      int ch = ch_begin;
+      for (; ch + 2 <= ch_end; ch += 2) {
+        if (n0 + ch * 16 >= p.Cout) break;     // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 16, r);
+        tmem_ld_wait();
+        epi16(r, n0 + ch * 16);
+        if (n0 + ch * 16 + 16 < p.Cout) epi16(r + 16, n0 + ch * 16 + 16);
+      }
+      if (ch < ch_end && n0 + ch * 16 < p.Cout) {
+        uint32_t r[16];
+        tmem_ld16(taddr + ch * 16, r);
+        tmem_ld_wait();
+        epi16(r, n0 + ch * 16);
       }
       tc_fence_before();
       __syncwarp();
@@ -291,23 +303,37 @@ static int plan_geom(const LaunchGeom& g, ConvPlan* pl) {
   if (g.force_kc == 16 || g.force_kc == 32 || g.force_kc == 64) KC = g.force_kc;   // test hook
   pl->KC = KC;
   pl->cchunks = (g.in_c + KC - 1) / KC;
-  // N tile: whole cout when it fits one accumulator stage, else the smallest even split into <= 256-wide multiples of 16
-  int cout16 = (g.out_c + 15) / 16 * 16;
-  int n_tiles = (cout16 + 255) / 256;
-  int BN = ((cout16 / 16 + n_tiles - 1) / n_tiles) * 16;
-  if (BN < 16) BN = 16;
-  pl->BN = BN;
-  pl->n_tiles = (cout16 + BN - 1) / BN;
-  pl->cout_pad = pl->n_tiles * BN;
   int TW = 16, TH = 8;
   if (g.sub_w <= 8) { TW = 8; TH = 16; }
   pl->TW = TW; pl->TH = TH;
   pl->tiles_w = (g.sub_w + TW - 1) / TW;
   pl->tiles_h = (g.sub_h + TH - 1) / TH;
+  // N tile: every (tap, chunk) stage refetches its 128 x KC activation box from L2, so a tile costs about
+  // k16 x (64 + BN/2) clocks (L2->smem fill of A and B at ~64 B/clk); pick the Cout split that minimises waves x tile.
+  {
+    const int cout16 = (g.out_c + 15) / 16 * 16;
+    const int m_tiles = g.n * pl->tiles_h * pl->tiles_w;
+    const int k16 = g.ntaps * pl->cchunks * (KC / 16);
+    int best_nt = 0;
+    double best = 0;
+    for (int nt = 1; nt <= 16; ++nt) {
+      const int BN = ((cout16 / 16 + nt - 1) / nt) * 16;
+      if (BN > 256) continue;
+      if ((cout16 + BN - 1) / BN != nt) continue;
+      const long long tiles = (long long)m_tiles * nt;
+      const double waves = (double)((tiles + B200SEG_MAX_CTAS - 1) / B200SEG_MAX_CTAS);
+      const double cost = waves * k16 * (64.0 + BN / 2) + 8.0 * BN + 2000.0 + 64.0 * nt;
+      if (best_nt == 0 || cost < best) { best = cost; best_nt = nt; }
+      if (BN <= 16) break;
+    }
+    pl->n_tiles = best_nt;
+    pl->BN = ((cout16 / 16 + best_nt - 1) / best_nt) * 16;
+    pl->cout_pad = cout16;     // row pitch of the statistics partials (independent of the tiling)
+  }
   pl->total_tiles = g.n * pl->tiles_h * pl->tiles_w * pl->n_tiles;
   pl->grid = pl->total_tiles < B200SEG_MAX_CTAS ? pl->total_tiles : B200SEG_MAX_CTAS;
   pl->a_bytes = 128 * KC * 2;
-  pl->b_bytes = BN * KC * 2;
+  pl->b_bytes = pl->BN * KC * 2;
   pl->stage_bytes = (pl->a_bytes + pl->b_bytes + 1023) / 1024 * 1024;
   size_t fixed = 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16 + (size_t)4 * 2 * pl->cout_pad * 4;
   int nst = (int)((227 * 1024 - fixed) / pl->stage_bytes);
@@ -400,17 +426,15 @@ static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const 
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  conv_igemm_kernel<<<pl.grid, kThreads, pl.smem_bytes, stream>>>(tmA, tmB, p, out, bias, stats_partials,
-                                                                  (const __nv_bfloat16*)addend);
   if (stats_grid) *stats_grid = pl.grid;
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(conv_igemm_kernel, dim3(pl.grid), dim3(kThreads), pl.smem_bytes, stream, tmA, tmB, p, out,
+                           bias, stats_partials, (const __nv_bfloat16*)addend);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
 int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
                         const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
-                        int* cout_pad_out, const void* addend, int addend_ld, int emit_stats, cudaStream_t stream,
-                        bool plan_only);
+                        const void* addend, int addend_ld, int emit_stats, cudaStream_t stream);
 
 }  // namespace b200seg
 
@@ -419,7 +443,7 @@ using namespace b200seg;
 extern "C" size_t b200seg_conv2d_stats_elems(const b200seg_conv_desc* d) {
   ConvPlan pl;
   if (conv_plan(d, &pl) != 0) return 0;
-  return (size_t)B200SEG_MAX_CTAS * 2 * pl.cout_pad;
+  return (size_t)B200SEG_MAX_CTAS * 2 * ((d->cout + 15) / 16 * 16);   // [grid <= 148][2][roundup16(cout)]
 }
 
 extern "C" int b200seg_conv2d_fwd(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
@@ -429,8 +453,7 @@ extern "C" int b200seg_conv2d_fwd(const b200seg_conv_desc* d, const void* x, con
     if (d->emit_stats && !stats_partials) return B200SEG_E_BADARG;
     // halo-tile kernel: the input is read once per tile instead of once per filter tap (conv3x3_halo.cu)
     return conv3x3_halo_launch(d->n, d->h, d->w, d->cin, d->x_ld, x, d->cout, w_ohwi, d->has_bias ? bias : nullptr, y,
-                               d->y_ld, stats_partials, stats_grid, nullptr, nullptr, 0, d->emit_stats,
-                               (cudaStream_t)stream, false);
+                               d->y_ld, stats_partials, stats_grid, nullptr, 0, d->emit_stats, (cudaStream_t)stream);
   }
   return launch_geom(fwd_geom(d), x, w_ohwi, bias, y, stats_partials, stats_grid, nullptr, 0, (cudaStream_t)stream);
 }
@@ -452,7 +475,7 @@ extern "C" int b200seg_conv2d_dgrad(const b200seg_conv_desc* d, const void* dy, 
   g.out_fp32 = 0; g.has_bias = 0; g.emit_stats = 0; g.force_kc = d->reserved;
   if (d->stride == 1 && K == 3 && d->cin % 16 == 0 && d->reserved == 0)
     return conv3x3_halo_launch(d->n, d->h, d->w, g.in_c, dy_ld, dy, d->cin, w_dgrad, nullptr, dx, dx_ld, nullptr, nullptr,
-                               nullptr, addend, addend_ld, 0, (cudaStream_t)stream, false);
+                               addend, addend_ld, 0, (cudaStream_t)stream);
   if (d->stride == 1) {
     g.sub_h = d->h; g.sub_w = d->w; g.out_stride = 1; g.out_off_h = g.out_off_w = 0;
     g.ntaps = taps;

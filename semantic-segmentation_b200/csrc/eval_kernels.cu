@@ -5,6 +5,7 @@
 //   resize_nchw      NCHW -> NCHW bilinear (scale_as between full-resolution maps of different scales)
 //   blend            out = a*x + (1-a)*y   |  out = x + (1-a)*y   |  out = a*x      (a: [n,1,H,W] broadcast over C)
 #include "ptx.cuh"
+#include "launch.h"
 #include "../../include/b200seg.h"
 #include "vec.cuh"
 
@@ -13,6 +14,7 @@ namespace b200seg {
 __global__ void __launch_bounds__(256)
 resize_to_nchw_kernel(const float* __restrict__ src, int ld, int n, int h, int w, int C, int apply_sigmoid,
                       float* __restrict__ dst, int H, int W) {
+  pdl_sync();
   const long long total = (long long)n * C * H * W;
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -38,6 +40,7 @@ resize_to_nchw_kernel(const float* __restrict__ src, int ld, int n, int h, int w
 
 __global__ void __launch_bounds__(256)
 resize_nchw_kernel(const float* __restrict__ src, int planes, int h, int w, float* __restrict__ dst, int H, int W) {
+  pdl_sync();
   const long long total = (long long)planes * H * W;
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -59,6 +62,7 @@ resize_nchw_kernel(const float* __restrict__ src, int planes, int h, int w, floa
 __global__ void __launch_bounds__(256)
 blend_kernel(const float* __restrict__ a, const float* __restrict__ x, const float* __restrict__ y,
              float* __restrict__ out, int n, int C, long long hw, int mode) {
+  pdl_sync();
   const long long total = (long long)n * C * hw;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -86,7 +90,7 @@ using namespace b200seg;
 extern "C" int b200seg_resize_to_nchw(const float* src_nhwc, int32_t ld, int32_t n, int32_t h, int32_t w, int32_t c,
                                       int32_t apply_sigmoid, float* dst_nchw, int32_t H, int32_t W, void* stream) {
   if (!src_nhwc || !dst_nchw || c > ld) return B200SEG_E_BADARG;
-  resize_to_nchw_kernel<<<egrid((long long)n * c * H * W), 256, 0, (cudaStream_t)stream>>>(src_nhwc, ld, n, h, w, c,
+  launch_k(resize_to_nchw_kernel, dim3(egrid((long long)n * c * H * W)), dim3(256), 0, (cudaStream_t)stream, src_nhwc, ld, n, h, w, c,
                                                                                          apply_sigmoid, dst_nchw, H, W);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
@@ -95,7 +99,7 @@ extern "C" int b200seg_resize_to_nchw(const float* src_nhwc, int32_t ld, int32_t
 extern "C" int b200seg_resize_nchw(const float* src, int32_t planes, int32_t h, int32_t w, float* dst, int32_t H,
                                    int32_t W, void* stream) {
   if (!src || !dst) return B200SEG_E_BADARG;
-  resize_nchw_kernel<<<egrid((long long)planes * H * W), 256, 0, (cudaStream_t)stream>>>(src, planes, h, w, dst, H, W);
+  launch_k(resize_nchw_kernel, dim3(egrid((long long)planes * H * W)), dim3(256), 0, (cudaStream_t)stream, src, planes, h, w, dst, H, W);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -103,7 +107,7 @@ extern "C" int b200seg_resize_nchw(const float* src, int32_t planes, int32_t h, 
 extern "C" int b200seg_blend(const float* a, const float* x, const float* y, float* out, int32_t n, int32_t c,
                              int64_t hw, int32_t mode, void* stream) {
   if (!a || !x || !out || (mode != 2 && !y) || mode < 0 || mode > 2) return B200SEG_E_BADARG;
-  blend_kernel<<<egrid((long long)n * c * hw), 256, 0, (cudaStream_t)stream>>>(a, x, y, out, n, c, hw, mode);
+  launch_k(blend_kernel, dim3(egrid((long long)n * c * hw)), dim3(256), 0, (cudaStream_t)stream, a, x, y, out, n, c, hw, mode);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -17,6 +17,7 @@
 //   mid_bwd      adjoint of the x2 upsample + product rule at the mid grid -> D[m][40]
 //   lo_bwd       adjoint of the x4 upsample on the lo pass -> d cls_lo, d aux_lo, d attn_logit (through the sigmoid)
 #include "ptx.cuh"
+#include "launch.h"
 #include "../../include/b200seg.h"
 #include "vec.cuh"
 
@@ -95,6 +96,7 @@ struct MsGeom {
 __global__ void __launch_bounds__(256)
 mid_fwd_kernel(const MsGeom g, const float* __restrict__ lo_cls, const float* __restrict__ lo_aux,
                const float* __restrict__ lo_attn, float* __restrict__ M, float* __restrict__ M2) {
+  pdl_sync();
   const long long total = (long long)g.N * g.Hm * g.Wm;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -167,6 +169,7 @@ loss_fwd_kernel(const MsGeom g, const long long* __restrict__ labels, const floa
                 const float* __restrict__ hi_cls, const float* __restrict__ hi_aux, const float* __restrict__ M,
                 const float* __restrict__ M2, __nv_bfloat16* __restrict__ Ghi, __nv_bfloat16* __restrict__ Glo,
                 __nv_bfloat16* __restrict__ Gsup, float* __restrict__ partial) {
+  pdl_sync();
   const long long total = (long long)g.N * g.H * g.W;
   const bool has_lo = g.Hm > 0;
   const float icnt = *inv_count;
@@ -262,6 +265,7 @@ loss_fwd_kernel(const MsGeom g, const long long* __restrict__ labels, const floa
 // loss = icnt * (w0*s0 + w1*s1 + sup*(s2 + s3)); also returns the four mean NLLs
 __global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ inv_count,
                                      float w0, float w1, float sup, float* __restrict__ out) {
+  pdl_sync();
   __shared__ double s[4][32];
   double a[4] = {0, 0, 0, 0};
   for (int b = threadIdx.x; b < nblocks; b += 32)
@@ -280,6 +284,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblo
 
 __global__ void count_valid_kernel(const long long* __restrict__ labels, long long total, int ignore_index,
                                    unsigned long long* __restrict__ counter) {
+  pdl_sync();
   unsigned int c = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     c += labels[i] != (long long)ignore_index;
@@ -288,6 +293,7 @@ __global__ void count_valid_kernel(const long long* __restrict__ labels, long lo
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);   // integer: order independent
 }
 __global__ void inv_count_kernel(const unsigned long long* __restrict__ counter, float* __restrict__ inv_count) {
+  pdl_sync();
   *inv_count = 1.f / (float)(*counter);    // mean over non-ignored pixels; all-ignored -> inf/NaN like the reference
 }
 
@@ -296,6 +302,7 @@ __global__ void inv_count_kernel(const unsigned long long* __restrict__ counter,
 __global__ void __launch_bounds__(128)
 hi_bwd_kernel(const MsGeom g, const __nv_bfloat16* __restrict__ Ghi, __nv_bfloat16* __restrict__ d_cls,
               __nv_bfloat16* __restrict__ d_aux) {
+  pdl_sync();
   const long long total = (long long)g.N * g.Hq * g.Wq * g.nheads;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -361,6 +368,7 @@ __global__ void __launch_bounds__(128)
 mid_bwd_kernel(const MsGeom g, const __nv_bfloat16* __restrict__ Glo, const __nv_bfloat16* __restrict__ Gsup,
                const float* __restrict__ lo_cls, const float* __restrict__ lo_aux, const float* __restrict__ M,
                float* __restrict__ D) {
+  pdl_sync();
   const long long total = (long long)g.N * g.Hm * g.Wm;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -431,6 +439,7 @@ mid_bwd_kernel(const MsGeom g, const __nv_bfloat16* __restrict__ Glo, const __nv
 __global__ void __launch_bounds__(128)
 lo_bwd_kernel(const MsGeom g, const float* __restrict__ D, const float* __restrict__ lo_attn,
               __nv_bfloat16* __restrict__ d_cls, __nv_bfloat16* __restrict__ d_aux, __nv_bfloat16* __restrict__ d_attn) {
+  pdl_sync();
   const long long total = (long long)g.N * g.Hl * g.Wl;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -516,18 +525,17 @@ extern "C" int b200seg_count_valid(const int64_t* labels, int64_t total, int32_t
   if (!labels || !counter_ws || !inv_count) return B200SEG_E_BADARG;
   cudaError_t e = cudaMemsetAsync(counter_ws, 0, sizeof(uint64_t), (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
-  count_valid_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const long long*)labels, total,
+  launch_k(count_valid_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const long long*)labels, total,
                                                                               ignore_index,
                                                                               (unsigned long long*)counter_ws);
-  inv_count_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned long long*)counter_ws, inv_count);
+  launch_k(inv_count_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (const unsigned long long*)counter_ws, inv_count);
   RET_LAUNCH();
 }
 
 extern "C" int b200seg_mscale_mid_fwd(const b200seg_mscale_desc* d, const float* lo_cls, const float* lo_aux,
                                       const float* lo_attn_logit, float* mid, float* mid_sup, void* stream) {
   if (!d || !lo_cls || !lo_attn_logit || !mid || d->hm <= 0 || (d->nheads > 1 && !lo_aux)) return B200SEG_E_BADARG;
-  mid_fwd_kernel<<<blocks_for((long long)d->n * d->hm * d->wm, 256), 256, 0, (cudaStream_t)stream>>>(
-      to_geom(d), lo_cls, lo_aux, lo_attn_logit, mid, mid_sup);
+  launch_k(mid_fwd_kernel, dim3(blocks_for((long long)d->n * d->hm * d->wm, 256)), dim3(256), 0, (cudaStream_t)stream, to_geom(d), lo_cls, lo_aux, lo_attn_logit, mid, mid_sup);
   RET_LAUNCH();
 }
 
@@ -540,10 +548,10 @@ extern "C" int b200seg_mscale_loss_fwd(const b200seg_mscale_desc* d, const int64
   if (d->hm > 0 && (!mid || !g_lo)) return B200SEG_E_BADARG;
   if (d->sup_wt != 0.f && d->hm > 0 && (!mid_sup || !g_sup)) return B200SEG_E_BADARG;
   const int nb = b200seg_mscale_loss_blocks(d);
-  loss_fwd_kernel<<<nb, 128, 0, (cudaStream_t)stream>>>(to_geom(d), (const long long*)labels, inv_count, hi_cls, hi_aux,
+  launch_k(loss_fwd_kernel, dim3(nb), dim3(128), 0, (cudaStream_t)stream, to_geom(d), (const long long*)labels, inv_count, hi_cls, hi_aux,
                                                         mid, mid_sup, (__nv_bfloat16*)g_hi, (__nv_bfloat16*)g_lo,
                                                         (__nv_bfloat16*)g_sup, partial_ws);
-  loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partial_ws, nb, inv_count, d->w_head0,
+  launch_k(loss_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, partial_ws, nb, inv_count, d->w_head0,
                                                            d->nheads > 1 ? d->w_head1 : 0.f, d->sup_wt, loss_out);
   RET_LAUNCH();
 }
@@ -551,8 +559,7 @@ extern "C" int b200seg_mscale_loss_fwd(const b200seg_mscale_desc* d, const int64
 extern "C" int b200seg_mscale_hi_bwd(const b200seg_mscale_desc* d, const void* g_hi, void* d_cls, void* d_aux,
                                      void* stream) {
   if (!d || !g_hi || !d_cls || (d->nheads > 1 && !d_aux)) return B200SEG_E_BADARG;
-  hi_bwd_kernel<<<blocks_for((long long)d->n * d->hq * d->wq * d->nheads, 128), 128, 0, (cudaStream_t)stream>>>(
-      to_geom(d), (const __nv_bfloat16*)g_hi, (__nv_bfloat16*)d_cls, (__nv_bfloat16*)d_aux);
+  launch_k(hi_bwd_kernel, dim3(blocks_for((long long)d->n * d->hq * d->wq * d->nheads, 128)), dim3(128), 0, (cudaStream_t)stream, to_geom(d), (const __nv_bfloat16*)g_hi, (__nv_bfloat16*)d_cls, (__nv_bfloat16*)d_aux);
   RET_LAUNCH();
 }
 
@@ -563,10 +570,8 @@ extern "C" int b200seg_mscale_lo_bwd(const b200seg_mscale_desc* d, const void* g
   if (!d || !g_lo || !lo_cls || !lo_attn_logit || !mid || !dmid_ws || !d_cls || !d_attn || d->hm <= 0)
     return B200SEG_E_BADARG;
   const MsGeom g = to_geom(d);
-  mid_bwd_kernel<<<blocks_for((long long)d->n * d->hm * d->wm, 128), 128, 0, (cudaStream_t)stream>>>(
-      g, (const __nv_bfloat16*)g_lo, d->sup_wt != 0.f ? (const __nv_bfloat16*)g_sup : nullptr, lo_cls, lo_aux, mid,
+  launch_k(mid_bwd_kernel, dim3(blocks_for((long long)d->n * d->hm * d->wm, 128)), dim3(128), 0, (cudaStream_t)stream, g, (const __nv_bfloat16*)g_lo, d->sup_wt != 0.f ? (const __nv_bfloat16*)g_sup : nullptr, lo_cls, lo_aux, mid,
       dmid_ws);
-  lo_bwd_kernel<<<blocks_for((long long)d->n * d->hl * d->wl, 128), 128, 0, (cudaStream_t)stream>>>(
-      g, dmid_ws, lo_attn_logit, (__nv_bfloat16*)d_cls, (__nv_bfloat16*)d_aux, (__nv_bfloat16*)d_attn);
+  launch_k(lo_bwd_kernel, dim3(blocks_for((long long)d->n * d->hl * d->wl, 128)), dim3(128), 0, (cudaStream_t)stream, g, dmid_ws, lo_attn_logit, (__nv_bfloat16*)d_cls, (__nv_bfloat16*)d_aux, (__nv_bfloat16*)d_attn);
   RET_LAUNCH();
 }

@@ -7,6 +7,7 @@
 //   class softmax    : over the classes of each pixel, with the key_channels^-0.5 scale -> sim bf16 [pixels][32]
 // plus their backward passes and two layout helpers (transpose+pad, fp32->bf16 cast).
 #include "ptx.cuh"
+#include "launch.h"
 #include "../../include/b200seg.h"
 #include "vec.cuh"
 
@@ -18,6 +19,7 @@ constexpr int KP = 32;   // padded class count of every bf16 class-operand
 // partial[n][b][k] = (max, sum exp(x - max)) over the block's pixel range
 __global__ void __launch_bounds__(256)
 spatial_stats_kernel(const float* __restrict__ x, int ld, int P, int K, float* __restrict__ partial) {
+  pdl_sync();
   const int n = blockIdx.y, b = blockIdx.x, B = gridDim.x;
   const float* xn = x + (size_t)n * P * ld;
   float mx[KP], sm[KP];
@@ -67,6 +69,7 @@ spatial_stats_kernel(const float* __restrict__ x, int ld, int P, int K, float* _
 __global__ void __launch_bounds__(256)
 spatial_apply_kernel(const float* __restrict__ x, int ld, int P, int K, const float* __restrict__ partial, int B,
                      __nv_bfloat16* __restrict__ probs, float* __restrict__ stat_out) {
+  pdl_sync();
   const int n = blockIdx.y;
   __shared__ float s_max[KP], s_inv[KP];
   if (threadIdx.x < KP) {
@@ -106,6 +109,7 @@ spatial_apply_kernel(const float* __restrict__ x, int ld, int P, int K, const fl
 __global__ void __launch_bounds__(256)
 spatial_bwd_reduce_kernel(const float* __restrict__ dprobs, int ldd, const __nv_bfloat16* __restrict__ probs, int P,
                           int K, float* __restrict__ partial) {
+  pdl_sync();
   const int n = blockIdx.y, b = blockIdx.x, B = gridDim.x;
   float acc[KP];
 #pragma unroll
@@ -142,6 +146,7 @@ spatial_bwd_reduce_kernel(const float* __restrict__ dprobs, int ldd, const __nv_
 __global__ void __launch_bounds__(256)
 spatial_bwd_apply_kernel(const float* __restrict__ dprobs, int ldd, const __nv_bfloat16* __restrict__ probs, int P, int K,
                          const float* __restrict__ partial, int B, __nv_bfloat16* __restrict__ dlogit, int accumulate) {
+  pdl_sync();
   const int n = blockIdx.y;
   __shared__ float s_S[KP];
   if (threadIdx.x < KP) {
@@ -178,6 +183,7 @@ spatial_bwd_apply_kernel(const float* __restrict__ dprobs, int ldd, const __nv_b
 __global__ void __launch_bounds__(256)
 class_softmax_fwd_kernel(const float* __restrict__ x, int ld, long long P, int K, float scale,
                          __nv_bfloat16* __restrict__ sim) {
+  pdl_sync();
   for (long long pix = (long long)blockIdx.x * 256 + threadIdx.x; pix < P; pix += (long long)gridDim.x * 256) {
     const float* r = x + pix * ld;
     float v[KP];
@@ -205,6 +211,7 @@ class_softmax_fwd_kernel(const float* __restrict__ x, int ld, long long P, int K
 __global__ void __launch_bounds__(256)
 class_softmax_bwd_kernel(const float* __restrict__ dsim, int ld, const __nv_bfloat16* __restrict__ sim, long long P,
                          int K, float scale, __nv_bfloat16* __restrict__ ds) {
+  pdl_sync();
   for (long long pix = (long long)blockIdx.x * 256 + threadIdx.x; pix < P; pix += (long long)gridDim.x * 256) {
     const float* d = dsim + pix * ld;
     float s[KP], g[KP];
@@ -238,6 +245,7 @@ class_softmax_bwd_kernel(const float* __restrict__ dsim, int ld, const __nv_bflo
 // dst[c][r] (pitch rpad, zero padded) = src[r][c]   (src bf16 [R][C] with pitch ld, or fp32 when src_fp32)
 __global__ void transpose_pad_kernel(const void* __restrict__ src, int src_fp32, int R, int C, int ld,
                                      __nv_bfloat16* __restrict__ dst, int rpad) {
+  pdl_sync();
   const int total = C * rpad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i / rpad, r = i - c * rpad;
@@ -252,6 +260,7 @@ __global__ void transpose_pad_kernel(const void* __restrict__ src, int src_fp32,
 // dst bf16 [rows][dst_ld] = (accumulate? dst : 0) + src fp32 [rows][src_ld] for cols < C
 __global__ void cast_rows_kernel(const float* __restrict__ src, int src_ld, __nv_bfloat16* __restrict__ dst, int dst_ld,
                                  long long rows, int C, int accumulate) {
+  pdl_sync();
   const long long total = rows * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / C;
@@ -266,6 +275,7 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, int src_ld, __nv
 // db[c] += sum_rows dy[row][c]  for c < C  (conv bias gradient of the logit heads; dy bf16 [rows][ld])
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ dy, int ld, long long rows, int C, float* __restrict__ db) {
+  pdl_sync();
   // thread (r, c): 8 row-lanes x 32 columns
   const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
   float acc = 0.f;
@@ -303,8 +313,8 @@ extern "C" int b200seg_spatial_softmax_fwd(const float* logits, int32_t ld, int3
                                            float* partial_ws, void* probs_bf16, float* stat_out, void* stream) {
   if (!logits || !partial_ws || !probs_bf16 || K > KP || K < 1) return B200SEG_E_BADARG;
   const int B = pix_blocks(P);
-  spatial_stats_kernel<<<dim3(B, n), 256, 0, (cudaStream_t)stream>>>(logits, ld, P, K, partial_ws);
-  spatial_apply_kernel<<<dim3(B, n), 256, 0, (cudaStream_t)stream>>>(logits, ld, P, K, partial_ws, B,
+  launch_k(spatial_stats_kernel, dim3(B, n), dim3(256), 0, (cudaStream_t)stream, logits, ld, P, K, partial_ws);
+  launch_k(spatial_apply_kernel, dim3(B, n), dim3(256), 0, (cudaStream_t)stream, logits, ld, P, K, partial_ws, B,
                                                                      (__nv_bfloat16*)probs_bf16, stat_out);
   RET_LAUNCH();
 }
@@ -314,17 +324,16 @@ extern "C" int b200seg_spatial_softmax_bwd(const float* dprobs, int32_t ldd, con
                                            void* stream) {
   if (!dprobs || !probs_bf16 || !partial_ws || !dlogit_bf16 || K > KP) return B200SEG_E_BADARG;
   const int B = pix_blocks(P);
-  spatial_bwd_reduce_kernel<<<dim3(B, n), 256, 0, (cudaStream_t)stream>>>(dprobs, ldd, (const __nv_bfloat16*)probs_bf16,
+  launch_k(spatial_bwd_reduce_kernel, dim3(B, n), dim3(256), 0, (cudaStream_t)stream, dprobs, ldd, (const __nv_bfloat16*)probs_bf16,
                                                                           P, K, partial_ws);
-  spatial_bwd_apply_kernel<<<dim3(B, n), 256, 0, (cudaStream_t)stream>>>(
-      dprobs, ldd, (const __nv_bfloat16*)probs_bf16, P, K, partial_ws, B, (__nv_bfloat16*)dlogit_bf16, accumulate);
+  launch_k(spatial_bwd_apply_kernel, dim3(B, n), dim3(256), 0, (cudaStream_t)stream, dprobs, ldd, (const __nv_bfloat16*)probs_bf16, P, K, partial_ws, B, (__nv_bfloat16*)dlogit_bf16, accumulate);
   RET_LAUNCH();
 }
 
 extern "C" int b200seg_class_softmax_fwd(const float* x, int32_t ld, int64_t P, int32_t K, float scale, void* sim_bf16,
                                          void* stream) {
   if (!x || !sim_bf16 || K > KP) return B200SEG_E_BADARG;
-  class_softmax_fwd_kernel<<<pix_blocks(P) * 4, 256, 0, (cudaStream_t)stream>>>(x, ld, P, K, scale,
+  launch_k(class_softmax_fwd_kernel, dim3(pix_blocks(P) * 4), dim3(256), 0, (cudaStream_t)stream, x, ld, P, K, scale,
                                                                                 (__nv_bfloat16*)sim_bf16);
   RET_LAUNCH();
 }
@@ -332,15 +341,14 @@ extern "C" int b200seg_class_softmax_fwd(const float* x, int32_t ld, int64_t P, 
 extern "C" int b200seg_class_softmax_bwd(const float* dsim, int32_t ld, const void* sim_bf16, int64_t P, int32_t K,
                                          float scale, void* ds_bf16, void* stream) {
   if (!dsim || !sim_bf16 || !ds_bf16 || K > KP) return B200SEG_E_BADARG;
-  class_softmax_bwd_kernel<<<pix_blocks(P) * 4, 256, 0, (cudaStream_t)stream>>>(
-      dsim, ld, (const __nv_bfloat16*)sim_bf16, P, K, scale, (__nv_bfloat16*)ds_bf16);
+  launch_k(class_softmax_bwd_kernel, dim3(pix_blocks(P) * 4), dim3(256), 0, (cudaStream_t)stream, dsim, ld, (const __nv_bfloat16*)sim_bf16, P, K, scale, (__nv_bfloat16*)ds_bf16);
   RET_LAUNCH();
 }
 
 extern "C" int b200seg_transpose_pad(const void* src, int32_t src_fp32, int32_t R, int32_t C, int32_t ld, void* dst_bf16,
                                      int32_t rpad, void* stream) {
   if (!src || !dst_bf16 || rpad < R) return B200SEG_E_BADARG;
-  transpose_pad_kernel<<<(C * rpad + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, src_fp32, R, C, ld,
+  launch_k(transpose_pad_kernel, dim3((C * rpad + 255) / 256), dim3(256), 0, (cudaStream_t)stream, src, src_fp32, R, C, ld,
                                                                                 (__nv_bfloat16*)dst_bf16, rpad);
   RET_LAUNCH();
 }
@@ -351,7 +359,7 @@ extern "C" int b200seg_cast_rows(const float* src, int32_t src_ld, void* dst_bf1
   long long total = rows * C;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  cast_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_ld, (__nv_bfloat16*)dst_bf16, dst_ld, rows, C,
+  launch_k(cast_rows_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, src, src_ld, (__nv_bfloat16*)dst_bf16, dst_ld, rows, C,
                                                              accumulate);
   RET_LAUNCH();
 }
@@ -360,6 +368,6 @@ extern "C" int b200seg_bias_grad(const void* dy_bf16, int32_t ld, int64_t rows, 
   if (!dy_bf16 || !db || C > 32) return B200SEG_E_BADARG;
   long long b = (rows + 7) / 8;
   if (b > 148 * 4) b = 148 * 4;
-  colsum_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy_bf16, ld, rows, C, db);
+  launch_k(colsum_kernel, dim3((int)b), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy_bf16, ld, rows, C, db);
   RET_LAUNCH();
 }

@@ -2,6 +2,7 @@
 // fp32 accumulate, one final rounding) used as an on-device cross-check by the GPU tests; (2) weight repacking from the
 // fp32 OIHW master copies (reference checkpoint layout, SURVEY.md §8b "State") into the kernels' bf16 operand layouts.
 #include "ptx.cuh"
+#include "launch.h"
 #include "../../include/b200seg.h"
 #include <cuda_bf16.h>
 
@@ -10,6 +11,7 @@ namespace b200seg {
 __global__ void direct_conv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                    const float* __restrict__ bias, void* __restrict__ y, int N, int H, int W, int Cin,
                                    int Cout, int K, int S, int P, int Ho, int Wo, int x_ld, int y_ld, int out_fp32) {
+  pdl_sync();
   const size_t total = (size_t)N * Ho * Wo * Cout;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int co = idx % Cout;
@@ -37,6 +39,7 @@ __global__ void direct_conv_kernel(const __nv_bfloat16* __restrict__ x, const __
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, int K, __nv_bfloat16* __restrict__ ohwi,
                                    __nv_bfloat16* __restrict__ dgrad, int Opad) {
+  pdl_sync();
   const int taps = K * K;
   const size_t total = (size_t)O * I * taps;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -65,8 +68,7 @@ extern "C" int b200seg_conv2d_fwd_direct(const b200seg_conv_desc* d, const void*
   const size_t total = (size_t)d->n * Ho * Wo * d->cout;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  direct_conv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)w_ohwi, d->has_bias ? bias : nullptr, y, d->n, d->h, d->w, d->cin,
+  launch_k(direct_conv_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w_ohwi, d->has_bias ? bias : nullptr, y, d->n, d->h, d->w, d->cin,
       d->cout, d->ksize, d->stride, d->pad, Ho, Wo, d->x_ld, d->y_ld, d->out_fp32);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
@@ -79,7 +81,7 @@ extern "C" int b200seg_pack_weight(const float* w_oihw, int32_t o, int32_t i, in
   const size_t total = (size_t)o * i * ksize * ksize;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, o, i, ksize, (__nv_bfloat16*)w_ohwi,
+  launch_k(pack_weight_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, w_oihw, o, i, ksize, (__nv_bfloat16*)w_ohwi,
                                                                (__nv_bfloat16*)w_dgrad, o_pad);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;

@@ -8,6 +8,7 @@
 //   image_prep         NCHW fp32 image -> NHWC bf16 padded to 16 channels, with the ResizeX bilinear rescale
 //                      (network/mynn.py:102-114; scale 0.5 == 2x2 mean) folded in.
 #include "ptx.cuh"
+#include "launch.h"
 #include "../../include/b200seg.h"
 #include "vec.cuh"
 
@@ -28,6 +29,7 @@ struct FuseParams {
 
 __global__ void __launch_bounds__(256)
 fuse_fwd_kernel(const FuseParams p, __nv_bfloat16* __restrict__ out, int out_ld) {
+  pdl_sync();
   const int groups = p.C >> 3;
   const long long total = (long long)p.N * p.H * p.W * groups;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(256)
 upsample_adjoint_kernel(const __nv_bfloat16* __restrict__ g, int g_ld, const __nv_bfloat16* __restrict__ mask,
                         int mask_ld, int N, int H, int W, int C, __nv_bfloat16* __restrict__ out, int out_ld, int h,
                         int w, int accumulate) {
+  pdl_sync();
   const int groups = C >> 3;
   const long long total = (long long)N * h * w * groups;
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
@@ -143,6 +146,7 @@ upsample_adjoint_kernel(const __nv_bfloat16* __restrict__ g, int g_ld, const __n
 // images fp32 NCHW [N,3,H,W] -> bf16 NHWC [N,h,w,16] (channels 3..15 zero), bilinear-resized to (h,w).
 __global__ void __launch_bounds__(256)
 image_prep_kernel(const float* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ out, int h, int w) {
+  pdl_sync();
   const long long total = (long long)N * h * w;
   const float sy = (float)H / (float)h, sx = (float)W / (float)w;
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
@@ -201,7 +205,7 @@ extern "C" int b200seg_fuse_fwd(const b200seg_fuse_desc* d, void* out, int32_t o
     p.t[i].ld = d->term[i].ld; p.t[i].h = d->term[i].h; p.t[i].w = d->term[i].w;
   }
   const long long total = (long long)d->n * d->h * d->w * (d->c / 8);
-  fuse_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(p, (__nv_bfloat16*)out, out_ld);
+  launch_k(fuse_fwd_kernel, dim3(ew_grid(total)), dim3(256), 0, (cudaStream_t)stream, p, (__nv_bfloat16*)out, out_ld);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -211,8 +215,7 @@ extern "C" int b200seg_upsample_adjoint(const void* g, int32_t g_ld, const void*
                                         int32_t accumulate, void* stream) {
   if (!g || !out || c % 8 || g_ld % 8 || out_ld % 8 || h > H || w > W) return B200SEG_E_BADARG;
   const long long total = (long long)n * h * w * (c / 8);
-  upsample_adjoint_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)mask, mask_ld, n, H, W, c, (__nv_bfloat16*)out, out_ld, h, w,
+  launch_k(upsample_adjoint_kernel, dim3(ew_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)mask, mask_ld, n, H, W, c, (__nv_bfloat16*)out, out_ld, h, w,
       accumulate);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
@@ -221,7 +224,7 @@ extern "C" int b200seg_upsample_adjoint(const void* g, int32_t g_ld, const void*
 extern "C" int b200seg_image_prep(const float* img_nchw, int32_t n, int32_t H, int32_t W, void* out_nhwc16, int32_t h,
                                   int32_t w, void* stream) {
   if (!img_nchw || !out_nhwc16 || h <= 0 || w <= 0) return B200SEG_E_BADARG;
-  image_prep_kernel<<<ew_grid((long long)n * h * w), 256, 0, (cudaStream_t)stream>>>(img_nchw, n, H, W,
+  launch_k(image_prep_kernel, dim3(ew_grid((long long)n * h * w)), dim3(256), 0, (cudaStream_t)stream, img_nchw, n, H, W,
                                                                                     (__nv_bfloat16*)out_nhwc16, h, w);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;

@@ -12,6 +12,7 @@
 // Replaces cuDNN convolution_backward (weight part) behind every nn.Conv2d listed in SURVEY.md §2b K1-K5.
 #include "ptx.cuh"
 #include "tma_host.h"
+#include "launch.h"
 #include "../../include/b200seg.h"
 
 namespace b200seg {
@@ -64,6 +65,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();   // the prologue above overlapped the previous kernel; global memory is touched only below
 
   // unit decode helpers (identical in every role)
   auto decode = [&](int unit, int& m_tile, int& n_tile, int& tg, int& split) {
@@ -75,7 +77,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
   };
 
   if (warp == 0) {
-    {   // warp-uniform control flow; issuing lane chosen by elect.sync (keeps TMA operands in uniform registers)
+    if (elect_one()) {   // one elected lane runs the whole producer loop (TMA operands stay in uniform registers)
       int a_slot = 0, b_slot = 0;
       uint32_t a_phase = 0, b_phase = 0;
       for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
@@ -91,24 +93,18 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
           const int img = t / (p.tiles_w * p.tiles_h);
           mbar_wait(&a_empty[a_slot], a_phase ^ 1);
           uint8_t* sa = a_base + (size_t)a_slot * p.a_slot_bytes;
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&a_full[a_slot], (a_two ? 2 : 1) * kABlock);
-            tma_load_4d(&tmDy, &a_full[a_slot], sa, m_tile * 128, tw_i * p.TW, th_i * p.TH, img);
-            if (a_two)
-              tma_load_4d(&tmDy, &a_full[a_slot], sa + kABlock, m_tile * 128 + 64, tw_i * p.TW, th_i * p.TH, img);
-          }
-          __syncwarp();
+          mbar_arrive_expect_tx(&a_full[a_slot], (a_two ? 2 : 1) * kABlock);
+          tma_load_4d(&tmDy, &a_full[a_slot], sa, m_tile * 128, tw_i * p.TW, th_i * p.TH, img);
+          if (a_two)
+            tma_load_4d(&tmDy, &a_full[a_slot], sa + kABlock, m_tile * 128 + 64, tw_i * p.TW, th_i * p.TH, img);
           if (++a_slot == 2) { a_slot = 0; a_phase ^= 1; }
           if (p.halo) {
             mbar_wait(&b_empty[b_slot], b_phase ^ 1);
             uint8_t* sb = b_base + (size_t)b_slot * p.b_slot_bytes;
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&b_full[b_slot], nblk * 18 * 10 * 128);
-              for (int b = 0; b < nblk; ++b)
-                tma_load_4d(&tmX, &b_full[b_slot], sb + (size_t)b * p.b_block_bytes, n0 + b * 64, tw_i * p.TW - 1,
-                            th_i * p.TH - 1, img);
-            }
-            __syncwarp();
+            mbar_arrive_expect_tx(&b_full[b_slot], nblk * 18 * 10 * 128);
+            for (int b = 0; b < nblk; ++b)
+              tma_load_4d(&tmX, &b_full[b_slot], sb + (size_t)b * p.b_block_bytes, n0 + b * 64, tw_i * p.TW - 1,
+                          th_i * p.TH - 1, img);
             if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
             continue;
           }
@@ -116,13 +112,10 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
             const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
             mbar_wait(&b_empty[b_slot], b_phase ^ 1);
             uint8_t* sb = b_base + (size_t)b_slot * p.b_slot_bytes;
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&b_full[b_slot], nblk * kABlock);
-              for (int b = 0; b < nblk; ++b)
-                tma_load_4d(&tmX, &b_full[b_slot], sb + (size_t)b * kABlock, n0 + b * 64,
-                            tw_i * p.TW * p.stride + kw - p.pad, th_i * p.TH * p.stride + kh - p.pad, img);
-            }
-            __syncwarp();
+            mbar_arrive_expect_tx(&b_full[b_slot], nblk * kABlock);
+            for (int b = 0; b < nblk; ++b)
+              tma_load_4d(&tmX, &b_full[b_slot], sb + (size_t)b * kABlock, n0 + b * 64,
+                          tw_i * p.TW * p.stride + kw - p.pad, th_i * p.TH * p.stride + kh - p.pad, img);
             if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
           }
         }
@@ -130,72 +123,68 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 1) {
-    int a_slot = 0, b_slot = 0;
-    uint32_t a_phase = 0, b_phase = 0;
-    int uit = 0;
-    for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++uit) {
-      int m_tile, n_tile, tg, split;
-      decode(unit, m_tile, n_tile, tg, split);
-      const int n0 = n_tile * p.ntile_w;
-      const int Nn = min(p.ntile_w, p.Cin - n0);         // multiple of 16
-      const uint32_t idesc = make_idesc_bf16(128, Nn, 1, 1);
-      const int tap0 = tg * p.taps_per_group, tap1 = min(p.taps, tap0 + p.taps_per_group);
-      mbar_wait(acc_empty, (uit & 1) ^ 1);
-      tc_fence_after();
-      bool first = true;
-      for (int t = split; t < p.pix_tiles; t += p.splits) {
-        mbar_wait(&a_full[a_slot], a_phase);
+    if (elect_one()) {   // one elected thread: barrier waits + unrolled tcgen05.mma issue for the whole CTA
+      // 16 pixels per MMA = two 8-pixel tile rows: dy rows are dense (2048 B per K step); halo x rows sit 10 apart
+      const uint64_t a_tmpl = make_smem_desc(0, kABlock, 1024, 2);
+      const uint64_t bh_tmpl = make_smem_desc(0, p.b_block_bytes, 1280, 2);
+      const uint64_t bd_tmpl = make_smem_desc(0, kABlock, 1024, 2);
+      const uint32_t a0 = smem_u32(a_base) >> 4, b0 = smem_u32(b_base) >> 4;
+      const uint32_t aslot16 = (uint32_t)p.a_slot_bytes >> 4, bslot16 = (uint32_t)p.b_slot_bytes >> 4;
+      int a_slot = 0, b_slot = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      int uit = 0;
+      for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++uit) {
+        int m_tile, n_tile, tg, split;
+        decode(unit, m_tile, n_tile, tg, split);
+        const int n0 = n_tile * p.ntile_w;
+        const int Nn = min(p.ntile_w, p.Cin - n0);         // multiple of 16
+        const uint32_t idesc = make_idesc_bf16(128, Nn, 1, 1);
+        const int tap0 = tg * p.taps_per_group, tap1 = min(p.taps, tap0 + p.taps_per_group);
+        mbar_wait(acc_empty, (uit & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(a_base + (size_t)a_slot * p.a_slot_bytes);
-        if (p.halo) {
-          mbar_wait(&b_full[b_slot], b_phase);
+        uint32_t acc = 0;
+        for (int t = split; t < p.pix_tiles; t += p.splits) {
+          mbar_wait(&a_full[a_slot], a_phase);
           tc_fence_after();
-          const uint32_t sb = smem_u32(b_base + (size_t)b_slot * p.b_slot_bytes);
-          if (elect_one()) {
-            for (int tap = tap0; tap < tap1; ++tap) {
+          const uint64_t ad = a_tmpl + (uint64_t)(a0 + (uint32_t)a_slot * aslot16);
+          if (p.halo) {
+            mbar_wait(&b_full[b_slot], b_phase);
+            tc_fence_after();
+            const uint64_t bd = bh_tmpl + (uint64_t)(b0 + (uint32_t)b_slot * bslot16);
+            uint32_t d_tmem = tmem_base;
+            for (int tap = tap0; tap < tap1; ++tap, d_tmem += Nn) {
               const int kh = tap / 3, kw = tap - kh * 3;
-              const uint32_t d_tmem = tmem_base + (tap - tap0) * Nn;
-#pragma unroll 1
-              for (int k = 0; k < 8; ++k) {   // 16 pixels = two 8-pixel tile rows: dy rows are dense, x rows sit 10 apart
-                const uint64_t ad = make_smem_desc(sa + k * 2048, kABlock, 1024, 2);
-                const uint64_t bd = make_smem_desc(sb + (kh * 10 + kw) * 128 + k * 2560, p.b_block_bytes, 1280, 2);
-                umma_f16(d_tmem, ad, bd, idesc, (!first || k > 0) ? 1u : 0u);
-              }
+              const uint64_t bt = bd + (uint64_t)((kh * 10 + kw) * 8);
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma_f16(d_tmem, ad + (uint64_t)(k * 128), bt + (uint64_t)(k * 160), idesc, k ? 1u : acc);
             }
             umma_commit(&b_empty[b_slot]);
             umma_commit(&a_empty[a_slot]);
+            if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
+            if (++a_slot == 2) { a_slot = 0; a_phase ^= 1; }
+            acc = 1;
+            continue;
           }
-          __syncwarp();
-          if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
-          if (++a_slot == 2) { a_slot = 0; a_phase ^= 1; }
-          first = false;
-          continue;
-        }
-        for (int tap = tap0; tap < tap1; ++tap) {
-          mbar_wait(&b_full[b_slot], b_phase);
-          tc_fence_after();
-          const uint32_t sb = smem_u32(b_base + (size_t)b_slot * p.b_slot_bytes);
-          const uint32_t d_tmem = tmem_base + (tap - tap0) * Nn;
-          if (elect_one()) {
-#pragma unroll 1
-            for (int k = 0; k < 8; ++k) {   // 16 pixel rows (2 groups of 8 rows x 128 B) per MMA
-              const uint64_t ad = make_smem_desc(sa + k * 2048, kABlock, 1024, 2);
-              const uint64_t bd = make_smem_desc(sb + k * 2048, kABlock, 1024, 2);
-              umma_f16(d_tmem, ad, bd, idesc, (!first || k > 0) ? 1u : 0u);
-            }
+          uint32_t d_tmem = tmem_base;
+          for (int tap = tap0; tap < tap1; ++tap, d_tmem += Nn) {
+            mbar_wait(&b_full[b_slot], b_phase);
+            tc_fence_after();
+            const uint64_t bd = bd_tmpl + (uint64_t)(b0 + (uint32_t)b_slot * bslot16);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_f16(d_tmem, ad + (uint64_t)(k * 128), bd + (uint64_t)(k * 128), idesc, k ? 1u : acc);
             umma_commit(&b_empty[b_slot]);
+            if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
           }
-          __syncwarp();
-          if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
+          umma_commit(&a_empty[a_slot]);
+          if (++a_slot == 2) { a_slot = 0; a_phase ^= 1; }
+          acc = 1;
         }
-        if (elect_one()) umma_commit(&a_empty[a_slot]);
-        __syncwarp();
-        if (++a_slot == 2) { a_slot = 0; a_phase ^= 1; }
-        first = false;
+        umma_commit(acc_full);
       }
-      if (elect_one()) umma_commit(acc_full);
-      __syncwarp();
     }
+    __syncwarp();
   } else if (warp >= 4) {
     const uint32_t q = warp - 4;
     int uit = 0;
@@ -243,6 +232,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const WgradParams p, const float* __restrict__ ws, float* __restrict__ dw) {
   __shared__ float sh[8][32];
+  pdl_sync();
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int ci_blocks = (p.Cin + 31) / 32;
   const long long rows = (long long)p.Cout * p.taps * ci_blocks;
@@ -368,10 +358,11 @@ extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, c
     attr_set = true;
   }
   const int grid = p.total_units < B200SEG_MAX_CTAS ? p.total_units : B200SEG_MAX_CTAS;
-  wgrad_igemm_kernel<<<grid, kWThreads, smem_bytes, (cudaStream_t)stream>>>(tmDy, tmX, p, (float*)workspace);
+  cudaError_t e = launch_k(wgrad_igemm_kernel, dim3(grid), dim3(kWThreads), smem_bytes, (cudaStream_t)stream, tmDy, tmX, p,
+                           (float*)workspace);
+  if (e != cudaSuccess) return (int)e;
   long long rb = (long long)p.Cout * p.taps * ((p.Cin + 31) / 32);
   if (rb > 148 * 8) rb = 148 * 8;
-  wgrad_reduce_kernel<<<(int)rb, 256, 0, (cudaStream_t)stream>>>(p, (const float*)workspace, dw_oihw);
-  cudaError_t e = cudaGetLastError();
+  e = launch_k(wgrad_reduce_kernel, dim3((int)rb), dim3(256), 0, (cudaStream_t)stream, p, (const float*)workspace, dw_oihw);
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -110,10 +110,11 @@ def test_sgd_on_fixed_batch_tracks_oracle():
         loss.backward()
         opt2.step()
         curve.append(float(loss))
-    assert ref_curve[-1] < 0.7 * ref_curve[0], ref_curve
-    assert curve[-1] < 0.7 * curve[0], curve
     for a, b in zip(curve, ref_curve):
         assert abs(a - b) <= 0.08 * abs(b) + 0.02, (curve, ref_curve)
+    drop_ref = ref_curve[0] - ref_curve[-1]
+    assert drop_ref > 0.1, ref_curve                       # the oracle itself descends on this batch
+    assert curve[0] - curve[-1] > 0.5 * drop_ref, (curve, ref_curve)
 
 
 def test_cuda_graph_replay_equals_eager():
