@@ -80,13 +80,32 @@ int b200seg_conv2d_dgrad(const b200seg_conv_desc* d, const void* dy, int32_t dy_
                          const void* addend, int32_t addend_ld, void* dx, int32_t dx_ld, void* stream);
 
 
-/* Weight gradient: dw_oihw[co][ci][kh][kw] (fp32, the nn.Parameter .grad layout) += sum_pixels dy * x_shifted.
- * d describes the FORWARD convolution (input geometry, stride, pad); dy is bf16 NHWC [n,ho,wo,cout] with pitch dy_ld.
- * cin multiple of 16. Two launches: the tcgen05 kernel writes per-work-unit fp32 partial slabs into the caller's
- * workspace, a reduce kernel adds them into dw in a fixed order (deterministic; dw accumulates across calls). */
+/* Weight gradient: dw_ohwi[co][kh*kw][ci] (fp32 accumulator in the kernels' own layout, 16-byte aligned)
+ *   += sum_pixels dy[.., co] * x_shifted[.., ci]        (the convolution weight gradient).
+ * d describes the FORWARD convolution (input geometry, stride, pad); dy is bf16 NHWC [n,ho,wo,cout] with pitch dy_ld;
+ * cin multiple of 16. Deterministic. Depending on the shape the tcgen05 kernel either owns every gradient element
+ * (one launch, no workspace) or writes per-work-unit fp32 slabs into the caller's workspace that a second kernel sums
+ * in a fixed order; _ws_bytes / _launches report which. b200seg_grad_fold turns the accumulators into OIHW gradients. */
 size_t b200seg_conv2d_wgrad_ws_bytes(const b200seg_conv_desc* d);
-int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, int32_t dy_ld, float* dw_oihw,
+int32_t b200seg_conv2d_wgrad_launches(const b200seg_conv_desc* d);
+int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, int32_t dy_ld, float* dw_ohwi,
                          void* workspace, size_t ws_bytes, void* stream);
+
+/* End-of-step gradient fold over ONE flat fp32 buffer layout shared by dst / acc_a / acc_b (element offsets in segs):
+ *   conv weights (is_conv): dst[co][ci][tap] (OIHW, the nn.Parameter .grad layout) += acc_a[co][tap][ci] + acc_b[...]
+ *   vectors (BN affine, biases; cout = 1, taps = 1, cin = numel): dst[i] += acc_b[i]
+ * and, with clear != 0, zeroes what it read from acc_a / acc_b (either may be NULL). One thread block per chunk of
+ * b200seg_grad_fold_chunk() consecutive elements of one segment: blk_seg[b] indexes segs, blk_start[b] is the first
+ * element of the chunk inside its segment. Replaces autograd's gradient accumulation across the two scale passes
+ * (network/ocrnet.py:278-281). */
+typedef struct b200seg_grad_seg {
+  int64_t offset;          /* first element of the parameter in the flat buffers */
+  int32_t cout, cin, taps; /* conv: [cout][cin][taps]; vector: cout = 1, cin = numel, taps = 1 */
+  int32_t is_conv;
+} b200seg_grad_seg;
+int32_t b200seg_grad_fold_chunk(void);
+int b200seg_grad_fold(float* dst, float* acc_a, float* acc_b, const b200seg_grad_seg* segs, const int32_t* blk_seg,
+                      const int32_t* blk_start, int32_t n_blocks, int32_t clear, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training-mode BatchNorm around the convolutions. Replaces cuDNN/Apex BN behind Norm2d (network/mynn.py:18-24),

@@ -166,14 +166,50 @@ class B200SegModule(nn.Module):
                     self._packed[n[: -len(".weight")]] = (w_f, w_d)
             self._stem_pad = None
             self._graphs = {}
-            # private gradient buffer of the concurrently executed low-resolution pass (folded in at the end of a step)
-            self._flat_grad_lo = torch.zeros_like(self._flat_grad)
-            self._grad_views_lo = {}
-            off = 0
-            for n, p in params:
-                self._grad_views_lo[n] = self._flat_grad_lo[off:off + p.numel()].view(p.shape)
-                off += (p.numel() + 63) // 64 * 64
+            self._build_grad_accumulators(params, dev)
         self._ensure_flat_running(dev)
+
+    def _build_grad_accumulators(self, params, dev):
+        """Step-private fp32 gradient accumulators sharing the flat layout of ``_flat_grad``:
+          _acc_hi : conv-weight gradients of the main (1.0x / only) pass in the kernels' [O][taps][I] layout (vector
+                    parameters of that pass accumulate straight into ``_flat_grad``);
+          _acc_lo : everything the concurrently executed 0.5x pass produces (conv weights [O][taps][I], vectors as is).
+        They are zeroed at the start of a step; ``raw.grad_fold`` adds them into the OIHW ``_flat_grad`` at its end."""
+        self._acc_hi = torch.zeros_like(self._flat_grad)
+        self._acc_lo = torch.zeros_like(self._flat_grad)
+        self._eng_grads = {"hi": {}, "lo": {}}
+        segs = []
+        off = 0
+        for n, p in params:
+            numel = p.numel()
+            if p.dim() == 4:
+                o, i, k, _ = p.shape
+                self._eng_grads["hi"][n] = self._acc_hi[off:off + numel].view(o, k * k, i)
+                self._eng_grads["lo"][n] = self._acc_lo[off:off + numel].view(o, k * k, i)
+                if i != 3:     # the stem accumulates on the 16-channel padded image and is folded separately
+                    segs.append((off, o, i, k * k, 1))
+            else:
+                self._eng_grads["hi"][n] = self._grad_views[n]
+                self._eng_grads["lo"][n] = self._acc_lo[off:off + numel].view(p.shape)
+                segs.append((off, 1, numel, 1, 0))
+            off += (numel + 63) // 64 * 64
+        self._fold_table = raw.grad_fold_table(segs, dev)
+
+    def _engine_grads(self, which="hi"):
+        """name -> fp32 tensor an Engine accumulates into, plus the stem's padded [O][9][16] scratch accumulator."""
+        g = dict(self._eng_grads[which])
+        stem = "backbone.conv1.weight"
+        dev = self._flat_grad.device
+        pad = torch.zeros((g[stem].shape[0], 9, 16), dtype=F32, device=dev)
+        g[stem] = pad
+        return g, pad
+
+    def _fold_grads(self, stem_pads, with_lo):
+        stem = "backbone.conv1.weight"
+        for pad in stem_pads:
+            o = pad.shape[0]
+            self._grad_views[stem].add_(pad[:, :, :3].permute(0, 2, 1).reshape(o, 3, 3, 3))
+        raw.grad_fold(self._flat_grad, self._acc_hi, self._acc_lo if with_lo else None, self._fold_table, clear=False)
 
     def _ensure_flat_running(self, dev):
         """BatchNorm running statistics live in ONE flat fp32 buffer ([mean C | var C] per layer) and the module's
@@ -236,26 +272,22 @@ class B200SegModule(nn.Module):
     def _step_body(self, images, gts, drop_mask):
         self._repack()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
-        stem = "backbone.conv1.weight"
-
-        def grad_table(views):
-            g = dict(views)
-            pad = torch.zeros((g[stem].shape[0], 16, 3, 3), dtype=F32, device=images.device)
-            g[stem] = pad                    # the stem runs on the 16-channel padded image
-            return g, pad
-
         if self.loss_kind != "ce":
             raise NotImplementedError("RMI loss kernels are not wired into the fused step yet")
         if getattr(self, "_side_stream", None) is None:
             self._side_stream = torch.cuda.Stream()
-        grads, stem_pad_grad = grad_table(self._grad_views)
         par = self.parallel_scales and self.arch == "ocrnet.HRNet_Mscale"
+        self._acc_hi.zero_()         # two memsets (45 us each) beat clearing inside the fold's transposed gather
+        if par:
+            self._acc_lo.zero_()
+        grads, stem_pad = self._engine_grads("hi")
+        stem_pads = [stem_pad]
         E_lo = None
         if par:
             if getattr(self, "_lo_stream", None) is None:
                 self._lo_stream, self._side_stream_lo = torch.cuda.Stream(), torch.cuda.Stream()
-            self._flat_grad_lo.zero_()
-            grads_lo, stem_pad_grad_lo = grad_table(self._grad_views_lo)
+            grads_lo, stem_pad_lo = self._engine_grads("lo")
+            stem_pads.append(stem_pad_lo)
             E_lo = Engine(tensors, grads_lo, self._packed, True, drop_mask, side_stream=self._side_stream_lo,
                           bstat=self._bstat_views[0], stream=self._lo_stream)
         E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream,
@@ -263,11 +295,9 @@ class B200SegModule(nn.Module):
         loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,
                             self.ignore_index, E_lo=E_lo)
         M.run_backward(E, E_lo)
-        self._grad_views[stem].add_(stem_pad_grad[:, :3])
+        self._fold_grads(stem_pads, par)
         if par:
             assert E.bn_seen == E_lo.bn_seen and len(E.bn_seen) == len(self._bn_slots), "BN bookkeeping out of sync"
-            self._grad_views_lo[stem].add_(stem_pad_grad_lo[:, :3])
-            raw.accum_f32(self._flat_grad, self._flat_grad_lo)
             raw.bn_running_update(self._run_flat, self._bstat[0], self._bstat[1], BN_MOMENTUM, self._nbt_flat, 2)
         return loss
 

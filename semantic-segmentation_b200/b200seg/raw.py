@@ -106,17 +106,46 @@ def conv2d_dgrad(dy, w_dgrad, x_shape, ksize, stride, addend=None, out=None, for
     return out
 
 
-def conv2d_wgrad(x, dy, dw_oihw, cout, ksize, stride):
-    """dw_oihw (fp32 [Cout,Cin,k,k], contiguous) += sum_pixels dy x shifted(x)."""
+def conv2d_wgrad(x, dy, dw_ohwi, cout, ksize, stride):
+    """dw_ohwi (fp32 accumulator [Cout][k*k][Cin], contiguous; a [Cout,Cin,1,1] tensor is the same memory for 1x1)
+    += sum_pixels dy x shifted(x). Returns the workspace tensor (keep it alive while the launch is in flight)."""
     n, h, w, cin = x.shape
-    assert dw_oihw.is_contiguous() and dw_oihw.dtype == F32
+    assert dw_ohwi.is_contiguous() and dw_ohwi.dtype == F32 and dw_ohwi.numel() == cout * cin * ksize * ksize
     d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(dy))
     L = lib()
     nbytes = L.b200seg_conv2d_wgrad_ws_bytes(ctypes.byref(d))
-    ws = torch.empty((nbytes // 4,), dtype=F32, device=x.device)
-    check(L.b200seg_conv2d_wgrad(ctypes.byref(d), ptr(x), ptr(dy), _ld(dy), ptr(dw_oihw), ptr(ws), nbytes,
-                                 stream_ptr()), "conv2d_wgrad", 2)
+    ws = torch.empty((max(nbytes, 16) // 4,), dtype=F32, device=x.device)
+    check(L.b200seg_conv2d_wgrad(ctypes.byref(d), ptr(x), ptr(dy), _ld(dy), ptr(dw_ohwi), ptr(ws), nbytes,
+                                 stream_ptr()), "conv2d_wgrad", L.b200seg_conv2d_wgrad_launches(ctypes.byref(d)))
     return ws
+
+
+def ohwi_to_oihw(dw_ohwi, ksize):
+    """[O][k*k][I] accumulator -> the nn.Parameter .grad layout [O,I,k,k] (a permuted view)."""
+    o, taps, i = dw_ohwi.shape
+    return dw_ohwi.view(o, ksize, ksize, i).permute(0, 3, 1, 2)
+
+
+def grad_fold_table(segs, device):
+    """segs: list of (offset, cout, cin, taps, is_conv) over one flat layout -> device tables for grad_fold."""
+    import numpy as np
+    chunk = lib().b200seg_grad_fold_chunk()
+    blk_seg, blk_start = [], []
+    for si, (_off, cout, cin, taps, _c) in enumerate(segs):
+        numel = cout * cin * taps
+        for st in range(0, numel, chunk):
+            blk_seg.append(si)
+            blk_start.append(st)
+    seg_np = np.array(segs, dtype=np.dtype([("offset", "<i8"), ("cout", "<i4"), ("cin", "<i4"), ("taps", "<i4"),
+                                            ("is_conv", "<i4")]))
+    return dict(segs=torch.from_numpy(seg_np.view(np.uint8).copy()).to(device),
+                blk_seg=torch.tensor(blk_seg, dtype=torch.int32, device=device),
+                blk_start=torch.tensor(blk_start, dtype=torch.int32, device=device), n_blocks=len(blk_seg))
+
+
+def grad_fold(dst, acc_a, acc_b, table, clear=True):
+    check(lib().b200seg_grad_fold(ptr(dst), ptr(acc_a), ptr(acc_b), ptr(table["segs"]), ptr(table["blk_seg"]),
+                                  ptr(table["blk_start"]), table["n_blocks"], int(clear), stream_ptr()), "grad_fold")
 
 
 # ----------------------------------------------------------------------------------------------- batch norm

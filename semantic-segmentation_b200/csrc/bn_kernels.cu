@@ -14,30 +14,48 @@
 namespace b200seg {
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int Cpad, float count,
+constexpr int kFinSlices = 16;
+// Sum rows slice, slice+16, ... of a [G][pitch] partial table for channel c (first statistic at +c, second at +off2+c).
+__device__ __forceinline__ void fold_rows(const float* __restrict__ partials, int G, int pitch, int off2, int c,
+                                          int slice, double& a1, double& a2) {
+  int g = slice;
+  for (; g + 3 * kFinSlices < G; g += 4 * kFinSlices) {
+    const float* p0 = partials + (size_t)g * pitch + c;
+    const float u0 = p0[0], v0 = p0[off2];
+    const float u1 = p0[(size_t)kFinSlices * pitch], v1 = p0[(size_t)kFinSlices * pitch + off2];
+    const float u2 = p0[(size_t)2 * kFinSlices * pitch], v2 = p0[(size_t)2 * kFinSlices * pitch + off2];
+    const float u3 = p0[(size_t)3 * kFinSlices * pitch], v3 = p0[(size_t)3 * kFinSlices * pitch + off2];
+    a1 += (double)u0; a1 += (double)u1; a1 += (double)u2; a1 += (double)u3;
+    a2 += (double)v0; a2 += (double)v1; a2 += (double)v2; a2 += (double)v3;
+  }
+  for (; g < G; g += kFinSlices) {
+    a1 += (double)partials[(size_t)g * pitch + c];
+    a2 += (double)partials[(size_t)g * pitch + off2 + c];
+  }
+}
+
+__global__ void __launch_bounds__(32 * kFinSlices)
+bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int Cpad, float count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, float* __restrict__ batch_stats_out) {
   pdl_sync();
-  // block = 32 channels x 8 slices of the G partial rows (coalesced 128-byte reads), then a fixed-order fold
-  __shared__ double sh1[8][32], sh2[8][32];
+  // block = 32 channels x 16 slices of the G partial rows (coalesced 128-byte reads, four independent rows in flight per
+  // thread: the kernel is a pure latency chain otherwise), then a fixed-order fold -> deterministic
+  __shared__ double sh1[kFinSlices][32], sh2[kFinSlices][32];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
   double a1 = 0.0, a2 = 0.0;
-  if (c < C)
-    for (int g = slice; g < G; g += 8) {
-      a1 += (double)partials[(size_t)g * 2 * Cpad + c];
-      a2 += (double)partials[(size_t)g * 2 * Cpad + Cpad + c];
-    }
+  if (c < C) fold_rows(partials, G, 2 * Cpad, Cpad, c, slice, a1, a2);
   sh1[slice][lane] = a1;
   sh2[slice][lane] = a2;
   __syncthreads();
   if (slice != 0 || c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < 8; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
+  for (int k = 0; k < kFinSlices; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
   const double mean = s1 / count;
   double var = s2 / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -190,25 +208,22 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, float count,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
-                                       float* __restrict__ c2) {
+__global__ void __launch_bounds__(32 * kFinSlices)
+bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, float count,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
+                       float* __restrict__ c2) {
   pdl_sync();
-  __shared__ double sh1[8][32], sh2[8][32];
+  __shared__ double sh1[kFinSlices][32], sh2[kFinSlices][32];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   double a1 = 0.0, a2 = 0.0;
-  if (c < C)
-    for (int g = slice; g < G; g += 8) {
-      a1 += (double)partials[(size_t)g * 2 * C + c];
-      a2 += (double)partials[(size_t)g * 2 * C + C + c];
-    }
+  if (c < C) fold_rows(partials, G, 2 * C, C, c, slice, a1, a2);
   sh1[slice][lane] = a1;
   sh2[slice][lane] = a2;
   __syncthreads();
   if (slice != 0 || c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < 8; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
+  for (int k = 0; k < kFinSlices; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
   if (dbeta) dbeta[c] += (float)s1;     // parameter gradients accumulate (two scale passes share the weights)
   if (dgamma) dgamma[c] += (float)s2;
   c1[c] = (float)(s1 / count);
@@ -319,7 +334,7 @@ extern "C" int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t 
                                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
                                    float* shift, float* mean, float* invstd, float* batch_stats_out, void* stream) {
   if (!partials || !scale || !shift || !mean || !invstd || c <= 0 || grid <= 0) return B200SEG_E_BADARG;
-  launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(256), 0, (cudaStream_t)stream, partials, grid, c, cpad, count, gamma, beta, eps, momentum, running_mean, running_var,
+  launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinSlices), 0, (cudaStream_t)stream, partials, grid, c, cpad, count, gamma, beta, eps, momentum, running_mean, running_var,
       (long long*)num_batches_tracked, scale, shift, mean, invstd, batch_stats_out);
   CHECK_LAUNCH();
 }
@@ -393,7 +408,7 @@ extern "C" int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* 
 extern "C" int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int32_t c, float count, float* dgamma,
                                        float* dbeta, float* c1, float* c2, void* stream) {
   if (!partials || !c1 || !c2) return B200SEG_E_BADARG;
-  launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(256), 0, (cudaStream_t)stream, partials, grid, c, count, dgamma, dbeta,
+  launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinSlices), 0, (cudaStream_t)stream, partials, grid, c, count, dgamma, dbeta,
                                                                            c1, c2);
   CHECK_LAUNCH();
 }

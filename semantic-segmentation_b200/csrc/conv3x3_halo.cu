@@ -36,6 +36,7 @@ struct HaloParams {
   int resident;                // weights stay in smem for the CTA lifetime
   int a_slots, b_slots;        // ring depths (b_slots unused when resident)
   int b_tile_bytes;            // BN * 128 rounded to 1024
+  int dbg;                     // B200SEG_DBG=8: block 0 records a per-role ns timeline behind the statistics partials
 };
 
 constexpr int kHThreads = 384;
@@ -57,6 +58,18 @@ __device__ __forceinline__ void h_butterfly16(float (&v)[16], uint32_t lane) {
   }
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// bench-only timeline (tools/gpu_timeline.py): role r, tile iteration it -> ns timestamp
+#define DBG_TS(role, it)                                                                                      \
+  do {                                                                                                        \
+    if ((p.dbg & 8) && blockIdx.x == 0 && (it) < 16)                                                          \
+      reinterpret_cast<unsigned long long*>(stats_partials + 148 * 2 * 1024)[(role) * 16 + (it)] = gtime();  \
+  } while (0)
 
 // All nine taps of one resident 64-channel chunk: 9 x KS MMAs, compile-time offsets only.
 template <int KS>
@@ -108,6 +121,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) DBG_TS(6, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one elected lane)
@@ -130,6 +144,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_arrive_expect_tx(&a_full[a_slot], kHaloH * kHaloW * 128);
           tma_load_4d(&tmA, &a_full[a_slot], a_base + (size_t)a_slot * kASlotBytes, cc * 64, tw_i * kTW - 1,
                       th_i * kTH - 1, img);
+          DBG_TS(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
           if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
           if (!p.resident) {
             for (int t = 0; t < 9; ++t) {
@@ -164,6 +179,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int cc = 0; cc <= last; ++cc) {
           mbar_wait(&a_full[a_slot], a_phase);
           tc_fence_after();
+          DBG_TS(1, it);
           const uint64_t ad = a_tmpl + (uint64_t)(a0 + (uint32_t)a_slot * (kASlotBytes >> 4));
           const int ks = (cc == last) ? p.ksteps_last : 4;
           const uint32_t acc_first = cc != 0 ? 1u : 0u;
@@ -192,6 +208,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           umma_commit(&a_empty[a_slot]);
           if (cc == last) umma_commit(&tfull[as]);
+          DBG_TS(2, it);
           if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
         }
       }
@@ -221,6 +238,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const size_t pix = ((size_t)img * p.H + ho) * p.W + wo;
       mbar_wait(&tfull[as], (it >> 1) & 1);
       tc_fence_after();
+      if (warp == 4 && lane == 0) DBG_TS(3, it);
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * 256;
 
       // one 16-column group: bias, gradient addend, bf16 store, batch statistics of the stored values
@@ -278,6 +296,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         tmem_ld32(taddr + ch * 16, r);
         tmem_ld_wait();
+        if (warp == 4 && lane == 0) DBG_TS(5, it);
         epi16(r, n0 + ch * 16);
         if (n0 + ch * 16 + 16 < p.Cout) epi16(r + 16, n0 + ch * 16 + 16);
       }
@@ -290,8 +309,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
+      if (warp == 4 && lane == 0) DBG_TS(4, it);
     }
   }
+  if (threadIdx.x == 0) DBG_TS(6, 1);
 
   tc_fence_before();
   __syncthreads();
@@ -348,6 +369,7 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   const size_t fixed = 1024 + (2 * kMaxASlots + 2 * kMaxBSlots2 + 4) * 8 + 16 + (size_t)4 * 2 * p.cout_pad * 4;
   const size_t budget = 227 * 1024 - fixed;
   const size_t resident_bytes = (size_t)9 * p.cchunks * p.b_tile_bytes;
+  { const char* e = getenv("B200SEG_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.resident = (p.n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) ? 1 : 0;
   size_t smem_bytes;
   if (p.resident) {

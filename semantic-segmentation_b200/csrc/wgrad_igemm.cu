@@ -6,9 +6,16 @@
 //   B = x   [pixels][cin]   -> N <= 256 input channels (64-channel blocks), one shifted TMA box per filter tap
 //   D[tap]  = fp32 accumulator in TMEM, taps of a group side by side (taps_in_group * N <= 512 columns)
 //
-// Work unit = (M tile, N tile, tap group, pixel split). Units are distributed round-robin over a persistent grid;
-// each unit reduces its share of the pixels in TMEM and adds the result into the fp32 OIHW gradient with red.global
-// (parameter gradients accumulate across the two scale passes and, later, across micro-batches).
+// Work unit = (M tile, N tile, tap group, pixel split). Units are distributed round-robin over a persistent grid; each
+// unit reduces its share of the pixels in TMEM. The gradient accumulator is fp32 in the kernels' own [Cout][tap][Cin]
+// ("OHWI") layout, so an accumulator row is a contiguous run of input channels:
+//   * splits == 1 (low-resolution / wide layers: enough (tile, tap-group) items to fill the SMs): exactly one unit owns
+//     every gradient element, which it adds with 16-byte red.global.add.v4.f32 — no workspace, no second kernel,
+//     deterministic;
+//   * splits  > 1 (high-resolution narrow layers): units store fp32 slabs and wgrad_reduce_kernel sums the splits in a
+//     fixed order (deterministic) with coalesced float4 traffic.
+// The decomposition (N tile width, taps per group, splits) is picked per layer by a small cost model (wgrad_plan).
+// The step folds the OHWI accumulators into the OIHW master gradients once, at the end (grad_fold_kernel).
 // Replaces cuDNN convolution_backward (weight part) behind every nn.Conv2d listed in SURVEY.md §2b K1-K5.
 #include "ptx.cuh"
 #include "tma_host.h"
@@ -29,6 +36,7 @@ struct WgradParams {
   int unit_n;            // accumulator row pitch of a unit slab (= min(256, Cin))
   long long unit_stride; // floats per unit slab
   int a_slot_bytes, b_slot_bytes, b_slots;
+  int direct;            // splits == 1: units add straight into the gradient accumulator
 };
 
 constexpr int kWThreads = 256;
@@ -37,7 +45,7 @@ constexpr int kMaxBSlots = 6;
 
 __global__ void __launch_bounds__(kWThreads, 1)
 wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
-                   const WgradParams p, float* __restrict__ ws) {
+                   const WgradParams p, float* __restrict__ ws, float* __restrict__ dw) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_base = smem;                               // 2 slots
@@ -205,13 +213,22 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
             tmem_ld16(tmem_base + ((q * 32u) << 16) + (tap - tap0) * Nn + ch * 16, r);
             tmem_ld_wait();
             if (co < p.Cout) {
-              // per-unit slab [tap_local][128 rows][unit_n] fp32: plain 16-byte stores, summed by wgrad_reduce_kernel
-              float4* dst = reinterpret_cast<float4*>(ws + (size_t)unit * p.unit_stride +
-                                                      ((size_t)(tap - tap0) * 128 + q * 32 + lane) * p.unit_n + ch * 16);
-              dst[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
-              dst[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
-              dst[2] = make_float4(__uint_as_float(r[8]), __uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
-              dst[3] = make_float4(__uint_as_float(r[12]), __uint_as_float(r[13]), __uint_as_float(r[14]), __uint_as_float(r[15]));
+              if (p.direct) {
+                // the only unit that touches dw[co][tap][n0 + 16 ch ..]: four 16-byte fire-and-forget reductions
+                float* dst = dw + ((size_t)co * p.taps + tap) * p.Cin + n0 + ch * 16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  red_add_v4(dst + 4 * j, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+              } else {
+                // per-unit slab [tap_local][128 rows][unit_n] fp32: plain 16-byte stores, summed by wgrad_reduce_kernel
+                float4* dst = reinterpret_cast<float4*>(ws + (size_t)unit * p.unit_stride +
+                                                        ((size_t)(tap - tap0) * 128 + q * 32 + lane) * p.unit_n + ch * 16);
+                dst[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+                dst[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+                dst[2] = make_float4(__uint_as_float(r[8]), __uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
+                dst[3] = make_float4(__uint_as_float(r[12]), __uint_as_float(r[13]), __uint_as_float(r[14]), __uint_as_float(r[15]));
+              }
             }
           }
         }
@@ -227,45 +244,114 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
 }
 
 
-// dw[co][ci][tap] += sum over the pixel splits of the unit slabs (fixed order -> deterministic).
-// Block = 32 consecutive ci (coalesced slab reads) x 8 split-slices; one (co, tap) row per blockIdx.y iteration.
+// dw[co][tap][ci] += sum over the pixel splits of the unit slabs, splits summed in a fixed order (deterministic).
+// One thread block = 32 consecutive float4 of an item's [tap_local][row][col] index space (coalesced 512-byte slab reads)
+// x 8 slices of the split range; the 8 partial sums are folded in slice order.
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const WgradParams p, const float* __restrict__ ws, float* __restrict__ dw) {
-  __shared__ float sh[8][32];
+wgrad_reduce_kernel(const WgradParams p, const float* __restrict__ ws, float* __restrict__ dw, int blocks_per_item) {
+  __shared__ float4 sh[8][32];
   pdl_sync();
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int ci_blocks = (p.Cin + 31) / 32;
-  const long long rows = (long long)p.Cout * p.taps * ci_blocks;
-  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int cb = (int)(r % ci_blocks);
-    const int tap = (int)((r / ci_blocks) % p.taps);
-    const int co = (int)(r / ((long long)ci_blocks * p.taps));
-    const int ci = cb * 32 + lane;
-    float acc = 0.f;
-    if (ci < p.Cin) {
-      const int m_tile = co >> 7, row = co & 127;
-      const int n_tile = ci / p.ntile_w, col = ci - n_tile * p.ntile_w;
-      const int tg = tap / p.taps_per_group, tl = tap - tg * p.taps_per_group;
-      const int item = (m_tile * p.n_tiles + n_tile) * p.tap_groups + tg;
-      const float* src = ws + (size_t)item * p.splits * p.unit_stride + ((size_t)tl * 128 + row) * p.unit_n + col;
-      float a0 = 0.f, a1 = 0.f;
-      int s_ = slice;
-      for (; s_ + 8 < p.splits; s_ += 16) {
-        a0 += src[(size_t)s_ * p.unit_stride];
-        a1 += src[(size_t)(s_ + 8) * p.unit_stride];
-      }
-      if (s_ < p.splits) a0 += src[(size_t)s_ * p.unit_stride];
-      acc = a0 + a1;
+  const int item = blockIdx.x / blocks_per_item, chunk = blockIdx.x - item * blocks_per_item;
+  int it = item;
+  const int tg = it % p.tap_groups; it /= p.tap_groups;
+  const int n_tile = it % p.n_tiles;
+  const int m_tile = it / p.n_tiles;
+  const int n0 = n_tile * p.ntile_w;
+  const int Nn = min(p.ntile_w, p.Cin - n0);
+  const int rows = min(128, p.Cout - m_tile * 128);
+  const int tap0 = tg * p.taps_per_group, ntap = min(p.taps, tap0 + p.taps_per_group) - tap0;
+  const int c4 = Nn >> 2;                               // float4 per accumulator row
+  const int f = chunk * 32 + lane;                      // float4 index inside [ntap][rows][c4]
+  const bool live = f < ntap * rows * c4;
+  int tl = 0, row = 0, col4 = 0;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    col4 = f % c4;
+    row = (f / c4) % rows;
+    tl = f / (c4 * rows);
+    const float4* src = reinterpret_cast<const float4*>(ws + (size_t)item * p.splits * p.unit_stride +
+                                                        ((size_t)tl * 128 + row) * p.unit_n) + col4;
+    const size_t stride4 = (size_t)p.unit_stride >> 2;
+    float4 a0 = acc, a1 = acc;
+    int s_ = slice;
+    for (; s_ + 8 < p.splits; s_ += 16) {
+      const float4 u = src[(size_t)s_ * stride4], v = src[(size_t)(s_ + 8) * stride4];
+      a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+      a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
     }
-    sh[slice][lane] = acc;
-    __syncthreads();
-    if (slice == 0 && ci < p.Cin) {
-      float t = 0.f;
+    if (s_ < p.splits) {
+      const float4 u = src[(size_t)s_ * stride4];
+      a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+    }
+    acc = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+  }
+  sh[slice][lane] = acc;
+  __syncthreads();
+  if (slice == 0 && live) {
+    float4 t = sh[0][lane];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t += sh[k][lane];
-      dw[((size_t)co * p.Cin + ci) * p.taps + tap] += t;
+    for (int k = 1; k < 8; ++k) { const float4 u = sh[k][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    float4* dst = reinterpret_cast<float4*>(dw + ((size_t)(m_tile * 128 + row) * p.taps + tap0 + tl) * p.Cin + n0) + col4;
+    float4 o = *dst;
+    o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+    *dst = o;
+  }
+}
+
+// Folds the step's gradient accumulators into the published gradient and clears them (no per-step memsets):
+//   conv weights : dst[co][ci][tap] (OIHW master layout) += acc_a[co][tap][ci] + acc_b[co][tap][ci]   (OHWI accumulators)
+//   vectors      : dst[i] += acc_b[i]                                    (BN affine / bias gradients of the second pass)
+// One block = up to kFoldChunk consecutive elements of one parameter: coalesced read-modify-write of dst, transposed
+// gather from the accumulators (each accumulator element is read, and cleared, by exactly one thread).
+constexpr int kFoldChunk = 4096;
+__global__ void __launch_bounds__(256)
+grad_fold_kernel(float* __restrict__ dst, float* __restrict__ acc_a, float* __restrict__ acc_b,
+                 const b200seg_grad_seg* __restrict__ segs, const int32_t* __restrict__ blk_seg,
+                 const int32_t* __restrict__ blk_start, int clear) {
+  pdl_sync();
+  const b200seg_grad_seg sg = segs[blk_seg[blockIdx.x]];
+  const uint32_t numel = (uint32_t)sg.cout * sg.cin * sg.taps;     // a parameter has < 2^31 elements
+  const uint32_t j0 = (uint32_t)blk_start[blockIdx.x];
+  const uint32_t len = (uint32_t)(sg.cin * sg.taps), taps = (uint32_t)sg.taps, cin = (uint32_t)sg.cin;
+  float* a = (sg.is_conv && acc_a) ? acc_a + sg.offset : nullptr;
+  float* b = acc_b ? acc_b + sg.offset : nullptr;
+  float* d = dst + sg.offset;
+  for (int t0 = threadIdx.x; t0 < kFoldChunk; t0 += 4 * 256) {   // four elements in flight per thread
+    uint32_t js[4], srcs[4];
+    float v[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t j = j0 + t0 + u * 256;
+      ok[u] = j < numel;
+      uint32_t src = j;
+      if (taps > 1) {
+        const uint32_t r = j / len;
+        const uint32_t jj = j - r * len;
+        const uint32_t ci = jj / taps, tap = jj - ci * taps;
+        src = r * len + tap * cin + ci;
+      }
+      js[u] = j; srcs[u] = src;
+      v[u] = 0.f;
+      if (ok[u]) {
+        v[u] = d[j];
+        if (a) v[u] += a[src];
+        if (b) v[u] += b[src];
+      }
     }
-    __syncthreads();
+    // The clearing stores must not be issued while loads of the same addresses are still in flight (a store that
+    // chases an outstanding load miss to the same line serialises the memory pipeline: measured 25x slower).
+    asm volatile("" ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      d[js[u]] = v[u];
+      if (clear) {
+        if (a) a[srcs[u]] = 0.f;
+        if (b) b[srcs[u]] = 0.f;
+      }
+    }
   }
 }
 
@@ -283,7 +369,6 @@ static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
   p.Ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
   p.Wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
   p.halo = (d->ksize == 3 && d->stride == 1 && d->reserved == 0) ? 1 : 0;
-  p.ntile_w = p.halo ? 128 : 256;
   p.b_block_bytes = p.halo ? 24576 : kABlock;
   p.TW = 16; p.TH = 8;
   if (p.Wo <= 8 || p.halo) { p.TW = 8; p.TH = 16; }
@@ -291,18 +376,58 @@ static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
   p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
   p.pix_tiles = d->n * p.tiles_h * p.tiles_w;
   p.m_tiles = (d->cout + 127) / 128;
+  const bool a_two = d->cout > 64;
+
+  // Decomposition search. Clock estimates per 128-pixel tile of one unit: tensor issue (M=128: the MN-major dy read of
+  // 4 KB per K=16 step bounds a narrow MMA at ~32 clk) against L2->smem fill at ~64 B/clk; a split run pays the slab
+  // round trip through HBM (~3 KB/clk) and a second kernel.
+  double best = 0;
+  int best_w = 0, best_tpg = 0, best_splits = 0;
+  const int widths[3] = {64, 128, 256};
+  for (int wi = 0; wi < 3; ++wi) {
+    const int ntw = widths[wi];
+    if (p.halo && ntw > 128) continue;                       // halo B slot: <= 2 blocks of 24 KB
+    if (wi > 0 && d->cin <= widths[wi - 1]) continue;        // same tiling as the narrower candidate
+    const int n_tiles = (d->cin + ntw - 1) / ntw;
+    const int Nmax = d->cin < ntw ? d->cin : ntw;
+    const int nblk = (Nmax + 63) / 64;
+    int tpg_max = 512 / Nmax;
+    if (tpg_max > p.taps) tpg_max = p.taps;
+    for (int tg = (p.taps + tpg_max - 1) / tpg_max; tg <= p.taps; ++tg) {
+      const int tpg = (p.taps + tg - 1) / tg;
+      if ((p.taps + tpg - 1) / tpg != tg) continue;
+      const int items = p.m_tiles * n_tiles * tg;
+      int sp_max = B200SEG_MAX_CTAS / items;
+      if (sp_max > p.pix_tiles) sp_max = p.pix_tiles;
+      if (sp_max < 1) sp_max = 1;
+      for (int pass = 0; pass < 2; ++pass) {
+        const int splits = pass == 0 ? 1 : sp_max;
+        if (pass == 1 && sp_max == 1) break;
+        const double tiles_per_unit = (double)((p.pix_tiles + splits - 1) / splits);
+        const double mma = (double)tpg * 8.0 * (Nmax / 2 > 32 ? Nmax / 2 : 32);
+        const double bytes = (a_two ? 32768.0 : 16384.0) + (p.halo ? nblk * 23040.0 : (double)tpg * nblk * 16384.0);
+        const double per_tile = mma > bytes / 64.0 ? mma : bytes / 64.0;
+        const double unit = tiles_per_unit * per_tile + (double)tpg * Nmax * 4.0 + 1500.0;
+        const double waves = (double)(((long long)items * splits + B200SEG_MAX_CTAS - 1) / B200SEG_MAX_CTAS);
+        double cost = waves * unit;
+        if (splits > 1) {
+          const double slab = (double)items * splits * tpg * (d->cout < 128 ? d->cout : 128) * Nmax * 4.0;
+          cost += 6000.0 + 2.0 * slab / 3000.0;
+        }
+        if (best_w == 0 || cost < best) { best = cost; best_w = ntw; best_tpg = tpg; best_splits = splits; }
+      }
+    }
+  }
+  if (best_w == 0) return B200SEG_E_BADARG;
+  p.ntile_w = best_w;
   p.n_tiles = (d->cin + p.ntile_w - 1) / p.ntile_w;
   const int Nmax = d->cin < p.ntile_w ? d->cin : p.ntile_w;
-  int tpg = 512 / Nmax;
-  if (tpg > p.taps) tpg = p.taps;
-  p.tap_groups = (p.taps + tpg - 1) / tpg;
-  p.taps_per_group = (p.taps + p.tap_groups - 1) / p.tap_groups;   // balanced groups
+  p.taps_per_group = best_tpg;
+  p.tap_groups = (p.taps + best_tpg - 1) / best_tpg;
+  p.splits = best_splits;
+  p.direct = best_splits == 1 ? 1 : 0;
   const int items = p.m_tiles * p.n_tiles * p.tap_groups;
-  int splits = (B200SEG_MAX_CTAS + items - 1) / items;              // ~1 unit per SM
-  if (splits > p.pix_tiles) splits = p.pix_tiles;
-  if (splits < 1) splits = 1;
-  p.splits = splits;
-  p.total_units = items * splits;
+  p.total_units = items * p.splits;
   p.nblocksB_max = (Nmax + 63) / 64;
   p.unit_n = Nmax;
   p.unit_stride = (long long)p.taps_per_group * 128 * Nmax;
@@ -314,18 +439,22 @@ static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
 extern "C" size_t b200seg_conv2d_wgrad_ws_bytes(const b200seg_conv_desc* d) {
   WgradParams p;
   if (wgrad_plan(d, p) != 0) return 0;
+  if (p.direct) return 16;   // no slabs: the workspace is not touched (a non-zero size keeps callers' allocation uniform)
   return (size_t)p.total_units * p.unit_stride * sizeof(float);
 }
 
 extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, int32_t dy_ld,
-                                    float* dw_oihw, void* workspace, size_t ws_bytes, void* stream) {
-  if (!d || !x || !dy || !dw_oihw || !workspace) return B200SEG_E_BADARG;
+                                    float* dw_ohwi, void* workspace, size_t ws_bytes, void* stream) {
+  if (!d || !x || !dy || !dw_ohwi) return B200SEG_E_BADARG;
   if (dy_ld % 8 || dy_ld < 8) return B200SEG_E_BADARG;
   WgradParams p;
   int rc0 = wgrad_plan(d, p);
   if (rc0) return rc0;
-  if (ws_bytes < (size_t)p.total_units * p.unit_stride * sizeof(float)) return B200SEG_E_BADARG;
-  if (reinterpret_cast<uintptr_t>(workspace) & 15) return B200SEG_E_BADARG;
+  if (reinterpret_cast<uintptr_t>(dw_ohwi) & 15) return B200SEG_E_BADARG;
+  if (!p.direct) {
+    if (!workspace || ws_bytes < (size_t)p.total_units * p.unit_stride * sizeof(float)) return B200SEG_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(workspace) & 15) return B200SEG_E_BADARG;
+  }
   const size_t fixed = 1024 + 2 * (size_t)p.a_slot_bytes + (4 + 2 * kMaxBSlots + 2) * 8 + 16;
   int bs = (int)((227 * 1024 - fixed) / p.b_slot_bytes);
   if (bs > kMaxBSlots) bs = kMaxBSlots;
@@ -359,10 +488,32 @@ extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, c
   }
   const int grid = p.total_units < B200SEG_MAX_CTAS ? p.total_units : B200SEG_MAX_CTAS;
   cudaError_t e = launch_k(wgrad_igemm_kernel, dim3(grid), dim3(kWThreads), smem_bytes, (cudaStream_t)stream, tmDy, tmX, p,
-                           (float*)workspace);
+                           (float*)workspace, dw_ohwi);
   if (e != cudaSuccess) return (int)e;
-  long long rb = (long long)p.Cout * p.taps * ((p.Cin + 31) / 32);
-  if (rb > 148 * 8) rb = 148 * 8;
-  e = launch_k(wgrad_reduce_kernel, dim3((int)rb), dim3(256), 0, (cudaStream_t)stream, p, (const float*)workspace, dw_oihw);
+  if (p.direct) return 0;
+  const int items = p.m_tiles * p.n_tiles * p.tap_groups;
+  const int rows_max = p.Cout < 128 ? p.Cout : 128;
+  const int f_max = p.taps_per_group * rows_max * (p.unit_n / 4);
+  const int bpi = (f_max + 31) / 32;
+  e = launch_k(wgrad_reduce_kernel, dim3(items * bpi), dim3(256), 0, (cudaStream_t)stream, p, (const float*)workspace,
+               dw_ohwi, bpi);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+/* number of kernels b200seg_conv2d_wgrad launches for this shape (1: direct, 2: split + reduce) */
+extern "C" int32_t b200seg_conv2d_wgrad_launches(const b200seg_conv_desc* d) {
+  WgradParams p;
+  if (wgrad_plan(d, p) != 0) return 0;
+  return p.direct ? 1 : 2;
+}
+
+extern "C" int32_t b200seg_grad_fold_chunk(void) { return kFoldChunk; }
+
+extern "C" int b200seg_grad_fold(float* dst, float* acc_a, float* acc_b, const b200seg_grad_seg* segs,
+                                 const int32_t* blk_seg, const int32_t* blk_start, int32_t n_blocks, int32_t clear,
+                                 void* stream) {
+  if (!dst || (!acc_a && !acc_b) || !segs || !blk_seg || !blk_start || n_blocks <= 0) return B200SEG_E_BADARG;
+  cudaError_t e = launch_k(grad_fold_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, dst, acc_a, acc_b, segs,
+                           blk_seg, blk_start, (int)clear);
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -40,7 +40,7 @@ class Harness:
         net._repack()
         net._flat_grad.zero_()
         tensors = {k: v.detach() for k, v in net._tensors().items()}
-        self.grads = dict(net._grad_views)
+        self.grads, _ = net._engine_grads("hi")     # conv weights: kernel-layout [O][taps][I] accumulators
         self.E = Engine(tensors, self.grads, net._packed, True, torch.ones((2, 512), device="cuda"))
 
     def rand_bf16(self, shape, seed, scale=1.0):
@@ -67,7 +67,10 @@ class Harness:
             if name.startswith(prefix) and v.grad is not None and name in self.grads:
                 if name in ("ocr.conv3x3_ocr.0.bias", "ocr.aux_head.0.bias"):
                     continue   # conv bias in front of a training-mode BN: exactly zero here, float noise in the oracle
-                self.check(self.grads[name], v.grad, "grad " + name, tol, 0.998)
+                g = self.grads[name]
+                if v.grad.dim() == 4:
+                    g = self.raw.ohwi_to_oihw(g, v.grad.shape[2])
+                self.check(g, v.grad, "grad " + name, tol, 0.998)
                 n += 1
         assert n > 0
 

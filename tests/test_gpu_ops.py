@@ -39,6 +39,9 @@ CONV_CASES = [
     (1, 32, 64, 720, 512, 3, 1, True, 0), (1, 32, 64, 720, 720, 1, 1, True, 0), (1, 32, 64, 64, 64, 3, 2, False, 0),
     (1, 32, 64, 48, 96, 3, 2, False, 0), (1, 30, 52, 96, 192, 3, 2, False, 0), (1, 19, 1, 512, 256, 1, 1, False, 0),
     (2, 33, 47, 16, 64, 3, 2, False, 0), (1, 9, 7, 256, 48, 3, 1, False, 0),
+    # weight-gradient decompositions: split-over-pixels + reduce (narrow, many pixels) and single-owner units (wide)
+    (1, 128, 256, 48, 48, 3, 1, False, 0), (1, 64, 64, 192, 192, 3, 1, False, 0), (2, 16, 32, 384, 384, 3, 1, False, 0),
+    (1, 64, 128, 720, 256, 1, 1, False, 0),
 ]
 
 
@@ -74,10 +77,49 @@ def test_conv_fwd_dgrad_wgrad(case):
         dx2 = raw.conv2d_dgrad(dy, w_d, (n, h, w, cin), k, s, addend=add.clone(), force_kc=kc)
         close(dx2, xr.grad.permute(0, 2, 3, 1) + add.float(), BF16_TOL, "dgrad+addend")
     if cin % 16 == 0:
-        dw = torch.zeros_like(wt)
+        dw = torch.zeros((cout, k * k, cin), dtype=torch.float32, device="cuda")    # kernel-layout accumulator
         raw.conv2d_wgrad(x, dy, dw, cout, k, s)
         raw.conv2d_wgrad(x, dy, dw, cout, k, s)        # accumulates
-        close(dw, 2 * wr.grad, 2e-3, "wgrad")
+        close(raw.ohwi_to_oihw(dw, k), 2 * wr.grad, 2e-3, "wgrad")
+
+
+def test_grad_fold_layouts_and_clearing():
+    """End-of-step fold: OHWI accumulators of two passes -> OIHW gradient (+=), vectors of the second pass added,
+    accumulators cleared."""
+    import numpy as np
+    raw = _setup()
+    shapes = [(48, 32, 3, 3), (19, 512, 1, 1), (96,), (64, 16, 3, 3), (7,), (96, 96, 3, 3)]
+    offs, off = [], 0
+    for shp in shapes:
+        offs.append(off)
+        off += (int(np.prod(shp)) + 63) // 64 * 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    dst = torch.randn(off, generator=g, device="cuda")
+    a = torch.randn(off, generator=g, device="cuda")
+    b = torch.randn(off, generator=g, device="cuda")
+    want = dst.clone()
+    segs = []
+    for shp, o_ in zip(shapes, offs):
+        n = int(np.prod(shp))
+        if len(shp) == 4:
+            co, ci, k, _ = shp
+            src = (a[o_:o_ + n] + b[o_:o_ + n]).view(co, k * k, ci)
+            want[o_:o_ + n] += src.permute(0, 2, 1).reshape(-1)
+            segs.append((o_, co, ci, k * k, 1))
+        else:
+            want[o_:o_ + n] += b[o_:o_ + n]
+            segs.append((o_, 1, n, 1, 0))
+    table = raw.grad_fold_table(segs, "cuda")
+    a_vec_before = a[offs[2]:offs[2] + 96].clone()
+    raw.grad_fold(dst, a, b, table)
+    torch.cuda.synchronize()
+    for shp, o_ in zip(shapes, offs):
+        n = int(np.prod(shp))
+        assert torch.allclose(dst[o_:o_ + n], want[o_:o_ + n], rtol=0, atol=1e-6), shp
+        assert float(b[o_:o_ + n].abs().max()) == 0.0
+        if len(shp) == 4:
+            assert float(a[o_:o_ + n].abs().max()) == 0.0
+    assert torch.equal(a[offs[2]:offs[2] + 96], a_vec_before)     # vectors never live in the first accumulator
 
 
 def test_conv_logit_head_fp32_and_padded_grads():
