@@ -221,25 +221,45 @@ typedef struct b200seg_mscale_desc {
   float w_head0, w_head1;   /* loss weights (1.0, cfg.LOSS.OCR_ALPHA) */
   float sup_wt;             /* cfg.LOSS.SUPERVISED_MSCALE_WT (0 disables) */
   int32_t ignore_index;     /* 255 */
-  int32_t reserved[2];
+  int32_t loss_kind;        /* 0: CrossEntropyLoss2d heads (loss/utils.py:133-134); 1: RMILoss criterion (loss/rmi.py) */
+  int32_t reserved;
 } b200seg_mscale_desc;
-/* counter_ws: one uint64; inv_count <- 1 / #(labels != ignore) */
-int b200seg_count_valid(const int64_t* labels, int64_t total, int32_t ignore_index, uint64_t* counter_ws,
-                        float* inv_count, void* stream);
+/* counter_ws: one uint64; inv_count <- 1 / (#(labels != ignore) + plus_one)   (plus_one: RMILoss normalisation) */
+int b200seg_count_valid(const int64_t* labels, int64_t total, int32_t ignore_index, int32_t plus_one,
+                        uint64_t* counter_ws, float* inv_count, void* stream);
 /* mid[n][hm][wm][40] fp32 (attn4*cls4, attn4*aux4, attn4, 0); mid_sup[n][hm][wm][20] = cls4 when sup_wt != 0 */
 int b200seg_mscale_mid_fwd(const b200seg_mscale_desc* d, const float* lo_cls, const float* lo_aux,
                            const float* lo_attn_logit, float* mid, float* mid_sup, void* stream);
 int32_t b200seg_mscale_loss_blocks(const b200seg_mscale_desc* d);   /* partial_ws: blocks * 4 floats */
-/* loss_out[0] = total loss, [1..4] = mean NLL of {cls, aux, supervised lo, supervised hi};
- * g_hi / g_lo / g_sup: bf16 [n*h*w][40] per-pixel gradients consumed by the two backward entry points below */
+/* loss_out (8 floats): [0] total loss, [1..4] mean pointwise loss of {cls, aux, supervised lo, supervised hi},
+ * [5] the RMI term; g_hi / g_lo / g_sup: bf16 [n*h*w][40] per-pixel gradients consumed by the backward entry points.
+ * loss_kind 1 (RMILoss criterion): the pointwise loss is sigmoid BCE; rmi_dpr (fp32 [n][h/4+1][w/4+1][20], from
+ * b200seg_rmi_grad) is the RMI gradient w.r.t. the pooled probabilities of head 0 and rmi_terms[n_rmi_terms] the
+ * already weighted RMI values summed into the total (both NULL / 0 otherwise). */
 int b200seg_mscale_loss_fwd(const b200seg_mscale_desc* d, const int64_t* labels, const float* inv_count,
                             const float* hi_cls, const float* hi_aux, const float* mid, const float* mid_sup, void* g_hi,
-                            void* g_lo, void* g_sup, float* partial_ws, float* loss_out, void* stream);
+                            void* g_lo, void* g_sup, float* partial_ws, float* loss_out, const float* rmi_dpr,
+                            const float* rmi_terms, int32_t n_rmi_terms, void* stream);
 int b200seg_mscale_hi_bwd(const b200seg_mscale_desc* d, const void* g_hi, void* d_cls, void* d_aux, void* stream);
 /* dmid_ws: fp32 [n*hm*wm][40]; d_attn: bf16 [n*hl*wl][8] gradient w.r.t. the PRE-sigmoid attention logit */
 int b200seg_mscale_lo_bwd(const b200seg_mscale_desc* d, const void* g_lo, const void* g_sup, const float* lo_cls,
                           const float* lo_aux, const float* lo_attn_logit, const float* mid, float* dmid_ws, void* d_cls,
                           void* d_aux, void* d_attn, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Region Mutual Information head of the RMILoss criterion (loss/rmi.py:70-215, loss/rmi_utils.py:15-56,95-107) on the
+ * blended logits of head 0: radius 3, avg-pool 4/4/pad 2, sigmoid probabilities, fp64 covariances, lambda 0.5.
+ * Used with b200seg_mscale_desc.loss_kind = 1; the pointwise BCE part lives in b200seg_mscale_loss_fwd.
+ * ------------------------------------------------------------------------------------------------ */
+/* pr_pool / la_pool: fp32 [n][h/4+1][w/4+1][20] = avg_pool2d(sigmoid(joint)*mask + 1e-6) / avg_pool2d(onehot*mask) */
+int b200seg_rmi_pool(const b200seg_mscale_desc* d, const int64_t* labels, const float* hi_cls, const float* mid,
+                     float* pr_pool, float* la_pool, void* stream);
+size_t b200seg_rmi_ws_bytes(int32_t n);
+/* Second moments (fp64) -> per (image, class) 9x9 Cholesky solves -> rmi_terms[n*19] (each already multiplied by
+ * scale = w_head0 * (1 - lambda) / (n * 9)) and dpr = d(sum rmi_terms) / d pr_pool, fp32 [n][h/4+1][w/4+1][20].
+ * G: fp64 scratch [n][19][180]; ws: b200seg_rmi_ws_bytes(n) bytes, 8-byte aligned. Three launches. */
+int b200seg_rmi_solve_grad(int32_t n, int32_t h, int32_t w, const float* pr_pool, const float* la_pool, float scale,
+                           void* ws, size_t ws_bytes, double* G, float* rmi_terms, float* dpr, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Eval-mode output assembly: full-resolution fp32 NCHW maps and the hierarchical blend of

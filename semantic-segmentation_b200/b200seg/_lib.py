@@ -37,7 +37,7 @@ class MscaleDesc(ctypes.Structure):
     _fields_ = [("n", c_int32), ("h", c_int32), ("w", c_int32), ("hq", c_int32), ("wq", c_int32),
                 ("hm", c_int32), ("wm", c_int32), ("hl", c_int32), ("wl", c_int32), ("nheads", c_int32),
                 ("w_head0", c_float), ("w_head1", c_float), ("sup_wt", c_float), ("ignore_index", c_int32),
-                ("reserved", c_int32 * 2)]
+                ("loss_kind", c_int32), ("reserved", c_int32)]
 
 
 class ProbeOperand(ctypes.Structure):
@@ -90,10 +90,14 @@ SIGNATURES = {
     "b200seg_transpose_pad": (ctypes.c_int, [V, I32, I32, I32, I32, V, I32, V]),
     "b200seg_cast_rows": (ctypes.c_int, [V, I32, V, I32, I64, I32, I32, V]),
     "b200seg_bias_grad": (ctypes.c_int, [V, I32, I64, I32, V, V]),
-    "b200seg_count_valid": (ctypes.c_int, [V, I64, I32, V, V, V]),
+    "b200seg_count_valid": (ctypes.c_int, [V, I64, I32, I32, V, V, V]),
+    "b200seg_rmi_pool": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V, V, V]),
+    "b200seg_rmi_ws_bytes": (c_size_t, [I32]),
+    "b200seg_rmi_solve_grad": (ctypes.c_int, [I32, I32, I32, V, V, F, V, c_size_t, V, V, V, V]),
     "b200seg_mscale_mid_fwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V, V, V]),
     "b200seg_mscale_loss_blocks": (I32, [ctypes.POINTER(MscaleDesc)]),
-    "b200seg_mscale_loss_fwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V, V, V, V, V, V, V, V, V]),
+    "b200seg_mscale_loss_fwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V, V, V, V, V, V, V, V, V, V, I32,
+                                               V]),
     "b200seg_mscale_hi_bwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V]),
     "b200seg_mscale_lo_bwd": (ctypes.c_int, [ctypes.POINTER(MscaleDesc), V, V, V, V, V, V, V, V, V, V, V]),
     "b200seg_resize_to_nchw": (ctypes.c_int, [V, I32, I32, I32, I32, I32, I32, V, I32, I32, V]),

@@ -242,10 +242,14 @@ def scale_pass(E, images, size_hw, arch, hcfg, ocfg):
     return dict(cls=cls, aux=aux, attn=attn)
 
 
-def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, sup_wt=0.0, ignore_index=255, E_lo=None):
+def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, sup_wt=0.0, ignore_index=255, E_lo=None,
+               loss_kind="ce"):
     """Training forward + loss. ocrnet.HRNet_Mscale: MscaleOCR.two_scale_forward (network/ocrnet.py:264-319);
     ocrnet.HRNet: OCRNet.forward (:104-122); basic.HRNet: Basic.forward (network/basic.py:50-64).
-    Returns the fp32 loss vector [total, cls, aux, sup_lo, sup_hi]; pushes the loss backward on the tape.
+    Returns the fp32 loss vector [total, cls, aux, sup_lo, sup_hi, rmi, 0, 0]; pushes the loss backward on the tape.
+    loss_kind "ce": CrossEntropyLoss2d (loss/utils.py:133-134); "rmi": RMILoss (loss/rmi.py:70-215) = sigmoid BCE on
+    every head (the auxiliary / supervised terms are called with do_rmi=False, network/ocrnet.py:303-318) plus the
+    region-mutual-information term on the main prediction.
 
     E_lo (optional, two-scale only): a second engine with its own stream, gradient buffer and BN batch-statistics
     slots. The 0.5x and 1.0x passes are independent until the blend, so the low-resolution program is enqueued on
@@ -271,17 +275,22 @@ def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, su
         main.wait_stream(E_lo.stream)
     nheads = 1 if arch == "basic.HRNet" else 2
     hq, wq = hi["cls"].logits.shape[1:3]
+    rmi = loss_kind == "rmi"
+    kind = 1 if rmi else 0
     if two_scale:
         hl, wl = lo["cls"].logits.shape[1:3]
-        d = raw.mscale_desc(n, H, W, hq, wq, hm, wm, hl, wl, nheads, 1.0, ocr_alpha, sup_wt, ignore_index)
+        d = raw.mscale_desc(n, H, W, hq, wq, hm, wm, hl, wl, nheads, 1.0, ocr_alpha, sup_wt, ignore_index, kind)
         lo_attn = lo["attn"].logits
         mid, mid_sup = raw.mscale_mid_fwd(d, lo["cls"].logits, lo["aux"].logits, lo_attn)
     else:
-        d = raw.mscale_desc(n, H, W, hq, wq, 0, 0, 0, 0, nheads, 1.0, ocr_alpha, 0.0, ignore_index)
+        d = raw.mscale_desc(n, H, W, hq, wq, 0, 0, 0, 0, nheads, 1.0, ocr_alpha, 0.0, ignore_index, kind)
         mid = mid_sup = None
-    inv_count = raw.count_valid(gts, ignore_index)
+    inv_count = raw.count_valid(gts, ignore_index, plus_one=rmi)
+    dpr = terms = None
+    if rmi:
+        dpr, terms = raw.rmi_head(d, gts, hi["cls"].logits, mid)
     loss, g_hi, g_lo, g_sup = raw.mscale_loss_fwd(d, gts, inv_count, hi["cls"].logits,
-                                                  hi["aux"].logits if nheads > 1 else None, mid, mid_sup)
+                                                  hi["aux"].logits if nheads > 1 else None, mid, mid_sup, dpr, terms)
 
     def loss_bwd():
         d_cls, d_aux = raw.mscale_hi_bwd(d, g_hi)

@@ -29,10 +29,14 @@ def _criterion_kind(criterion):
     """Map the reference criterion object (loss/utils.py:40-67) to the fused loss implementation."""
     if criterion is None:
         return "ce"
+    if isinstance(criterion, str):
+        if criterion in ("ce", "rmi"):
+            return criterion
+        raise NotImplementedError("criterion %r: expected 'ce' or 'rmi'" % criterion)
     name = type(criterion).__name__
-    if name in ("CrossEntropyLoss2d", "CrossEntropyLoss", "str") or criterion == "ce":
+    if name in ("CrossEntropyLoss2d", "CrossEntropyLoss"):
         return "ce"
-    if name == "RMILoss" or criterion == "rmi":
+    if name == "RMILoss":
         return "rmi"
     raise NotImplementedError("criterion %s is outside the B200 hot path (CE and RMI are covered)" % name)
 
@@ -272,8 +276,6 @@ class B200SegModule(nn.Module):
     def _step_body(self, images, gts, drop_mask):
         self._repack()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
-        if self.loss_kind != "ce":
-            raise NotImplementedError("RMI loss kernels are not wired into the fused step yet")
         if getattr(self, "_side_stream", None) is None:
             self._side_stream = torch.cuda.Stream()
         par = self.parallel_scales and self.arch == "ocrnet.HRNet_Mscale"
@@ -293,7 +295,7 @@ class B200SegModule(nn.Module):
         E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream,
                    bstat=self._bstat_views[1] if par else None)
         loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,
-                            self.ignore_index, E_lo=E_lo)
+                            self.ignore_index, E_lo=E_lo, loss_kind=self.loss_kind)
         M.run_backward(E, E_lo)
         self._fold_grads(stem_pads, par)
         if par:

@@ -310,19 +310,46 @@ def bias_grad(dy, C, db):
 
 
 # ----------------------------------------------------------------------------------------------- mscale + loss
-def mscale_desc(n, h, w, hq, wq, hm=0, wm=0, hl=0, wl=0, nheads=2, w0=1.0, w1=0.4, sup_wt=0.0, ignore_index=255):
+RMI_LAMBDA = 0.5   # RMILoss(loss_weight_lambda=0.5), loss/rmi.py:48
+
+
+def mscale_desc(n, h, w, hq, wq, hm=0, wm=0, hl=0, wl=0, nheads=2, w0=1.0, w1=0.4, sup_wt=0.0, ignore_index=255,
+                loss_kind=0):
+    """loss_kind 0: CrossEntropyLoss2d heads; 1: RMILoss criterion (sigmoid BCE heads + RMI on head 0)."""
     d = MscaleDesc()
     d.n, d.h, d.w, d.hq, d.wq, d.hm, d.wm, d.hl, d.wl = n, h, w, hq, wq, hm, wm, hl, wl
     d.nheads, d.w_head0, d.w_head1, d.sup_wt, d.ignore_index = nheads, w0, w1, sup_wt, ignore_index
+    d.loss_kind = loss_kind
     return d
 
 
-def count_valid(labels, ignore_index=255):
+def count_valid(labels, ignore_index=255, plus_one=False):
+    """-> fp32 [1] = 1 / (#valid labels (+1 for the RMILoss normalisation, loss/rmi.py:95))."""
     ws = torch.empty((1,), dtype=torch.int64, device=labels.device)
     inv = torch.empty((1,), dtype=F32, device=labels.device)
-    check(lib().b200seg_count_valid(ptr(labels), labels.numel(), ignore_index, ptr(ws), ptr(inv), stream_ptr()),
-          "count_valid", 2)
+    check(lib().b200seg_count_valid(ptr(labels), labels.numel(), ignore_index, int(plus_one), ptr(ws), ptr(inv),
+                                    stream_ptr()), "count_valid", 2)
     return inv
+
+
+def rmi_head(d, labels, hi_cls, mid):
+    """RMI term of head 0 (loss/rmi.py rmi_lower_bound): -> (dpr fp32 [n,h/4+1,w/4+1,20], rmi_terms fp32 [n*19])."""
+    dev = hi_cls.device
+    n, hp, wp = d.n, d.h // 4 + 1, d.w // 4 + 1
+    L = lib()
+    pr = torch.empty((n, hp, wp, 20), dtype=F32, device=dev)
+    la = torch.empty((n, hp, wp, 20), dtype=F32, device=dev)
+    check(L.b200seg_rmi_pool(ctypes.byref(d), ptr(labels), ptr(hi_cls), ptr(mid), ptr(pr), ptr(la), stream_ptr()),
+          "rmi_pool")
+    nbytes = L.b200seg_rmi_ws_bytes(n)
+    ws = torch.empty((nbytes // 8,), dtype=torch.float64, device=dev)
+    G = torch.empty((n, 19, 180), dtype=torch.float64, device=dev)
+    terms = torch.empty((n * 19,), dtype=F32, device=dev)
+    dpr = torch.empty((n, hp, wp, 20), dtype=F32, device=dev)
+    scale = d.w_head0 * (1.0 - RMI_LAMBDA) / (n * 9.0)
+    check(L.b200seg_rmi_solve_grad(n, d.h, d.w, ptr(pr), ptr(la), scale, ptr(ws), nbytes, ptr(G), ptr(terms), ptr(dpr),
+                                   stream_ptr()), "rmi_solve_grad", 3)
+    return dpr, terms
 
 
 def mscale_mid_fwd(d, lo_cls, lo_aux, lo_attn):
@@ -334,7 +361,7 @@ def mscale_mid_fwd(d, lo_cls, lo_aux, lo_attn):
     return mid, mid_sup
 
 
-def mscale_loss_fwd(d, labels, inv_count, hi_cls, hi_aux, mid, mid_sup):
+def mscale_loss_fwd(d, labels, inv_count, hi_cls, hi_aux, mid, mid_sup, rmi_dpr=None, rmi_terms=None):
     dev = hi_cls.device
     L = lib()
     nb = L.b200seg_mscale_loss_blocks(ctypes.byref(d))
@@ -343,9 +370,10 @@ def mscale_loss_fwd(d, labels, inv_count, hi_cls, hi_aux, mid, mid_sup):
     g_lo = torch.empty((npix, 40), dtype=BF16, device=dev) if d.hm > 0 else None
     g_sup = torch.empty((npix, 40), dtype=BF16, device=dev) if (d.hm > 0 and d.sup_wt != 0.0) else None
     ws = torch.empty((nb * 4,), dtype=F32, device=dev)
-    loss = torch.empty((5,), dtype=F32, device=dev)
+    loss = torch.zeros((8,), dtype=F32, device=dev)   # total, 4 pointwise means, RMI term, 2 pad
     check(L.b200seg_mscale_loss_fwd(ctypes.byref(d), ptr(labels), ptr(inv_count), ptr(hi_cls), ptr(hi_aux), ptr(mid),
-                                    ptr(mid_sup), ptr(g_hi), ptr(g_lo), ptr(g_sup), ptr(ws), ptr(loss), stream_ptr()),
+                                    ptr(mid_sup), ptr(g_hi), ptr(g_lo), ptr(g_sup), ptr(ws), ptr(loss), ptr(rmi_dpr),
+                                    ptr(rmi_terms), rmi_terms.numel() if rmi_terms is not None else 0, stream_ptr()),
           "mscale_loss_fwd", 2)
     return loss, g_hi, g_lo, g_sup
 

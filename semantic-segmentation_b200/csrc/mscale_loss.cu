@@ -20,77 +20,9 @@
 #include "launch.h"
 #include "../../include/b200seg.h"
 #include "vec.cuh"
+#include "mscale_common.cuh"
 
 namespace b200seg {
-
-constexpr int NC = 19;      // classes
-constexpr int LD = 20;      // logits pitch (floats)
-constexpr int MW = 40;      // mid / gradient buffer width
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
-struct Taps {
-  int i00, i01, i10, i11;   // linear pixel indices within the image
-  float w00, w01, w10, w11;
-};
-__device__ __forceinline__ Taps make_taps(int Y, int X, int H, int W, int h, int w) {
-  int y0, y1, x0, x1;
-  float ly, lx;
-  bilinear_src(Y, (float)h / (float)H, h, y0, y1, ly);
-  bilinear_src(X, (float)w / (float)W, w, x0, x1, lx);
-  Taps t;
-  t.i00 = y0 * w + x0; t.i01 = y0 * w + x1; t.i10 = y1 * w + x0; t.i11 = y1 * w + x1;
-  const float hy = 1.f - ly, hx = 1.f - lx;
-  t.w00 = hy * hx; t.w01 = hy * lx; t.w10 = ly * hx; t.w11 = ly * lx;
-  return t;
-}
-// PyTorch evaluates h0*(w0*a + w1*b) + h1*(w0*c + w1*d); keep that association.
-__device__ __forceinline__ float tap_eval(const Taps& t, float a, float b, float c, float d, float hy, float ly, float hx,
-                                          float lx) {
-  return hy * (hx * a + lx * b) + ly * (hx * c + lx * d);
-}
-
-struct TapW {   // separable weights kept for the PyTorch association order
-  int y0, y1, x0, x1;
-  float hy, ly, hx, lx;
-};
-__device__ __forceinline__ TapW make_tapw(int Y, int X, int H, int W, int h, int w) {
-  TapW t;
-  bilinear_src(Y, (float)h / (float)H, h, t.y0, t.y1, t.ly);
-  bilinear_src(X, (float)w / (float)W, w, t.x0, t.x1, t.lx);
-  t.hy = 1.f - t.ly; t.hx = 1.f - t.lx;
-  return t;
-}
-__device__ __forceinline__ float interp(const TapW& t, const float* __restrict__ base, int w, int ld, int c) {
-  const float a = base[((size_t)t.y0 * w + t.x0) * ld + c], b = base[((size_t)t.y0 * w + t.x1) * ld + c];
-  const float cc = base[((size_t)t.y1 * w + t.x0) * ld + c], d = base[((size_t)t.y1 * w + t.x1) * ld + c];
-  return t.hy * (t.hx * a + t.lx * b) + t.ly * (t.hx * cc + t.lx * d);
-}
-
-// adjoint helpers: fine index range that can touch coarse index y, and the weight of coarse y for fine Y
-__device__ __forceinline__ void adj_range(int y, int h, int H, int& lo, int& hi) {
-  const float r = (float)H / (float)h;
-  lo = (int)floorf(r * (y - 1)) - 1;
-  hi = (int)ceilf(r * (y + 2)) + 1;
-  if (y == 0 || lo < 0) lo = 0;
-  if (y == h - 1 || hi > H) hi = H;
-}
-__device__ __forceinline__ float adj_weight(int Y, int y, int h, int H) {
-  int y0, y1;
-  float l;
-  bilinear_src(Y, (float)h / (float)H, h, y0, y1, l);
-  return (y0 == y ? 1.f - l : 0.f) + (y1 == y ? l : 0.f);
-}
-
-struct MsGeom {
-  int N, H, W;        // full resolution (labels)
-  int Hq, Wq;         // hi-pass quarter maps
-  int Hm, Wm;         // mid grid (= lo-pass input size); 0 when there is no lo pass
-  int Hl, Wl;         // lo-pass quarter maps
-  int nheads;         // 1 (cls only) or 2 (cls, aux)
-  float w_head0, w_head1, sup_wt;
-  int ignore_index;
-};
 
 // ------------------------------------------------------------------------------------------------ mid_fwd
 __global__ void __launch_bounds__(256)
@@ -147,6 +79,24 @@ __device__ __forceinline__ float ce_grad(float (&J)[NC], int label, bool valid, 
   return valid ? nll : 0.f;
 }
 
+// RMILoss criterion, pointwise part (loss/rmi.py:88-96): binary cross-entropy with logits against the one-hot target,
+// summed over the 19 classes of a valid pixel; overwrites J with (sigmoid - onehot) * coef. P (optional) receives sigmoid.
+__device__ __forceinline__ float bce_grad(float (&J)[NC], int label, bool valid, float coef, float* P) {
+  float loss = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float z = J[c];
+    const float y = c == label ? 1.f : 0.f;
+    const float sp = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
+    const float pr = sigmoidf_(z);
+    if (P) P[c] = pr;
+    loss += sp;
+    J[c] = valid ? (pr - y) * coef : 0.f;
+  }
+  return valid ? loss : 0.f;
+}
+constexpr float kRmiLambda = 0.5f;     // cfg.LOSS / RMILoss(loss_weight_lambda=0.5), loss/rmi.py:48
+
 __device__ __forceinline__ void store_row40(__nv_bfloat16* dst, const float (&a)[NC], const float (&b)[NC], float e38,
                                             float e39) {
   float v[MW];
@@ -168,10 +118,12 @@ __global__ void __launch_bounds__(128)
 loss_fwd_kernel(const MsGeom g, const long long* __restrict__ labels, const float* __restrict__ inv_count,
                 const float* __restrict__ hi_cls, const float* __restrict__ hi_aux, const float* __restrict__ M,
                 const float* __restrict__ M2, __nv_bfloat16* __restrict__ Ghi, __nv_bfloat16* __restrict__ Glo,
-                __nv_bfloat16* __restrict__ Gsup, float* __restrict__ partial) {
+                __nv_bfloat16* __restrict__ Gsup, float* __restrict__ partial, const float* __restrict__ rmi_dpr,
+                int Hp, int Wp) {
   pdl_sync();
   const long long total = (long long)g.N * g.H * g.W;
   const bool has_lo = g.Hm > 0;
+  const bool rmi = g.loss_kind == 1;
   const float icnt = *inv_count;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -211,9 +163,22 @@ loss_fwd_kernel(const MsGeom g, const long long* __restrict__ labels, const floa
 #pragma unroll
       for (int c = 0; c < NC; ++c) { Jc[c] = hc[c]; Ja[c] = ha[c]; }
     }
-    acc[0] += ce_grad(Jc, label, valid, g.w_head0 * icnt);
-    if (g.nheads > 1) acc[1] += ce_grad(Ja, label, valid, g.w_head1 * icnt);
-    else {
+    if (rmi) {
+      // head 0: lambda * BCE + (1 - lambda) * RMI; the RMI gradient arrives per 4x4 pooling cell (rmi_loss.cu):
+      // d probs / d z = mask * p (1 - p), avg-pool adjoint = 1/16 (loss/rmi.py:99-111)
+      float P[NC];
+      acc[0] += bce_grad(Jc, label, valid, g.w_head0 * kRmiLambda * icnt, P);
+      if (rmi_dpr != nullptr && valid) {
+        const float* dp = rmi_dpr + (((size_t)n * Hp + ((Y + 2) >> 2)) * Wp + ((X + 2) >> 2)) * LD;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) Jc[c] += dp[c] * 0.0625f * P[c] * (1.f - P[c]);
+      }
+      if (g.nheads > 1) acc[1] += bce_grad(Ja, label, valid, g.w_head1 * icnt, nullptr);   // aux head: do_rmi=False
+    } else {
+      acc[0] += ce_grad(Jc, label, valid, g.w_head0 * icnt);
+      if (g.nheads > 1) acc[1] += ce_grad(Ja, label, valid, g.w_head1 * icnt);
+    }
+    if (g.nheads <= 1) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) Ja[c] = 0.f;
     }
@@ -232,13 +197,13 @@ loss_fwd_kernel(const MsGeom g, const long long* __restrict__ labels, const floa
       float S[NC];
 #pragma unroll
       for (int c = 0; c < NC; ++c) S[c] = hc[c];
-      acc[3] += ce_grad(S, label, valid, g.sup_wt * icnt);
+      acc[3] += rmi ? bce_grad(S, label, valid, g.sup_wt * icnt, nullptr) : ce_grad(S, label, valid, g.sup_wt * icnt);
 #pragma unroll
       for (int c = 0; c < NC; ++c) gh[c] += S[c];
       if (has_lo) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) S[c] = interp(tm, M2 + imm * LD, g.Wm, LD, c);
-        acc[2] += ce_grad(S, label, valid, g.sup_wt * icnt);
+        acc[2] += rmi ? bce_grad(S, label, valid, g.sup_wt * icnt, nullptr) : ce_grad(S, label, valid, g.sup_wt * icnt);
         float z[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) z[c] = 0.f;
@@ -264,7 +229,8 @@ loss_fwd_kernel(const MsGeom g, const long long* __restrict__ labels, const floa
 
 // loss = icnt * (w0*s0 + w1*s1 + sup*(s2 + s3)); also returns the four mean NLLs
 __global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ inv_count,
-                                     float w0, float w1, float sup, float* __restrict__ out) {
+                                     float w0, float w1, float sup, float* __restrict__ out,
+                                     const float* __restrict__ rmi_terms, int n_rmi) {
   pdl_sync();
   __shared__ double s[4][32];
   double a[4] = {0, 0, 0, 0};
@@ -277,8 +243,11 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblo
     for (int k = 0; k < 4; ++k)
       for (int i = 0; i < 32; ++i) t[k] += s[k][i];
     const double ic = (double)*inv_count;
-    out[0] = (float)(ic * (w0 * t[0] + w1 * t[1] + sup * (t[2] + t[3])));
+    double r = 0.0;                          // (1 - lambda) * w0 * sum_c mean_n(rmi_nc) / 9, already scaled per term
+    for (int i = 0; i < n_rmi; ++i) r += (double)rmi_terms[i];
+    out[0] = (float)(ic * (w0 * t[0] + w1 * t[1] + sup * (t[2] + t[3])) + r);
     for (int k = 0; k < 4; ++k) out[1 + k] = (float)(ic * t[k]);
+    out[5] = (float)r;
   }
 }
 
@@ -292,9 +261,11 @@ __global__ void count_valid_kernel(const long long* __restrict__ labels, long lo
   for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);   // integer: order independent
 }
-__global__ void inv_count_kernel(const unsigned long long* __restrict__ counter, float* __restrict__ inv_count) {
+__global__ void inv_count_kernel(const unsigned long long* __restrict__ counter, float* __restrict__ inv_count,
+                                 int plus_one) {
   pdl_sync();
-  *inv_count = 1.f / (float)(*counter);    // mean over non-ignored pixels; all-ignored -> inf/NaN like the reference
+  // CE: mean over non-ignored pixels (all-ignored -> inf/NaN like the reference); RMILoss: sum / (valid + 1), rmi.py:95
+  *inv_count = 1.f / ((float)(*counter) + (plus_one ? 1.f : 0.f));
 }
 
 // ------------------------------------------------------------------------------------------------ hi_bwd
@@ -498,14 +469,6 @@ static inline int blocks_for(long long total, int threads) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-static MsGeom to_geom(const b200seg_mscale_desc* d) {
-  MsGeom g;
-  g.N = d->n; g.H = d->h; g.W = d->w; g.Hq = d->hq; g.Wq = d->wq; g.Hm = d->hm; g.Wm = d->wm; g.Hl = d->hl; g.Wl = d->wl;
-  g.nheads = d->nheads; g.w_head0 = d->w_head0; g.w_head1 = d->w_head1; g.sup_wt = d->sup_wt;
-  g.ignore_index = d->ignore_index;
-  return g;
-}
-
 }  // namespace b200seg
 
 using namespace b200seg;
@@ -520,15 +483,16 @@ extern "C" int32_t b200seg_mscale_loss_blocks(const b200seg_mscale_desc* d) {
   return blocks_for((long long)d->n * d->h * d->w, 128);
 }
 
-extern "C" int b200seg_count_valid(const int64_t* labels, int64_t total, int32_t ignore_index, uint64_t* counter_ws,
-                                   float* inv_count, void* stream) {
+extern "C" int b200seg_count_valid(const int64_t* labels, int64_t total, int32_t ignore_index, int32_t plus_one,
+                                   uint64_t* counter_ws, float* inv_count, void* stream) {
   if (!labels || !counter_ws || !inv_count) return B200SEG_E_BADARG;
   cudaError_t e = cudaMemsetAsync(counter_ws, 0, sizeof(uint64_t), (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
   launch_k(count_valid_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const long long*)labels, total,
                                                                               ignore_index,
                                                                               (unsigned long long*)counter_ws);
-  launch_k(inv_count_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (const unsigned long long*)counter_ws, inv_count);
+  launch_k(inv_count_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (const unsigned long long*)counter_ws, inv_count,
+           (int)plus_one);
   RET_LAUNCH();
 }
 
@@ -542,17 +506,23 @@ extern "C" int b200seg_mscale_mid_fwd(const b200seg_mscale_desc* d, const float*
 extern "C" int b200seg_mscale_loss_fwd(const b200seg_mscale_desc* d, const int64_t* labels, const float* inv_count,
                                        const float* hi_cls, const float* hi_aux, const float* mid, const float* mid_sup,
                                        void* g_hi, void* g_lo, void* g_sup, float* partial_ws, float* loss_out,
+                                       const float* rmi_dpr, const float* rmi_terms, int32_t n_rmi_terms,
                                        void* stream) {
   if (!d || !labels || !inv_count || !hi_cls || !g_hi || !partial_ws || !loss_out) return B200SEG_E_BADARG;
   if (d->nheads > 1 && !hi_aux) return B200SEG_E_BADARG;
   if (d->hm > 0 && (!mid || !g_lo)) return B200SEG_E_BADARG;
   if (d->sup_wt != 0.f && d->hm > 0 && (!mid_sup || !g_sup)) return B200SEG_E_BADARG;
+  if (d->loss_kind != 0 && d->loss_kind != 1) return B200SEG_E_BADARG;
+  if (n_rmi_terms > 0 && !rmi_terms) return B200SEG_E_BADARG;
   const int nb = b200seg_mscale_loss_blocks(d);
+  const int Hp = d->h / 4 + 1, Wp = d->w / 4 + 1;     // avg_pool2d(kernel 4, stride 4, padding 2) output size
   launch_k(loss_fwd_kernel, dim3(nb), dim3(128), 0, (cudaStream_t)stream, to_geom(d), (const long long*)labels, inv_count, hi_cls, hi_aux,
                                                         mid, mid_sup, (__nv_bfloat16*)g_hi, (__nv_bfloat16*)g_lo,
-                                                        (__nv_bfloat16*)g_sup, partial_ws);
-  launch_k(loss_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, partial_ws, nb, inv_count, d->w_head0,
-                                                           d->nheads > 1 ? d->w_head1 : 0.f, d->sup_wt, loss_out);
+                                                        (__nv_bfloat16*)g_sup, partial_ws, rmi_dpr, Hp, Wp);
+  launch_k(loss_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, partial_ws, nb, inv_count,
+           d->loss_kind == 1 ? d->w_head0 * kRmiLambda : d->w_head0,
+                                                           d->nheads > 1 ? d->w_head1 : 0.f, d->sup_wt, loss_out, rmi_terms,
+           (int)n_rmi_terms);
   RET_LAUNCH();
 }
 

@@ -16,18 +16,19 @@ def _mods():
     return O, B200SegModule
 
 
-def _oracle_step(O, arch, hcfg, sd, images, gts, sup_wt=0.0):
+def _oracle_step(O, arch, hcfg, sd, images, gts, sup_wt=0.0, crit=None):
     sd = O.clone_sd(sd)
     for k, v in sd.items():
         if v.is_floating_point() and "running" not in k:
             v.requires_grad_(True)
     ctx = O.Ctx(sd, training=True)
+    crit = crit or O.criterion_ce
     if arch == "ocrnet.HRNet_Mscale":
-        loss = O.mscale_two_scale(ctx, images, gts, hcfg=hcfg, supervised_mscale_wt=sup_wt)
+        loss = O.mscale_two_scale(ctx, images, gts, criterion=crit, hcfg=hcfg, supervised_mscale_wt=sup_wt)
     elif arch == "ocrnet.HRNet":
-        loss = O.ocrnet_forward(ctx, images, gts, hcfg=hcfg)
+        loss = O.ocrnet_forward(ctx, images, gts, criterion=crit, hcfg=hcfg)
     else:
-        loss = O.basic_forward(ctx, images, gts, hcfg=hcfg)
+        loss = O.basic_forward(ctx, images, gts, criterion=crit, hcfg=hcfg)
     loss.backward()
     return sd, float(loss)
 
@@ -72,6 +73,38 @@ def test_train_step_matches_oracle_w16(arch, sup):
         a, b = sd_new[key].cpu(), sd_ref[key]
         assert (a - b).abs().max() <= 3e-2 * b.abs().max() + 1e-4, key
     assert int(sd_new["backbone.bn1.num_batches_tracked"]) == int(sd_ref["backbone.bn1.num_batches_tracked"])
+
+
+@pytest.mark.parametrize("arch,sup", [("ocrnet.HRNet_Mscale", 0.05), ("ocrnet.HRNet", 0.0)])
+def test_train_step_with_rmi_criterion_w16(arch, sup):
+    """The fused step with the RMILoss criterion (scripts/train_cityscapes.yml: rmi_loss: true): loss against the oracle,
+    finite gradients everywhere, CUDA-graph replay equals the eager step."""
+    O, B200SegModule = _mods()
+    torch.set_num_threads(8)
+    hcfg = O.HRNET_W16_TEST
+    sd0 = O.synth_state_dict(arch, hcfg, seed=3)
+    images, gts = O.synth_batch(2, 64, 128, seed=5)
+    _, loss_ref = _oracle_step(O, arch, hcfg, sd0, images, gts, sup, crit=O.criterion_rmi)
+    ocfg = dict(O.OCR_CFG)
+    ocfg["dropout"] = 0.0
+    losses = []
+    for use_graph in (False, True):
+        net = B200SegModule(arch, 19, criterion="rmi", hcfg=hcfg, ocfg=ocfg, supervised_mscale_wt=sup,
+                            use_cuda_graph=use_graph)
+        net.load_state_dict(sd0)
+        net = net.cuda().train()
+        for _ in range(3 if use_graph else 1):       # eager warm-up, capture, replay
+            net.load_state_dict(sd0)                  # same weights / running stats for every call
+            net.zero_grad(set_to_none=True)
+            loss = net({"images": images.cuda(), "gts": gts.cuda()})
+            loss.backward()
+        torch.cuda.synchronize()
+        losses.append(float(loss))
+        for name, p in net.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        assert float(net.last_loss_terms[5]) != 0.0
+    assert abs(losses[0] - loss_ref) <= 3e-2 * abs(loss_ref), (losses, loss_ref)
+    assert abs(losses[0] - losses[1]) <= 1e-4 * abs(losses[0]), losses
 
 
 def test_sgd_on_fixed_batch_tracks_oracle():

@@ -314,3 +314,64 @@ def test_mscale_loss_fwd_bwd(two_scale, sup):
         close(dl_cls[..., :19], leaves[2].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d lo cls")
         close(dl_aux[..., :19], leaves[3].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d lo aux")
         close(dl_attn[..., :1], leaves[4].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d lo attn logit")
+
+
+@pytest.mark.parametrize("two_scale,sup", [(True, 0.0), (True, 0.05), (False, 0.0)])
+def test_rmi_criterion_fwd_bwd(two_scale, sup):
+    """RMILoss criterion (loss/rmi.py) on the blended logits: sigmoid-BCE heads + the region-mutual-information term of
+    the main head, against the oracle's fp64 restatement (pinned to the reference by tests/golden) with autograd."""
+    from oracle import seg_oracle as O
+    raw = _setup()
+    n, H, W = 2, 64, 96
+    hq, wq = H // 4, W // 4
+    hm, wm, hl, wl = (H // 2, W // 2, H // 8, W // 8) if two_scale else (0, 0, 0, 0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    mk = lambda *s: torch.randn(s, generator=g, device="cuda")
+    hi_cls, hi_aux = torch.zeros((n, hq, wq, 20), device="cuda"), torch.zeros((n, hq, wq, 20), device="cuda")
+    hi_cls[..., :19], hi_aux[..., :19] = mk(n, hq, wq, 19) * 2, mk(n, hq, wq, 19) * 2
+    gts = torch.randint(0, 19, (n, H, W), generator=g, device="cuda")
+    gts[:, :5] = 255
+    gts[:, 20:30, 40:50] = 3          # a coherent region: non-trivial label covariance
+    d = raw.mscale_desc(n, H, W, hq, wq, hm, wm, hl, wl, 2, 1.0, 0.4, sup, loss_kind=1)
+    # contiguous NCHW leaves, like the reference network's logits: torch's CUDA avg_pool2d backward gives different
+    # (wrong) gradients for channels-last strided inputs (checked against the CPU and against the closed form)
+    nchw = lambda t: t.permute(0, 3, 1, 2).contiguous().clone().requires_grad_(True)
+    leaves = [nchw(hi_cls[..., :19]), nchw(hi_aux[..., :19])]
+    up = lambda t, size: F.interpolate(t, size=size, mode="bilinear", align_corners=False)
+    crit = lambda t, do_rmi: O.rmi_loss(t, gts, do_rmi=do_rmi)
+    if two_scale:
+        lo_cls, lo_aux = torch.zeros((n, hl, wl, 20), device="cuda"), torch.zeros((n, hl, wl, 20), device="cuda")
+        lo_cls[..., :19], lo_aux[..., :19] = mk(n, hl, wl, 19) * 2, mk(n, hl, wl, 19) * 2
+        lo_attn = mk(n, hl, wl, 1).contiguous()
+        leaves += [nchw(lo_cls[..., :19]), nchw(lo_aux[..., :19]), nchw(lo_attn)]
+        a = up(torch.sigmoid(leaves[4]), (hm, wm))
+        p_lo = up(a * up(leaves[2], (hm, wm)), (H, W))
+        aux_lo = up(a * up(leaves[3], (hm, wm)), (H, W))
+        a_up = up(a, (H, W))
+        joint = p_lo + (1 - a_up) * up(leaves[0], (H, W))
+        joint_aux = aux_lo + (1 - a_up) * up(leaves[1], (H, W))
+        ref = 0.4 * crit(joint_aux, False) + crit(joint, True)
+        if sup:
+            ref = ref + sup * crit(up(up(leaves[2], (hm, wm)), (H, W)), False) + sup * crit(up(leaves[0], (H, W)), False)
+        mid, mid_sup = raw.mscale_mid_fwd(d, lo_cls, lo_aux, lo_attn)
+    else:
+        ref = 0.4 * crit(up(leaves[1], (H, W)), False) + crit(up(leaves[0], (H, W)), True)
+        mid = mid_sup = None
+    ref.backward()
+    inv = raw.count_valid(gts, plus_one=True)
+    dpr, terms = raw.rmi_head(d, gts, hi_cls, mid)
+    loss, g_hi, g_lo, g_sup = raw.mscale_loss_fwd(d, gts, inv, hi_cls, hi_aux, mid, mid_sup, dpr, terms)
+    # the RMI value alone, against the oracle evaluated on the same blended logits
+    with torch.no_grad():
+        jt = joint if two_scale else up(leaves[0], (H, W))
+        rmi_ref = 2.0 * (O.rmi_loss(jt, gts, do_rmi=True) - 0.5 * O.rmi_loss(jt, gts, do_rmi=False)) * 0.5
+    assert abs(float(loss[5]) - float(rmi_ref)) <= 1e-4 * abs(float(rmi_ref)) + 1e-6, (float(loss[5]), float(rmi_ref))
+    assert abs(float(loss[0]) - float(ref)) <= 1e-4 * abs(float(ref)), (float(loss[0]), float(ref))
+    d_cls, d_aux = raw.mscale_hi_bwd(d, g_hi)
+    close(d_cls[..., :19], leaves[0].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d hi cls (rmi)")
+    close(d_aux[..., :19], leaves[1].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d hi aux (bce)")
+    if two_scale:
+        dl_cls, dl_aux, dl_attn = raw.mscale_lo_bwd(d, g_lo, g_sup, lo_cls, lo_aux, lo_attn, mid)
+        close(dl_cls[..., :19], leaves[2].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d lo cls (rmi)")
+        close(dl_aux[..., :19], leaves[3].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d lo aux (bce)")
+        close(dl_attn[..., :1], leaves[4].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d lo attn logit (rmi)")
