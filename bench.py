@@ -15,6 +15,10 @@ import sys
 import threading
 import time
 
+# The SyncBN exchange spins inside kernels of two concurrent streams per GPU: give every stream its own hardware work
+# queue (the default 8 connections can alias streams and turn a peer wait into a false cross-stream dependency).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "semantic-segmentation_b200")):
     if p not in sys.path:
@@ -38,6 +42,7 @@ def parse():
     ap.add_argument("--width", type=int, default=2048)
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--sup-wt", type=float, default=0.0)
+    ap.add_argument("--criterion", default="ce", choices=["ce", "rmi"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -108,50 +113,55 @@ def synth_batch(n, h, w, seed, device):
 
 
 # ------------------------------------------------------------------------------------------------ reference (CPU) arm
-def cpu_reference_step_time(arch, h, w, steps, warmup=1):
+def cpu_reference_step_time(arch, h, w, steps, warmup=1, budget_s=60.0, criterion="ce"):
     """The reference algorithm (oracle/seg_oracle.py, pinned to /root/reference by tests/golden) on the host cores:
-    zero_grad -> two-scale fwd -> bwd -> SGD, fp32. Returns seconds per step at (h, w)."""
+    zero_grad -> two-scale fwd -> bwd -> SGD, fp32, PyTorch's default intra-op thread count (= the cores it can use).
+    Returns (seconds per step at (h, w), timed steps); stops early once `budget_s` of wall clock is spent."""
     from oracle import seg_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
     sd = O.synth_state_dict(arch, O.HRNET_W48, seed=0)
     params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k]
     opt = torch.optim.SGD(params, lr=0.01, momentum=0.9, weight_decay=1e-4)
     images, gts = O.synth_batch(1, h, w, seed=1)
+    crit = O.criterion_rmi if criterion == "rmi" else O.criterion_ce
     times = []
+    t_start = time.perf_counter()
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad()
         ctx = O.Ctx(sd, training=True)
         if arch == "ocrnet.HRNet_Mscale":
-            loss = O.mscale_two_scale(ctx, images, gts)
+            loss = O.mscale_two_scale(ctx, images, gts, criterion=crit)
         else:
-            loss = O.ocrnet_forward(ctx, images, gts)
+            loss = O.ocrnet_forward(ctx, images, gts, criterion=crit)
         loss.backward()
         opt.step()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    return sum(times) / len(times)
+        if times and time.perf_counter() - t_start > budget_s:
+            break
+    return sum(times) / len(times), len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: the full algorithm on a quarter-area crop; crops/s are rescaled by the pixel ratio (cost is
-    # proportional to pixels: every layer is a convolution / pointwise op, SURVEY.md §8d)
-    sh, sw = args.height // 2, args.width // 2
-    sec = cpu_reference_step_time(args.arch, sh, sw, max(1, min(args.steps, 2)), warmup=1 if args.warmup else 0)
+    # bounded sample: the full algorithm on a 256x512 crop (1/16 of the pixels); crops/s are rescaled by the pixel ratio
+    # (cost is proportional to pixels: every layer is a convolution / pointwise op, SURVEY.md §8d)
+    sh, sw = max(64, args.height // 4), max(128, args.width // 4)
+    sec, timed = cpu_reference_step_time(args.arch, sh, sw, max(1, args.steps), warmup=1 if args.warmup else 0,
+                                         budget_s=90.0, criterion=args.criterion)
     ratio = (sh * sw) / float(args.height * args.width)
     value = ratio / sec
     cores = torch.get_num_threads()
     line = dict(metric="1024x2048 crops/sec fwd+bwd HRNet-OCR-MScale", value=value, unit="crops/s", impl="reference",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 / value,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32", data="synthetic",
-                config=dict(workload="%s two-scale train step (fwd+bwd+SGD), %dx%d crop, bs1, CE loss" %
-                            (args.arch, args.height, args.width)),
+                config=dict(workload="%s two-scale train step (fwd+bwd+SGD), %dx%d crop, bs1, %s loss" %
+                            (args.arch, args.height, args.width, args.criterion.upper())),
                 cpu_baseline=dict(value=value, unit="crops/s", cores=cores, kind="port",
-                                  sample="1 warm-up + %d timed steps of the full algorithm at %dx%d (1/4 of the pixels), "
-                                         "rescaled by the pixel ratio" % (max(1, min(args.steps, 2)), sh, sw)),
+                                  sample="%d timed step(s) of the full algorithm at %dx%d (1/%d of the pixels, 90 s "
+                                         "budget), rescaled by the pixel ratio" % (timed, sh, sw, round(1 / ratio))),
                 e2e=dict(value=value, unit="crops/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -182,9 +192,14 @@ def dominant_kernel_roofline(pk):
     t = ms[len(ms) // 2]
     flops = 2.0 * 256 * 512 * 720 * 512 * 9
     achieved = flops / (t * 1e-3) / 1e12
-    return dict(bound="tensor", kernel="conv_igemm_kernel (conv3x3_ocr 720->512 3x3 @256x512, bf16, fp32 accum)",
+    # DRAM traffic of this launch from the committed `ncu --set full` capture (profiles/r1_ncu_full_prof_ocr.txt:
+    # dram__bytes_read.sum 195.6 MB + dram__bytes_write.sum 100.6 MB); algorithmic bytes = in + out + weights in bf16
+    algo_bytes = 2.0 * (256 * 512 * 720 + 256 * 512 * 512 + 512 * 720 * 9)
+    return dict(bound="tensor", kernel="conv3x3_halo_kernel (conv3x3_ocr 720->512 3x3 @256x512, bf16, fp32 accum, "
+                                       "BN statistics in the epilogue)",
                 achieved=achieved, peak=pk["tf_burst"], unit="TFLOP/s", frac=achieved / pk["tf_burst"],
-                peak_source=pk["src"] + " bf16_tflops (burst: kernel timed alone)", ms_per_launch=t, traffic=None)
+                peak_source=pk["src"] + " bf16_tflops (burst: kernel timed alone)", ms_per_launch=t,
+                traffic=296.26e6, traffic_unit="bytes/launch (ncu dram read+write)", algorithmic_bytes=algo_bytes)
 
 
 def run_b200(args):
@@ -201,7 +216,7 @@ def run_b200(args):
     from b200seg import _lib
 
     torch.manual_seed(0)
-    net = B200SegModule(args.arch, 19, criterion=None, supervised_mscale_wt=args.sup_wt,
+    net = B200SegModule(args.arch, 19, criterion=args.criterion, supervised_mscale_wt=args.sup_wt,
                         use_cuda_graph=not args.no_graph).cuda().train()
     net._ddp_allreduce = world > 1
     # well-scaled weights (the reference's default N(0,1e-3) init underflows activations after a few BN-free paths)
@@ -283,8 +298,10 @@ def run_b200(args):
         steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
         config=dict(workload="%s two-scale {0.5,1.0} train step (zero_grad, fused fwd+bwd, grad publish%s, SGD "
-                             "momentum), %dx%d crops, %d crop/GPU, CE loss, BN local to each GPU" %
-                             (args.arch, "+NCCL all-reduce" if world > 1 else "", H, W, B),
+                             "momentum), %dx%d crops, %d crop/GPU, %s loss, %s" %
+                             (args.arch, "+NCCL all-reduce" if world > 1 else "", H, W, B, args.criterion.upper(),
+                              "SyncBN: per-layer statistics exchanged through NVLink peer memory inside the BN "
+                              "finalisers" if world > 1 else "single GPU (BatchNorm over the local batch)"),
                     global_batch=B * world, parallelism="dp%d" % world, cuda_graph=not args.no_graph,
                     l2_policy="per-step working set (>4 GB of activations) far exceeds the 126 MB L2; the "
                               "single-kernel roofline run flushes L2 with a 256 MB write between iterations",
@@ -299,13 +316,13 @@ def run_b200(args):
         roofline=roof, clocks=clocks, last_loss=loss_val)
     if not args.no_cpu_baseline:
         try:
-            sh, sw = 256, 512
-            sec = cpu_reference_step_time(args.arch, sh, sw, 1, warmup=1)
+            sh, sw = 128, 256
+            sec, timed = cpu_reference_step_time(args.arch, sh, sw, 1, warmup=1, budget_s=30.0, criterion=args.criterion)
             ratio = (sh * sw) / float(H * W)
             line["cpu_baseline"] = dict(value=ratio / sec, unit="crops/s", cores=torch.get_num_threads(), kind="port",
-                                        sample="oracle (reference algorithm, fp32, all host threads): 1 warm-up + 1 "
-                                               "timed train step at %dx%d, rescaled by the pixel ratio %.4f" %
-                                               (sh, sw, ratio))
+                                        sample="oracle (reference algorithm, fp32, host threads): 1 warm-up + %d timed "
+                                               "train step at %dx%d, rescaled by the pixel ratio %.5f" %
+                                               (timed, sh, sw, ratio))
         except Exception as e:  # noqa
             line["cpu_baseline"] = dict(value=None, error=repr(e))
     print(json.dumps(line), flush=True)

@@ -111,13 +111,38 @@ int b200seg_grad_fold(float* dst, float* acc_a, float* acc_b, const b200seg_grad
  * Training-mode BatchNorm around the convolutions. Replaces cuDNN/Apex BN behind Norm2d (network/mynn.py:18-24),
  * in-place ReLU (network/hrnetv2.py:28,44) and the residual add (network/hrnetv2.py:63-64,103-104).
  * ------------------------------------------------------------------------------------------------ */
+/* SyncBN (apex.parallel.SyncBatchNorm behind Norm2d, config.py:216-225; collective C2 of SURVEY.md §2b): optional
+ * cross-GPU exchange fused into the two finalisers. Every rank owns a mailbox (fp64) and a flag array (uint32) that all
+ * peers of the node can write through NVLink (b200seg_p2p_*). NULL or world <= 1: per-GPU statistics.
+ *   mail layout : [parity 2][exchange][rank][2][c] doubles  (parity = step & 1, parity_stride doubles per half)
+ *   flag layout : [exchange][rank][ceil(c/32)] uint32, written with the step number (release), polled (acquire)
+ * Every rank must issue the same sequence of exchanges with the same offsets; *step is read on the device and must be
+ * incremented by the caller once per training step (inside the captured graph). */
+typedef struct b200seg_bn_sync {
+  const void* mail_peers;   /* device array [world] of double*: mailbox base of every rank as mapped on this rank */
+  const void* flag_peers;   /* device array [world] of uint32_t*: flag base of every rank as mapped on this rank */
+  const void* step;         /* device uint32_t* step counter */
+  int64_t mail_offset;      /* offset of this exchange inside a parity half, in doubles */
+  int64_t parity_stride;    /* doubles per parity half */
+  int32_t flag_offset;      /* offset of this exchange in the flag array */
+  int32_t world, rank;
+  int32_t reserved;
+} b200seg_bn_sync;
+/* Peer-mappable device memory for the SyncBN mailboxes: the ONLY allocations the library performs (a communicator
+ * owns its buffers). alloc: cudaMalloc + zero + CUDA IPC handle (64 bytes) to hand to the other ranks of the node;
+ * open: map a peer's buffer (lazy peer access over NVLink); close / free release them. */
+int b200seg_p2p_alloc(size_t bytes, void** dev_ptr, uint8_t* handle64);
+int b200seg_p2p_open(const uint8_t* handle64, void** dev_ptr);
+int b200seg_p2p_close(void* dev_ptr);
+int b200seg_p2p_free(void* dev_ptr);
+
 /* partials[grid][2][cpad] (conv epilogue) -> scale = gamma*invstd, shift = beta - mean*scale, saved mean/invstd;
  * running stats updated with `momentum` (unbiased variance), num_batches_tracked += 1 (all optional);
  * batch_stats_out (optional) receives [mean c | unbiased var c] for a deferred b200seg_bn_running_update. */
 int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t c, int32_t cpad, float count, const float* gamma,
                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                         int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
-                        float* batch_stats_out, void* stream);
+                        float* batch_stats_out, const b200seg_bn_sync* sync, void* stream);
 /* Momentum update of every BatchNorm layer's running statistics in one launch: running / batch_pass* are flat fp32
  * buffers of n elements with one layout ([mean c | var c] per layer); pass 0 is applied before pass 1 (the order of
  * the two _fwd calls in network/ocrnet.py:278-281); batch_pass1 may be NULL. num_batches_tracked[n_layers] += n_passes
@@ -143,7 +168,7 @@ int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* mask, int32
                           int32_t c, float* partials, void* stream);
 /* dgamma += sum g*xhat, dbeta += sum g (accumulating), c1 = sum g / count, c2 = sum g*xhat / count */
 int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int32_t c, float count, float* dgamma, float* dbeta,
-                            float* c1, float* c2, void* stream);
+                            float* c1, float* c2, const b200seg_bn_sync* sync, void* stream);
 /* dy = gamma*invstd*(g - c1 - xhat*c2); optionally g_out (=|+=) g for the residual / identity branch */
 int b200seg_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld, const float* post_scale,
                          const void* y, int32_t y_ld, const float* mean, const float* invstd, const float* gamma,

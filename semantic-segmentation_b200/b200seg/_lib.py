@@ -40,6 +40,12 @@ class MscaleDesc(ctypes.Structure):
                 ("loss_kind", c_int32), ("reserved", c_int32)]
 
 
+class BnSync(ctypes.Structure):
+    _fields_ = [("mail_peers", c_void_p), ("flag_peers", c_void_p), ("step", c_void_p), ("mail_offset", c_int64),
+                ("parity_stride", c_int64), ("flag_offset", c_int32), ("world", c_int32), ("rank", c_int32),
+                ("reserved", c_int32)]
+
+
 class ProbeOperand(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "rows", "cols", "box_cols", "box_rows", "nboxes", "c0", "r0", "dcol", "drow", "smem_stride",
@@ -68,14 +74,19 @@ SIGNATURES = {
     "b200seg_conv2d_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, I32, V, V, c_size_t, V]),
     "b200seg_grad_fold_chunk": (I32, []),
     "b200seg_grad_fold": (ctypes.c_int, [V, V, V, V, V, V, I32, I32, V]),
-    "b200seg_bn_finalize": (ctypes.c_int, [V, I32, I32, I32, F, V, V, F, F, V, V, V, V, V, V, V, V, V]),
+    "b200seg_bn_finalize": (ctypes.c_int, [V, I32, I32, I32, F, V, V, F, F, V, V, V, V, V, V, V, V,
+                                           ctypes.POINTER(BnSync), V]),
+    "b200seg_p2p_alloc": (ctypes.c_int, [c_size_t, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_uint8)]),
+    "b200seg_p2p_open": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(c_void_p)]),
+    "b200seg_p2p_close": (ctypes.c_int, [V]),
+    "b200seg_p2p_free": (ctypes.c_int, [V]),
     "b200seg_bn_running_update": (ctypes.c_int, [V, V, V, I64, F, V, I32, I32, V]),
     "b200seg_accum_f32": (ctypes.c_int, [V, V, I64, V]),
     "b200seg_bn_eval_params": (ctypes.c_int, [I32, V, V, F, V, V, V, V, V]),
     "b200seg_bn_apply": (ctypes.c_int, [V, I32, V, V, V, I32, V, I32, V, I32, I64, I32, I32, V]),
     "b200seg_bn_bwd_grid": (I32, [I64, I32]),
     "b200seg_bn_bwd_reduce": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, I64, I32, I32, V, V]),
-    "b200seg_bn_bwd_finalize": (ctypes.c_int, [V, I32, I32, F, V, V, V, V, V]),
+    "b200seg_bn_bwd_finalize": (ctypes.c_int, [V, I32, I32, F, V, V, V, V, ctypes.POINTER(BnSync), V]),
     "b200seg_bn_bwd_apply": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, V, V, V, V, I32, V, I32, I32, I64, I32,
                                             I32, V]),
     "b200seg_masked_accum": (ctypes.c_int, [V, I32, V, I32, V, I32, I32, I64, I32, V]),

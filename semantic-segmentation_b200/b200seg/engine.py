@@ -41,13 +41,15 @@ class HeadRec:
 
 
 class Engine:
-    def __init__(self, params, grads, packed, training, drop_mask=None, side_stream=None, bstat=None, stream=None):
+    def __init__(self, params, grads, packed, training, drop_mask=None, side_stream=None, bstat=None, stream=None,
+                 sync=None, pass_id=0):
         """params: name -> tensor (weights, BN buffers); grads: name -> fp32 tensor accumulated into (training);
         packed: name -> (w_fwd, w_dgrad) bf16 operand caches; drop_mask: fp32 [N, mid] post-ReLU multiplier;
         bstat: BN layer name -> fp32 [2*C] slot receiving the batch [mean | unbiased var] (the running statistics are
         then updated once per step by bn_running_update; without it bn_finalize updates them in place);
         stream: the stream this engine's program is enqueued on when it runs concurrently with another engine (the
-        low-resolution pass of the two-scale step), None = the caller's current stream."""
+        low-resolution pass of the two-scale step), None = the caller's current stream;
+        sync / pass_id: SyncBNContext (p2p.py) and this engine's pass index in its exchange table (data parallel)."""
         self.p = params
         self.g = grads
         self.packed = packed
@@ -55,6 +57,8 @@ class Engine:
         self.drop_mask = drop_mask
         self.bstat = bstat
         self.stream = stream
+        self.sync = sync
+        self.pass_id = pass_id
         self.tape = []
         self.bn_seen = set()
         self.hold = []      # tensors handed across streams: kept alive until the step's final join
@@ -115,11 +119,12 @@ class Engine:
             if self.bstat is not None:
                 self.bn_seen.add(bname)
                 par = raw.bn_finalize(stats, n * ho * wo, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
-                                      BN_MOMENTUM, None, None, None, rec.cout, batch_out=self.bstat[bname])
+                                      BN_MOMENTUM, None, None, None, rec.cout, batch_out=self.bstat[bname],
+                                      sync=self._sync(bname, 0))
             else:
                 par = raw.bn_finalize(stats, n * ho * wo, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
                                       BN_MOMENTUM, self.p[bname + ".running_mean"], self.p[bname + ".running_var"],
-                                      self.p[bname + ".num_batches_tracked"], rec.cout)
+                                      self.p[bname + ".num_batches_tracked"], rec.cout, sync=self._sync(bname, 0))
             rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], par[2], par[3]
         else:
             y = raw.conv2d_fwd(x.t, w_f, b, stride=stride)
@@ -129,11 +134,14 @@ class Engine:
         rec.y = y
         return rec
 
+    def _sync(self, bname, direction):
+        return self.sync.args(self.pass_id, bname, direction) if self.sync is not None else None
+
     def rec_backward(self, rec, dz, mask, post_scale=None, g_out=None, g_accumulate=False):
         """Backward of BN(conv(x)) given the gradient w.r.t. the BN output (dz, optionally ReLU-masked by `mask`)."""
         dy = raw.bn_bwd(dz, mask, post_scale, rec.y, rec.mean, rec.invstd, self.p[rec.bname + ".weight"],
                         self.g[rec.bname + ".weight"], self.g[rec.bname + ".bias"], g_out=g_out,
-                        g_accumulate=g_accumulate)
+                        g_accumulate=g_accumulate, sync=self._sync(rec.bname, 1))
         x = rec.x
         self.wgrad(x.t, dy, self.g[rec.cname + ".weight"], rec.cout, rec.ksize, rec.stride)
         # a conv bias in front of a training-mode BN has an exactly zero gradient (BN removes the mean): left at 0

@@ -74,7 +74,7 @@ class _PublishGrads(torch.autograd.Function):
 class B200SegModule(nn.Module):
     def __init__(self, arch, num_classes=19, criterion=None, hcfg=None, ocfg=None, lo_scale=0.5, ocr_alpha=0.4,
                  supervised_mscale_wt=0.0, ignore_index=255, n_scales=None, use_cuda_graph=True,
-                 parallel_scales=True):
+                 parallel_scales=True, syncbn=None):
         super().__init__()
         self.arch = arch
         self.criterion = criterion
@@ -87,6 +87,10 @@ class B200SegModule(nn.Module):
         self.n_scales = n_scales
         self.use_cuda_graph = use_cuda_graph
         self.parallel_scales = parallel_scales     # run the 0.5x and 1.0x passes of the two-scale step concurrently
+        # SyncBN (config.py:216-225, every scripts/*.yml sets syncbn: true): None = on whenever the data-parallel
+        # all-reduce is on (torch.distributed initialised, world > 1), False = per-GPU statistics
+        self.syncbn = syncbn
+        self._sync = None
         self._run_flat = None
         self._specs = A.tensor_specs(arch, self.hcfg, self.ocfg)
         self._build_parameters()
@@ -273,8 +277,28 @@ class B200SegModule(nn.Module):
         finally:
             self.kernels_per_step = _lib.KERNEL_LAUNCHES - launches0   # same count when the captured graph replays
 
+    def _sync_context(self):
+        """Lazily builds the SyncBN mailboxes (collective: every rank must reach its first training step)."""
+        want = self.syncbn
+        if want is None:
+            want = self._ddp_allreduce
+        if not want:
+            return None
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+            return None
+        if self._sync is None:
+            from .p2p import SyncBNContext
+            chans = {n[: -len(".running_mean")]: shp[0] for n, shp, k in self._specs if k == "bn_rm"}
+            self._sync = SyncBNContext(chans, n_passes=2 if self.arch == "ocrnet.HRNet_Mscale" else 1)
+            self._graphs = {}
+        return self._sync
+
     def _step_body(self, images, gts, drop_mask):
         self._repack()
+        sync = self._sync
+        if sync is not None:
+            sync.advance()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
         if getattr(self, "_side_stream", None) is None:
             self._side_stream = torch.cuda.Stream()
@@ -291,9 +315,12 @@ class B200SegModule(nn.Module):
             grads_lo, stem_pad_lo = self._engine_grads("lo")
             stem_pads.append(stem_pad_lo)
             E_lo = Engine(tensors, grads_lo, self._packed, True, drop_mask, side_stream=self._side_stream_lo,
-                          bstat=self._bstat_views[0], stream=self._lo_stream)
+                          bstat=self._bstat_views[0], stream=self._lo_stream, sync=sync, pass_id=0)
+        two_pass = self.arch == "ocrnet.HRNet_Mscale"
+        if sync is not None and two_pass and not par:
+            raise RuntimeError("SyncBN needs parallel_scales=True for the two-scale step (one engine per pass)")
         E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream,
-                   bstat=self._bstat_views[1] if par else None)
+                   bstat=self._bstat_views[1] if par else None, sync=sync, pass_id=1 if two_pass else 0)
         loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,
                             self.ignore_index, E_lo=E_lo, loss_kind=self.loss_kind)
         M.run_backward(E, E_lo)
@@ -316,6 +343,7 @@ class B200SegModule(nn.Module):
 
     def _train_forward(self, images, gts):
         self._ensure_device_state()
+        self._sync_context()
         images = images.contiguous().float()
         gts = gts.contiguous().long()
         key = (tuple(images.shape), str(images.device))

@@ -149,14 +149,19 @@ def grad_fold(dst, acc_a, acc_b, table, clear=True):
 
 
 # ----------------------------------------------------------------------------------------------- batch norm
-def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, c, batch_out=None):
+def _sync_ref(sync):
+    return ctypes.byref(sync) if sync is not None else None
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, c, batch_out=None, sync=None):
     """batch_out (fp32 [2*c], optional): receives [mean | unbiased var] for a deferred bn_running_update; pass
-    running_mean = running_var = nbt = None with it."""
+    running_mean = running_var = nbt = None with it. sync (BnSync, optional): SyncBN exchange descriptor."""
     buf, grid, cpad = stats
     out = torch.empty((4, c), dtype=F32, device=buf.device)   # scale, shift, mean, invstd
     check(lib().b200seg_bn_finalize(ptr(buf), grid, c, cpad, float(count), ptr(gamma), ptr(beta), eps, momentum,
                                     ptr(running_mean), ptr(running_var), ptr(nbt), ptr(out[0]), ptr(out[1]),
-                                    ptr(out[2]), ptr(out[3]), ptr(batch_out), stream_ptr()), "bn_finalize")
+                                    ptr(out[2]), ptr(out[3]), ptr(batch_out), _sync_ref(sync), stream_ptr()),
+          "bn_finalize")
     return out
 
 
@@ -189,7 +194,8 @@ def bn_apply(y, scale, shift, res=None, post_scale=None, relu=True, out=None):
     return out
 
 
-def bn_bwd(dz, mask, post_scale, y, mean, invstd, gamma, dgamma, dbeta, g_out=None, g_accumulate=False, dy_out=None):
+def bn_bwd(dz, mask, post_scale, y, mean, invstd, gamma, dgamma, dbeta, g_out=None, g_accumulate=False, dy_out=None,
+           sync=None):
     """Returns dy (gradient w.r.t. the BN input). dgamma/dbeta (fp32 views) are accumulated into."""
     n, h, w, c = y.shape
     npix = n * h * w
@@ -201,7 +207,7 @@ def bn_bwd(dz, mask, post_scale, y, mean, invstd, gamma, dgamma, dbeta, g_out=No
                                   stream_ptr()), "bn_bwd_reduce")
     cc = torch.empty((2, c), dtype=F32, device=y.device)
     check(L.b200seg_bn_bwd_finalize(ptr(partials), grid, c, float(npix), ptr(dgamma), ptr(dbeta), ptr(cc[0]),
-                                    ptr(cc[1]), stream_ptr()), "bn_bwd_finalize")
+                                    ptr(cc[1]), _sync_ref(sync), stream_ptr()), "bn_bwd_finalize")
     dy = dy_out if dy_out is not None else torch.empty((n, h, w, c), dtype=BF16, device=y.device)
     check(L.b200seg_bn_bwd_apply(ptr(dz), _ld(dz), ptr(mask), _ld(mask) if mask is not None else 0, ptr(post_scale),
                                  ptr(y), _ld(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(cc[0]), ptr(cc[1]), ptr(dy),

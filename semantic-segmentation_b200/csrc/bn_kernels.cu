@@ -10,6 +10,7 @@
 #include "launch.h"
 #include "../../include/b200seg.h"
 #include "vec.cuh"
+#include <cstring>
 
 namespace b200seg {
 
@@ -34,14 +35,84 @@ __device__ __forceinline__ void fold_rows(const float* __restrict__ partials, in
   }
 }
 
+// ---------------------------------------------------------------- SyncBN exchange over NVLink peer memory
+// Replaces apex.parallel.SyncBatchNorm's per-layer all_gather / all_reduce (SURVEY.md §2b collective C2, config.py:216-225)
+// with a one-shot exchange fused into the finalisers: every rank stores its two per-channel sums (fp64) straight into
+// every peer's mailbox (P2P stores through NVSwitch), publishes a step-numbered flag with release semantics, waits for
+// the flags of all ranks in its OWN mailbox and folds the ranks in rank order (bitwise identical result on every GPU).
+// mail[parity][exchange][rank][2][C] doubles; flags[exchange][rank][block] uint32 (monotonic step numbers).
+struct SyncArgs {
+  double* const* mail_peers;      // device array [world] of every rank's mailbox base (own entry = local pointer)
+  unsigned* const* flag_peers;    // device array [world] of every rank's flag base
+  const unsigned* step;           // device step counter (incremented once per training step)
+  long long mail_off;             // this exchange's offset inside one parity half, in doubles
+  long long parity_stride;        // doubles per parity half
+  int flag_off;                   // this exchange's offset in the flag array
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by ALL threads of a finaliser block (blockDim = 32 channels x kFinSlices); threads with slice == 0 and c < C
+// carry the local sums in (s1, s2) and receive the global sums.
+__device__ __forceinline__ void sync_exchange(const SyncArgs& sy, int C, int c, int slice, double& s1, double& s2) {
+  const unsigned step = *sy.step;
+  const long long base = (long long)(step & 1u) * sy.parity_stride + sy.mail_off;
+  const bool owner = slice == 0 && c < C;
+  if (owner) {
+    for (int r = 0; r < sy.world; ++r) {
+      double* dst = sy.mail_peers[r] + base + (long long)sy.rank * 2 * C;
+      dst[c] = s1;
+      dst[C + c] = s2;
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int nblk = gridDim.x;
+  if (threadIdx.x == 0)
+    for (int r = 0; r < sy.world; ++r)
+      st_release_sys(sy.flag_peers[r] + sy.flag_off + sy.rank * nblk + blockIdx.x, step);
+  if (owner) {
+    const unsigned* myflags = sy.flag_peers[sy.rank] + sy.flag_off + blockIdx.x;
+    const double* mymail = sy.mail_peers[sy.rank] + base;
+    double t1 = 0.0, t2 = 0.0;
+    for (int r = 0; r < sy.world; ++r) {
+      unsigned spins = 0;
+      while (ld_acquire_sys(myflags + r * nblk) != step) {
+        if (++spins > (1u << 30)) __trap();       // a lost peer traps instead of hanging the GPU
+      }
+      t1 += ld_volatile_f64(mymail + (long long)r * 2 * C + c);
+      t2 += ld_volatile_f64(mymail + (long long)r * 2 * C + C + c);
+    }
+    s1 = t1;
+    s2 = t2;
+  }
+}
+
 __global__ void __launch_bounds__(32 * kFinSlices)
 bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int Cpad, float count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out, float* __restrict__ batch_stats_out) {
-  pdl_sync();
+                                   float* __restrict__ invstd_out, float* __restrict__ batch_stats_out,
+                                   const SyncArgs sy) {
+  // Dependents are released only AFTER the cross-GPU exchange: a successor that became resident early (PDL) would hold
+  // its SMs / TMEM while this kernel spins on a peer, and two ranks doing that on different streams deadlock.
+  pdl_wait();
+  if (sy.world <= 1) pdl_launch();
   // block = 32 channels x 16 slices of the G partial rows (coalesced 128-byte reads, four independent rows in flight per
   // thread: the kernel is a pure latency chain otherwise), then a fixed-order fold -> deterministic
   __shared__ double sh1[kFinSlices][32], sh2[kFinSlices][32];
@@ -53,9 +124,15 @@ bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int Cpad, f
   sh1[slice][lane] = a1;
   sh2[slice][lane] = a2;
   __syncthreads();
-  if (slice != 0 || c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < kFinSlices; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
+  if (slice == 0 && c < C)
+    for (int k = 0; k < kFinSlices; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
+  if (sy.world > 1) {            // SyncBN: statistics of the global batch (equal pixel counts on every rank)
+    sync_exchange(sy, C, c, slice, s1, s2);
+    count *= (float)sy.world;
+    pdl_launch();
+  }
+  if (slice != 0 || c >= C) return;
   const double mean = s1 / count;
   double var = s2 / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -211,8 +288,9 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv
 __global__ void __launch_bounds__(32 * kFinSlices)
 bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, float count,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
-                       float* __restrict__ c2) {
-  pdl_sync();
+                       float* __restrict__ c2, const SyncArgs sy) {
+  pdl_wait();                       // see bn_finalize_kernel: dependents are released after the exchange
+  if (sy.world <= 1) pdl_launch();
   __shared__ double sh1[kFinSlices][32], sh2[kFinSlices][32];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -221,11 +299,19 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, float c
   sh1[slice][lane] = a1;
   sh2[slice][lane] = a2;
   __syncthreads();
-  if (slice != 0 || c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < kFinSlices; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
-  if (dbeta) dbeta[c] += (float)s1;     // parameter gradients accumulate (two scale passes share the weights)
-  if (dgamma) dgamma[c] += (float)s2;
+  if (slice == 0 && c < C) {
+    for (int k = 0; k < kFinSlices; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
+    // parameter gradients stay LOCAL sums (the data-parallel gradient all-reduce averages them like every other grad)
+    if (dbeta) dbeta[c] += (float)s1;
+    if (dgamma) dgamma[c] += (float)s2;
+  }
+  if (sy.world > 1) {            // SyncBN backward: the mean terms run over the global batch
+    sync_exchange(sy, C, c, slice, s1, s2);
+    count *= (float)sy.world;
+    pdl_launch();
+  }
+  if (slice != 0 || c >= C) return;
   c1[c] = (float)(s1 / count);
   c2[c] = (float)(s2 / count);
 }
@@ -323,6 +409,22 @@ static inline int ew_grid(long long total_threads) {
 
 using namespace b200seg;
 
+static int make_sync(const b200seg_bn_sync* s, SyncArgs* out) {
+  SyncArgs sy;
+  sy.mail_peers = nullptr; sy.flag_peers = nullptr; sy.step = nullptr;
+  sy.mail_off = 0; sy.parity_stride = 0; sy.flag_off = 0; sy.world = 1; sy.rank = 0;
+  if (s && s->world > 1) {
+    if (!s->mail_peers || !s->flag_peers || !s->step || s->rank < 0 || s->rank >= s->world) return B200SEG_E_BADARG;
+    sy.mail_peers = (double* const*)s->mail_peers;
+    sy.flag_peers = (unsigned* const*)s->flag_peers;
+    sy.step = (const unsigned*)s->step;
+    sy.mail_off = s->mail_offset; sy.parity_stride = s->parity_stride; sy.flag_off = s->flag_offset;
+    sy.world = s->world; sy.rank = s->rank;
+  }
+  *out = sy;
+  return 0;
+}
+
 #define CHECK_LAUNCH()                      \
   do {                                      \
     cudaError_t e_ = cudaGetLastError();    \
@@ -332,10 +434,13 @@ using namespace b200seg;
 extern "C" int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t c, int32_t cpad, float count,
                                    const float* gamma, const float* beta, float eps, float momentum,
                                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
-                                   float* shift, float* mean, float* invstd, float* batch_stats_out, void* stream) {
+                                   float* shift, float* mean, float* invstd, float* batch_stats_out,
+                                   const b200seg_bn_sync* sync, void* stream) {
   if (!partials || !scale || !shift || !mean || !invstd || c <= 0 || grid <= 0) return B200SEG_E_BADARG;
+  SyncArgs sy;
+  if (int rc = make_sync(sync, &sy)) return rc;
   launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinSlices), 0, (cudaStream_t)stream, partials, grid, c, cpad, count, gamma, beta, eps, momentum, running_mean, running_var,
-      (long long*)num_batches_tracked, scale, shift, mean, invstd, batch_stats_out);
+      (long long*)num_batches_tracked, scale, shift, mean, invstd, batch_stats_out, sy);
   CHECK_LAUNCH();
 }
 
@@ -406,10 +511,12 @@ extern "C" int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* 
 }
 
 extern "C" int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int32_t c, float count, float* dgamma,
-                                       float* dbeta, float* c1, float* c2, void* stream) {
+                                       float* dbeta, float* c1, float* c2, const b200seg_bn_sync* sync, void* stream) {
   if (!partials || !c1 || !c2) return B200SEG_E_BADARG;
+  SyncArgs sy;
+  if (int rc = make_sync(sync, &sy)) return rc;
   launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinSlices), 0, (cudaStream_t)stream, partials, grid, c, count, dgamma, dbeta,
-                                                                           c1, c2);
+                                                                           c1, c2, sy);
   CHECK_LAUNCH();
 }
 
@@ -430,4 +537,36 @@ extern "C" int b200seg_masked_accum(const void* src, int32_t src_ld, const void*
   launch_k(masked_accum_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, src_ld, (const __nv_bfloat16*)mask, mask_ld, (__nv_bfloat16*)dst, dst_ld, accumulate,
       npix, c);
   CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------- peer memory (SyncBN)
+extern "C" int b200seg_p2p_alloc(size_t bytes, void** dev_ptr, uint8_t* handle64) {
+  if (!dev_ptr || !handle64 || bytes == 0) return B200SEG_E_BADARG;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemset(p, 0, bytes);
+  if (e != cudaSuccess) { cudaFree(p); return (int)e; }
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return (int)e; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return 0;
+}
+extern "C" int b200seg_p2p_open(const uint8_t* handle64, void** dev_ptr) {
+  if (!handle64 || !dev_ptr) return B200SEG_E_BADARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+extern "C" int b200seg_p2p_close(void* dev_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+extern "C" int b200seg_p2p_free(void* dev_ptr) {
+  cudaError_t e = cudaFree(dev_ptr);
+  return e == cudaSuccess ? 0 : (int)e;
 }

@@ -1,0 +1,71 @@
+"""Data-parallel step on 2 GPUs of one node: SyncBN over NVLink peer memory + NCCL gradient all-reduce must reproduce
+the single-GPU step on the concatenated batch. Skipped on boxes with fewer than two GPUs."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, use_graph, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="env://", rank=rank, world_size=world)
+    from oracle import seg_oracle as O
+    from b200seg.module import B200SegModule
+    arch, hcfg = "ocrnet.HRNet_Mscale", O.HRNET_W16_TEST
+    sd0 = O.synth_state_dict(arch, hcfg, seed=3)
+    images, gts = O.synth_batch(world, 64, 128, seed=5)
+    ocfg = dict(O.OCR_CFG)
+    ocfg["dropout"] = 0.0
+
+    def run(batch_slice, ddp, steps):
+        net = B200SegModule(arch, 19, hcfg=hcfg, ocfg=ocfg, use_cuda_graph=use_graph)
+        net.load_state_dict(sd0)
+        net = net.cuda().train()
+        net._ddp_allreduce = ddp
+        im, gt = images[batch_slice].cuda(), gts[batch_slice].cuda()
+        losses = []
+        for _ in range(steps):
+            net.zero_grad(set_to_none=True)
+            loss = net({"images": im, "gts": gt})
+            loss.backward()
+            losses.append(loss.detach().clone())
+        torch.cuda.synchronize()
+        return net, torch.stack(losses)
+
+    steps = 3                                   # eager warm-up, capture, replay
+    net, losses = run(slice(rank, rank + 1), True, steps)
+    dist.all_reduce(losses)
+    losses /= world
+    if rank == 0:
+        ref, ref_losses = run(slice(0, world), False, steps)      # one GPU, whole batch, local BN == SyncBN over ranks
+        rel = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+        res = dict(loss=losses.cpu().tolist(), ref_loss=ref_losses.cpu().tolist(),
+                   grad_rel=rel(net._flat_grad, ref._flat_grad),
+                   run_rel=rel(net._run_flat, ref._run_flat),
+                   nbt=(int(net._nbt_flat[0]), int(ref._nbt_flat[0])))
+        torch.save(res, out)
+    dist.barrier()
+    if net._sync is not None:
+        net._sync.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_two_gpu_syncbn_step_equals_single_gpu_batch(tmp_path, use_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res.pt")
+    port = 29500 + (os.getpid() % 1000) + (1 if use_graph else 0)
+    mp.spawn(_worker, args=(2, port, use_graph, out), nprocs=2, join=True)
+    res = torch.load(out)
+    for a, b in zip(res["loss"], res["ref_loss"]):
+        assert abs(a - b) <= 2e-3 * abs(b), res
+    assert res["run_rel"] <= 2e-3, res          # running statistics come from the global batch
+    assert res["grad_rel"] <= 0.05, res         # bf16 activations, different reduction order across the two layouts
+    assert res["nbt"][0] == res["nbt"][1]
