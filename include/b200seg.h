@@ -72,6 +72,20 @@ int b200seg_conv2d_fwd_direct(const b200seg_conv_desc* d, const void* x, const v
 int b200seg_pack_weight(const float* w_oihw, int32_t o, int32_t i, int32_t ksize, void* w_ohwi, void* w_dgrad,
                         int32_t o_pad, void* stream);
 
+/* The same repack for every convolution of the model in one launch (the weights change every optimizer step).
+ * items: DEVICE array; block b handles b200seg_pack_chunk() consecutive OIHW elements of items[blk_item[b]] starting
+ * at blk_start[b]. i_dst >= i is the input-channel extent of the destination layouts (the 3-channel stem runs on a
+ * 16-channel padded image; pad entries must have been zeroed once by the caller). */
+typedef struct b200seg_pack_item {
+  const void* w_oihw;      /* fp32 [o][i][k][k] */
+  void* w_ohwi;            /* bf16 [o][k*k][i_dst] or NULL */
+  void* w_dgrad;           /* bf16 [i_dst][k*k flipped][o_pad] or NULL */
+  int32_t o, i, i_dst, ksize, o_pad, reserved;
+} b200seg_pack_item;
+int32_t b200seg_pack_chunk(void);
+int b200seg_pack_weights(const b200seg_pack_item* items, const int32_t* blk_item, const int32_t* blk_start,
+                         int32_t n_blocks, void* stream);
+
 /* Data gradient: dx[n,h,w,cin] = conv_transpose(dy, W) (+ addend, e.g. a gradient that already arrived at x).
  * d describes the FORWARD convolution; dy: bf16 [n,ho,wo,*] whose channel extent is roundup8(cout) (pad channels
  * zero); w_dgrad from b200seg_pack_weight with o_pad = roundup8(cout). Stride-2 convolutions run as four parity-class
@@ -299,6 +313,16 @@ int b200seg_resize_nchw(const float* src, int32_t planes, int32_t h, int32_t w, 
 /* a: [n,1,hw]; mode 0: out = a*x + (1-a)*y; 1: out = x + (1-a)*y; 2: out = a*x   (x, y, out: [n,c,hw]) */
 int b200seg_blend(const float* a, const float* x, const float* y, float* out, int32_t n, int32_t c, int64_t hw,
                   int32_t mode, void* stream);
+
+/* Evaluation tail on the device (utils/trnval_utils.py:116-196 eval_minibatch, utils/misc.py:50-85 fast_hist):
+ * out (=|+=) pred [n,c,h,w] fp32, optionally mirrored along w (the do_flip / multi-scale averaging loop) */
+int b200seg_accum_pred(const float* pred, float* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t flip,
+                       int32_t accumulate, void* stream);
+/* per pixel of pred*scale [n,c,hw]: argmax class (int64, first maximum), softmax max probability (fp32) and the
+ * confusion histogram hist[gt*c + pred] += 1 (int64, caller-zeroed, accumulates) over pixels with 0 <= gt < c.
+ * Every output is optional (NULL); hist needs labels. */
+int b200seg_argmax_hist(const float* pred_nchw, int32_t n, int32_t c, int64_t hw, float scale, const int64_t* labels,
+                        int64_t* pred_out, float* maxprob_out, int64_t* hist, void* stream);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,8 @@ SIGNATURES = {
     "b200seg_conv2d_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V, P32, V]),
     "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
     "b200seg_pack_weight": (ctypes.c_int, [V, I32, I32, I32, V, V, I32, V]),
+    "b200seg_pack_chunk": (I32, []),
+    "b200seg_pack_weights": (ctypes.c_int, [V, V, V, I32, V]),
     "b200seg_conv2d_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, I32, V, V, I32, V, I32, V]),
     "b200seg_conv2d_wgrad_ws_bytes": (c_size_t, [ctypes.POINTER(ConvDesc)]),
     "b200seg_conv2d_wgrad_launches": (I32, [ctypes.POINTER(ConvDesc)]),
@@ -114,6 +116,8 @@ SIGNATURES = {
     "b200seg_resize_to_nchw": (ctypes.c_int, [V, I32, I32, I32, I32, I32, I32, V, I32, I32, V]),
     "b200seg_resize_nchw": (ctypes.c_int, [V, I32, I32, I32, V, I32, I32, V]),
     "b200seg_blend": (ctypes.c_int, [V, V, V, V, I32, I32, I64, I32, V]),
+    "b200seg_accum_pred": (ctypes.c_int, [V, V, I32, I32, I32, I32, I32, I32, V]),
+    "b200seg_argmax_hist": (ctypes.c_int, [V, I32, I32, I64, F, V, V, V, V, V]),
 }
 # test-only probe entry point (csrc/probe.h), not part of include/b200seg.h
 PROBE_SIGNATURES = {

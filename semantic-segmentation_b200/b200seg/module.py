@@ -255,18 +255,16 @@ class B200SegModule(nn.Module):
         self._graphs = {}
 
     def _repack(self):
-        """fp32 OIHW master weights -> bf16 kernel layouts (inside the captured step: weights change every step)."""
-        for n, p in self.named_parameters():
-            if p.dim() != 4:
-                continue
-            w_f, w_d = self._packed[n[: -len(".weight")]]
-            src = p.detach()
-            if src.shape[1] == 3:
-                if self._stem_pad is None:
-                    self._stem_pad = torch.zeros((src.shape[0], 16, 3, 3), dtype=F32, device=src.device)
-                self._stem_pad[:, :3].copy_(src)
-                src = self._stem_pad
-            raw.pack_weight_into(src.contiguous(), w_f, w_d)
+        """fp32 OIHW master weights -> bf16 kernel layouts, one launch for the whole model (inside the captured step:
+        the weights change every optimizer step)."""
+        convs = [(n, p) for n, p in self.named_parameters() if p.dim() == 4]
+        ptrs = tuple(p.data_ptr() for _, p in convs)
+        tab = getattr(self, "_pack_table", None)
+        if tab is None or tab["ptrs"] != ptrs:
+            entries = [(p.detach(), *self._packed[n[: -len(".weight")]]) for n, p in convs]
+            tab = self._pack_table = raw.pack_table(entries, convs[0][1].device)
+            self._graphs = {}
+        raw.pack_weights(tab)
 
     # ------------------------------------------------------------------------------------------ training step
     def _step_eager(self, images, gts, drop_mask):

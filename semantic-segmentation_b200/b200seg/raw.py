@@ -44,6 +44,34 @@ def pack_weight_into(w_oihw, w_f, w_d):
     check(lib().b200seg_pack_weight(ptr(w_oihw), o, i, k, ptr(w_f), ptr(w_d), o_pad, stream_ptr()), "pack_weight")
 
 
+def pack_table(entries, device):
+    """entries: list of (w_oihw fp32 tensor, w_f, w_d) -> device tables for pack_weights (one launch for all of them).
+    The table stores raw pointers: rebuild it when a parameter's storage moves."""
+    import numpy as np
+    chunk = lib().b200seg_pack_chunk()
+    items, blk_item, blk_start = [], [], []
+    for idx, (w, w_f, w_d) in enumerate(entries):
+        o, i, k, _ = w.shape
+        i_dst = w_f.shape[2]
+        assert w.is_contiguous() and w.dtype == F32
+        items.append((w.data_ptr(), w_f.data_ptr(), w_d.data_ptr() if w_d is not None else 0, o, i, i_dst, k,
+                      w_d.shape[2] if w_d is not None else 0, 0))
+        for st in range(0, w.numel(), chunk):
+            blk_item.append(idx)
+            blk_start.append(st)
+    it_np = np.array(items, dtype=np.dtype([("w", "<u8"), ("f", "<u8"), ("d", "<u8"), ("o", "<i4"), ("i", "<i4"),
+                                            ("i_dst", "<i4"), ("k", "<i4"), ("o_pad", "<i4"), ("r", "<i4")]))
+    return dict(items=torch.from_numpy(it_np.view(np.uint8).copy()).to(device),
+                blk_item=torch.tensor(blk_item, dtype=torch.int32, device=device),
+                blk_start=torch.tensor(blk_start, dtype=torch.int32, device=device), n_blocks=len(blk_item),
+                ptrs=tuple(e[0].data_ptr() for e in entries))
+
+
+def pack_weights(table):
+    check(lib().b200seg_pack_weights(ptr(table["items"]), ptr(table["blk_item"]), ptr(table["blk_start"]),
+                                     table["n_blocks"], stream_ptr()), "pack_weights")
+
+
 def conv_desc(n, h, w, cin, cout, ksize, stride, x_ld, y_ld, out_fp32=False, has_bias=False, emit_stats=False,
               force_kc=0):
     d = ConvDesc()
@@ -430,3 +458,27 @@ def blend(a, x, y, mode):
     out = torch.empty_like(x)
     check(lib().b200seg_blend(ptr(a), ptr(x), ptr(y), ptr(out), n, c, h * w, mode, stream_ptr()), "blend")
     return out
+
+
+# ----------------------------------------------------------------------------------------------- evaluation tail
+def accum_pred(pred, out=None, flip=False):
+    """out (+)= pred [n,c,h,w] fp32 (mirrored along w when flip); allocates out on the first call."""
+    n, c, h, w = pred.shape
+    acc = out is not None
+    if out is None:
+        out = torch.empty_like(pred)
+    check(lib().b200seg_accum_pred(ptr(pred), ptr(out), n, c, h, w, int(flip), int(acc), stream_ptr()), "accum_pred")
+    return out
+
+
+def argmax_hist(pred, labels=None, scale=1.0, hist=None):
+    """-> (argmax int64 [n,h,w], max softmax prob fp32 [n,h,w], hist int64 [c,c] (accumulated) or None)."""
+    n, c, h, w = pred.shape
+    assert pred.dtype == F32 and pred.is_contiguous()
+    pm = torch.empty((n, h, w), dtype=torch.int64, device=pred.device)
+    mp = torch.empty((n, h, w), dtype=F32, device=pred.device)
+    if labels is not None and hist is None:
+        hist = torch.zeros((c, c), dtype=torch.int64, device=pred.device)
+    check(lib().b200seg_argmax_hist(ptr(pred), n, c, h * w, float(scale), ptr(labels), ptr(pm), ptr(mp), ptr(hist),
+                                    stream_ptr()), "argmax_hist")
+    return pm, mp, hist

@@ -83,6 +83,59 @@ static inline int egrid(long long total) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// out (=|+=) pred, optionally mirrored along W: the flip / multi-scale averaging loop of eval_minibatch
+// (utils/trnval_utils.py:116-160) without leaving the device.
+__global__ void __launch_bounds__(256)
+accum_pred_kernel(const float* __restrict__ pred, float* __restrict__ out, long long planes_h, int W, int flip,
+                  int accumulate) {
+  pdl_sync();
+  const long long total = planes_h * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    const long long row = idx / W;
+    const float v = pred[row * W + (flip ? W - 1 - x : x)];
+    out[idx] = accumulate ? out[idx] + v : v;
+  }
+}
+
+// Evaluation tail (utils/trnval_utils.py:160-196, utils/misc.py:50-85): softmax over the classes of the averaged
+// prediction, max probability + argmax per pixel, and the C x C confusion histogram hist[gt][pred] += 1 over the pixels
+// with 0 <= gt < C. Integer counters (block-local shared histogram, then 64-bit global atomics): order independent.
+__global__ void __launch_bounds__(256)
+argmax_hist_kernel(const float* __restrict__ pred, int n, int C, long long hw, float scale,
+                   const long long* __restrict__ labels, long long* __restrict__ pred_out,
+                   float* __restrict__ maxprob_out, unsigned long long* __restrict__ hist) {
+  pdl_sync();
+  extern __shared__ unsigned int s_hist[];     // [C*C]
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_hist[i] = 0u;
+  __syncthreads();
+  const long long total = (long long)n * hw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long b = idx / hw, p = idx - b * hw;
+    const float* src = pred + (size_t)b * C * hw + p;
+    float m = src[0] * scale;
+    int arg = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = src[(size_t)c * hw] * scale;
+      if (v > m) { m = v; arg = c; }          // first maximum wins, like torch.max
+    }
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += expf(src[(size_t)c * hw] * scale - m);
+    if (pred_out) pred_out[idx] = arg;
+    if (maxprob_out) maxprob_out[idx] = 1.f / sum;
+    if (labels && hist) {
+      const long long gt = labels[idx];
+      if (gt >= 0 && gt < C) atomicAdd(&s_hist[(int)gt * C + arg], 1u);
+    }
+  }
+  __syncthreads();
+  if (hist)
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+      if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
 }  // namespace b200seg
 
 using namespace b200seg;
@@ -109,5 +162,23 @@ extern "C" int b200seg_blend(const float* a, const float* x, const float* y, flo
   if (!a || !x || !out || (mode != 2 && !y) || mode < 0 || mode > 2) return B200SEG_E_BADARG;
   launch_k(blend_kernel, dim3(egrid((long long)n * c * hw)), dim3(256), 0, (cudaStream_t)stream, a, x, y, out, n, c, hw, mode);
   cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int b200seg_accum_pred(const float* pred, float* out, int32_t n, int32_t c, int32_t h, int32_t w,
+                                  int32_t flip, int32_t accumulate, void* stream) {
+  if (!pred || !out || n <= 0 || c <= 0 || h <= 0 || w <= 0) return B200SEG_E_BADARG;
+  cudaError_t e = launch_k(accum_pred_kernel, dim3(egrid((long long)n * c * h * w)), dim3(256), 0, (cudaStream_t)stream,
+                           pred, out, (long long)n * c * h, (int)w, (int)flip, (int)accumulate);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int b200seg_argmax_hist(const float* pred_nchw, int32_t n, int32_t c, int64_t hw, float scale,
+                                   const int64_t* labels, int64_t* pred_out, float* maxprob_out, int64_t* hist,
+                                   void* stream) {
+  if (!pred_nchw || n <= 0 || c <= 0 || c > 64 || hw <= 0 || (hist && !labels)) return B200SEG_E_BADARG;
+  cudaError_t e = launch_k(argmax_hist_kernel, dim3(egrid((long long)n * hw)), dim3(256), (size_t)c * c * sizeof(unsigned),
+                           (cudaStream_t)stream, pred_nchw, (int)n, (int)c, (long long)hw, scale,
+                           (const long long*)labels, (long long*)pred_out, maxprob_out, (unsigned long long*)hist);
   return e == cudaSuccess ? 0 : (int)e;
 }

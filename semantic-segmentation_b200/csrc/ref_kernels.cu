@@ -53,9 +53,46 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, in
   }
 }
 
+// All weights of the model in ONE launch: block b repacks kPackChunk consecutive OIHW elements of item blk_item[b]
+// (fp32 master -> bf16 forward operand [O][taps][I_dst] and data-gradient operand [I_dst][taps flipped][o_pad]).
+constexpr int kPackChunk = 4096;
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const b200seg_pack_item* __restrict__ items, const int32_t* __restrict__ blk_item,
+                    const int32_t* __restrict__ blk_start) {
+  pdl_sync();
+  const b200seg_pack_item it = items[blk_item[blockIdx.x]];
+  const float* __restrict__ w = reinterpret_cast<const float*>(it.w_oihw);
+  __nv_bfloat16* __restrict__ ohwi = reinterpret_cast<__nv_bfloat16*>(it.w_ohwi);
+  __nv_bfloat16* __restrict__ dgrad = reinterpret_cast<__nv_bfloat16*>(it.w_dgrad);
+  const uint32_t taps = (uint32_t)(it.ksize * it.ksize), I = (uint32_t)it.i, Id = (uint32_t)it.i_dst;
+  const uint32_t total = (uint32_t)it.o * I * taps;
+  const uint32_t j0 = (uint32_t)blk_start[blockIdx.x];
+#pragma unroll 4
+  for (uint32_t tt = threadIdx.x; tt < (uint32_t)kPackChunk; tt += 256) {
+    const uint32_t idx = j0 + tt;
+    if (idx >= total) break;
+    const uint32_t t = idx % taps;
+    const uint32_t i = (idx / taps) % I;
+    const uint32_t o = idx / (taps * I);
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[idx]);
+    if (ohwi) ohwi[((size_t)o * taps + t) * Id + i] = v;
+    if (dgrad) dgrad[((size_t)i * taps + (taps - 1 - t)) * it.o_pad + o] = v;
+  }
+}
+
 }  // namespace b200seg
 
 using namespace b200seg;
+
+extern "C" int32_t b200seg_pack_chunk(void) { return kPackChunk; }
+
+extern "C" int b200seg_pack_weights(const b200seg_pack_item* items, const int32_t* blk_item, const int32_t* blk_start,
+                                    int32_t n_blocks, void* stream) {
+  if (!items || !blk_item || !blk_start || n_blocks <= 0) return B200SEG_E_BADARG;
+  cudaError_t e = launch_k(pack_weights_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, items, blk_item,
+                           blk_start);
+  return e == cudaSuccess ? 0 : (int)e;
+}
 
 extern "C" int b200seg_abi_version(void) { return 1; }
 extern "C" const char* b200seg_build_info(void) { return "b200seg sm_100a " __DATE__ " " __TIME__; }

@@ -230,3 +230,41 @@ def test_eval_forward_matches_oracle(arch, n_scales):
         assert rel < 0.03, (k, rel)
     agree = float((out["pred"].argmax(1) == ref["pred"].argmax(1)).float().mean())
     assert agree > 0.97, agree
+
+
+def test_eval_minibatch_device_tail_matches_host_scoring():
+    """b200seg.evaltail.eval_minibatch (flip + two input scales, utils/trnval_utils.py:116-196) against the same loop
+    written with torch ops on the module's own 'pred' outputs: identical class map and confusion matrix."""
+    import torch.nn.functional as F
+    O, B200SegModule = _mods()
+    from b200seg.evaltail import eval_minibatch, iou_from_hist
+    arch, hcfg = "ocrnet.HRNet", O.HRNET_W16_TEST
+    sd0 = O.synth_state_dict(arch, hcfg, seed=3)
+    _condition_eval_weights(sd0)
+    images, gts = O.synth_batch(2, 64, 128, seed=5)
+    net = B200SegModule(arch, 19, hcfg=hcfg)
+    net.load_state_dict(sd0)
+    net = net.cuda().eval()
+    im, gt = images.cuda(), gts.cuda()
+    scales = (0.5, 1.0)
+    res = eval_minibatch(net, im, gt, scales=scales, do_flip=True)
+    out = 0.0
+    with torch.no_grad():
+        for flip in (1, 0):
+            for s in scales:
+                x = torch.flip(im, dims=[3]) if flip else im
+                if s != 1.0:
+                    x = F.interpolate(x, size=(round(64 * s), round(128 * s)), mode="bilinear", align_corners=False)
+                p = net({"images": x})["pred"]
+                if s != 1.0:
+                    p = F.interpolate(p, size=(64, 128), mode="bilinear", align_corners=False)
+                out = out + (torch.flip(p, dims=[3]) if flip else p)
+    out = out / 4
+    prob, arg = F.softmax(out, dim=1).max(1)
+    agree = float((res["predictions"] == arg).float().mean())
+    assert agree > 0.999, agree                                    # resize arithmetic differs in the last ulp only
+    mask = gt < 19
+    ref_hist = torch.bincount(19 * gt[mask] + arg[mask], minlength=361).view(19, 19)
+    assert int((res["hist"] - ref_hist).abs().sum()) <= 4
+    assert res["hist"].sum() == mask.sum()
+    assert iou_from_hist(res["hist"]).shape == (19,)

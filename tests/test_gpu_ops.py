@@ -375,3 +375,28 @@ def test_rmi_criterion_fwd_bwd(two_scale, sup):
         close(dl_cls[..., :19], leaves[2].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d lo cls (rmi)")
         close(dl_aux[..., :19], leaves[3].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d lo aux (bce)")
         close(dl_attn[..., :1], leaves[4].grad.permute(0, 2, 3, 1), 2 * BF16_TOL, "d lo attn logit (rmi)")
+
+
+def test_eval_tail_argmax_confusion_and_flip_average():
+    """Device evaluation tail vs the reference's host-side softmax / max / fast_hist (utils/misc.py:50-85)."""
+    raw = _setup()
+    n, c, h, w = 2, 19, 37, 53
+    g = torch.Generator(device="cuda").manual_seed(0)
+    p0 = torch.randn((n, c, h, w), generator=g, device="cuda") * 3
+    p1 = torch.randn((n, c, h, w), generator=g, device="cuda") * 3
+    gts = torch.randint(0, 19, (n, h, w), generator=g, device="cuda")
+    gts[:, :4] = 255
+    out = raw.accum_pred(p0, None, flip=False)
+    out = raw.accum_pred(p1, out, flip=True)
+    ref_out = p0 + torch.flip(p1, dims=[3])
+    assert torch.equal(out, ref_out)
+    pm, mp, hist = raw.argmax_hist(out, gts, 0.5)
+    sm = F.softmax(ref_out * 0.5, dim=1)
+    rmax, rarg = sm.max(1)
+    assert torch.equal(pm, rarg)                                   # bit-exact class map
+    assert float((mp - rmax).abs().max()) <= 1e-6
+    mask = (gts >= 0) & (gts < c)
+    ref_hist = torch.bincount(c * gts[mask] + rarg[mask], minlength=c * c).view(c, c)
+    assert torch.equal(hist, ref_hist)
+    _, _, hist2 = raw.argmax_hist(out, gts, 0.5, hist)             # accumulates
+    assert torch.equal(hist2, 2 * ref_hist)
