@@ -64,12 +64,16 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// bench-only timeline (tools/gpu_timeline.py): role r, tile iteration it -> ns timestamp
+// bench-only timeline (tools/gpu_timeline.py; build with EXTRA=-DB200SEG_TIMELINE): role r, tile iteration it -> ns
+#ifdef B200SEG_TIMELINE
 #define DBG_TS(role, it)                                                                                      \
   do {                                                                                                        \
     if ((p.dbg & 8) && blockIdx.x == 0 && (it) < 16)                                                          \
       reinterpret_cast<unsigned long long*>(stats_partials + 148 * 2 * 1024)[(role) * 16 + (it)] = gtime();  \
   } while (0)
+#else
+#define DBG_TS(role, it) do { } while (0)
+#endif
 
 // All nine taps of one resident 64-channel chunk: 9 x KS MMAs, compile-time offsets only.
 template <int KS>
