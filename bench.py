@@ -313,7 +313,8 @@ def run_b200(args):
         gpu_launches_note="%d b200seg kernels per step (inside one CUDA graph replay), two timed loops" % kernels_per_step,
         model_flops_utilisation=dict(achieved_tflops=step_tflops / 1.0, peak=pk["tf_sust"],
                                      frac=step_tflops / pk["tf_sust"], peak_source=pk["src"] + " sustained bf16"),
-        roofline=roof, clocks=clocks, last_loss=loss_val)
+        roofline=roof, clocks=clocks, last_loss=loss_val,
+        max_memory_allocated_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
     if not args.no_cpu_baseline:
         try:
             sh, sw = 128, 256

@@ -11,6 +11,8 @@ Design notes
     its epilogue, ``bn_finalize`` turns them into scale/shift (+ running stats), ``bn_apply`` fuses affine, residual,
     ReLU and the Dropout2d mask. The backward mirrors it (``bn_bwd`` = reduce + finalize + apply, then wgrad, dgrad).
 """
+import contextlib
+
 import torch
 
 from . import raw
@@ -42,14 +44,16 @@ class HeadRec:
 
 class Engine:
     def __init__(self, params, grads, packed, training, drop_mask=None, side_stream=None, bstat=None, stream=None,
-                 sync=None, pass_id=0):
+                 sync=None, pass_id=0, branch_streams=None, ws_holder=None):
         """params: name -> tensor (weights, BN buffers); grads: name -> fp32 tensor accumulated into (training);
         packed: name -> (w_fwd, w_dgrad) bf16 operand caches; drop_mask: fp32 [N, mid] post-ReLU multiplier;
         bstat: BN layer name -> fp32 [2*C] slot receiving the batch [mean | unbiased var] (the running statistics are
         then updated once per step by bn_running_update; without it bn_finalize updates them in place);
         stream: the stream this engine's program is enqueued on when it runs concurrently with another engine (the
         low-resolution pass of the two-scale step), None = the caller's current stream;
-        sync / pass_id: SyncBNContext (p2p.py) and this engine's pass index in its exchange table (data parallel)."""
+        sync / pass_id: SyncBNContext (p2p.py) and this engine's pass index in its exchange table (data parallel);
+        branch_streams: up to three extra streams for the parallel branches of a HighResolutionModule (branch 0 stays
+        on the engine's own stream); ws_holder: reusable weight-gradient slab workspace of the side stream."""
         self.p = params
         self.g = grads
         self.packed = packed
@@ -59,6 +63,9 @@ class Engine:
         self.stream = stream
         self.sync = sync
         self.pass_id = pass_id
+        self.bstreams = list(branch_streams or [])
+        self.ws_holder = ws_holder
+        self._ctx = None         # stream of the branch section being recorded (None = the engine's own stream)
         self.tape = []
         self.bn_seen = set()
         self.hold = []      # tensors handed across streams: kept alive until the step's final join
@@ -70,13 +77,63 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------ tape
     def run_backward(self):
+        """Pops the tape: ops run on the stream they were recorded on; a forward join becomes a fork and vice versa."""
         tape = self.tape
         while tape:
-            fn = tape.pop()
-            fn()
+            kind, fn, st = tape.pop()
+            if kind == "op":
+                if st is None:
+                    fn()
+                else:
+                    with torch.cuda.stream(st):
+                        fn()
+            elif kind == "join":          # forward joined k branches here: backward forks them
+                self._fork_streams(fn)
+            else:                          # forward forked here: backward joins
+                self._join_streams(fn)
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
         self._keepalive.clear()
+
+    # ------------------------------------------------------------------------------------------ branch sections
+    def _fork_streams(self, k):
+        base = torch.cuda.current_stream()
+        for s in self.bstreams[: k - 1]:
+            s.wait_stream(base)
+
+    def _join_streams(self, k):
+        base = torch.cuda.current_stream()
+        for s in self.bstreams[: k - 1]:
+            base.wait_stream(s)
+
+    def fork(self, k):
+        """k independent branches follow (HighResolutionModule.branches, network/hrnetv2.py:236-239): branch i > 0 is
+        recorded on self.bstreams[i-1], a parallel branch of the captured graph."""
+        if not self.bstreams:
+            return
+        self._fork_streams(k)
+        if self.training:
+            self.tape.append(("fork", k, None))
+
+    def join(self, k):
+        if not self.bstreams:
+            return
+        self._join_streams(k)
+        if self.training:
+            self.tape.append(("join", k, None))
+
+    @contextlib.contextmanager
+    def on_branch(self, i):
+        if i == 0 or not self.bstreams:
+            yield
+            return
+        st = self.bstreams[i - 1]
+        prev, self._ctx = self._ctx, st
+        try:
+            with torch.cuda.stream(st):
+                yield
+        finally:
+            self._ctx = prev
 
     def finish(self):
         """After every stream of the step has been joined: drop the cross-stream keep-alive references."""
@@ -91,12 +148,12 @@ class Engine:
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            ws = raw.conv2d_wgrad(x_t, dy, dw, cout, ksize, stride)
+            ws = raw.conv2d_wgrad(x_t, dy, dw, cout, ksize, stride, ws_holder=self.ws_holder)
         self._keepalive.append((x_t, dy, ws))
 
     def _push(self, fn):
         if self.training:
-            self.tape.append(fn)
+            self.tape.append(("op", fn, self._ctx))
 
     @staticmethod
     def _accumulate(act, new_grad_fn):
@@ -164,7 +221,7 @@ class Engine:
             g_out, g_acc = None, False
             if residual is not None and residual.needs_grad:
                 if residual.grad is None:
-                    residual.grad = torch.empty(residual.t.shape, dtype=BF16, device=z.device)
+                    residual.grad = raw._new(residual.t.shape, dtype=BF16, device=z.device)
                 else:
                     g_acc = True
                 g_out = residual.grad
@@ -202,7 +259,7 @@ class Engine:
                         continue
                     if obj.t.shape[1] == h and obj.t.shape[2] == w:
                         if obj.grad is None:
-                            obj.grad = torch.empty(obj.t.shape, dtype=BF16, device=z.device)
+                            obj.grad = raw._new(obj.t.shape, dtype=BF16, device=z.device)
                             raw.masked_accum(dz, mask, obj.grad, False)
                         else:
                             raw.masked_accum(dz, mask, obj.grad, True)

@@ -31,9 +31,12 @@ def hr_module(E, p, xs, num_blocks, out0=None):
     """HighResolutionModule.forward (network/hrnetv2.py:230-254). out0: optional view for the branch-0 output."""
     nb = len(xs)
     xs = list(xs)
+    E.fork(nb)                       # the branches are independent: parallel streams / graph branches
     for i in range(nb):
-        for k in range(num_blocks[i]):
-            xs[i] = basic_block(E, "%s.branches.%d.%d" % (p, i, k), xs[i])
+        with E.on_branch(i):
+            for k in range(num_blocks[i]):
+                xs[i] = basic_block(E, "%s.branches.%d.%d" % (p, i, k), xs[i])
+    E.join(nb)
     outs = []
     for i in range(nb):
         terms = []
@@ -85,7 +88,7 @@ def hrnet_forward(E, x16, hcfg, p="backbone"):
             if key == "stage4" and m == sc["num_modules"] - 1:
                 # final module: branch 0 is written straight into the concat buffer (network/hrnetv2.py:438-447)
                 n, h, w, _ = xs[0].t.shape
-                cat = Act(torch.empty((n, h, w, sum(ch)), dtype=BF16, device=xs[0].t.device))
+                cat = Act(raw._new((n, h, w, sum(ch)), dtype=BF16, device=xs[0].t.device))
                 out0 = cat.t[..., : ch[0]]
             xs = hr_module(E, "%s.%s.%d" % (p, key, m), xs, sc["num_blocks"], out0=out0)
         ys = xs
@@ -113,18 +116,18 @@ def spatial_gather(E, feats, aux, K):
     dev = feats.t.device
     ld = aux.logits.stride(2)
     probs = raw.spatial_softmax_fwd(aux.logits.as_strided((n, P, ld), (P * ld, ld, 1)), K)     # [n,P,32] bf16
-    ctx32 = torch.zeros((n, K, C), dtype=F32, device=dev)
+    ctx32 = raw._newz((n, K, C), dtype=F32, device=dev)
     for i in range(n):
         raw.conv2d_wgrad(feats.t[i:i + 1], probs[i].view(1, h, w, 32), ctx32[i].view(K, C, 1, 1), K, 1, 1)
-    proxy = Act(torch.empty((n, K, 1, C), dtype=BF16, device=dev))
+    proxy = Act(raw._new((n, K, 1, C), dtype=BF16, device=dev))
     raw.cast_rows(ctx32.view(n * K, C), proxy.t.view(n * K, C), C)
 
     def gather_bwd():
         if proxy.grad is None:
             return
-        dprob = torch.empty((n, P, 20), dtype=F32, device=dev)
+        dprob = raw._new((n, P, 20), dtype=F32, device=dev)
         if feats.grad is None:
-            feats.grad = torch.zeros(feats.t.shape, dtype=BF16, device=dev)
+            feats.grad = raw._newz(feats.t.shape, dtype=BF16, device=dev)
         for i in range(n):
             dctx = proxy.grad[i].view(K, C)                         # bf16 [K, C]
             raw.conv2d_fwd(feats.t[i:i + 1], dctx.view(K, 1, C), out_fp32=True,
@@ -133,7 +136,7 @@ def spatial_gather(E, feats, aux, K):
             raw.conv2d_dgrad(probs[i].view(1, h, w, 32)[..., :24], wT, (1, h, w, C), 1, 1,
                              addend=feats.grad[i:i + 1], out=feats.grad[i:i + 1])
         if aux.dlogits is None:
-            aux.dlogits = torch.zeros((n, h, w, 32), dtype=BF16, device=dev)
+            aux.dlogits = raw._newz((n, h, w, 32), dtype=BF16, device=dev)
         raw.spatial_softmax_bwd(dprob, probs, K, aux.dlogits.view(n, P, 32), True)
         proxy.grad = None
     E._push(gather_bwd)
@@ -147,7 +150,7 @@ def object_attention(E, q, kk, vv, K):
     P = h * w
     dev = q.t.device
     scale = float(C) ** -0.5
-    ctx = Act(torch.empty((n, h, w, C), dtype=BF16, device=dev))
+    ctx = Act(raw._new((n, h, w, C), dtype=BF16, device=dev))
     sims = []
     for i in range(n):
         kmat = kk.t[i].view(K, 1, C)
@@ -162,11 +165,11 @@ def object_attention(E, q, kk, vv, K):
         if dctx is None:
             return
         if q.grad is None:
-            q.grad = torch.zeros(q.t.shape, dtype=BF16, device=dev)
+            q.grad = raw._newz(q.t.shape, dtype=BF16, device=dev)
         if kk.grad is None:
-            kk.grad = torch.zeros(kk.t.shape, dtype=BF16, device=dev)
+            kk.grad = raw._newz(kk.t.shape, dtype=BF16, device=dev)
         if vv.grad is None:
-            vv.grad = torch.zeros(vv.t.shape, dtype=BF16, device=dev)
+            vv.grad = raw._newz(vv.t.shape, dtype=BF16, device=dev)
         for i in range(n):
             sim = sims[i]
             vmat = vv.t[i].view(K, 1, C)
@@ -175,10 +178,10 @@ def object_attention(E, q, kk, vv, K):
             kT = raw.transpose_pad(kk.t[i].view(K, C), 24).view(C, 1, 24)
             raw.conv2d_dgrad(ds.view(1, h, w, 32)[..., :24], kT, (1, h, w, C), 1, 1, addend=q.grad[i:i + 1],
                              out=q.grad[i:i + 1])
-            dk = torch.zeros((K, C), dtype=F32, device=dev)
+            dk = raw._newz((K, C), dtype=F32, device=dev)
             raw.conv2d_wgrad(q.t[i:i + 1], ds.view(1, h, w, 32), dk.view(K, C, 1, 1), K, 1, 1)
             raw.cast_rows(dk, kk.grad[i].view(K, C), C, accumulate=True)
-            dv = torch.zeros((K, C), dtype=F32, device=dev)
+            dv = raw._newz((K, C), dtype=F32, device=dev)
             raw.conv2d_wgrad(dctx[i:i + 1], sim.view(1, h, w, 32), dv.view(K, C, 1, 1), K, 1, 1)
             raw.cast_rows(dv, vv.grad[i].view(K, C), C, accumulate=True)
         ctx.grad = None
@@ -192,7 +195,7 @@ def ocr_block(E, feats_in, ocfg, p="ocr"):
     mid, K = ocfg["mid_channels"], ocfg["num_classes"]
     n, h, w, _ = feats_in.t.shape
     dev = feats_in.t.device
-    catbuf = Act(torch.empty((n, h, w, 2 * mid), dtype=BF16, device=dev))     # [context | feats]
+    catbuf = Act(raw._new((n, h, w, 2 * mid), dtype=BF16, device=dev))     # [context | feats]
     feats = E.conv_bn(feats_in, p + ".conv3x3_ocr.0", p + ".conv3x3_ocr.1.0", 3, relu=True, bias=True,
                       out=catbuf.t[..., mid:])
     a = E.conv_bn(feats_in, p + ".aux_head.0", p + ".aux_head.1.0", 1, relu=True, bias=True)

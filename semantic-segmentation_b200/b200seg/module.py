@@ -74,7 +74,7 @@ class _PublishGrads(torch.autograd.Function):
 class B200SegModule(nn.Module):
     def __init__(self, arch, num_classes=19, criterion=None, hcfg=None, ocfg=None, lo_scale=0.5, ocr_alpha=0.4,
                  supervised_mscale_wt=0.0, ignore_index=255, n_scales=None, use_cuda_graph=True,
-                 parallel_scales=True, syncbn=None):
+                 parallel_scales=True, syncbn=None, parallel_branches=True):
         super().__init__()
         self.arch = arch
         self.criterion = criterion
@@ -87,6 +87,7 @@ class B200SegModule(nn.Module):
         self.n_scales = n_scales
         self.use_cuda_graph = use_cuda_graph
         self.parallel_scales = parallel_scales     # run the 0.5x and 1.0x passes of the two-scale step concurrently
+        self.parallel_branches = parallel_branches  # HRNet branches of a module on parallel streams
         # SyncBN (config.py:216-225, every scripts/*.yml sets syncbn: true): None = on whenever the data-parallel
         # all-reduce is on (torch.distributed initialised, world > 1), False = per-GPU statistics
         self.syncbn = syncbn
@@ -273,6 +274,7 @@ class B200SegModule(nn.Module):
         try:
             return self._step_body(images, gts, drop_mask)
         finally:
+            raw.KEEP = None
             self.kernels_per_step = _lib.KERNEL_LAUNCHES - launches0   # same count when the captured graph replays
 
     def _sync_context(self):
@@ -304,6 +306,11 @@ class B200SegModule(nn.Module):
         self._acc_hi.zero_()         # two memsets (45 us each) beat clearing inside the fold's transposed gather
         if par:
             self._acc_lo.zero_()
+        raw.KEEP = []               # every allocation of the step stays referenced until its final join (raw.py)
+        if getattr(self, "_bstreams", None) is None:
+            mk = lambda: [torch.cuda.Stream() for _ in range(3)] if self.parallel_branches else []
+            self._bstreams = {"hi": mk(), "lo": mk()}
+            self._ws_holders = {"hi": [None], "lo": [None]}
         grads, stem_pad = self._engine_grads("hi")
         stem_pads = [stem_pad]
         E_lo = None
@@ -313,12 +320,14 @@ class B200SegModule(nn.Module):
             grads_lo, stem_pad_lo = self._engine_grads("lo")
             stem_pads.append(stem_pad_lo)
             E_lo = Engine(tensors, grads_lo, self._packed, True, drop_mask, side_stream=self._side_stream_lo,
-                          bstat=self._bstat_views[0], stream=self._lo_stream, sync=sync, pass_id=0)
+                          bstat=self._bstat_views[0], stream=self._lo_stream, sync=sync, pass_id=0,
+                          branch_streams=self._bstreams["lo"], ws_holder=self._ws_holders["lo"])
         two_pass = self.arch == "ocrnet.HRNet_Mscale"
         if sync is not None and two_pass and not par:
             raise RuntimeError("SyncBN needs parallel_scales=True for the two-scale step (one engine per pass)")
         E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream,
-                   bstat=self._bstat_views[1] if par else None, sync=sync, pass_id=1 if two_pass else 0)
+                   bstat=self._bstat_views[1] if par else None, sync=sync, pass_id=1 if two_pass else 0,
+                   branch_streams=self._bstreams["hi"], ws_holder=self._ws_holders["hi"])
         loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,
                             self.ignore_index, E_lo=E_lo, loss_kind=self.loss_kind)
         M.run_backward(E, E_lo)
@@ -326,6 +335,7 @@ class B200SegModule(nn.Module):
         if par:
             assert E.bn_seen == E_lo.bn_seen and len(E.bn_seen) == len(self._bn_slots), "BN bookkeeping out of sync"
             raw.bn_running_update(self._run_flat, self._bstat[0], self._bstat[1], BN_MOMENTUM, self._nbt_flat, 2)
+        raw.KEEP = None
         return loss
 
     def _drop_mask(self, n, device):

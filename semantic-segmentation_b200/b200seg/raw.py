@@ -12,6 +12,33 @@ from ._lib import ConvDesc, FuseDesc, MscaleDesc, check, lib, ptr, stream_ptr
 BF16 = torch.bfloat16
 F32 = torch.float32
 
+# Step-scoped keep-alive: a training step runs on several streams (scale passes, HRNet branches, weight-gradient side
+# streams); the caching allocator hands a freed block back to the stream that allocated it, which may overwrite it while
+# another stream still reads it. While KEEP is a list every tensor allocated here stays referenced until the step's final
+# join clears it (the step is static, so nothing is ever needed twice; costs memory, not time).
+KEEP = None
+
+
+def _new(*a, **k):
+    t = torch.empty(*a, **k)
+    if KEEP is not None:
+        KEEP.append(t)
+    return t
+
+
+def _newz(*a, **k):
+    t = torch.zeros(*a, **k)
+    if KEEP is not None:
+        KEEP.append(t)
+    return t
+
+
+def _new_like(x):
+    t = torch.empty_like(x)
+    if KEEP is not None:
+        KEEP.append(t)
+    return t
+
 
 def _ld(t):
     assert t.stride(-1) == 1, "channel dimension must be contiguous"
@@ -23,7 +50,7 @@ def _dev(t):
 
 
 def empty_act(n, h, w, c, device, dtype=BF16):
-    return torch.empty((n, h, w, c), dtype=dtype, device=device)
+    return _new((n, h, w, c), dtype=dtype, device=device)
 
 
 # ----------------------------------------------------------------------------------------------- convolution
@@ -32,8 +59,8 @@ def pack_weight(w_oihw, want_dgrad=True):
     assert w_oihw.is_cuda and w_oihw.dtype == F32 and w_oihw.is_contiguous()
     o, i, k, _ = w_oihw.shape
     o_pad = (o + 7) // 8 * 8
-    w_f = torch.empty((o, k * k, i), dtype=BF16, device=w_oihw.device)
-    w_d = torch.zeros((i, k * k, o_pad), dtype=BF16, device=w_oihw.device) if want_dgrad else None
+    w_f = _new((o, k * k, i), dtype=BF16, device=w_oihw.device)
+    w_d = _newz((i, k * k, o_pad), dtype=BF16, device=w_oihw.device) if want_dgrad else None
     check(lib().b200seg_pack_weight(ptr(w_oihw), o, i, k, ptr(w_f), ptr(w_d), o_pad, stream_ptr()), "pack_weight")
     return w_f, w_d
 
@@ -99,7 +126,7 @@ def conv2d_fwd(x, w_ohwi, bias=None, stride=1, out=None, out_fp32=False, emit_st
     ho, wo = out_hw(h, w, ksize, stride)
     if out is None:
         width = cout if out_ld is None else out_ld
-        buf = torch.empty((n, ho, wo, width), dtype=F32 if out_fp32 else BF16, device=x.device)
+        buf = _new((n, ho, wo, width), dtype=F32 if out_fp32 else BF16, device=x.device)
         out = buf[..., :cout] if width != cout else buf
     d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(out), out_fp32, bias is not None, emit_stats,
                   force_kc)
@@ -111,7 +138,7 @@ def conv2d_fwd(x, w_ohwi, bias=None, stride=1, out=None, out_fp32=False, emit_st
     grid = ctypes.c_int32(0)
     if emit_stats:
         nelem = lib().b200seg_conv2d_stats_elems(ctypes.byref(d))
-        stats = torch.empty(nelem, dtype=F32, device=x.device)
+        stats = _new(nelem, dtype=F32, device=x.device)
     check(lib().b200seg_conv2d_fwd(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out), ptr(stats),
                                    ctypes.byref(grid), stream_ptr()), "conv2d_fwd")
     if emit_stats:
@@ -126,7 +153,7 @@ def conv2d_dgrad(dy, w_dgrad, x_shape, ksize, stride, addend=None, out=None, for
     cout_pad = w_dgrad.shape[2]
     assert dy.shape[3] >= cout_pad or dy.shape[3] == cout_pad, (dy.shape, w_dgrad.shape)
     if out is None:
-        out = addend if addend is not None else torch.empty((n, h, w, cin), dtype=BF16, device=dy.device)
+        out = addend if addend is not None else _new((n, h, w, cin), dtype=BF16, device=dy.device)
     d = conv_desc(n, h, w, cin, cout_pad, ksize, stride, _ld(out), _ld(out), force_kc=force_kc)
     check(lib().b200seg_conv2d_dgrad(ctypes.byref(d), ptr(dy), _ld(dy), ptr(w_dgrad), ptr(addend),
                                      _ld(addend) if addend is not None else 0, ptr(out), _ld(out), stream_ptr()),
@@ -134,15 +161,23 @@ def conv2d_dgrad(dy, w_dgrad, x_shape, ksize, stride, addend=None, out=None, for
     return out
 
 
-def conv2d_wgrad(x, dy, dw_ohwi, cout, ksize, stride):
+def conv2d_wgrad(x, dy, dw_ohwi, cout, ksize, stride, ws_holder=None):
     """dw_ohwi (fp32 accumulator [Cout][k*k][Cin], contiguous; a [Cout,Cin,1,1] tensor is the same memory for 1x1)
-    += sum_pixels dy x shifted(x). Returns the workspace tensor (keep it alive while the launch is in flight)."""
+    += sum_pixels dy x shifted(x). Returns the workspace tensor (keep it alive while the launch is in flight).
+    ws_holder: optional one-element list holding a reusable workspace of the calling stream (grown on demand): all
+    weight gradients of one side stream run back to back, so they can share one slab buffer."""
     n, h, w, cin = x.shape
     assert dw_ohwi.is_contiguous() and dw_ohwi.dtype == F32 and dw_ohwi.numel() == cout * cin * ksize * ksize
     d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(dy))
     L = lib()
     nbytes = L.b200seg_conv2d_wgrad_ws_bytes(ctypes.byref(d))
-    ws = torch.empty((max(nbytes, 16) // 4,), dtype=F32, device=x.device)
+    need = max(nbytes, 16) // 4
+    if ws_holder is not None:
+        if ws_holder[0] is None or ws_holder[0].numel() < need:
+            ws_holder[0] = _new((need,), dtype=F32, device=x.device)
+        ws = ws_holder[0]
+    else:
+        ws = _new((need,), dtype=F32, device=x.device)
     check(L.b200seg_conv2d_wgrad(ctypes.byref(d), ptr(x), ptr(dy), _ld(dy), ptr(dw_ohwi), ptr(ws), nbytes,
                                  stream_ptr()), "conv2d_wgrad", L.b200seg_conv2d_wgrad_launches(ctypes.byref(d)))
     return ws
@@ -185,7 +220,7 @@ def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_
     """batch_out (fp32 [2*c], optional): receives [mean | unbiased var] for a deferred bn_running_update; pass
     running_mean = running_var = nbt = None with it. sync (BnSync, optional): SyncBN exchange descriptor."""
     buf, grid, cpad = stats
-    out = torch.empty((4, c), dtype=F32, device=buf.device)   # scale, shift, mean, invstd
+    out = _new((4, c), dtype=F32, device=buf.device)   # scale, shift, mean, invstd
     check(lib().b200seg_bn_finalize(ptr(buf), grid, c, cpad, float(count), ptr(gamma), ptr(beta), eps, momentum,
                                     ptr(running_mean), ptr(running_var), ptr(nbt), ptr(out[0]), ptr(out[1]),
                                     ptr(out[2]), ptr(out[3]), ptr(batch_out), _sync_ref(sync), stream_ptr()),
@@ -206,7 +241,7 @@ def accum_f32(dst, src):
 
 def bn_eval_params(gamma, beta, eps, running_mean, running_var):
     c = gamma.shape[0]
-    out = torch.empty((2, c), dtype=F32, device=gamma.device)
+    out = _new((2, c), dtype=F32, device=gamma.device)
     check(lib().b200seg_bn_eval_params(c, ptr(gamma), ptr(beta), eps, ptr(running_mean), ptr(running_var), ptr(out[0]),
                                        ptr(out[1]), stream_ptr()), "bn_eval_params")
     return out
@@ -215,7 +250,7 @@ def bn_eval_params(gamma, beta, eps, running_mean, running_var):
 def bn_apply(y, scale, shift, res=None, post_scale=None, relu=True, out=None):
     n, h, w, c = y.shape
     if out is None:
-        out = torch.empty((n, h, w, c), dtype=BF16, device=y.device)
+        out = _new((n, h, w, c), dtype=BF16, device=y.device)
     check(lib().b200seg_bn_apply(ptr(y), _ld(y), ptr(scale), ptr(shift), ptr(res), _ld(res) if res is not None else 0,
                                  ptr(post_scale), int(relu), ptr(out), _ld(out), n * h * w, h * w, c, stream_ptr()),
           "bn_apply")
@@ -229,14 +264,14 @@ def bn_bwd(dz, mask, post_scale, y, mean, invstd, gamma, dgamma, dbeta, g_out=No
     npix = n * h * w
     L = lib()
     grid = L.b200seg_bn_bwd_grid(npix, c)
-    partials = torch.empty((grid, 2, c), dtype=F32, device=y.device)
+    partials = _new((grid, 2, c), dtype=F32, device=y.device)
     check(L.b200seg_bn_bwd_reduce(ptr(dz), _ld(dz), ptr(mask), _ld(mask) if mask is not None else 0, ptr(post_scale),
                                   ptr(y), _ld(y), ptr(mean), ptr(invstd), npix, h * w, c, ptr(partials),
                                   stream_ptr()), "bn_bwd_reduce")
-    cc = torch.empty((2, c), dtype=F32, device=y.device)
+    cc = _new((2, c), dtype=F32, device=y.device)
     check(L.b200seg_bn_bwd_finalize(ptr(partials), grid, c, float(npix), ptr(dgamma), ptr(dbeta), ptr(cc[0]),
                                     ptr(cc[1]), _sync_ref(sync), stream_ptr()), "bn_bwd_finalize")
-    dy = dy_out if dy_out is not None else torch.empty((n, h, w, c), dtype=BF16, device=y.device)
+    dy = dy_out if dy_out is not None else _new((n, h, w, c), dtype=BF16, device=y.device)
     check(L.b200seg_bn_bwd_apply(ptr(dz), _ld(dz), ptr(mask), _ld(mask) if mask is not None else 0, ptr(post_scale),
                                  ptr(y), _ld(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(cc[0]), ptr(cc[1]), ptr(dy),
                                  _ld(dy), ptr(g_out), _ld(g_out) if g_out is not None else 0, int(g_accumulate), npix,
@@ -262,7 +297,7 @@ def fuse_fwd(terms, n, h, w, c, relu, out=None):
         t.x, t.scale, t.shift = ptr(x), ptr(sc), ptr(sh)
         t.ld, t.h, t.w = _ld(x), x.shape[1], x.shape[2]
     if out is None:
-        out = torch.empty((n, h, w, c), dtype=BF16, device=terms[0][0].device)
+        out = _new((n, h, w, c), dtype=BF16, device=terms[0][0].device)
     check(lib().b200seg_fuse_fwd(ctypes.byref(d), ptr(out), _ld(out), stream_ptr()), "fuse_fwd")
     return out
 
@@ -270,7 +305,7 @@ def fuse_fwd(terms, n, h, w, c, relu, out=None):
 def upsample_adjoint(g, mask, h, w, out=None, accumulate=False):
     n, H, W, c = g.shape
     if out is None:
-        out = torch.empty((n, h, w, c), dtype=BF16, device=g.device)
+        out = _new((n, h, w, c), dtype=BF16, device=g.device)
     check(lib().b200seg_upsample_adjoint(ptr(g), _ld(g), ptr(mask), _ld(mask) if mask is not None else 0, n, H, W, c,
                                          ptr(out), _ld(out), h, w, int(accumulate), stream_ptr()), "upsample_adjoint")
     return out
@@ -279,7 +314,7 @@ def upsample_adjoint(g, mask, h, w, out=None, accumulate=False):
 def image_prep(images_nchw, h, w):
     n, three, H, W = images_nchw.shape
     assert three == 3 and images_nchw.dtype == F32 and images_nchw.is_contiguous()
-    out = torch.empty((n, h, w, 16), dtype=BF16, device=images_nchw.device)
+    out = _new((n, h, w, 16), dtype=BF16, device=images_nchw.device)
     check(lib().b200seg_image_prep(ptr(images_nchw), n, H, W, ptr(out), h, w, stream_ptr()), "image_prep")
     return out
 
@@ -290,8 +325,8 @@ def spatial_softmax_fwd(logits, K):
     n, P, ld = logits.shape
     L = lib()
     B = L.b200seg_spatial_softmax_blocks(P)
-    ws = torch.empty((n * B * 32 * 2,), dtype=F32, device=logits.device)
-    probs = torch.empty((n, P, 32), dtype=BF16, device=logits.device)
+    ws = _new((n * B * 32 * 2,), dtype=F32, device=logits.device)
+    probs = _new((n, P, 32), dtype=BF16, device=logits.device)
     check(L.b200seg_spatial_softmax_fwd(ptr(logits), ld, n, P, K, ptr(ws), ptr(probs), None, stream_ptr()),
           "spatial_softmax_fwd", 2)
     return probs
@@ -301,7 +336,7 @@ def spatial_softmax_bwd(dprobs, probs, K, dlogit, accumulate):
     n, P, ldd = dprobs.shape
     L = lib()
     B = L.b200seg_spatial_softmax_blocks(P)
-    ws = torch.empty((n * B * 32,), dtype=F32, device=dprobs.device)
+    ws = _new((n * B * 32,), dtype=F32, device=dprobs.device)
     check(L.b200seg_spatial_softmax_bwd(ptr(dprobs), ldd, ptr(probs), n, P, K, ptr(ws), ptr(dlogit), int(accumulate),
                                         stream_ptr()), "spatial_softmax_bwd", 2)
     return dlogit
@@ -309,14 +344,14 @@ def spatial_softmax_bwd(dprobs, probs, K, dlogit, accumulate):
 
 def class_softmax_fwd(x, K, scale):
     P, ld = x.shape
-    sim = torch.empty((P, 32), dtype=BF16, device=x.device)
+    sim = _new((P, 32), dtype=BF16, device=x.device)
     check(lib().b200seg_class_softmax_fwd(ptr(x), ld, P, K, scale, ptr(sim), stream_ptr()), "class_softmax_fwd")
     return sim
 
 
 def class_softmax_bwd(dsim, sim, K, scale):
     P, ld = dsim.shape
-    ds = torch.empty((P, 32), dtype=BF16, device=dsim.device)
+    ds = _new((P, 32), dtype=BF16, device=dsim.device)
     check(lib().b200seg_class_softmax_bwd(ptr(dsim), ld, ptr(sim), P, K, scale, ptr(ds), stream_ptr()),
           "class_softmax_bwd")
     return ds
@@ -325,7 +360,7 @@ def class_softmax_bwd(dsim, sim, K, scale):
 def transpose_pad(src, rpad):
     """src [R][C] (bf16 or fp32, row pitch = stride(0)) -> bf16 [C][rpad] zero padded."""
     R, C = src.shape
-    dst = torch.empty((C, rpad), dtype=BF16, device=src.device)
+    dst = _new((C, rpad), dtype=BF16, device=src.device)
     check(lib().b200seg_transpose_pad(ptr(src), int(src.dtype == F32), R, C, src.stride(0), ptr(dst), rpad,
                                       stream_ptr()), "transpose_pad")
     return dst
@@ -359,8 +394,8 @@ def mscale_desc(n, h, w, hq, wq, hm=0, wm=0, hl=0, wl=0, nheads=2, w0=1.0, w1=0.
 
 def count_valid(labels, ignore_index=255, plus_one=False):
     """-> fp32 [1] = 1 / (#valid labels (+1 for the RMILoss normalisation, loss/rmi.py:95))."""
-    ws = torch.empty((1,), dtype=torch.int64, device=labels.device)
-    inv = torch.empty((1,), dtype=F32, device=labels.device)
+    ws = _new((1,), dtype=torch.int64, device=labels.device)
+    inv = _new((1,), dtype=F32, device=labels.device)
     check(lib().b200seg_count_valid(ptr(labels), labels.numel(), ignore_index, int(plus_one), ptr(ws), ptr(inv),
                                     stream_ptr()), "count_valid", 2)
     return inv
@@ -371,15 +406,15 @@ def rmi_head(d, labels, hi_cls, mid):
     dev = hi_cls.device
     n, hp, wp = d.n, d.h // 4 + 1, d.w // 4 + 1
     L = lib()
-    pr = torch.empty((n, hp, wp, 20), dtype=F32, device=dev)
-    la = torch.empty((n, hp, wp, 20), dtype=F32, device=dev)
+    pr = _new((n, hp, wp, 20), dtype=F32, device=dev)
+    la = _new((n, hp, wp, 20), dtype=F32, device=dev)
     check(L.b200seg_rmi_pool(ctypes.byref(d), ptr(labels), ptr(hi_cls), ptr(mid), ptr(pr), ptr(la), stream_ptr()),
           "rmi_pool")
     nbytes = L.b200seg_rmi_ws_bytes(n)
-    ws = torch.empty((nbytes // 8,), dtype=torch.float64, device=dev)
-    G = torch.empty((n, 19, 180), dtype=torch.float64, device=dev)
-    terms = torch.empty((n * 19,), dtype=F32, device=dev)
-    dpr = torch.empty((n, hp, wp, 20), dtype=F32, device=dev)
+    ws = _new((nbytes // 8,), dtype=torch.float64, device=dev)
+    G = _new((n, 19, 180), dtype=torch.float64, device=dev)
+    terms = _new((n * 19,), dtype=F32, device=dev)
+    dpr = _new((n, hp, wp, 20), dtype=F32, device=dev)
     scale = d.w_head0 * (1.0 - RMI_LAMBDA) / (n * 9.0)
     check(L.b200seg_rmi_solve_grad(n, d.h, d.w, ptr(pr), ptr(la), scale, ptr(ws), nbytes, ptr(G), ptr(terms), ptr(dpr),
                                    stream_ptr()), "rmi_solve_grad", 3)
@@ -388,8 +423,8 @@ def rmi_head(d, labels, hi_cls, mid):
 
 def mscale_mid_fwd(d, lo_cls, lo_aux, lo_attn):
     dev = lo_cls.device
-    mid = torch.empty((d.n, d.hm, d.wm, 40), dtype=F32, device=dev)
-    mid_sup = torch.empty((d.n, d.hm, d.wm, 20), dtype=F32, device=dev) if d.sup_wt != 0.0 else None
+    mid = _new((d.n, d.hm, d.wm, 40), dtype=F32, device=dev)
+    mid_sup = _new((d.n, d.hm, d.wm, 20), dtype=F32, device=dev) if d.sup_wt != 0.0 else None
     check(lib().b200seg_mscale_mid_fwd(ctypes.byref(d), ptr(lo_cls), ptr(lo_aux), ptr(lo_attn), ptr(mid), ptr(mid_sup),
                                        stream_ptr()), "mscale_mid_fwd")
     return mid, mid_sup
@@ -400,11 +435,11 @@ def mscale_loss_fwd(d, labels, inv_count, hi_cls, hi_aux, mid, mid_sup, rmi_dpr=
     L = lib()
     nb = L.b200seg_mscale_loss_blocks(ctypes.byref(d))
     npix = d.n * d.h * d.w
-    g_hi = torch.empty((npix, 40), dtype=BF16, device=dev)
-    g_lo = torch.empty((npix, 40), dtype=BF16, device=dev) if d.hm > 0 else None
-    g_sup = torch.empty((npix, 40), dtype=BF16, device=dev) if (d.hm > 0 and d.sup_wt != 0.0) else None
-    ws = torch.empty((nb * 4,), dtype=F32, device=dev)
-    loss = torch.zeros((8,), dtype=F32, device=dev)   # total, 4 pointwise means, RMI term, 2 pad
+    g_hi = _new((npix, 40), dtype=BF16, device=dev)
+    g_lo = _new((npix, 40), dtype=BF16, device=dev) if d.hm > 0 else None
+    g_sup = _new((npix, 40), dtype=BF16, device=dev) if (d.hm > 0 and d.sup_wt != 0.0) else None
+    ws = _new((nb * 4,), dtype=F32, device=dev)
+    loss = _newz((8,), dtype=F32, device=dev)   # total, 4 pointwise means, RMI term, 2 pad
     check(L.b200seg_mscale_loss_fwd(ctypes.byref(d), ptr(labels), ptr(inv_count), ptr(hi_cls), ptr(hi_aux), ptr(mid),
                                     ptr(mid_sup), ptr(g_hi), ptr(g_lo), ptr(g_sup), ptr(ws), ptr(loss), ptr(rmi_dpr),
                                     ptr(rmi_terms), rmi_terms.numel() if rmi_terms is not None else 0, stream_ptr()),
@@ -414,8 +449,8 @@ def mscale_loss_fwd(d, labels, inv_count, hi_cls, hi_aux, mid, mid_sup, rmi_dpr=
 
 def mscale_hi_bwd(d, g_hi):
     dev = g_hi.device
-    d_cls = torch.empty((d.n, d.hq, d.wq, 32), dtype=BF16, device=dev)
-    d_aux = torch.empty((d.n, d.hq, d.wq, 32), dtype=BF16, device=dev) if d.nheads > 1 else None
+    d_cls = _new((d.n, d.hq, d.wq, 32), dtype=BF16, device=dev)
+    d_aux = _new((d.n, d.hq, d.wq, 32), dtype=BF16, device=dev) if d.nheads > 1 else None
     check(lib().b200seg_mscale_hi_bwd(ctypes.byref(d), ptr(g_hi), ptr(d_cls), ptr(d_aux), stream_ptr()),
           "mscale_hi_bwd")
     return d_cls, d_aux
@@ -423,10 +458,10 @@ def mscale_hi_bwd(d, g_hi):
 
 def mscale_lo_bwd(d, g_lo, g_sup, lo_cls, lo_aux, lo_attn, mid):
     dev = g_lo.device
-    ws = torch.empty((d.n, d.hm, d.wm, 40), dtype=F32, device=dev)
-    d_cls = torch.empty((d.n, d.hl, d.wl, 32), dtype=BF16, device=dev)
-    d_aux = torch.empty((d.n, d.hl, d.wl, 32), dtype=BF16, device=dev) if d.nheads > 1 else None
-    d_attn = torch.empty((d.n, d.hl, d.wl, 8), dtype=BF16, device=dev)
+    ws = _new((d.n, d.hm, d.wm, 40), dtype=F32, device=dev)
+    d_cls = _new((d.n, d.hl, d.wl, 32), dtype=BF16, device=dev)
+    d_aux = _new((d.n, d.hl, d.wl, 32), dtype=BF16, device=dev) if d.nheads > 1 else None
+    d_attn = _new((d.n, d.hl, d.wl, 8), dtype=BF16, device=dev)
     check(lib().b200seg_mscale_lo_bwd(ctypes.byref(d), ptr(g_lo), ptr(g_sup), ptr(lo_cls), ptr(lo_aux), ptr(lo_attn),
                                       ptr(mid), ptr(ws), ptr(d_cls), ptr(d_aux), ptr(d_attn), stream_ptr()),
           "mscale_lo_bwd", 2)
@@ -437,7 +472,7 @@ def mscale_lo_bwd(d, g_lo, g_sup, lo_cls, lo_aux, lo_attn, mid):
 def resize_to_nchw(src_nhwc, C, H, W, apply_sigmoid=False):
     """fp32 NHWC [n,h,w,ld] -> fp32 NCHW [n,C,H,W] (bilinear, align_corners=False)."""
     n, h, w, _ = src_nhwc.shape
-    dst = torch.empty((n, C, H, W), dtype=F32, device=src_nhwc.device)
+    dst = _new((n, C, H, W), dtype=F32, device=src_nhwc.device)
     check(lib().b200seg_resize_to_nchw(ptr(src_nhwc), _ld(src_nhwc), n, h, w, C, int(apply_sigmoid), ptr(dst), H, W,
                                        stream_ptr()), "resize_to_nchw")
     return dst
@@ -447,7 +482,7 @@ def resize_nchw(src, H, W):
     n, c, h, w = src.shape
     if (h, w) == (H, W):
         return src
-    dst = torch.empty((n, c, H, W), dtype=F32, device=src.device)
+    dst = _new((n, c, H, W), dtype=F32, device=src.device)
     check(lib().b200seg_resize_nchw(ptr(src), n * c, h, w, ptr(dst), H, W, stream_ptr()), "resize_nchw")
     return dst
 
@@ -455,7 +490,7 @@ def resize_nchw(src, H, W):
 def blend(a, x, y, mode):
     """mode 0: a*x + (1-a)*y; 1: x + (1-a)*y; 2: a*x   (a [n,1,H,W]; x,y [n,C,H,W])."""
     n, c, h, w = x.shape
-    out = torch.empty_like(x)
+    out = _new_like(x)
     check(lib().b200seg_blend(ptr(a), ptr(x), ptr(y), ptr(out), n, c, h * w, mode, stream_ptr()), "blend")
     return out
 
@@ -466,7 +501,7 @@ def accum_pred(pred, out=None, flip=False):
     n, c, h, w = pred.shape
     acc = out is not None
     if out is None:
-        out = torch.empty_like(pred)
+        out = _new_like(pred)
     check(lib().b200seg_accum_pred(ptr(pred), ptr(out), n, c, h, w, int(flip), int(acc), stream_ptr()), "accum_pred")
     return out
 
@@ -475,10 +510,10 @@ def argmax_hist(pred, labels=None, scale=1.0, hist=None):
     """-> (argmax int64 [n,h,w], max softmax prob fp32 [n,h,w], hist int64 [c,c] (accumulated) or None)."""
     n, c, h, w = pred.shape
     assert pred.dtype == F32 and pred.is_contiguous()
-    pm = torch.empty((n, h, w), dtype=torch.int64, device=pred.device)
-    mp = torch.empty((n, h, w), dtype=F32, device=pred.device)
+    pm = _new((n, h, w), dtype=torch.int64, device=pred.device)
+    mp = _new((n, h, w), dtype=F32, device=pred.device)
     if labels is not None and hist is None:
-        hist = torch.zeros((c, c), dtype=torch.int64, device=pred.device)
+        hist = _newz((c, c), dtype=torch.int64, device=pred.device)
     check(lib().b200seg_argmax_hist(ptr(pred), n, c, h * w, float(scale), ptr(labels), ptr(pm), ptr(mp), ptr(hist),
                                     stream_ptr()), "argmax_hist")
     return pm, mp, hist
