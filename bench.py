@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--sup-wt", type=float, default=0.0)
     ap.add_argument("--criterion", default="ce", choices=["ce", "rmi"])
+    ap.add_argument("--torch-sgd", action="store_true", help="torch.optim.SGD instead of b200seg.optim.FusedSGD")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -225,7 +226,11 @@ def run_b200(args):
             if p_.dim() == 4 and n_.startswith("backbone"):
                 fan_in = p_.shape[1] * p_.shape[2] * p_.shape[3]
                 p_.normal_(0, (2.0 / fan_in) ** 0.5)
-    opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    if args.torch_sgd:
+        opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    else:
+        from b200seg.optim import FusedSGD      # same update rule, one launch
+        opt = FusedSGD(net.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
     B, H, W = args.batch_per_gpu, args.height, args.width
     images_h, gts_h = synth_batch(B, H, W, 1 + rank, "cpu")
     images_h, gts_h = images_h.pin_memory(), gts_h.pin_memory()
@@ -298,7 +303,7 @@ def run_b200(args):
         steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
         config=dict(workload="%s two-scale {0.5,1.0} train step (zero_grad, fused fwd+bwd, grad publish%s, SGD "
-                             "momentum), %dx%d crops, %d crop/GPU, %s loss, %s" %
+                             "momentum + weight decay), %dx%d crops, %d crop/GPU, %s loss, %s" %
                              (args.arch, "+NCCL all-reduce" if world > 1 else "", H, W, B, args.criterion.upper(),
                               "SyncBN: per-layer statistics exchanged through NVLink peer memory inside the BN "
                               "finalisers" if world > 1 else "single GPU (BatchNorm over the local batch)"),

@@ -75,7 +75,8 @@ int b200seg_pack_weight(const float* w_oihw, int32_t o, int32_t i, int32_t ksize
 /* The same repack for every convolution of the model in one launch (the weights change every optimizer step).
  * items: DEVICE array; block b handles b200seg_pack_chunk() consecutive OIHW elements of items[blk_item[b]] starting
  * at blk_start[b]. i_dst >= i is the input-channel extent of the destination layouts (the 3-channel stem runs on a
- * 16-channel padded image; pad entries must have been zeroed once by the caller). */
+ * 16-channel padded image; pad entries must have been zeroed once by the caller). which: 1 = forward operands only,
+ * 2 = data-gradient operands only (needed from the backward on: can run on a side stream), 3 = both. */
 typedef struct b200seg_pack_item {
   const void* w_oihw;      /* fp32 [o][i][k][k] */
   void* w_ohwi;            /* bf16 [o][k*k][i_dst] or NULL */
@@ -84,7 +85,7 @@ typedef struct b200seg_pack_item {
 } b200seg_pack_item;
 int32_t b200seg_pack_chunk(void);
 int b200seg_pack_weights(const b200seg_pack_item* items, const int32_t* blk_item, const int32_t* blk_start,
-                         int32_t n_blocks, void* stream);
+                         int32_t n_blocks, int32_t which, void* stream);
 
 /* Data gradient: dx[n,h,w,cin] = conv_transpose(dy, W) (+ addend, e.g. a gradient that already arrived at x).
  * d describes the FORWARD convolution; dy: bf16 [n,ho,wo,*] whose channel extent is roundup8(cout) (pad channels
@@ -164,6 +165,21 @@ int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t c, int32_t 
 int b200seg_bn_running_update(float* running, const float* batch_pass0, const float* batch_pass1, int64_t n,
                               float momentum, int64_t* num_batches_tracked, int32_t n_layers, int32_t n_passes,
                               void* stream);
+/* Multi-tensor SGD step (the update rule of the optimizer loss/optimizer.py:43-60 builds: momentum, weight decay,
+ * optional nesterov) for every parameter of a group in ONE launch. items: DEVICE array; block b updates
+ * b200seg_sgd_chunk() consecutive elements of items[blk_item[b]] from blk_start[b]. first_step: momentum buffers are
+ * initialised with the (decayed) gradient. SURVEY.md §8(f) row f3. */
+typedef struct b200seg_sgd_item {
+  void* param;             /* fp32 [numel] */
+  const void* grad;        /* fp32 [numel] */
+  void* momentum_buf;      /* fp32 [numel] (ignored when momentum == 0) */
+  int64_t numel;
+} b200seg_sgd_item;
+int32_t b200seg_sgd_chunk(void);
+int b200seg_sgd_step(const b200seg_sgd_item* items, const int32_t* blk_item, const int32_t* blk_start, int32_t n_blocks,
+                     float lr, float momentum, float dampening, float weight_decay, int32_t nesterov, int32_t first_step,
+                     void* stream);
+
 /* dst[n] += src[n] (fp32, n multiple of 4, 16-byte aligned): folds a scale pass' private parameter-gradient buffer
  * into the step gradient (the passes run concurrently; autograd's accumulation order lo -> hi is kept). */
 int b200seg_accum_f32(float* dst, const float* src, int64_t n, void* stream);

@@ -69,7 +69,7 @@ SIGNATURES = {
     "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
     "b200seg_pack_weight": (ctypes.c_int, [V, I32, I32, I32, V, V, I32, V]),
     "b200seg_pack_chunk": (I32, []),
-    "b200seg_pack_weights": (ctypes.c_int, [V, V, V, I32, V]),
+    "b200seg_pack_weights": (ctypes.c_int, [V, V, V, I32, I32, V]),
     "b200seg_conv2d_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, I32, V, V, I32, V, I32, V]),
     "b200seg_conv2d_wgrad_ws_bytes": (c_size_t, [ctypes.POINTER(ConvDesc)]),
     "b200seg_conv2d_wgrad_launches": (I32, [ctypes.POINTER(ConvDesc)]),
@@ -84,6 +84,8 @@ SIGNATURES = {
     "b200seg_p2p_free": (ctypes.c_int, [V]),
     "b200seg_bn_running_update": (ctypes.c_int, [V, V, V, I64, F, V, I32, I32, V]),
     "b200seg_accum_f32": (ctypes.c_int, [V, V, I64, V]),
+    "b200seg_sgd_chunk": (I32, []),
+    "b200seg_sgd_step": (ctypes.c_int, [V, V, V, I32, F, F, F, F, I32, I32, V]),
     "b200seg_bn_eval_params": (ctypes.c_int, [I32, V, V, F, V, V, V, V, V]),
     "b200seg_bn_apply": (ctypes.c_int, [V, I32, V, V, V, I32, V, I32, V, I32, I64, I32, I32, V]),
     "b200seg_bn_bwd_grid": (I32, [I64, I32]),

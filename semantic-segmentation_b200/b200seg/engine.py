@@ -66,6 +66,7 @@ class Engine:
         self.bstreams = list(branch_streams or [])
         self.ws_holder = ws_holder
         self._ctx = None         # stream of the branch section being recorded (None = the engine's own stream)
+        self.pre_backward_event = None   # e.g. "data-gradient weight operands packed" (recorded on another stream)
         self.tape = []
         self.bn_seen = set()
         self.hold = []      # tensors handed across streams: kept alive until the step's final join
@@ -79,6 +80,8 @@ class Engine:
     def run_backward(self):
         """Pops the tape: ops run on the stream they were recorded on; a forward join becomes a fork and vice versa."""
         tape = self.tape
+        if self.pre_backward_event is not None:
+            torch.cuda.current_stream().wait_event(self.pre_backward_event)
         while tape:
             kind, fn, st = tape.pop()
             if kind == "op":

@@ -255,9 +255,10 @@ class B200SegModule(nn.Module):
         self._bstat_views = [{b: t[o_:o_ + 2 * c_] for b, (o_, c_) in self._bn_slots.items()} for t in self._bstat]
         self._graphs = {}
 
-    def _repack(self):
+    def _repack(self, side=None):
         """fp32 OIHW master weights -> bf16 kernel layouts, one launch for the whole model (inside the captured step:
-        the weights change every optimizer step)."""
+        the weights change every optimizer step). With `side` (a stream) the data-gradient operands, which nothing
+        reads before the backward, are packed there; returns the event the backward has to wait for."""
         convs = [(n, p) for n, p in self.named_parameters() if p.dim() == 4]
         ptrs = tuple(p.data_ptr() for _, p in convs)
         tab = getattr(self, "_pack_table", None)
@@ -265,7 +266,17 @@ class B200SegModule(nn.Module):
             entries = [(p.detach(), *self._packed[n[: -len(".weight")]]) for n, p in convs]
             tab = self._pack_table = raw.pack_table(entries, convs[0][1].device)
             self._graphs = {}
-        raw.pack_weights(tab)
+        if side is None:
+            raw.pack_weights(tab, 3)
+            return None
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            raw.pack_weights(tab, 2)
+            evt = torch.cuda.Event()
+            evt.record()
+        raw.pack_weights(tab, 1)
+        return evt
 
     # ------------------------------------------------------------------------------------------ training step
     def _step_eager(self, images, gts, drop_mask):
@@ -295,7 +306,9 @@ class B200SegModule(nn.Module):
         return self._sync
 
     def _step_body(self, images, gts, drop_mask):
-        self._repack()
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream()
+        wd_ready = self._repack(side=self._side_stream)
         sync = self._sync
         if sync is not None:
             sync.advance()
@@ -330,6 +343,9 @@ class B200SegModule(nn.Module):
                    branch_streams=self._bstreams["hi"], ws_holder=self._ws_holders["hi"])
         loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,
                             self.ignore_index, E_lo=E_lo, loss_kind=self.loss_kind)
+        E.pre_backward_event = wd_ready
+        if E_lo is not None:
+            E_lo.pre_backward_event = wd_ready
         M.run_backward(E, E_lo)
         self._fold_grads(stem_pads, par)
         if par:

@@ -94,9 +94,10 @@ def pack_table(entries, device):
                 ptrs=tuple(e[0].data_ptr() for e in entries))
 
 
-def pack_weights(table):
+def pack_weights(table, which=3):
+    """which: 1 forward operands, 2 data-gradient operands, 3 both."""
     check(lib().b200seg_pack_weights(ptr(table["items"]), ptr(table["blk_item"]), ptr(table["blk_start"]),
-                                     table["n_blocks"], stream_ptr()), "pack_weights")
+                                     table["n_blocks"], which, stream_ptr()), "pack_weights")
 
 
 def conv_desc(n, h, w, cin, cout, ksize, stride, x_ld, y_ld, out_fp32=False, has_bias=False, emit_stats=False,

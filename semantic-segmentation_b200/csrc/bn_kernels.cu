@@ -171,6 +171,34 @@ __global__ void bn_running_update_kernel(float* __restrict__ running, const floa
   if (nbt && i < n_layers) nbt[i] += n_passes;
 }
 
+// Multi-tensor SGD with momentum and weight decay (torch.optim.SGD semantics, loss/optimizer.py:43-60): one launch for all
+// parameters of a group. Block b updates kSgdChunk consecutive elements of items[blk_item[b]].
+constexpr int kSgdChunk = 4096;
+__global__ void __launch_bounds__(256)
+sgd_step_kernel(const b200seg_sgd_item* __restrict__ items, const int32_t* __restrict__ blk_item,
+                const int32_t* __restrict__ blk_start, float lr, float momentum, float dampening, float weight_decay,
+                int nesterov, int first_step) {
+  pdl_sync();
+  const b200seg_sgd_item it = items[blk_item[blockIdx.x]];
+  float* __restrict__ p = reinterpret_cast<float*>(it.param);
+  const float* __restrict__ g = reinterpret_cast<const float*>(it.grad);
+  float* __restrict__ m = reinterpret_cast<float*>(it.momentum_buf);
+  const long long j0 = blk_start[blockIdx.x];
+#pragma unroll 4
+  for (int t = threadIdx.x; t < kSgdChunk; t += 256) {
+    const long long j = j0 + t;
+    if (j >= it.numel) break;
+    const float w = p[j];
+    float d = g[j] + weight_decay * w;
+    if (momentum != 0.f) {
+      const float b = first_step ? d : momentum * m[j] + (1.f - dampening) * d;
+      m[j] = b;
+      d = nesterov ? d + momentum * b : b;
+    }
+    p[j] = w - lr * d;
+  }
+}
+
 // dst += src (fp32): folds the low-resolution pass' private parameter-gradient buffer into the step's gradient.
 __global__ void accum_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4) {
   pdl_sync();
@@ -569,4 +597,15 @@ extern "C" int b200seg_p2p_close(void* dev_ptr) {
 extern "C" int b200seg_p2p_free(void* dev_ptr) {
   cudaError_t e = cudaFree(dev_ptr);
   return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int32_t b200seg_sgd_chunk(void) { return kSgdChunk; }
+
+extern "C" int b200seg_sgd_step(const b200seg_sgd_item* items, const int32_t* blk_item, const int32_t* blk_start,
+                                int32_t n_blocks, float lr, float momentum, float dampening, float weight_decay,
+                                int32_t nesterov, int32_t first_step, void* stream) {
+  if (!items || !blk_item || !blk_start || n_blocks <= 0) return B200SEG_E_BADARG;
+  launch_k(sgd_step_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, items, blk_item, blk_start, lr, momentum,
+           dampening, weight_decay, (int)nesterov, (int)first_step);
+  CHECK_LAUNCH();
 }

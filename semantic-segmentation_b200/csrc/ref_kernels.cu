@@ -58,12 +58,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, in
 constexpr int kPackChunk = 4096;
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const b200seg_pack_item* __restrict__ items, const int32_t* __restrict__ blk_item,
-                    const int32_t* __restrict__ blk_start) {
+                    const int32_t* __restrict__ blk_start, int which) {
   pdl_sync();
   const b200seg_pack_item it = items[blk_item[blockIdx.x]];
   const float* __restrict__ w = reinterpret_cast<const float*>(it.w_oihw);
-  __nv_bfloat16* __restrict__ ohwi = reinterpret_cast<__nv_bfloat16*>(it.w_ohwi);
-  __nv_bfloat16* __restrict__ dgrad = reinterpret_cast<__nv_bfloat16*>(it.w_dgrad);
+  __nv_bfloat16* __restrict__ ohwi = (which & 1) ? reinterpret_cast<__nv_bfloat16*>(it.w_ohwi) : nullptr;
+  __nv_bfloat16* __restrict__ dgrad = (which & 2) ? reinterpret_cast<__nv_bfloat16*>(it.w_dgrad) : nullptr;
   const uint32_t taps = (uint32_t)(it.ksize * it.ksize), I = (uint32_t)it.i, Id = (uint32_t)it.i_dst;
   const uint32_t total = (uint32_t)it.o * I * taps;
   const uint32_t j0 = (uint32_t)blk_start[blockIdx.x];
@@ -87,10 +87,10 @@ using namespace b200seg;
 extern "C" int32_t b200seg_pack_chunk(void) { return kPackChunk; }
 
 extern "C" int b200seg_pack_weights(const b200seg_pack_item* items, const int32_t* blk_item, const int32_t* blk_start,
-                                    int32_t n_blocks, void* stream) {
-  if (!items || !blk_item || !blk_start || n_blocks <= 0) return B200SEG_E_BADARG;
+                                    int32_t n_blocks, int32_t which, void* stream) {
+  if (!items || !blk_item || !blk_start || n_blocks <= 0 || which < 1 || which > 3) return B200SEG_E_BADARG;
   cudaError_t e = launch_k(pack_weights_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, items, blk_item,
-                           blk_start);
+                           blk_start, (int)which);
   return e == cudaSuccess ? 0 : (int)e;
 }
 

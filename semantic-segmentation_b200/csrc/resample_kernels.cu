@@ -79,6 +79,10 @@ fuse_fwd_kernel(const FuseParams p, __nv_bfloat16* __restrict__ out, int out_ld)
 }
 
 // gl[n,y,x,c] = sum over fine pixels (Y,X) of w(Y,y) * w(X,x) * g[n,Y,X,c] * (mask[n,Y,X,c] > 0)
+// LANES (1, 4, 16 or 32, by upsampling ratio) consecutive lanes share one (coarse pixel, 8-channel group): they stride
+// over the flattened fine window and fold their partial sums with a fixed xor butterfly (deterministic). A x8 adjoint
+// gathers ~256 fine pixels per output: one thread per output would be a 500-load latency chain on 12k threads.
+template <int LANES>
 __global__ void __launch_bounds__(256)
 upsample_adjoint_kernel(const __nv_bfloat16* __restrict__ g, int g_ld, const __nv_bfloat16* __restrict__ mask,
                         int mask_ld, int N, int H, int W, int C, __nv_bfloat16* __restrict__ out, int out_ld, int h,
@@ -88,10 +92,14 @@ upsample_adjoint_kernel(const __nv_bfloat16* __restrict__ g, int g_ld, const __n
   const long long total = (long long)N * h * w * groups;
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
   const float ry = (float)H / (float)h, rx = (float)W / (float)w;   // upsampling ratio
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long pix = idx / groups;
-    const int c0 = (int)(idx - pix * groups) << 3;
+  const int sub = threadIdx.x % LANES;
+  const long long total_padded = (total + (256 / LANES) - 1) / (256 / LANES) * (256 / LANES);
+  for (long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LANES; idx < total_padded;
+       idx += (long long)gridDim.x * blockDim.x / LANES) {
+    const bool live = idx < total;       // whole LANES-groups stay in the loop together (shuffles below)
+    const long long idc = live ? idx : total - 1;
+    const long long pix = idc / groups;
+    const int c0 = (int)(idc - pix * groups) << 3;
     const int x = (int)(pix % w);
     const int y = (int)((pix / w) % h);
     const int n = (int)(pix / ((long long)w * h));
@@ -107,39 +115,45 @@ upsample_adjoint_kernel(const __nv_bfloat16* __restrict__ g, int g_ld, const __n
     if (X_lo < 0) X_lo = 0;
     if (Y_hi > H || y == h - 1) Y_hi = H;
     if (X_hi > W || x == w - 1) X_hi = W;
-    for (int Y = Y_lo; Y < Y_hi; ++Y) {
-      int y0, y1;
-      float ly;
+    const int wx_n = X_hi - X_lo;
+    const int cells = (Y_hi - Y_lo) * wx_n;
+    for (int cell = sub; cell < cells; cell += LANES) {
+      const int Y = Y_lo + cell / wx_n, X = X_lo + cell % wx_n;
+      int y0, y1, x0, x1;
+      float ly, lx;
       bilinear_src(Y, sy, h, y0, y1, ly);
       const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
       if (wy == 0.f) continue;
-      for (int X = X_lo; X < X_hi; ++X) {
-        int x0, x1;
-        float lx;
-        bilinear_src(X, sx, w, x0, x1, lx);
-        const float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
-        if (wx == 0.f) continue;
-        const long long fp = ((long long)n * H + Y) * W + X;
-        float v[8];
-        load8(g + fp * g_ld + c0, v);
-        if (mask) {
-          float mk[8];
-          load8(mask + fp * mask_ld + c0, mk);
+      bilinear_src(X, sx, w, x0, x1, lx);
+      const float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+      if (wx == 0.f) continue;
+      const long long fp = ((long long)n * H + Y) * W + X;
+      float v[8];
+      load8(g + fp * g_ld + c0, v);
+      if (mask) {
+        float mk[8];
+        load8(mask + fp * mask_ld + c0, mk);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = mk[j] > 0.f ? v[j] : 0.f;
-        }
-        const float wgt = wy * wx;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += wgt * v[j];
+        for (int j = 0; j < 8; ++j) v[j] = mk[j] > 0.f ? v[j] : 0.f;
       }
-    }
-    if (accumulate) {
-      float old[8];
-      load8(out + pix * out_ld + c0, old);
+      const float wgt = wy * wx;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += old[j];
+      for (int j = 0; j < 8; ++j) acc[j] += wgt * v[j];
     }
-    store8(out + pix * out_ld + c0, acc);
+#pragma unroll
+    for (int off = LANES / 2; off >= 1; off >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    }
+    if (sub == 0 && live) {
+      if (accumulate) {
+        float old[8];
+        load8(out + pix * out_ld + c0, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += old[j];
+      }
+      store8(out + pix * out_ld + c0, acc);
+    }
   }
 }
 
@@ -215,9 +229,23 @@ extern "C" int b200seg_upsample_adjoint(const void* g, int32_t g_ld, const void*
                                         int32_t accumulate, void* stream) {
   if (!g || !out || c % 8 || g_ld % 8 || out_ld % 8 || h > H || w > W) return B200SEG_E_BADARG;
   const long long total = (long long)n * h * w * (c / 8);
-  launch_k(upsample_adjoint_kernel, dim3(ew_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)mask, mask_ld, n, H, W, c, (__nv_bfloat16*)out, out_ld, h, w,
-      accumulate);
-  cudaError_t e = cudaGetLastError();
+  const int ratio = (H + h - 1) / h;
+  const cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16 *gp = (const __nv_bfloat16*)g, *mp = (const __nv_bfloat16*)mask;
+  __nv_bfloat16* op = (__nv_bfloat16*)out;
+  cudaError_t e;
+  if (ratio >= 8)
+    e = launch_k(upsample_adjoint_kernel<32>, dim3(ew_grid(total * 32)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n, H, W, c,
+                 op, out_ld, h, w, accumulate);
+  else if (ratio >= 4)
+    e = launch_k(upsample_adjoint_kernel<16>, dim3(ew_grid(total * 16)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n, H, W, c,
+                 op, out_ld, h, w, accumulate);
+  else if (ratio >= 2)
+    e = launch_k(upsample_adjoint_kernel<4>, dim3(ew_grid(total * 4)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n, H, W, c,
+                 op, out_ld, h, w, accumulate);
+  else
+    e = launch_k(upsample_adjoint_kernel<1>, dim3(ew_grid(total)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n, H, W, c, op,
+                 out_ld, h, w, accumulate);
   return e == cudaSuccess ? 0 : (int)e;
 }
 

@@ -400,3 +400,28 @@ def test_eval_tail_argmax_confusion_and_flip_average():
     assert torch.equal(hist, ref_hist)
     _, _, hist2 = raw.argmax_hist(out, gts, 0.5, hist)             # accumulates
     assert torch.equal(hist2, 2 * ref_hist)
+
+
+def test_fused_sgd_matches_torch_sgd():
+    """b200seg.optim.FusedSGD vs torch.optim.SGD (the optimizer of loss/optimizer.py:43-60) over several steps."""
+    _setup()
+    from b200seg.optim import FusedSGD
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(48, 32, 3, 3), (96,), (19, 512, 1, 1), (5000,)]
+    pa = [torch.randn(s, generator=g, device="cuda").requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = torch.optim.SGD(pa, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    ob = FusedSGD(pb, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    for step in range(4):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, generator=g, device="cuda")
+            x.grad, y.grad = gr.clone(), (gr.clone() if y.grad is None else y.grad.copy_(gr))
+        for grp in ob.param_groups:
+            grp["lr"] = 0.05 * (1 - 0.1 * step)          # scheduler-style LR change
+        for grp in oa.param_groups:
+            grp["lr"] = 0.05 * (1 - 0.1 * step)
+        oa.step()
+        ob.step()
+    for x, y in zip(pa, pb):
+        assert float((x - y).abs().max()) <= 1e-6 * (1 + float(x.abs().max()))
+        assert float((oa.state[x]["momentum_buffer"] - ob.state[y]["momentum_buffer"]).abs().max()) <= 1e-5
