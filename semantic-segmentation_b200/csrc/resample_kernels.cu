@@ -106,9 +106,11 @@ upsample_adjoint_kernel(const __nv_bfloat16* __restrict__ g, int g_ld, const __n
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    // fine pixels whose source coordinate can touch coarse index y lie within [ry*(y-1), ry*(y+2)) (conservative, clamped); borders absorb more
-    int Y_lo = (int)floorf(ry * (y - 1)) - 1, Y_hi = (int)ceilf(ry * (y + 2)) + 1;
-    int X_lo = (int)floorf(rx * (x - 1)) - 1, X_hi = (int)ceilf(rx * (x + 2)) + 1;
+    // fine pixel Y touches coarse row y iff its source coordinate (Y + 0.5) / ry - 0.5 lies in (y - 1, y + 1), i.e.
+    // Y in (ry (y - 0.5) - 0.5, ry (y + 1.5) - 0.5): 2 ry candidates (+1 on each side against rounding); the clamped
+    // border rows / columns absorb everything beyond
+    int Y_lo = (int)floorf(ry * (y - 0.5f) - 0.5f) - 1, Y_hi = (int)ceilf(ry * (y + 1.5f) - 0.5f) + 1;
+    int X_lo = (int)floorf(rx * (x - 0.5f) - 0.5f) - 1, X_hi = (int)ceilf(rx * (x + 1.5f) - 0.5f) + 1;
     if (y == 0) Y_lo = 0;
     if (x == 0) X_lo = 0;
     if (Y_lo < 0) Y_lo = 0;
