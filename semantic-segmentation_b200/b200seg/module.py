@@ -321,7 +321,10 @@ class B200SegModule(nn.Module):
             self._acc_lo.zero_()
         raw.KEEP = []               # every allocation of the step stays referenced until its final join (raw.py)
         if getattr(self, "_bstreams", None) is None:
-            mk = lambda: [torch.cuda.Stream() for _ in range(3)] if self.parallel_branches else []
+            # SyncBN spins on peers inside the BN finalisers: keep the validated stream structure (one stream per scale
+            # pass + its side stream) there; branch-level streams are a single-GPU-statistics optimisation for now
+            use_b = self.parallel_branches and self._sync is None
+            mk = lambda: [torch.cuda.Stream() for _ in range(3)] if use_b else []
             self._bstreams = {"hi": mk(), "lo": mk()}
             self._ws_holders = {"hi": [None], "lo": [None]}
         grads, stem_pad = self._engine_grads("hi")

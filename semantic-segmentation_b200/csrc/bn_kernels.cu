@@ -91,7 +91,7 @@ __device__ __forceinline__ void sync_exchange(const SyncArgs& sy, int C, int c, 
     for (int r = 0; r < sy.world; ++r) {
       unsigned spins = 0;
       while (ld_acquire_sys(myflags + r * nblk) != step) {
-        if (++spins > (1u << 30)) __trap();       // a lost peer traps instead of hanging the GPU
+        if (++spins > (1u << 27)) __trap();       // a lost peer traps (after ~20-40 s) instead of hanging the GPU
       }
       t1 += ld_volatile_f64(mymail + (long long)r * 2 * C + c);
       t2 += ld_volatile_f64(mymail + (long long)r * 2 * C + C + c);
