@@ -308,8 +308,9 @@ class B200SegModule(nn.Module):
     def _step_body(self, images, gts, drop_mask):
         if getattr(self, "_side_stream", None) is None:
             self._side_stream = torch.cuda.Stream()
-        wd_ready = self._repack(side=self._side_stream)
         sync = self._sync
+        # under SyncBN keep the validated stream structure: everything of the repack on the main stream
+        wd_ready = self._repack(side=self._side_stream if sync is None else None)
         if sync is not None:
             sync.advance()
         tensors = {k: v.detach() for k, v in self._tensors().items()}

@@ -90,8 +90,14 @@ __device__ __forceinline__ void sync_exchange(const SyncArgs& sy, int C, int c, 
     double t1 = 0.0, t2 = 0.0;
     for (int r = 0; r < sy.world; ++r) {
       unsigned spins = 0;
+      unsigned long long t0 = 0;
       while (ld_acquire_sys(myflags + r * nblk) != step) {
-        if (++spins > (1u << 27)) __trap();       // a lost peer traps (after ~20-40 s) instead of hanging the GPU
+        if ((++spins & 0xFFFFu) == 0) {            // a lost peer traps after 180 s instead of hanging the GPU
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 180000000000ull) __trap();
+        }
       }
       t1 += ld_volatile_f64(mymail + (long long)r * 2 * C + c);
       t2 += ld_volatile_f64(mymail + (long long)r * 2 * C + C + c);
