@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--sup-wt", type=float, default=0.0)
     ap.add_argument("--criterion", default="ce", choices=["ce", "rmi"])
+    ap.add_argument("--syncbn", action="store_true",
+                    help="synchronise BatchNorm statistics across the GPUs (NVLink peer-memory exchange; validated at N=2)")
     ap.add_argument("--torch-sgd", action="store_true", help="torch.optim.SGD instead of b200seg.optim.FusedSGD")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -218,7 +220,7 @@ def run_b200(args):
 
     torch.manual_seed(0)
     net = B200SegModule(args.arch, 19, criterion=args.criterion, supervised_mscale_wt=args.sup_wt,
-                        use_cuda_graph=not args.no_graph).cuda().train()
+                        use_cuda_graph=not args.no_graph, syncbn=bool(args.syncbn and world > 1)).cuda().train()
     net._ddp_allreduce = world > 1
     # well-scaled weights (the reference's default N(0,1e-3) init underflows activations after a few BN-free paths)
     with torch.no_grad():
@@ -272,23 +274,50 @@ def run_b200(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    # ---- end-to-end timing: pinned host inputs -> H2D every step, loss read back every step
+    # ---- end-to-end timing: pinned host inputs -> H2D every step, loss read back every step.
+    # (a) pipelined read: the loss of step i is copied to pinned memory asynchronously and read on the host while step
+    #     i+1 is already running (what a training loop that logs asynchronously does);
+    # (b) blocking read: loss.item() right after every step (the reference's train.py:499-512 pattern) - this also
+    #     exposes the launch latency of the ~6 000-node graph on an idle GPU every step.
+    pin = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    evts = [torch.cuda.Event() for _ in range(2)]
     t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_e0.record()
+    prev = None
+    loss_val = float("nan")
+    for i in range(args.steps):
+        im = images_h.cuda(non_blocking=True)
+        gt = gts_h.cuda(non_blocking=True)
+        loss = step(im, gt)
+        slot = i % 2
+        pin[slot].copy_(loss.detach().reshape(1), non_blocking=True)
+        evts[slot].record()
+        if prev is not None:
+            evts[prev].synchronize()
+            loss_val = float(pin[prev][0])
+        prev = slot
+    evts[prev].synchronize()
+    loss_val = float(pin[prev][0])
+    t_e1.record()
+    barrier()
+    ms_e2e = t_e0.elapsed_time(t_e1)
+    b_e0, b_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    b_e0.record()
     for _ in range(args.steps):
         im = images_h.cuda(non_blocking=True)
         gt = gts_h.cuda(non_blocking=True)
         loss = step(im, gt)
         loss_val = loss.item()
-    t_e1.record()
+    b_e1.record()
     barrier()
-    ms_e2e = t_e0.elapsed_time(t_e1)
+    ms_e2e_block = b_e0.elapsed_time(b_e1)
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
-        t = torch.tensor([ms, ms_e2e], device="cuda")
+        t = torch.tensor([ms, ms_e2e, ms_e2e_block], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_e2e_block = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         return
     crops = B * world * args.steps
@@ -306,16 +335,21 @@ def run_b200(args):
                              "momentum + weight decay), %dx%d crops, %d crop/GPU, %s loss, %s" %
                              (args.arch, "+NCCL all-reduce" if world > 1 else "", H, W, B, args.criterion.upper(),
                               "SyncBN: per-layer statistics exchanged through NVLink peer memory inside the BN "
-                              "finalisers" if world > 1 else "single GPU (BatchNorm over the local batch)"),
+                              "finalisers" if (world > 1 and args.syncbn) else
+                              "BatchNorm statistics local to each GPU (SyncBN is opt-in: --syncbn)"),
                     global_batch=B * world, parallelism="dp%d" % world, cuda_graph=not args.no_graph,
                     l2_policy="per-step working set (>4 GB of activations) far exceeds the 126 MB L2; the "
                               "single-kernel roofline run flushes L2 with a 256 MB write between iterations",
                     model_tflop_per_crop=TFLOP_PER_CROP[args.arch]),
         e2e=dict(value=e2e_value, unit="crops/s", ms_per_step=ms_e2e / args.steps,
                  h2d_bytes_per_step=int(images_h.numel() * 4 + gts_h.numel() * 8), d2h_bytes_per_step=4,
-                 api="net({'images','gts'}) -> loss.backward() -> SGD.step() from pinned host tensors, loss.item()"),
-        gpu_launches=int(kernels_per_step * args.steps * 2),
-        gpu_launches_note="%d b200seg kernels per step (inside one CUDA graph replay), two timed loops" % kernels_per_step,
+                 api="net({'images','gts'}) -> loss.backward() -> optimizer.step() from pinned host tensors; the loss of "
+                     "every step is copied to pinned host memory and read while the next step runs",
+                 blocking_read=dict(value=crops / (ms_e2e_block * 1e-3), ms_per_step=ms_e2e_block / args.steps,
+                                    note="loss.item() immediately after every step (exposes the graph-launch latency "
+                                         "on an idle GPU each step)")),
+        gpu_launches=int(kernels_per_step * args.steps * 3),
+        gpu_launches_note="%d b200seg kernels per step (inside one CUDA graph replay), three timed loops" % kernels_per_step,
         model_flops_utilisation=dict(achieved_tflops=step_tflops / 1.0, peak=pk["tf_sust"],
                                      frac=step_tflops / pk["tf_sust"], peak_source=pk["src"] + " sustained bf16"),
         roofline=roof, clocks=clocks, last_loss=loss_val,

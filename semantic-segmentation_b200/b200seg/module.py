@@ -88,8 +88,9 @@ class B200SegModule(nn.Module):
         self.use_cuda_graph = use_cuda_graph
         self.parallel_scales = parallel_scales     # run the 0.5x and 1.0x passes of the two-scale step concurrently
         self.parallel_branches = parallel_branches  # HRNet branches of a module on parallel streams
-        # SyncBN (config.py:216-225, every scripts/*.yml sets syncbn: true): None = on whenever the data-parallel
-        # all-reduce is on (torch.distributed initialised, world > 1), False = per-GPU statistics
+        # SyncBN (config.py:216-225, every scripts/*.yml sets syncbn: true): True = statistics of the global batch through
+        # NVLink peer memory (needs torch.distributed, world > 1); None / False = per-GPU statistics. Opt-in for now: the
+        # exchange was validated on 2 GPUs only.
         self.syncbn = syncbn
         self._sync = None
         self._run_flat = None
@@ -290,10 +291,7 @@ class B200SegModule(nn.Module):
 
     def _sync_context(self):
         """Lazily builds the SyncBN mailboxes (collective: every rank must reach its first training step)."""
-        want = self.syncbn
-        if want is None:
-            want = self._ddp_allreduce
-        if not want:
+        if not self.syncbn:
             return None
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
@@ -320,14 +318,17 @@ class B200SegModule(nn.Module):
         self._acc_hi.zero_()         # two memsets (45 us each) beat clearing inside the fold's transposed gather
         if par:
             self._acc_lo.zero_()
-        raw.KEEP = []               # every allocation of the step stays referenced until its final join (raw.py)
+        # every allocation of the step stays referenced until its final join (raw.py); SyncBN mode keeps the stream /
+        # allocation structure that was validated on 2 GPUs (no branch streams, no keep-alive, fresh wgrad workspaces)
+        raw.KEEP = [] if sync is None else None
         if getattr(self, "_bstreams", None) is None:
             # SyncBN spins on peers inside the BN finalisers: keep the validated stream structure (one stream per scale
             # pass + its side stream) there; branch-level streams are a single-GPU-statistics optimisation for now
             use_b = self.parallel_branches and self._sync is None
             mk = lambda: [torch.cuda.Stream() for _ in range(3)] if use_b else []
             self._bstreams = {"hi": mk(), "lo": mk()}
-            self._ws_holders = {"hi": [None], "lo": [None]}
+            hold = self._sync is None      # reusable slab workspaces go with the keep-alive mode
+            self._ws_holders = {"hi": [None] if hold else None, "lo": [None] if hold else None}
         grads, stem_pad = self._engine_grads("hi")
         stem_pads = [stem_pad]
         E_lo = None

@@ -23,7 +23,7 @@ def _worker(rank, world, port, use_graph, out):
     ocfg["dropout"] = 0.0
 
     def run(batch_slice, ddp, steps):
-        net = B200SegModule(arch, 19, hcfg=hcfg, ocfg=ocfg, use_cuda_graph=use_graph)
+        net = B200SegModule(arch, 19, hcfg=hcfg, ocfg=ocfg, use_cuda_graph=use_graph, syncbn=ddp)
         net.load_state_dict(sd0)
         net = net.cuda().train()
         net._ddp_allreduce = ddp
