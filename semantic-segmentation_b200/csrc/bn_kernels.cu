@@ -473,8 +473,9 @@ extern "C" int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t 
   if (!partials || !scale || !shift || !mean || !invstd || c <= 0 || grid <= 0) return B200SEG_E_BADARG;
   SyncArgs sy;
   if (int rc = make_sync(sync, &sy)) return rc;
-  launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinSlices), 0, (cudaStream_t)stream, partials, grid, c, cpad, count, gamma, beta, eps, momentum, running_mean, running_var,
-      (long long*)num_batches_tracked, scale, shift, mean, invstd, batch_stats_out, sy);
+  launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinSlices), 0, (cudaStream_t)stream, partials, grid, c,
+           cpad, count, gamma, beta, eps, momentum, running_mean, running_var, (long long*)num_batches_tracked, scale,
+           shift, mean, invstd, batch_stats_out, sy);
   CHECK_LAUNCH();
 }
 
@@ -499,8 +500,8 @@ extern "C" int b200seg_bn_eval_params(int32_t c, const float* gamma, const float
                                       const float* running_mean, const float* running_var, float* scale, float* shift,
                                       void* stream) {
   if (!gamma || !beta || !running_mean || !running_var || !scale || !shift) return B200SEG_E_BADARG;
-  launch_k(bn_eval_params_kernel, dim3((c + 127) / 128), dim3(128), 0, (cudaStream_t)stream, c, gamma, beta, eps, running_mean,
-                                                                          running_var, scale, shift);
+  launch_k(bn_eval_params_kernel, dim3((c + 127) / 128), dim3(128), 0, (cudaStream_t)stream, c, gamma, beta, eps,
+           running_mean, running_var, scale, shift);
   CHECK_LAUNCH();
 }
 
@@ -508,8 +509,9 @@ extern "C" int b200seg_bn_apply(const void* y, int32_t y_ld, const float* scale,
                                 int32_t res_ld, const float* post_scale, int32_t relu, void* z, int32_t z_ld,
                                 int64_t npix, int32_t hw, int32_t c, void* stream) {
   if (!y || !z || !scale || !shift || c % 8 || y_ld % 8 || z_ld % 8 || (res && res_ld % 8)) return B200SEG_E_BADARG;
-  launch_k(bn_apply_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 2 * c * sizeof(float), (cudaStream_t)stream, (const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, post_scale, relu,
-      (__nv_bfloat16*)z, z_ld, npix, hw, c);
+  launch_k(bn_apply_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 2 * c * sizeof(float), (cudaStream_t)stream,
+           (const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, post_scale, relu,
+           (__nv_bfloat16*)z, z_ld, npix, hw, c);
   CHECK_LAUNCH();
 }
 
@@ -539,8 +541,9 @@ extern "C" int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* 
   if (threads > 256) return B200SEG_E_BADARG;
   const int grid = b200seg_bn_bwd_grid(npix, c);
   const size_t smem = (size_t)rows * (c / 8) * 16 * sizeof(float);
-  launch_k(bn_bwd_reduce_kernel, dim3(grid), dim3(threads), smem, (cudaStream_t)stream, (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y, y_ld,
-      mean, invstd, npix, hw, c, rows, partials);
+  launch_k(bn_bwd_reduce_kernel, dim3(grid), dim3(threads), smem, (cudaStream_t)stream, (const __nv_bfloat16*)dz,
+           dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y, y_ld, mean, invstd, npix,
+           hw, c, rows, partials);
   CHECK_LAUNCH();
 }
 
@@ -549,8 +552,8 @@ extern "C" int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int3
   if (!partials || !c1 || !c2) return B200SEG_E_BADARG;
   SyncArgs sy;
   if (int rc = make_sync(sync, &sy)) return rc;
-  launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinSlices), 0, (cudaStream_t)stream, partials, grid, c, count, dgamma, dbeta,
-                                                                           c1, c2, sy);
+  launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinSlices), 0, (cudaStream_t)stream, partials,
+           grid, c, count, dgamma, dbeta, c1, c2, sy);
   CHECK_LAUNCH();
 }
 
@@ -560,16 +563,19 @@ extern "C" int b200seg_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* m
                                     int32_t dy_ld, void* g_out, int32_t g_ld, int32_t g_accumulate, int64_t npix,
                                     int32_t hw, int32_t c, void* stream) {
   if (!dz || !y || !dy || !mean || !invstd || !c1 || !c2 || c % 8) return B200SEG_E_BADARG;
-  launch_k(bn_bwd_apply_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 5 * c * sizeof(float), (cudaStream_t)stream, (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y, y_ld,
-      mean, invstd, gamma, c1, c2, (__nv_bfloat16*)dy, dy_ld, (__nv_bfloat16*)g_out, g_ld, g_accumulate, npix, hw, c);
+  launch_k(bn_bwd_apply_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 5 * c * sizeof(float), (cudaStream_t)stream,
+           (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y,
+           y_ld, mean, invstd, gamma, c1, c2, (__nv_bfloat16*)dy, dy_ld, (__nv_bfloat16*)g_out, g_ld, g_accumulate,
+           npix, hw, c);
   CHECK_LAUNCH();
 }
 
 extern "C" int b200seg_masked_accum(const void* src, int32_t src_ld, const void* mask, int32_t mask_ld, void* dst,
                                     int32_t dst_ld, int32_t accumulate, int64_t npix, int32_t c, void* stream) {
   if (!src || !dst || c % 8) return B200SEG_E_BADARG;
-  launch_k(masked_accum_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, src_ld, (const __nv_bfloat16*)mask, mask_ld, (__nv_bfloat16*)dst, dst_ld, accumulate,
-      npix, c);
+  launch_k(masked_accum_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 0, (cudaStream_t)stream,
+           (const __nv_bfloat16*)src, src_ld, (const __nv_bfloat16*)mask, mask_ld, (__nv_bfloat16*)dst, dst_ld,
+           accumulate, npix, c);
   CHECK_LAUNCH();
 }
 
@@ -611,7 +617,7 @@ extern "C" int b200seg_sgd_step(const b200seg_sgd_item* items, const int32_t* bl
                                 int32_t n_blocks, float lr, float momentum, float dampening, float weight_decay,
                                 int32_t nesterov, int32_t first_step, void* stream) {
   if (!items || !blk_item || !blk_start || n_blocks <= 0) return B200SEG_E_BADARG;
-  launch_k(sgd_step_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, items, blk_item, blk_start, lr, momentum,
-           dampening, weight_decay, (int)nesterov, (int)first_step);
+  launch_k(sgd_step_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, items, blk_item, blk_start, lr,
+           momentum, dampening, weight_decay, (int)nesterov, (int)first_step);
   CHECK_LAUNCH();
 }

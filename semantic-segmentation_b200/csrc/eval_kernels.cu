@@ -143,8 +143,8 @@ using namespace b200seg;
 extern "C" int b200seg_resize_to_nchw(const float* src_nhwc, int32_t ld, int32_t n, int32_t h, int32_t w, int32_t c,
                                       int32_t apply_sigmoid, float* dst_nchw, int32_t H, int32_t W, void* stream) {
   if (!src_nhwc || !dst_nchw || c > ld) return B200SEG_E_BADARG;
-  launch_k(resize_to_nchw_kernel, dim3(egrid((long long)n * c * H * W)), dim3(256), 0, (cudaStream_t)stream, src_nhwc, ld, n, h, w, c,
-                                                                                         apply_sigmoid, dst_nchw, H, W);
+  launch_k(resize_to_nchw_kernel, dim3(egrid((long long)n * c * H * W)), dim3(256), 0, (cudaStream_t)stream, src_nhwc,
+           ld, n, h, w, c, apply_sigmoid, dst_nchw, H, W);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -152,7 +152,8 @@ extern "C" int b200seg_resize_to_nchw(const float* src_nhwc, int32_t ld, int32_t
 extern "C" int b200seg_resize_nchw(const float* src, int32_t planes, int32_t h, int32_t w, float* dst, int32_t H,
                                    int32_t W, void* stream) {
   if (!src || !dst) return B200SEG_E_BADARG;
-  launch_k(resize_nchw_kernel, dim3(egrid((long long)planes * H * W)), dim3(256), 0, (cudaStream_t)stream, src, planes, h, w, dst, H, W);
+  launch_k(resize_nchw_kernel, dim3(egrid((long long)planes * H * W)), dim3(256), 0, (cudaStream_t)stream, src,
+           planes, h, w, dst, H, W);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -160,7 +161,8 @@ extern "C" int b200seg_resize_nchw(const float* src, int32_t planes, int32_t h, 
 extern "C" int b200seg_blend(const float* a, const float* x, const float* y, float* out, int32_t n, int32_t c,
                              int64_t hw, int32_t mode, void* stream) {
   if (!a || !x || !out || (mode != 2 && !y) || mode < 0 || mode > 2) return B200SEG_E_BADARG;
-  launch_k(blend_kernel, dim3(egrid((long long)n * c * hw)), dim3(256), 0, (cudaStream_t)stream, a, x, y, out, n, c, hw, mode);
+  launch_k(blend_kernel, dim3(egrid((long long)n * c * hw)), dim3(256), 0, (cudaStream_t)stream, a, x, y, out, n, c,
+           hw, mode);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -177,8 +179,9 @@ extern "C" int b200seg_argmax_hist(const float* pred_nchw, int32_t n, int32_t c,
                                    const int64_t* labels, int64_t* pred_out, float* maxprob_out, int64_t* hist,
                                    void* stream) {
   if (!pred_nchw || n <= 0 || c <= 0 || c > 64 || hw <= 0 || (hist && !labels)) return B200SEG_E_BADARG;
-  cudaError_t e = launch_k(argmax_hist_kernel, dim3(egrid((long long)n * hw)), dim3(256), (size_t)c * c * sizeof(unsigned),
-                           (cudaStream_t)stream, pred_nchw, (int)n, (int)c, (long long)hw, scale,
-                           (const long long*)labels, (long long*)pred_out, maxprob_out, (unsigned long long*)hist);
+  cudaError_t e = launch_k(argmax_hist_kernel, dim3(egrid((long long)n * hw)), dim3(256),
+                           (size_t)c * c * sizeof(unsigned), (cudaStream_t)stream, pred_nchw, (int)n, (int)c,
+                           (long long)hw, scale, (const long long*)labels, (long long*)pred_out, maxprob_out,
+                           (unsigned long long*)hist);
   return e == cudaSuccess ? 0 : (int)e;
 }

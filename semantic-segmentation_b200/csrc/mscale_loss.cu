@@ -488,18 +488,18 @@ extern "C" int b200seg_count_valid(const int64_t* labels, int64_t total, int32_t
   if (!labels || !counter_ws || !inv_count) return B200SEG_E_BADARG;
   cudaError_t e = cudaMemsetAsync(counter_ws, 0, sizeof(uint64_t), (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
-  launch_k(count_valid_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const long long*)labels, total,
-                                                                              ignore_index,
-                                                                              (unsigned long long*)counter_ws);
-  launch_k(inv_count_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (const unsigned long long*)counter_ws, inv_count,
-           (int)plus_one);
+  launch_k(count_valid_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream,
+           (const long long*)labels, total, ignore_index, (unsigned long long*)counter_ws);
+  launch_k(inv_count_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (const unsigned long long*)counter_ws,
+           inv_count, (int)plus_one);
   RET_LAUNCH();
 }
 
 extern "C" int b200seg_mscale_mid_fwd(const b200seg_mscale_desc* d, const float* lo_cls, const float* lo_aux,
                                       const float* lo_attn_logit, float* mid, float* mid_sup, void* stream) {
   if (!d || !lo_cls || !lo_attn_logit || !mid || d->hm <= 0 || (d->nheads > 1 && !lo_aux)) return B200SEG_E_BADARG;
-  launch_k(mid_fwd_kernel, dim3(blocks_for((long long)d->n * d->hm * d->wm, 256)), dim3(256), 0, (cudaStream_t)stream, to_geom(d), lo_cls, lo_aux, lo_attn_logit, mid, mid_sup);
+  launch_k(mid_fwd_kernel, dim3(blocks_for((long long)d->n * d->hm * d->wm, 256)), dim3(256), 0, (cudaStream_t)stream,
+           to_geom(d), lo_cls, lo_aux, lo_attn_logit, mid, mid_sup);
   RET_LAUNCH();
 }
 
@@ -516,20 +516,21 @@ extern "C" int b200seg_mscale_loss_fwd(const b200seg_mscale_desc* d, const int64
   if (n_rmi_terms > 0 && !rmi_terms) return B200SEG_E_BADARG;
   const int nb = b200seg_mscale_loss_blocks(d);
   const int Hp = d->h / 4 + 1, Wp = d->w / 4 + 1;     // avg_pool2d(kernel 4, stride 4, padding 2) output size
-  launch_k(loss_fwd_kernel, dim3(nb), dim3(128), 0, (cudaStream_t)stream, to_geom(d), (const long long*)labels, inv_count, hi_cls, hi_aux,
-                                                        mid, mid_sup, (__nv_bfloat16*)g_hi, (__nv_bfloat16*)g_lo,
-                                                        (__nv_bfloat16*)g_sup, partial_ws, rmi_dpr, Hp, Wp);
+  launch_k(loss_fwd_kernel, dim3(nb), dim3(128), 0, (cudaStream_t)stream, to_geom(d), (const long long*)labels,
+           inv_count, hi_cls, hi_aux, mid, mid_sup, (__nv_bfloat16*)g_hi, (__nv_bfloat16*)g_lo, (__nv_bfloat16*)g_sup,
+           partial_ws, rmi_dpr, Hp, Wp);
   launch_k(loss_finalize_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, partial_ws, nb, inv_count,
-           d->loss_kind == 1 ? d->w_head0 * kRmiLambda : d->w_head0,
-                                                           d->nheads > 1 ? d->w_head1 : 0.f, d->sup_wt, loss_out, rmi_terms,
-           (int)n_rmi_terms);
+           d->loss_kind == 1 ? d->w_head0 * kRmiLambda : d->w_head0, d->nheads > 1 ? d->w_head1 : 0.f, d->sup_wt,
+           loss_out, rmi_terms, (int)n_rmi_terms);
   RET_LAUNCH();
 }
 
 extern "C" int b200seg_mscale_hi_bwd(const b200seg_mscale_desc* d, const void* g_hi, void* d_cls, void* d_aux,
                                      void* stream) {
   if (!d || !g_hi || !d_cls || (d->nheads > 1 && !d_aux)) return B200SEG_E_BADARG;
-  launch_k(hi_bwd_kernel, dim3(blocks_for((long long)d->n * d->hq * d->wq * d->nheads, 128)), dim3(128), 0, (cudaStream_t)stream, to_geom(d), (const __nv_bfloat16*)g_hi, (__nv_bfloat16*)d_cls, (__nv_bfloat16*)d_aux);
+  launch_k(hi_bwd_kernel, dim3(blocks_for((long long)d->n * d->hq * d->wq * d->nheads, 128)), dim3(128), 0,
+           (cudaStream_t)stream, to_geom(d), (const __nv_bfloat16*)g_hi, (__nv_bfloat16*)d_cls,
+           (__nv_bfloat16*)d_aux);
   RET_LAUNCH();
 }
 
@@ -540,8 +541,10 @@ extern "C" int b200seg_mscale_lo_bwd(const b200seg_mscale_desc* d, const void* g
   if (!d || !g_lo || !lo_cls || !lo_attn_logit || !mid || !dmid_ws || !d_cls || !d_attn || d->hm <= 0)
     return B200SEG_E_BADARG;
   const MsGeom g = to_geom(d);
-  launch_k(mid_bwd_kernel, dim3(blocks_for((long long)d->n * d->hm * d->wm, 128)), dim3(128), 0, (cudaStream_t)stream, g, (const __nv_bfloat16*)g_lo, d->sup_wt != 0.f ? (const __nv_bfloat16*)g_sup : nullptr, lo_cls, lo_aux, mid,
-      dmid_ws);
-  launch_k(lo_bwd_kernel, dim3(blocks_for((long long)d->n * d->hl * d->wl, 128)), dim3(128), 0, (cudaStream_t)stream, g, dmid_ws, lo_attn_logit, (__nv_bfloat16*)d_cls, (__nv_bfloat16*)d_aux, (__nv_bfloat16*)d_attn);
+  launch_k(mid_bwd_kernel, dim3(blocks_for((long long)d->n * d->hm * d->wm, 128)), dim3(128), 0, (cudaStream_t)stream,
+           g, (const __nv_bfloat16*)g_lo, d->sup_wt != 0.f ? (const __nv_bfloat16*)g_sup : nullptr, lo_cls, lo_aux,
+           mid, dmid_ws);
+  launch_k(lo_bwd_kernel, dim3(blocks_for((long long)d->n * d->hl * d->wl, 128)), dim3(128), 0, (cudaStream_t)stream,
+           g, dmid_ws, lo_attn_logit, (__nv_bfloat16*)d_cls, (__nv_bfloat16*)d_aux, (__nv_bfloat16*)d_attn);
   RET_LAUNCH();
 }

@@ -324,9 +324,10 @@ extern "C" int b200seg_spatial_softmax_bwd(const float* dprobs, int32_t ldd, con
                                            void* stream) {
   if (!dprobs || !probs_bf16 || !partial_ws || !dlogit_bf16 || K > KP) return B200SEG_E_BADARG;
   const int B = pix_blocks(P);
-  launch_k(spatial_bwd_reduce_kernel, dim3(B, n), dim3(256), 0, (cudaStream_t)stream, dprobs, ldd, (const __nv_bfloat16*)probs_bf16,
-                                                                          P, K, partial_ws);
-  launch_k(spatial_bwd_apply_kernel, dim3(B, n), dim3(256), 0, (cudaStream_t)stream, dprobs, ldd, (const __nv_bfloat16*)probs_bf16, P, K, partial_ws, B, (__nv_bfloat16*)dlogit_bf16, accumulate);
+  launch_k(spatial_bwd_reduce_kernel, dim3(B, n), dim3(256), 0, (cudaStream_t)stream, dprobs, ldd,
+           (const __nv_bfloat16*)probs_bf16, P, K, partial_ws);
+  launch_k(spatial_bwd_apply_kernel, dim3(B, n), dim3(256), 0, (cudaStream_t)stream, dprobs, ldd,
+           (const __nv_bfloat16*)probs_bf16, P, K, partial_ws, B, (__nv_bfloat16*)dlogit_bf16, accumulate);
   RET_LAUNCH();
 }
 
@@ -341,15 +342,16 @@ extern "C" int b200seg_class_softmax_fwd(const float* x, int32_t ld, int64_t P, 
 extern "C" int b200seg_class_softmax_bwd(const float* dsim, int32_t ld, const void* sim_bf16, int64_t P, int32_t K,
                                          float scale, void* ds_bf16, void* stream) {
   if (!dsim || !sim_bf16 || !ds_bf16 || K > KP) return B200SEG_E_BADARG;
-  launch_k(class_softmax_bwd_kernel, dim3(pix_blocks(P) * 4), dim3(256), 0, (cudaStream_t)stream, dsim, ld, (const __nv_bfloat16*)sim_bf16, P, K, scale, (__nv_bfloat16*)ds_bf16);
+  launch_k(class_softmax_bwd_kernel, dim3(pix_blocks(P) * 4), dim3(256), 0, (cudaStream_t)stream, dsim, ld,
+           (const __nv_bfloat16*)sim_bf16, P, K, scale, (__nv_bfloat16*)ds_bf16);
   RET_LAUNCH();
 }
 
 extern "C" int b200seg_transpose_pad(const void* src, int32_t src_fp32, int32_t R, int32_t C, int32_t ld, void* dst_bf16,
                                      int32_t rpad, void* stream) {
   if (!src || !dst_bf16 || rpad < R) return B200SEG_E_BADARG;
-  launch_k(transpose_pad_kernel, dim3((C * rpad + 255) / 256), dim3(256), 0, (cudaStream_t)stream, src, src_fp32, R, C, ld,
-                                                                                (__nv_bfloat16*)dst_bf16, rpad);
+  launch_k(transpose_pad_kernel, dim3((C * rpad + 255) / 256), dim3(256), 0, (cudaStream_t)stream, src, src_fp32, R,
+           C, ld, (__nv_bfloat16*)dst_bf16, rpad);
   RET_LAUNCH();
 }
 
@@ -359,8 +361,8 @@ extern "C" int b200seg_cast_rows(const float* src, int32_t src_ld, void* dst_bf1
   long long total = rows * C;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(cast_rows_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, src, src_ld, (__nv_bfloat16*)dst_bf16, dst_ld, rows, C,
-                                                             accumulate);
+  launch_k(cast_rows_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, src, src_ld, (__nv_bfloat16*)dst_bf16,
+           dst_ld, rows, C, accumulate);
   RET_LAUNCH();
 }
 
@@ -368,6 +370,7 @@ extern "C" int b200seg_bias_grad(const void* dy_bf16, int32_t ld, int64_t rows, 
   if (!dy_bf16 || !db || C > 32) return B200SEG_E_BADARG;
   long long b = (rows + 7) / 8;
   if (b > 148 * 4) b = 148 * 4;
-  launch_k(colsum_kernel, dim3((int)b), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy_bf16, ld, rows, C, db);
+  launch_k(colsum_kernel, dim3((int)b), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy_bf16, ld, rows,
+           C, db);
   RET_LAUNCH();
 }

@@ -105,8 +105,9 @@ extern "C" int b200seg_conv2d_fwd_direct(const b200seg_conv_desc* d, const void*
   const size_t total = (size_t)d->n * Ho * Wo * d->cout;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  launch_k(direct_conv_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w_ohwi, d->has_bias ? bias : nullptr, y, d->n, d->h, d->w, d->cin,
-      d->cout, d->ksize, d->stride, d->pad, Ho, Wo, d->x_ld, d->y_ld, d->out_fp32);
+  launch_k(direct_conv_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x,
+           (const __nv_bfloat16*)w_ohwi, d->has_bias ? bias : nullptr, y, d->n, d->h, d->w, d->cin, d->cout, d->ksize,
+           d->stride, d->pad, Ho, Wo, d->x_ld, d->y_ld, d->out_fp32);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -118,8 +119,8 @@ extern "C" int b200seg_pack_weight(const float* w_oihw, int32_t o, int32_t i, in
   const size_t total = (size_t)o * i * ksize * ksize;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(pack_weight_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, w_oihw, o, i, ksize, (__nv_bfloat16*)w_ohwi,
-                                                               (__nv_bfloat16*)w_dgrad, o_pad);
+  launch_k(pack_weight_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, w_oihw, o, i, ksize,
+           (__nv_bfloat16*)w_ohwi, (__nv_bfloat16*)w_dgrad, o_pad);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

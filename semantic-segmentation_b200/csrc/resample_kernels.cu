@@ -237,25 +237,25 @@ extern "C" int b200seg_upsample_adjoint(const void* g, int32_t g_ld, const void*
   __nv_bfloat16* op = (__nv_bfloat16*)out;
   cudaError_t e;
   if (ratio >= 8)
-    e = launch_k(upsample_adjoint_kernel<32>, dim3(ew_grid(total * 32)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n, H, W, c,
-                 op, out_ld, h, w, accumulate);
+    e = launch_k(upsample_adjoint_kernel<32>, dim3(ew_grid(total * 32)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n,
+                 H, W, c, op, out_ld, h, w, accumulate);
   else if (ratio >= 4)
-    e = launch_k(upsample_adjoint_kernel<16>, dim3(ew_grid(total * 16)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n, H, W, c,
-                 op, out_ld, h, w, accumulate);
+    e = launch_k(upsample_adjoint_kernel<16>, dim3(ew_grid(total * 16)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n,
+                 H, W, c, op, out_ld, h, w, accumulate);
   else if (ratio >= 2)
-    e = launch_k(upsample_adjoint_kernel<4>, dim3(ew_grid(total * 4)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n, H, W, c,
-                 op, out_ld, h, w, accumulate);
+    e = launch_k(upsample_adjoint_kernel<4>, dim3(ew_grid(total * 4)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n, H,
+                 W, c, op, out_ld, h, w, accumulate);
   else
-    e = launch_k(upsample_adjoint_kernel<1>, dim3(ew_grid(total)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n, H, W, c, op,
-                 out_ld, h, w, accumulate);
+    e = launch_k(upsample_adjoint_kernel<1>, dim3(ew_grid(total)), dim3(256), 0, st, gp, g_ld, mp, mask_ld, n, H, W,
+                 c, op, out_ld, h, w, accumulate);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
 extern "C" int b200seg_image_prep(const float* img_nchw, int32_t n, int32_t H, int32_t W, void* out_nhwc16, int32_t h,
                                   int32_t w, void* stream) {
   if (!img_nchw || !out_nhwc16 || h <= 0 || w <= 0) return B200SEG_E_BADARG;
-  launch_k(image_prep_kernel, dim3(ew_grid((long long)n * h * w)), dim3(256), 0, (cudaStream_t)stream, img_nchw, n, H, W,
-                                                                                    (__nv_bfloat16*)out_nhwc16, h, w);
+  launch_k(image_prep_kernel, dim3(ew_grid((long long)n * h * w)), dim3(256), 0, (cudaStream_t)stream, img_nchw, n, H,
+           W, (__nv_bfloat16*)out_nhwc16, h, w);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -253,7 +253,8 @@ extern "C" int b200seg_rmi_pool(const b200seg_mscale_desc* d, const int64_t* lab
   if (d->h < 12 || d->w < 12) return B200SEG_E_BADARG;     // at least one 3x3 view of pooled cells
   const int Hp = d->h / 4 + 1, Wp = d->w / 4 + 1;
   cudaError_t e = launch_k(rmi_pool_kernel, dim3(blocks_for_total((long long)d->n * Hp * Wp, 128)), dim3(128), 0,
-                           (cudaStream_t)stream, to_geom(d), (const long long*)labels, hi_cls, mid, pr_pool, la_pool, Hp, Wp);
+                           (cudaStream_t)stream, to_geom(d), (const long long*)labels, hi_cls, mid, pr_pool, la_pool,
+                           Hp, Wp);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -268,13 +269,14 @@ extern "C" int b200seg_rmi_solve_grad(int32_t n, int32_t h, int32_t w, const flo
   const int Hp = h / 4 + 1, Wp = w / 4 + 1;
   if (Hp < 3 || Wp < 3) return B200SEG_E_BADARG;
   const size_t smem = (size_t)kGroups * kV * (kV + 1) * sizeof(double);
-  cudaError_t e = launch_k(rmi_moments_kernel, dim3(kChunks, NC, n), dim3(256), smem, (cudaStream_t)stream, pr_pool, la_pool,
-                           Hp, Wp, (double*)ws);
+  cudaError_t e = launch_k(rmi_moments_kernel, dim3(kChunks, NC, n), dim3(256), smem, (cudaStream_t)stream, pr_pool,
+                           la_pool, Hp, Wp, (double*)ws);
   if (e != cudaSuccess) return (int)e;
   e = launch_k(rmi_solve_kernel, dim3(NC, n), dim3(96), 0, (cudaStream_t)stream, (const double*)ws, Hp, Wp, scale, G,
                rmi_terms);
   if (e != cudaSuccess) return (int)e;
   e = launch_k(rmi_grad_kernel, dim3(blocks_for_total((long long)Hp * Wp * LD, 256), n), dim3(256),
-               (size_t)NC * kGPitch * sizeof(double), (cudaStream_t)stream, pr_pool, la_pool, (const double*)G, Hp, Wp, dpr);
+               (size_t)NC * kGPitch * sizeof(double), (cudaStream_t)stream, pr_pool, la_pool, (const double*)G, Hp,
+               Wp, dpr);
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -487,8 +487,8 @@ extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, c
     attr_set = true;
   }
   const int grid = p.total_units < B200SEG_MAX_CTAS ? p.total_units : B200SEG_MAX_CTAS;
-  cudaError_t e = launch_k(wgrad_igemm_kernel, dim3(grid), dim3(kWThreads), smem_bytes, (cudaStream_t)stream, tmDy, tmX, p,
-                           (float*)workspace, dw_ohwi);
+  cudaError_t e = launch_k(wgrad_igemm_kernel, dim3(grid), dim3(kWThreads), smem_bytes, (cudaStream_t)stream, tmDy,
+                           tmX, p, (float*)workspace, dw_ohwi);
   if (e != cudaSuccess) return (int)e;
   if (p.direct) return 0;
   const int items = p.m_tiles * p.n_tiles * p.tap_groups;
@@ -513,7 +513,7 @@ extern "C" int b200seg_grad_fold(float* dst, float* acc_a, float* acc_b, const b
                                  const int32_t* blk_seg, const int32_t* blk_start, int32_t n_blocks, int32_t clear,
                                  void* stream) {
   if (!dst || (!acc_a && !acc_b) || !segs || !blk_seg || !blk_start || n_blocks <= 0) return B200SEG_E_BADARG;
-  cudaError_t e = launch_k(grad_fold_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, dst, acc_a, acc_b, segs,
-                           blk_seg, blk_start, (int)clear);
+  cudaError_t e = launch_k(grad_fold_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, dst, acc_a, acc_b,
+                           segs, blk_seg, blk_start, (int)clear);
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -1,6 +1,6 @@
 """Per-role timeline of CTA 0 of the halo convolution (B200SEG_DBG=8): usage gpu_timeline.py H W C"""
 import os, sys, ctypes
-os.environ["B200SEG_DBG"] = "8"
+os.environ["B200SEG_DBG"] = "8"   # needs a library built with: make EXTRA=-DB200SEG_TIMELINE
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "semantic-segmentation_b200"))
 import torch
