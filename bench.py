@@ -107,6 +107,21 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def usable_cores():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 64))
+
+
 def synth_batch(n, h, w, seed, device):
     g = torch.Generator().manual_seed(seed)
     images = torch.randn((n, 3, h, w), generator=g)
@@ -121,6 +136,9 @@ def cpu_reference_step_time(arch, h, w, steps, warmup=1, budget_s=60.0, criterio
     zero_grad -> two-scale fwd -> bwd -> SGD, fp32, PyTorch's default intra-op thread count (= the cores it can use).
     Returns (seconds per step at (h, w), timed steps); stops early once `budget_s` of wall clock is spent."""
     from oracle import seg_oracle as O
+    # the cores this process may really use: affinity mask and cgroup CPU quota (a 64-thread pool on an 8-core quota
+    # runs the oracle ~10x slower); also undoes torchrun's OMP_NUM_THREADS=1
+    torch.set_num_threads(usable_cores())
     sd = O.synth_state_dict(arch, O.HRNET_W48, seed=0)
     params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k]
     opt = torch.optim.SGD(params, lr=0.01, momentum=0.9, weight_decay=1e-4)
@@ -149,9 +167,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: the full algorithm on a 256x512 crop (1/16 of the pixels); crops/s are rescaled by the pixel ratio
+    # bounded sample: the full algorithm on a 128x256 crop (1/64 of the pixels); crops/s are rescaled by the pixel ratio
     # (cost is proportional to pixels: every layer is a convolution / pointwise op)
-    sh, sw = max(64, args.height // 4), max(128, args.width // 4)
+    sh, sw = max(64, args.height // 8), max(128, args.width // 8)
     sec, timed = cpu_reference_step_time(args.arch, sh, sw, max(1, args.steps), warmup=1 if args.warmup else 0,
                                          budget_s=90.0, criterion=args.criterion)
     ratio = (sh * sw) / float(args.height * args.width)

@@ -55,6 +55,7 @@ def _worker(rank, world, port, use_graph, out):
     dist.destroy_process_group()
 
 
+@pytest.mark.timeout(420)
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_two_gpu_syncbn_step_equals_single_gpu_batch(tmp_path, use_graph):
     if torch.cuda.device_count() < 2:
