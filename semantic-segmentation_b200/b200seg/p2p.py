@@ -11,6 +11,22 @@ import torch
 from ._lib import BnSync, check, lib
 
 
+def exchange_layout(bn_channels, world, n_passes):
+    """Offsets of every (pass, layer, direction) exchange: -> (mail_off, flag_off, doubles per parity half, flags).
+    Exchange id order = pass-major, then layer, then direction (0 forward statistics, 1 backward sums); a mail region
+    is [rank][2][C] doubles, a flag region [rank][ceil(C/32)] uint32. Pure function (unit-tested on the CPU)."""
+    mail_off, flag_off = {}, {}
+    moff = foff = 0
+    for p in range(n_passes):
+        for name, c in bn_channels.items():
+            for d in (0, 1):
+                mail_off[(p, name, d)] = moff
+                flag_off[(p, name, d)] = foff
+                moff += world * 2 * c
+                foff += world * ((c + 31) // 32)
+    return mail_off, flag_off, moff, foff
+
+
 class SyncBNContext:
     def __init__(self, bn_channels, n_passes=2, group=None):
         """bn_channels: ordered {bn layer name: channels}; every rank must pass the same table."""
@@ -22,17 +38,7 @@ class SyncBNContext:
         self.names = list(bn_channels)
         self.n_passes = n_passes
         dev = torch.device("cuda", torch.cuda.current_device())
-        # exchange id = ((pass * L + layer) * 2 + direction); direction 0 = forward statistics, 1 = backward sums
-        self.mail_off, self.flag_off = {}, {}
-        moff = foff = 0
-        for p in range(n_passes):
-            for name in self.names:
-                c = bn_channels[name]
-                for d in (0, 1):
-                    self.mail_off[(p, name, d)] = moff
-                    self.flag_off[(p, name, d)] = foff
-                    moff += self.world * 2 * c
-                    foff += self.world * ((c + 31) // 32)
+        self.mail_off, self.flag_off, moff, foff = exchange_layout(bn_channels, self.world, n_passes)
         self.parity_stride = moff
         L = lib()
         self._own = []

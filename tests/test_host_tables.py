@@ -51,3 +51,17 @@ def test_iou_from_hist():
     h = torch.tensor([[5, 1], [2, 7]])
     iou = iou_from_hist(h)
     assert torch.allclose(iou, torch.tensor([5 / 8, 7 / 10], dtype=torch.float64))
+
+
+def test_syncbn_exchange_layout_regions_are_disjoint():
+    from b200seg.p2p import exchange_layout
+    chans = {"a.bn1": 48, "a.bn2": 96, "b.bn": 720, "c.bn": 19}
+    world, passes = 4, 2
+    mail, flag, msize, fsize = exchange_layout(chans, world, passes)
+    assert len(mail) == len(flag) == passes * len(chans) * 2
+    spans = sorted((mail[k], mail[k] + world * 2 * chans[k[1]]) for k in mail)
+    assert spans[0][0] == 0 and spans[-1][1] == msize
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))              # contiguous, non-overlapping
+    fsp = sorted((flag[k], flag[k] + world * ((chans[k[1]] + 31) // 32)) for k in flag)
+    assert fsp[0][0] == 0 and fsp[-1][1] == fsize and all(a[1] == b[0] for a, b in zip(fsp, fsp[1:]))
+    assert mail[(0, "a.bn1", 1)] == world * 2 * 48                           # direction 1 follows direction 0
