@@ -103,13 +103,13 @@ class Ctx:
 
 
 # ----------------------------------------------------------------------------------------------- primitives
-def conv(ctx, name, x, stride=1, padding=0):
+def conv(ctx, name, x, stride=1, padding=0, dilation=1):
     """nn.Conv2d call sites, e.g. hrnetv2.py:31-34; bias present only where the reference leaves bias=True."""
     w = ctx.sd[name + ".weight"]
     b = ctx.sd.get(name + ".bias")
     if ctx.emulate_bf16:
         w = _RoundFwdOnly.apply(w)
-    return F.conv2d(x, w, b, stride=stride, padding=padding)
+    return F.conv2d(x, w, b, stride=stride, padding=padding, dilation=dilation)
 
 
 def bn(ctx, name, x):
@@ -430,6 +430,141 @@ def basic_forward(ctx, images, gts=None, criterion=criterion_ce, hcfg=HRNET_W48)
     return dict(pred=pred)
 
 
+
+
+# ----------------------------------------------------------------------------------------------- DeepLabV3+ / WRN-38 (§8 f2)
+# network/wider_resnet.py:270-435 (WiderResNetA2, dilation=True, structure 38) and :398-435 (wrn38 wrapper: no bn_out)
+WRN38 = dict(structure=[3, 3, 6, 3, 1, 1],
+             channels=[(128, 128), (256, 256), (512, 512), (512, 1024), (512, 1024, 2048), (1024, 2048, 4096)])
+ASPP_RATES = (12, 24, 36)      # utils.py:176-183: rates (6, 12, 18) doubled at output stride 8
+ASPP_DIM = 256                 # deepv3.py:50-53 bottleneck_ch
+
+
+def _wrn_block_plan(wcfg=WRN38):
+    """-> list of (module name, block name, in_ch, channels tuple, stride, dilation, dropout p) in forward order
+    (wider_resnet.py:313-345 with dilation=True)."""
+    plan = []
+    in_ch = 64
+    for mod_id, num in enumerate(wcfg["structure"]):
+        for block_id in range(num):
+            dil = 2 if mod_id == 3 else (4 if mod_id > 3 else 1)
+            stride = 2 if (block_id == 0 and mod_id == 2) else 1
+            drop = 0.3 if mod_id == 4 else (0.5 if mod_id == 5 else None)
+            plan.append(("mod%d" % (mod_id + 2), "block%d" % (block_id + 1), in_ch, wcfg["channels"][mod_id], stride,
+                         dil, drop))
+            in_ch = wcfg["channels"][mod_id][-1]
+    return plan
+
+
+def wrn_block(ctx, p, x, in_ch, channels, stride, dil, drop):
+    """IdentityResidualBlock.forward (wider_resnet.py:170-183): pre-activation BN-ReLU, optional 1x1 projection of the
+    ACTIVATED input, 2x(3x3) or 1x1-3x3-1x1 body (dilated), Dropout2d before the last conv (mod6/mod7)."""
+    q = ctx.q
+    need_proj = stride != 1 or in_ch != channels[-1]
+    a = q(F.relu(bn(ctx, p + ".bn1.0", x)))
+    shortcut = conv(ctx, p + ".proj_conv", a, stride) if need_proj else x
+    c = p + ".convs"
+
+    def dropout(t):
+        if drop is not None and ctx.training and ctx.drop_mask_fn is not None:
+            m = ctx.drop_mask_fn((t.shape[0], t.shape[1], 1, 1)).to(t.dtype)
+            return t * m / (1.0 - drop)
+        return t
+
+    if len(channels) == 2:
+        t = q(conv(ctx, c + ".conv1", a, stride, dil, dil))
+        t = q(F.relu(bn(ctx, c + ".bn2.0", t)))
+        t = conv(ctx, c + ".conv2", dropout(t), 1, dil, dil)
+    else:
+        t = q(conv(ctx, c + ".conv1", a, stride))
+        t = q(F.relu(bn(ctx, c + ".bn2.0", t)))
+        t = q(conv(ctx, c + ".conv2", t, 1, dil, dil))
+        t = q(F.relu(bn(ctx, c + ".bn3.0", t)))
+        t = conv(ctx, c + ".conv3", dropout(t))
+    return q(t + shortcut)
+
+
+def wrn38_forward(ctx, p, x, wcfg=WRN38):
+    """wrn38.forward (wider_resnet.py:423-435): -> (s2 features [/2], s4 features [/4], final [/8], all pre-activation)."""
+    x = ctx.q(conv(ctx, p + ".mod1.conv1", x, 1, 1))
+    feats = {}
+    for mod, blk, in_ch, channels, stride, dil, drop in _wrn_block_plan(wcfg):
+        if blk == "block1" and mod in ("mod2", "mod3"):
+            x = F.max_pool2d(x, 3, stride=2, padding=1)          # pool2 / pool3
+        x = wrn_block(ctx, "%s.%s.%s" % (p, mod, blk), x, in_ch, channels, stride, dil, drop)
+        feats[mod] = x
+    return feats["mod2"], feats["mod3"], x
+
+
+def aspp(ctx, p, x):
+    """AtrousSpatialPyramidPoolingModule.forward (utils.py:204-216): image pooling branch first, then 1x1 and the three
+    dilated 3x3 branches, concatenated."""
+    q = ctx.q
+    img = F.adaptive_avg_pool2d(x, 1)
+    img = q(F.relu(bn(ctx, p + ".img_conv.1", q(conv(ctx, p + ".img_conv.0", img)))))
+    out = [bilinear(img, x.shape[2:])]
+    out.append(q(F.relu(bn(ctx, p + ".features.0.1", q(conv(ctx, p + ".features.0.0", x))))))
+    for i, r in enumerate(ASPP_RATES):
+        f = "%s.features.%d" % (p, i + 1)
+        out.append(q(F.relu(bn(ctx, f + ".1", q(conv(ctx, f + ".0", x, 1, r, r))))))
+    return torch.cat(out, 1)
+
+
+def deepv3_forward(ctx, images, gts=None, criterion=criterion_ce, wcfg=WRN38):
+    """DeepV3Plus.forward (deepv3.py:75-96), arch 'deepv3.DeepV3PlusW38' (BASELINE config 4)."""
+    q = ctx.q
+    s2, _s4, final = wrn38_forward(ctx, "backbone", images, wcfg)
+    a = aspp(ctx, "aspp", final)
+    conv_aspp = q(conv(ctx, "bot_aspp", a))
+    conv_s2 = q(conv(ctx, "bot_fine", s2))
+    cat = torch.cat([conv_s2, bilinear(conv_aspp, s2.shape[2:])], 1)
+    t = q(F.relu(bn(ctx, "final.1", q(conv(ctx, "final.0", cat, 1, 1)))))
+    t = q(F.relu(bn(ctx, "final.4", q(conv(ctx, "final.3", t, 1, 1)))))
+    out = bilinear(ctx.qg(conv(ctx, "final.6", t)), images.shape[2:])
+    if ctx.training:
+        return criterion(out, gts)
+    return dict(pred=out)
+
+
+def _deepv3_names(wcfg=WRN38, num_classes=19):
+    """(name, shape) of every tensor of DeepV3PlusW38's state_dict, in registration order (deepv3.py:46-65,
+    wider_resnet.py:303-350, utils.py:171-202)."""
+    out = []
+
+    def conv_(name, o, i, k):
+        out.append((name + ".weight", (o, i, k, k)))
+
+    def bn_(name, c):
+        out.extend([(name + ".weight", (c,)), (name + ".bias", (c,)), (name + ".running_mean", (c,)),
+                    (name + ".running_var", (c,)), (name + ".num_batches_tracked", ())])
+
+    conv_("backbone.mod1.conv1", 64, 3, 3)
+    for mod, blk, in_ch, ch, stride, dil, drop in _wrn_block_plan(wcfg):
+        b = "backbone.%s.%s" % (mod, blk)
+        bn_(b + ".bn1.0", in_ch)
+        if len(ch) == 2:
+            conv_(b + ".convs.conv1", ch[0], in_ch, 3); bn_(b + ".convs.bn2.0", ch[0])
+            conv_(b + ".convs.conv2", ch[1], ch[0], 3)
+        else:
+            conv_(b + ".convs.conv1", ch[0], in_ch, 1); bn_(b + ".convs.bn2.0", ch[0])
+            conv_(b + ".convs.conv2", ch[1], ch[0], 3); bn_(b + ".convs.bn3.0", ch[1])
+            conv_(b + ".convs.conv3", ch[2], ch[1], 1)
+        if stride != 1 or in_ch != ch[-1]:
+            conv_(b + ".proj_conv", ch[-1], in_ch, 1)
+    high = wcfg["channels"][-1][-1]
+    s2_ch = wcfg["channels"][0][-1]
+    conv_("aspp.features.0.0", ASPP_DIM, high, 1); bn_("aspp.features.0.1", ASPP_DIM)
+    for i in range(len(ASPP_RATES)):
+        conv_("aspp.features.%d.0" % (i + 1), ASPP_DIM, high, 3); bn_("aspp.features.%d.1" % (i + 1), ASPP_DIM)
+    conv_("aspp.img_conv.0", ASPP_DIM, high, 1); bn_("aspp.img_conv.1", ASPP_DIM)
+    conv_("bot_fine", 48, s2_ch, 1)
+    conv_("bot_aspp", 256, ASPP_DIM * (2 + len(ASPP_RATES)), 1)
+    conv_("final.0", 256, 256 + 48, 3); bn_("final.1", 256)
+    conv_("final.3", 256, 256, 3); bn_("final.4", 256)
+    conv_("final.6", num_classes, 256, 1)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- state dict synthesis
 def _conv_names(hcfg, ocfg, arch):
     """Enumerate (name, shape) of every tensor of the reference state_dict for the given arch, in no particular
@@ -530,7 +665,9 @@ def synth_state_dict(arch="ocrnet.HRNet_Mscale", hcfg=HRNET_W48, ocfg=OCR_CFG, s
     use a fan-in scaled normal (well-conditioned activations, unlike the reference's N(0, 1e-3) default init),
     BN affine parameters are perturbed around (1, 0), running stats start at (0, 1) like a fresh BatchNorm2d."""
     sd = {}
-    for name, shape in _conv_names(hcfg, ocfg, arch):
+    names = _deepv3_names(hcfg if "structure" in hcfg else WRN38, ocfg["num_classes"]) \
+        if arch == "deepv3.DeepV3PlusW38" else _conv_names(hcfg, ocfg, arch)
+    for name, shape in names:
         g = torch.Generator().manual_seed((zlib.crc32(name.encode()) ^ seed) & 0x7FFFFFFF)
         if name.endswith("num_batches_tracked"):
             t = torch.zeros((), dtype=torch.long)

@@ -20,6 +20,68 @@ OCR_DEFAULT = dict(mid_channels=512, key_channels=256, num_classes=19, segattn_b
 
 ARCHS = ("ocrnet.HRNet_Mscale", "ocrnet.HRNet", "basic.HRNet")
 
+# network/wider_resnet.py:303-345 (WiderResNetA2, structure "38", dilation=True) — SURVEY.md §8(f) row f2. Only the
+# parameter specification exists so far (checked against the reference's state_dict order); the dilated-convolution /
+# pre-activation program is the next row to be built.
+WRN38 = dict(structure=[3, 3, 6, 3, 1, 1],
+             channels=[(128, 128), (256, 256), (512, 512), (512, 1024), (512, 1024, 2048), (1024, 2048, 4096)])
+ASPP_RATES = (12, 24, 36)
+
+
+def wrn_block_plan(wcfg=WRN38):
+    """(module, block, in_ch, channels, stride, dilation, dropout p) per IdentityResidualBlock, forward order."""
+    plan, in_ch = [], 64
+    for mod_id, num in enumerate(wcfg["structure"]):
+        for block_id in range(num):
+            dil = 2 if mod_id == 3 else (4 if mod_id > 3 else 1)
+            stride = 2 if (block_id == 0 and mod_id == 2) else 1
+            drop = 0.3 if mod_id == 4 else (0.5 if mod_id == 5 else None)
+            plan.append(("mod%d" % (mod_id + 2), "block%d" % (block_id + 1), in_ch, wcfg["channels"][mod_id], stride,
+                         dil, drop))
+            in_ch = wcfg["channels"][mod_id][-1]
+    return plan
+
+
+def deepv3_tensor_specs(num_classes=19, wcfg=WRN38):
+    """(name, shape, kind) of deepv3.DeepV3PlusW38 in the reference's registration order (network/deepv3.py:46-65,
+    network/utils.py:171-202)."""
+    out = []
+
+    def conv(name, o, i, k):
+        out.append((name + ".weight", (o, i, k, k), "conv_w"))
+
+    def bn(name, c):
+        out.append((name + ".weight", (c,), "bn_w"))
+        out.append((name + ".bias", (c,), "bn_b"))
+        out.append((name + ".running_mean", (c,), "bn_rm"))
+        out.append((name + ".running_var", (c,), "bn_rv"))
+        out.append((name + ".num_batches_tracked", (), "bn_nbt"))
+
+    conv("backbone.mod1.conv1", 64, 3, 3)
+    for mod, blk, in_ch, ch, stride, _dil, _drop in wrn_block_plan(wcfg):
+        b = "backbone.%s.%s" % (mod, blk)
+        bn(b + ".bn1.0", in_ch)
+        if len(ch) == 2:
+            conv(b + ".convs.conv1", ch[0], in_ch, 3); bn(b + ".convs.bn2.0", ch[0])
+            conv(b + ".convs.conv2", ch[1], ch[0], 3)
+        else:
+            conv(b + ".convs.conv1", ch[0], in_ch, 1); bn(b + ".convs.bn2.0", ch[0])
+            conv(b + ".convs.conv2", ch[1], ch[0], 3); bn(b + ".convs.bn3.0", ch[1])
+            conv(b + ".convs.conv3", ch[2], ch[1], 1)
+        if stride != 1 or in_ch != ch[-1]:
+            conv(b + ".proj_conv", ch[-1], in_ch, 1)
+    high, s2_ch = wcfg["channels"][-1][-1], wcfg["channels"][0][-1]
+    conv("aspp.features.0.0", 256, high, 1); bn("aspp.features.0.1", 256)
+    for i in range(len(ASPP_RATES)):
+        conv("aspp.features.%d.0" % (i + 1), 256, high, 3); bn("aspp.features.%d.1" % (i + 1), 256)
+    conv("aspp.img_conv.0", 256, high, 1); bn("aspp.img_conv.1", 256)
+    conv("bot_fine", 48, s2_ch, 1)
+    conv("bot_aspp", 256, 256 * (2 + len(ASPP_RATES)), 1)
+    conv("final.0", 256, 256 + 48, 3); bn("final.1", 256)
+    conv("final.3", 256, 256, 3); bn("final.4", 256)
+    conv("final.6", num_classes, 256, 1)
+    return out
+
 
 def hrnet_cfg_from_reference_cfg(cfg):
     """Read the HRNet widths from a reference-style cfg (cfg.MODEL.OCR_EXTRA) when one is importable."""

@@ -85,3 +85,20 @@ def test_conv_planner_rejects_bad_shapes():
     d.cin, d.ksize = 48, 5
     assert L.b200seg_conv2d_stats_elems(ctypes.byref(d)) == 0
     assert L.b200seg_conv2d_fwd(ctypes.byref(d), None, None, None, None, None, None, None) == -1
+
+
+def test_deepv3_parameter_spec_matches_reference_order():
+    """SURVEY §8(f) f2 groundwork: the parameter table of deepv3.DeepV3PlusW38 equals the reference's state_dict
+    (names, registration order, 137.1 M parameters) as recorded by tests/golden/make_golden_deepv3.py."""
+    from b200seg import arch as A
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "reference_deepv3.pt"), map_location="cpu")
+    specs = A.deepv3_tensor_specs(19)
+    assert [n for n, _s, _k in specs] == g["keys"]
+    nparams = 0
+    for n, shape, kind in specs:
+        if kind in ("conv_w", "bn_w", "bn_b"):
+            k = 1
+            for d in shape:
+                k *= d
+            nparams += k
+    assert nparams == g["nparams"]

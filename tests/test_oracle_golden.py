@@ -98,3 +98,31 @@ def test_w48_state_dict_and_step_match_reference(golden):
         o2 = O.mscale_two_scale(O.Ctx(sd, training=False), images)
     close(O.sample_like(o2["pred"]), g["eval_pred_sample"])
     close(O.sample_like(o2["attn_05x"]), g["eval_attn_sample"])
+
+
+def test_deepv3_wrn38_matches_reference():
+    """SURVEY §8(f) row f2 (BASELINE config 4): the DeepLabV3+ / WideResNet-38 restatement against the unmodified
+    reference (tests/golden/make_golden_deepv3.py): state_dict registration order, train loss, sampled gradients,
+    running statistics, eval prediction."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_deepv3.pt"),
+                   map_location="cpu")
+    arch = "deepv3.DeepV3PlusW38"
+    sd = O.synth_state_dict(arch, O.WRN38, seed=4)
+    assert list(sd.keys()) == g["keys"] and len(g["keys"]) == 268
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    assert [k for k, v in sd.items() if v.requires_grad] == g["param_order"]
+    assert sum(v.numel() for v in sd.values() if v.requires_grad) == g["nparams"] == 137103936
+    images, gts = O.synth_batch(2, 64, 128, seed=6)
+    loss = O.deepv3_forward(O.Ctx(sd, training=True), images, gts)
+    loss.backward()
+    close(loss.detach(), g["loss"], rtol=1e-5)
+    for name, ref in g["grads"].items():
+        close(O.sample_like(sd[name].grad), ref, rtol=1e-3)
+    close(sd["backbone.mod5.block3.convs.bn2.0.running_var"].detach(), g["running_var_mod5"])
+    sd = {k: v.detach() for k, v in sd.items()}
+    with torch.no_grad():
+        o = O.deepv3_forward(O.Ctx(sd, training=False), images)
+    close(O.sample_like(o["pred"]), g["eval_pred"])
