@@ -392,8 +392,17 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
-    else:
+        return
+    try:
         run_b200(args)
+    except Exception:
+        # SyncBN post-mortem: which exchange every rank entered / completed last (pinned host record, p2p.py)
+        import gc
+        from b200seg.module import B200SegModule
+        for obj in gc.get_objects():
+            if isinstance(obj, B200SegModule) and getattr(obj, "_sync", None) is not None:
+                print(obj._sync.describe_beacon(), file=sys.stderr, flush=True)
+        raise
 
 
 if __name__ == "__main__":

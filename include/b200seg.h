@@ -142,6 +142,8 @@ typedef struct b200seg_bn_sync {
   int32_t flag_offset;      /* offset of this exchange in the flag array */
   int32_t world, rank;
   int32_t reserved;
+  void* beacon;             /* optional host-mapped int32[8] post-mortem record: [0,1] = (flag_offset, step) of the last
+                               exchange this rank entered, [4,5] = of the last one it completed; NULL = off */
 } b200seg_bn_sync;
 /* Peer-mappable device memory for the SyncBN mailboxes: the ONLY allocations the library performs (a communicator
  * owns its buffers). alloc: cudaMalloc + zero + CUDA IPC handle (64 bytes) to hand to the other ranks of the node;

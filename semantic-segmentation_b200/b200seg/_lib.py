@@ -43,7 +43,7 @@ class MscaleDesc(ctypes.Structure):
 class BnSync(ctypes.Structure):
     _fields_ = [("mail_peers", c_void_p), ("flag_peers", c_void_p), ("step", c_void_p), ("mail_offset", c_int64),
                 ("parity_stride", c_int64), ("flag_offset", c_int32), ("world", c_int32), ("rank", c_int32),
-                ("reserved", c_int32)]
+                ("reserved", c_int32), ("beacon", c_void_p)]
 
 
 class ProbeOperand(ctypes.Structure):

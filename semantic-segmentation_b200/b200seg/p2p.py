@@ -48,6 +48,8 @@ class SyncBNContext:
         self.mail_table = torch.tensor(mail_ptrs, dtype=torch.int64, device=dev)
         self.flag_table = torch.tensor(flag_ptrs, dtype=torch.int64, device=dev)
         self.step = torch.zeros((1,), dtype=torch.int32, device=dev)     # uint32 on the device; +1 per training step
+        # pinned host record the kernels write (UVA: same pointer on the device): readable after a trapped / hung run
+        self.beacon = torch.zeros((8,), dtype=torch.int32).pin_memory()
         dist.barrier(group)
 
     def _shared_alloc(self, L, nbytes):
@@ -83,7 +85,14 @@ class SyncBNContext:
         s.parity_stride = self.parity_stride
         s.flag_offset = self.flag_off[(pass_id, name, direction)]
         s.world, s.rank = self.world, self.rank
+        s.beacon = self.beacon.data_ptr()
         return s
+
+    def describe_beacon(self):
+        """Human-readable post-mortem: the exchange this rank entered / completed last (see b200seg_bn_sync.beacon)."""
+        inv = {v: k for k, v in self.flag_off.items()}
+        b = self.beacon.tolist()
+        return "rank %d: entered %s at step %d, completed %s at step %d" % (self.rank, inv.get(b[0]), b[1], inv.get(b[4]), b[5])
 
     def close(self):
         L = lib()

@@ -49,6 +49,7 @@ struct SyncArgs {
   long long parity_stride;        // doubles per parity half
   int flag_off;                   // this exchange's offset in the flag array
   int world, rank;
+  volatile int* beacon;           // optional host-mapped int32[8]: {entered: flag_off, step, 0, 0, left: flag_off, step}
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
@@ -71,6 +72,10 @@ __device__ __forceinline__ void sync_exchange(const SyncArgs& sy, int C, int c, 
   const unsigned step = *sy.step;
   const long long base = (long long)(step & 1u) * sy.parity_stride + sy.mail_off;
   const bool owner = slice == 0 && c < C;
+  if (sy.beacon && blockIdx.x == 0 && threadIdx.x == 0) {   // post-mortem aid: which exchange this rank entered last
+    sy.beacon[0] = sy.flag_off;
+    sy.beacon[1] = (int)step;
+  }
   if (owner) {
     for (int r = 0; r < sy.world; ++r) {
       double* dst = sy.mail_peers[r] + base + (long long)sy.rank * 2 * C;
@@ -104,6 +109,10 @@ __device__ __forceinline__ void sync_exchange(const SyncArgs& sy, int C, int c, 
     }
     s1 = t1;
     s2 = t2;
+  }
+  if (sy.beacon && blockIdx.x == 0 && threadIdx.x == 0) {   // ... and which one it left last
+    sy.beacon[4] = sy.flag_off;
+    sy.beacon[5] = (int)step;
   }
 }
 
@@ -446,7 +455,7 @@ using namespace b200seg;
 static int make_sync(const b200seg_bn_sync* s, SyncArgs* out) {
   SyncArgs sy;
   sy.mail_peers = nullptr; sy.flag_peers = nullptr; sy.step = nullptr;
-  sy.mail_off = 0; sy.parity_stride = 0; sy.flag_off = 0; sy.world = 1; sy.rank = 0;
+  sy.mail_off = 0; sy.parity_stride = 0; sy.flag_off = 0; sy.world = 1; sy.rank = 0; sy.beacon = nullptr;
   if (s && s->world > 1) {
     if (!s->mail_peers || !s->flag_peers || !s->step || s->rank < 0 || s->rank >= s->world) return B200SEG_E_BADARG;
     sy.mail_peers = (double* const*)s->mail_peers;
@@ -454,6 +463,7 @@ static int make_sync(const b200seg_bn_sync* s, SyncArgs* out) {
     sy.step = (const unsigned*)s->step;
     sy.mail_off = s->mail_offset; sy.parity_stride = s->parity_stride; sy.flag_off = s->flag_offset;
     sy.world = s->world; sy.rank = s->rank;
+    sy.beacon = (volatile int*)s->beacon;
   }
   *out = sy;
   return 0;
