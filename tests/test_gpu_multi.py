@@ -105,7 +105,7 @@ def test_two_gpu_data_parallel_gradients_are_the_rank_mean(tmp_path):
     mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
     res = torch.load(out)
     assert res["rel"] <= 1e-5, res               # same kernels on the same data; only the all-reduce's sum order differs
-    assert res["loss"] == res["loss_single"], res
+    assert abs(res["loss"] - res["loss_single"]) <= 1e-6 * abs(res["loss_single"]), res
 
 
 @pytest.mark.timeout(420)
