@@ -122,6 +122,12 @@ def usable_cores():
     return max(1, min(n, 64))
 
 
+def workload_name(args):
+    """config.workload, identical for both arms (the driver pairs their lines)."""
+    return ("%s two-scale {0.5,1.0} train step (zero_grad, fwd+bwd, SGD momentum + weight decay), %dx%d crops, "
+            "%d crop/GPU, %s loss" % (args.arch, args.height, args.width, args.batch_per_gpu, args.criterion.upper()))
+
+
 def synth_batch(n, h, w, seed, device):
     g = torch.Generator().manual_seed(seed)
     images = torch.randn((n, 3, h, w), generator=g)
@@ -178,8 +184,7 @@ def run_reference(args):
     line = dict(metric="1024x2048 crops/sec fwd+bwd HRNet-OCR-MScale", value=value, unit="crops/s", impl="reference",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 / value,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32", data="synthetic",
-                config=dict(workload="%s two-scale train step (fwd+bwd+SGD), %dx%d crop, bs1, %s loss" %
-                            (args.arch, args.height, args.width, args.criterion.upper())),
+                config=dict(workload=workload_name(args)),
                 cpu_baseline=dict(value=value, unit="crops/s", cores=cores, kind="port",
                                   sample="%d timed step(s) of the full algorithm at %dx%d (1/%d of the pixels, 90 s "
                                          "budget), rescaled by the pixel ratio" % (timed, sh, sw, round(1 / ratio))),
@@ -349,12 +354,13 @@ def run_b200(args):
         metric="1024x2048 crops/sec fwd+bwd HRNet-OCR-MScale", value=value, unit="crops/s", n_gpus=world,
         steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-        config=dict(workload="%s two-scale {0.5,1.0} train step (zero_grad, fused fwd+bwd, grad publish%s, SGD "
-                             "momentum + weight decay), %dx%d crops, %d crop/GPU, %s loss, %s" %
-                             (args.arch, "+NCCL all-reduce" if world > 1 else "", H, W, B, args.criterion.upper(),
-                              "SyncBN: per-layer statistics exchanged through NVLink peer memory inside the BN "
-                              "finalisers" if (world > 1 and args.syncbn) else
-                              "BatchNorm statistics local to each GPU (SyncBN is opt-in: --syncbn)"),
+        config=dict(workload=workload_name(args),
+                    step="fused fwd+bwd through the C ABI inside one CUDA graph, gradient publish%s, %s" %
+                         (" + one NCCL all-reduce over the flat gradient buffer" if world > 1 else "",
+                          "torch.optim.SGD" if args.torch_sgd else "b200seg FusedSGD"),
+                    batchnorm="SyncBN: per-layer statistics exchanged through NVLink peer memory inside the BN finalisers"
+                              if (world > 1 and args.syncbn) else
+                              "statistics local to each GPU (SyncBN is opt-in: --syncbn)",
                     global_batch=B * world, parallelism="dp%d" % world, cuda_graph=not args.no_graph,
                     l2_policy="per-step working set (>4 GB of activations) far exceeds the 126 MB L2; the "
                               "single-kernel roofline run flushes L2 with a 256 MB write between iterations",
