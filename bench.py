@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--torch-sgd", action="store_true", help="torch.optim.SGD instead of b200seg.optim.FusedSGD")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-gpu-baseline", action="store_true",
+                    help="also time the reference algorithm through stock PyTorch (ATen / cuDNN, autocast bf16 and fp32) on "
+                         "this GPU: the practical kernel to beat (BASELINE.md §5); adds `torch_gpu_baseline` to the line")
     return ap.parse_args()
 
 
@@ -167,6 +170,43 @@ def cpu_reference_step_time(arch, h, w, steps, warmup=1, budget_s=60.0, criterio
         if times and time.perf_counter() - t_start > budget_s:
             break
     return sum(times) / len(times), len(times)
+
+
+def torch_gpu_step_time(arch, h, w, autocast, criterion="ce", steps=5, warmup=3):
+    """The reference algorithm (oracle restatement = the reference's own call sequence of F.conv2d / batch_norm /
+    interpolate / softmax ...) through stock PyTorch on the current GPU: ATen + cuDNN kernels, NCHW, cudnn.benchmark as
+    in train.py:330, optionally under torch.autocast(bf16) (the modern spelling of the reference's apex AMP O1).
+    Baseline measurement only, rank 0, never on the product path. Returns milliseconds per step (CUDA events)."""
+    from oracle import seg_oracle as O
+    torch.backends.cudnn.benchmark = True
+    sd = {k: v.cuda() for k, v in O.synth_state_dict(arch, O.HRNET_W48, seed=0).items()}
+    params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    images, gts = O.synth_batch(1, h, w, seed=1)
+    images, gts = images.cuda(), gts.cuda()
+    crit = O.criterion_rmi if criterion == "rmi" else O.criterion_ce
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            ctx = O.Ctx(sd, training=True)
+            if arch == "ocrnet.HRNet_Mscale":
+                loss = O.mscale_two_scale(ctx, images, gts, criterion=crit)
+            else:
+                loss = O.ocrnet_forward(ctx, images, gts, criterion=crit)
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
 
 def run_reference(args):
@@ -378,6 +418,20 @@ def run_b200(args):
                                      frac=step_tflops / pk["tf_sust"], peak_source=pk["src"] + " sustained bf16"),
         roofline=roof, clocks=clocks, last_loss=loss_val,
         max_memory_allocated_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
+    if args.torch_gpu_baseline:
+        del net, opt
+        torch.cuda.empty_cache()
+        tg = {}
+        for name, ac in (("autocast_bf16", True), ("fp32_tf32_off", False)):
+            try:
+                ms_t = torch_gpu_step_time(args.arch, H, W, ac, args.criterion)
+                tg[name] = dict(ms_per_step=ms_t, value=1000.0 / ms_t, unit="crops/s")
+            except Exception as e:  # noqa
+                tg[name] = dict(error=repr(e))
+            torch.cuda.empty_cache()
+        tg["what"] = ("oracle restatement of the reference algorithm through stock PyTorch eager (ATen/cuDNN, NCHW, "
+                      "cudnn.benchmark, torch.optim.SGD), one crop, same GPU, device-resident inputs")
+        line["torch_gpu_baseline"] = tg
     if not args.no_cpu_baseline:
         try:
             sh, sw = 128, 256
