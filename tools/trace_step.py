@@ -56,7 +56,9 @@ class Recorder:
                     obj = a._obj
                     if isinstance(obj, _lib.ConvDesc):
                         k, s = obj.ksize, obj.stride
-                        ho, wo = (obj.h + 2 * obj.pad - k) // s + 1, (obj.w + 2 * obj.pad - k) // s + 1
+                        dil = max(1, getattr(obj, "dilation", 1))
+                        ho = (obj.h + 2 * obj.pad - dil * (k - 1) - 1) // s + 1
+                        wo = (obj.w + 2 * obj.pad - dil * (k - 1) - 1) // s + 1
                         flops = 2.0 * obj.n * ho * wo * obj.cin * obj.cout * k * k
                         detail = "%dx%d c%d->%d k%d s%d" % (obj.h, obj.w, obj.cin, obj.cout, k, s)
                     elif isinstance(obj, ctypes.c_int32):
