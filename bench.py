@@ -33,6 +33,10 @@ import torch  # noqa: E402
 # Algorithmic work per 1024x2048 crop (SURVEY.md §8d / BASELINE.md §2, conv FLOPs = 2*MAC)
 TFLOP_PER_CROP = {"ocrnet.HRNet_Mscale": 10.53, "ocrnet.HRNet": 7.77}
 FWD_TFLOP_1X = 3.0546
+# Launch-level roofline of one train step per 1024x2048 crop: sum over the step's launches of max(FLOPs / sustained bf16
+# peak, bytes / HBM copy bandwidth), from the static trace of the real step program (tools/trace_step.py,
+# profiles/r1_step_roofline_model.txt; peaks of MEASURED_PEAKS.json: 1386.7 TFLOP/s, 6572.9 GB/s)
+STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.10, "ocrnet.HRNet": 11.34}
 
 
 def parse():
@@ -420,6 +424,10 @@ def run_b200(args):
         gpu_launches_note="%d b200seg kernels per step (inside one CUDA graph replay), three timed loops" % kernels_per_step,
         model_flops_utilisation=dict(achieved_tflops=step_tflops / 1.0, peak=pk["tf_sust"],
                                      frac=step_tflops / pk["tf_sust"], peak_source=pk["src"] + " sustained bf16"),
+        step_roofline=dict(model_ms_per_step=STEP_ROOFLINE_MS[args.arch] * (H * W) / (1024.0 * 2048.0) * B,
+                           frac=STEP_ROOFLINE_MS[args.arch] * (H * W) / (1024.0 * 2048.0) * B / (ms / args.steps),
+                           what="sum over the step's launches of max(FLOPs/P, bytes/B), static trace of the step "
+                                "program (profiles/r1_step_roofline_model.txt)"),
         roofline=roof, clocks=clocks, last_loss=loss_val,
         max_memory_allocated_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
     if args.torch_gpu_baseline:
