@@ -1,0 +1,17 @@
+#!/bin/bash
+# First GPU call of a round (one box, ~10 GPU-minutes): confirms main, then the measurements DESIGN.md still lacks.
+#   gpurun --timeout 1200 -- 'bash tools/gpu_first_call.sh'
+# Everything lands in gpurun_out/first_*.log; nothing here is a bench value to report except first_bench.log's JSON line.
+set -u
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q -x > gpurun_out/first_tests.log 2>&1
+echo "tests rc=$?" | tee -a gpurun_out/first_tests.log
+python bench.py > gpurun_out/first_bench.log 2>&1
+python bench.py --no-cpu-baseline --torch-gpu-baseline --steps 10 > gpurun_out/first_bench_torch.log 2>&1
+python tools/gpu_stream_report.py > gpurun_out/first_streams.log 2>&1
+# launch list of one step (shares of the kernels, input of tools/conv_classes.py) - never a timing source for bench values
+B200SEG_PROFILE=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 7000 --csv \
+  --log-file gpurun_out/first_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/first_ncu.log 2>&1
+gzip -f gpurun_out/first_launches.csv
+tail -n 3 gpurun_out/first_tests.log
+grep -h '^{' gpurun_out/first_bench.log gpurun_out/first_bench_torch.log | cut -c1-600
