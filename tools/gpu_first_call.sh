@@ -9,9 +9,10 @@ echo "tests rc=$?" | tee -a gpurun_out/first_tests.log
 python bench.py > gpurun_out/first_bench.log 2>&1
 python bench.py --no-cpu-baseline --torch-gpu-baseline --steps 10 > gpurun_out/first_bench_torch.log 2>&1
 python tools/gpu_stream_report.py > gpurun_out/first_streams.log 2>&1
-# launch list of one step (shares of the kernels, input of tools/conv_classes.py) - never a timing source for bench values
-B200SEG_PROFILE=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 7000 --csv \
-  --log-file gpurun_out/first_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/first_ncu.log 2>&1
+# launch list (two eager steps: warm-up + one inside the "timed_step" NVTX range; shares of the kernels and the input of
+# tools/conv_classes.py, which takes the first step) - never a timing source for bench values
+B200SEG_PROFILE=1 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
+  --log-file gpurun_out/first_launches.csv python bench.py --no-graph --no-cpu-baseline > gpurun_out/first_ncu.log 2>&1
 gzip -f gpurun_out/first_launches.csv
 tail -n 3 gpurun_out/first_tests.log
 grep -h '^{' gpurun_out/first_bench.log gpurun_out/first_bench_torch.log | cut -c1-600
