@@ -14,5 +14,10 @@ python tools/gpu_stream_report.py > gpurun_out/first_streams.log 2>&1
 B200SEG_PROFILE=1 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
   --log-file gpurun_out/first_launches.csv python bench.py --no-graph --no-cpu-baseline > gpurun_out/first_ncu.log 2>&1
 gzip -f gpurun_out/first_launches.csv
+# the same with every ABI call logged: exact attribution of kernel time to convolution classes
+# (python -O tools/conv_classes.py gpurun_out/abi_launches.csv.gz --abi gpurun_out/abi_calls.json)
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/abi_launches.csv \
+  python tools/gpu_abi_log.py > gpurun_out/first_abi.log 2>&1
+gzip -f gpurun_out/abi_launches.csv
 tail -n 3 gpurun_out/first_tests.log
 grep -h '^{' gpurun_out/first_bench.log gpurun_out/first_bench_torch.log | cut -c1-600
