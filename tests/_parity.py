@@ -1,0 +1,76 @@
+"""Shared helpers of the whole-step parity tests: run ONE training step of the B200 module and of the oracle (on the
+GPU through stock PyTorch fp32, TF32 off, bf16-storage emulation) on identical weights and inputs, and report
+matched-precision agreement figures (loss, per-tensor gradient cosine / relative L2, running statistics, eval maps).
+
+Test infrastructure only (imports oracle/); used by tests/test_gpu_model.py, tests/test_gpu_zz_fullsize.py and
+tools/gpu_parity_report.py."""
+import torch
+
+
+def _tf32_off():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+
+
+def oracle_train_step(O, arch, hcfg, sd0, images, gts, sup_wt=0.0, crit=None, emulate_bf16=True, device="cuda"):
+    """-> (sd with .grad on every parameter and updated running statistics, loss float)."""
+    _tf32_off()
+    sd = {k: v.clone().to(device) for k, v in sd0.items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    ctx = O.Ctx(sd, training=True, emulate_bf16=emulate_bf16)
+    crit = crit or O.criterion_ce
+    images, gts = images.to(device), gts.to(device)
+    if arch == "ocrnet.HRNet_Mscale":
+        loss = O.mscale_two_scale(ctx, images, gts, criterion=crit, hcfg=hcfg, supervised_mscale_wt=sup_wt)
+    elif arch == "ocrnet.HRNet":
+        loss = O.ocrnet_forward(ctx, images, gts, criterion=crit, hcfg=hcfg)
+    else:
+        loss = O.basic_forward(ctx, images, gts, criterion=crit, hcfg=hcfg)
+    loss.backward()
+    return sd, float(loss)
+
+
+def product_train_step(B200SegModule, O, arch, hcfg, sd0, images, gts, sup_wt=0.0, criterion=None, graph=False):
+    ocfg = dict(O.OCR_CFG)
+    ocfg["dropout"] = 0.0
+    net = B200SegModule(arch, 19, criterion=criterion, hcfg=hcfg, ocfg=ocfg, supervised_mscale_wt=sup_wt,
+                        use_cuda_graph=graph)
+    net.load_state_dict(sd0)
+    net = net.cuda().train()
+    loss = net({"images": images.cuda(), "gts": gts.cuda()})
+    loss.backward()
+    torch.cuda.synchronize()
+    return net, float(loss)
+
+
+def cos_rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten().to(a.device)
+    na, nb = float(a.norm()), float(b.norm())
+    if na == 0.0 or nb == 0.0:
+        return (1.0 if na == nb else 0.0), (0.0 if na == nb else 1.0)
+    return float((a * b).sum() / (na * nb)), float((a - b).norm() / nb)
+
+
+def grad_report(net, sd_ref):
+    """name -> (cosine, relative L2, |ref|) over every parameter whose oracle gradient is non-zero."""
+    rep = {}
+    for name, p in net.named_parameters():
+        g_ref = sd_ref[name].grad
+        if g_ref is None or float(g_ref.abs().max()) < 1e-12:
+            continue
+        c, r = cos_rel(p.grad, g_ref)
+        rep[name] = (c, r, float(g_ref.norm()))
+    return rep
+
+
+def running_report(net, sd_ref):
+    rep = {}
+    sd = net.state_dict()
+    for k, v in sd.items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            ref = sd_ref[k].to(v.device)
+            rep[k] = float((v - ref).abs().max() / (ref.abs().max() + 1e-6))
+    return rep
