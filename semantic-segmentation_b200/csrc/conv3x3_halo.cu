@@ -36,6 +36,7 @@ struct HaloParams {
   int resident;                // weights stay in smem for the CTA lifetime
   int a_slots, b_slots;        // ring depths (b_slots unused when resident)
   int b_tile_bytes;            // BN * 128 rounded to 1024
+  int acc_stride, tmem_cols;   // TMEM: two accumulator buffers of acc_stride = pow2 >= BN columns (tmem_cols = 2 * acc_stride)
   int dbg;                     // B200SEG_DBG=8: block 0 records a per-role ns timeline behind the statistics partials
 };
 
@@ -69,7 +70,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define DBG_TS(role, it)                                                                                      \
   do {                                                                                                        \
     if ((p.dbg & 8) && blockIdx.x == 0 && (it) < 16)                                                          \
-      reinterpret_cast<unsigned long long*>(stats_partials + 148 * 2 * 1024)[(role) * 16 + (it)] = gtime();  \
+      reinterpret_cast<unsigned long long*>(stats_partials + B200SEG_MAX_GRID * 2 * 1024)[(role) * 16 + (it)] = gtime();  \
   } while (0)
 #else
 #define DBG_TS(role, it) do { } while (0)
@@ -90,7 +91,8 @@ __device__ __forceinline__ void halo_issue9(uint32_t d_tmem, uint64_t adesc, uin
   }
 }
 
-__global__ void __launch_bounds__(kHThreads, 1)
+template <int OCC>     // CTAs per SM the register budget allows: 2 -> 80 registers (co-resident narrow tiles), 1 -> 168
+__global__ void __launch_bounds__(kHThreads, OCC)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const HaloParams p, __nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
                     float* __restrict__ stats_partials, const __nv_bfloat16* __restrict__ addend) {
@@ -117,7 +119,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  if (warp == 2) { tmem_alloc(tmem_ptr_smem, p.tmem_cols); tmem_relinquish(); }
   if (p.emit_stats)
     for (int i = threadIdx.x; i < 4 * 2 * p.cout_pad; i += kHThreads) s_stats[i] = 0.f;
   tc_fence_before();
@@ -179,7 +181,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int as = it & 1;
         mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * 256;
+        const uint32_t d_tmem = tmem_base + as * p.acc_stride;
         for (int cc = 0; cc <= last; ++cc) {
           mbar_wait(&a_full[a_slot], a_phase);
           tc_fence_after();
@@ -243,7 +245,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull[as], (it >> 1) & 1);
       tc_fence_after();
       if (warp == 4 && lane == 0) DBG_TS(3, it);
-      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * 256;
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * p.acc_stride;
 
       // one 16-column group: bias, gradient addend, bf16 store, batch statistics of the stored values
       auto epi16 = [&](const uint32_t* r, int c0) {
@@ -325,11 +327,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = threadIdx.x; i < 2 * p.cout_pad; i += kHThreads)
       out[i] = (s_stats[i] + s_stats[2 * p.cout_pad + i]) + (s_stats[4 * p.cout_pad + i] + s_stats[6 * p.cout_pad + i]);
   }
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
 // Cout tile width: minimise (waves x per-tile clocks) with per-tile clocks = max(tensor issue, L2->smem fill).
 // A narrow tile costs ~32 clocks per MMA regardless of N (the A operand read from shared memory bounds it).
+// Two CTAs may share an SM when their Cout tile needs at most 128 accumulator columns per buffer (2 x 128 of the 512 TMEM
+// columns), 80 registers x 384 threads and half of the shared memory: CTAs of DIFFERENT launches (the 0.5x and 1.0x
+// passes, the HRNet branch streams, a PDL successor's prologue) then overlap their fill/drain latencies on one SM, and a
+// 256-tile layer runs as one round of 296 slots instead of two rounds of 148. B200SEG_CORESIDENT=0 restores one CTA/SM.
+static bool halo_coresident_enabled() {
+  static const bool on = []() { const char* e = getenv("B200SEG_CORESIDENT"); return !(e && e[0] == '0'); }();
+  return on;
+}
+constexpr size_t kHalfSmBudget = 115712;   // (228 KB - 2 x 1 KB reserved) / 2
+
 static int halo_pick_ntiles(int m_tiles, int cout, int cchunks, int k16) {
   int best_nt = 0;
   double best = 0;
@@ -338,7 +350,8 @@ static int halo_pick_ntiles(int m_tiles, int cout, int cchunks, int k16) {
     if (BN > 256) continue;
     if ((cout + BN - 1) / BN != nt) continue;          // same split as a smaller nt
     const long long tiles = (long long)m_tiles * nt;
-    const double waves = (double)((tiles + B200SEG_MAX_CTAS - 1) / B200SEG_MAX_CTAS);
+    const long long slots = (halo_coresident_enabled() && BN <= 128) ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
+    const double waves = (double)((tiles + slots - 1) / slots);
     const double mma = (double)k16 * (BN / 2 > 32 ? BN / 2 : 32);
     const double fill = ((double)cchunks * kHaloH * kHaloW * 128 + (double)k16 * 32.0 * BN) / 64.0;
     const double cost = waves * (mma > fill ? mma : fill) + 8.0 * BN + 2000.0 + 64.0 * nt;
@@ -370,27 +383,37 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   p.total_tiles = m_tiles * p.n_tiles;
   p.y_ld = out_ld; p.has_bias = bias != nullptr; p.emit_stats = emit_stats; p.addend_ld = addend_ld;
   p.b_tile_bytes = (p.BN * 128 + 1023) / 1024 * 1024;
+  p.acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
+  p.tmem_cols = 2 * p.acc_stride;
   const size_t fixed = 1024 + (2 * kMaxASlots + 2 * kMaxBSlots2 + 4) * 8 + 16 + (size_t)4 * 2 * p.cout_pad * 4;
-  const size_t budget = 227 * 1024 - fixed;
   const size_t resident_bytes = (size_t)9 * p.cchunks * p.b_tile_bytes;
   { const char* e = getenv("B200SEG_DBG"); p.dbg = e ? atoi(e) : 0; }
-  p.resident = (p.n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) ? 1 : 0;
-  size_t smem_bytes;
-  if (p.resident) {
-    int as_ = (int)((budget - resident_bytes) / kASlotBytes);
-    p.a_slots = as_ > kMaxASlots ? kMaxASlots : as_;
-    p.b_slots = 0;
-    smem_bytes = fixed + resident_bytes + (size_t)p.a_slots * kASlotBytes;
-  } else {
+  size_t smem_bytes = 0;
+  int occ = (halo_coresident_enabled() && p.BN <= 128) ? 2 : 1;
+  for (; occ >= 1; --occ) {
+    const size_t budget = (occ == 2 ? kHalfSmBudget : (size_t)227 * 1024) - fixed;
+    p.resident = (p.n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) ? 1 : 0;
+    if (p.resident) {
+      int as_ = (int)((budget - resident_bytes) / kASlotBytes);
+      p.a_slots = as_ > kMaxASlots ? kMaxASlots : as_;
+      p.b_slots = 0;
+      smem_bytes = fixed + resident_bytes + (size_t)p.a_slots * kASlotBytes;
+      break;
+    }
     p.a_slots = 2;
+    if (budget < 2 * (size_t)kASlotBytes + 2 * (size_t)p.b_tile_bytes) continue;      // try the full SM
     int bs = (int)((budget - 2 * (size_t)kASlotBytes) / p.b_tile_bytes);
     if (bs > kMaxBSlots2) bs = kMaxBSlots2;
-    if (bs < 2) return B200SEG_E_BADARG;
+    if (occ == 2 && bs < 4) continue;          // a two-deep weight ring starves the tensor pipe: take the whole SM instead
     p.b_slots = bs;
     smem_bytes = fixed + 2 * (size_t)kASlotBytes + (size_t)bs * p.b_tile_bytes;
+    break;
   }
-  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM: each allocates all 512 TMEM columns
-  const int grid = p.total_tiles < B200SEG_MAX_CTAS ? p.total_tiles : B200SEG_MAX_CTAS;
+  if (occ < 1) return B200SEG_E_BADARG;
+  // one CTA per SM unless the co-resident configuration was chosen (occupancy is bounded by shared memory and registers)
+  if (occ == 1 && smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
+  const int slots = occ == 2 ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
   if (stats_grid) *stats_grid = grid;
   if (!in || !wts || !out) return B200SEG_E_BADARG;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(wts) & 15) ||
@@ -413,12 +436,17 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  cudaError_t e = launch_k(conv3x3_halo_kernel, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, p,
-                           (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend);
+  cudaError_t e =
+      occ == 2 ? launch_k(conv3x3_halo_kernel<2>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, p,
+                          (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend)
+               : launch_k(conv3x3_halo_kernel<1>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, p,
+                          (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
