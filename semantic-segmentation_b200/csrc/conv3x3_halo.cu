@@ -126,18 +126,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
+  // Resident weights are static for the whole step (written by the pack kernels, which never trigger a programmatic
+  // launch): fetch them while the previous kernel on the stream is still draining.
+  if (warp == 0 && p.resident) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&b_full[0], 9 * p.cchunks * p.b_tile_bytes);
+      for (int cc = 0; cc < p.cchunks; ++cc)
+        for (int t = 0; t < 9; ++t)
+          tma_load_3d(&tmB, &b_full[0], b_base + (size_t)(cc * 9 + t) * p.b_tile_bytes, cc * 64, t, 0);
+    }
+    __syncwarp();
+  }
+  pdl_sync();   // everything above overlapped the previous kernel's tail; activations are touched only below
   if (threadIdx.x == 0) DBG_TS(6, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one elected lane)
     if (elect_one()) {
-      if (p.resident) {   // all weight tiles of this CTA's (single) Cout tile, once
-        mbar_arrive_expect_tx(&b_full[0], 9 * p.cchunks * p.b_tile_bytes);
-        for (int cc = 0; cc < p.cchunks; ++cc)
-          for (int t = 0; t < 9; ++t)
-            tma_load_3d(&tmB, &b_full[0], b_base + (size_t)(cc * 9 + t) * p.b_tile_bytes, cc * 64, t, 0);
-      }
       int a_slot = 0, b_slot = 0;
       uint32_t a_phase = 0, b_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
