@@ -52,6 +52,11 @@ typedef struct b200seg_conv_desc {
   int32_t reserved;
 } b200seg_conv_desc;
 
+/* Host-only introspection of the launch plan (tests, tuning): which = 0 forward, 1 stride-1 data gradient.
+ * out[10] = {kernel (1 = halo-tile 3x3, 0 = per-tap implicit GEMM), Cout tile, Cout tiles, grid, dynamic shared memory
+ * bytes, ring depth, CTAs per SM, TMEM columns, resident weights, weight slots}. Returns 0 or a negative error. */
+int b200seg_conv2d_plan_info(const b200seg_conv_desc* d, int32_t which, int32_t* out);
+
 /* Number of fp32 elements the stats partial buffer must hold: B200SEG_MAX_GRID * 2 * cout_padded. */
 size_t b200seg_conv2d_stats_elems(const b200seg_conv_desc* d);
 

@@ -347,16 +347,45 @@ static bool halo_coresident_enabled() {
 }
 constexpr size_t kHalfSmBudget = 115712;   // (228 KB - 2 x 1 KB reserved) / 2
 
+// Shared-memory layout of a CTA for a given Cout tile: returns the CTAs per SM it allows (2, 1, or 0 = does not fit).
+struct HaloSmem { int resident, a_slots, b_slots; size_t bytes; };
+static int halo_smem_layout(int BN, int n_tiles, int cchunks, int cout_pad, HaloSmem& L) {
+  const size_t b_tile = (size_t)(BN * 128 + 1023) / 1024 * 1024;
+  const size_t fixed = 1024 + (2 * kMaxASlots + 2 * kMaxBSlots2 + 4) * 8 + 16 + (size_t)4 * 2 * cout_pad * 4;
+  const size_t resident_bytes = (size_t)9 * cchunks * b_tile;
+  for (int occ = (halo_coresident_enabled() && BN <= 128) ? 2 : 1; occ >= 1; --occ) {
+    const size_t budget = (occ == 2 ? kHalfSmBudget : (size_t)227 * 1024) - fixed;
+    if (n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) {
+      const int as_ = (int)((budget - resident_bytes) / kASlotBytes);
+      L.resident = 1; L.a_slots = as_ > kMaxASlots ? kMaxASlots : as_; L.b_slots = 0;
+      L.bytes = fixed + resident_bytes + (size_t)L.a_slots * kASlotBytes;
+      return occ;
+    }
+    if (budget < 2 * (size_t)kASlotBytes + 2 * b_tile) continue;
+    int bs = (int)((budget - 2 * (size_t)kASlotBytes) / b_tile);
+    if (bs > kMaxBSlots2) bs = kMaxBSlots2;
+    if (occ == 2 && bs < 4) continue;        // a two-deep weight ring starves the tensor pipe: take the whole SM instead
+    L.resident = 0; L.a_slots = 2; L.b_slots = bs;
+    L.bytes = fixed + 2 * (size_t)kASlotBytes + (size_t)bs * b_tile;
+    return occ;
+  }
+  return 0;
+}
+
 static int halo_pick_ntiles(int m_tiles, int cout, int cchunks, int k16) {
   int best_nt = 0;
   double best = 0;
+  const int cout_pad = (cout + 15) / 16 * 16;
   for (int nt = 1; nt <= 16; ++nt) {
     const int BN = ((cout + nt - 1) / nt + 15) / 16 * 16;
     if (BN > 256) continue;
     if ((cout + BN - 1) / BN != nt) continue;          // same split as a smaller nt
+    HaloSmem L;
+    if (halo_smem_layout(BN, nt, cchunks, cout_pad, L) == 0) continue;
+    // Rounds are counted per SM, not per CTA slot: two co-resident CTAs share one tensor pipe and one L2->smem path, so
+    // co-residency hides latency but adds no throughput; the tiling is the one measured with one CTA per SM.
     const long long tiles = (long long)m_tiles * nt;
-    const long long slots = (halo_coresident_enabled() && BN <= 128) ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
-    const double waves = (double)((tiles + slots - 1) / slots);
+    const double waves = (double)((tiles + B200SEG_MAX_CTAS - 1) / B200SEG_MAX_CTAS);
     const double mma = (double)k16 * (BN / 2 > 32 ? BN / 2 : 32);
     const double fill = ((double)cchunks * kHaloH * kHaloW * 128 + (double)k16 * 32.0 * BN) / 64.0;
     const double cost = waves * (mma > fill ? mma : fill) + 8.0 * BN + 2000.0 + 64.0 * nt;
@@ -369,11 +398,9 @@ static int halo_pick_ntiles(int m_tiles, int cout, int cchunks, int k16) {
 // Host launcher shared by forward and stride-1 data gradient. `in` is the A-operand tensor [n,h,w,cin_ext] (pitch in_ld),
 // w is [cout][9][cin_ext] bf16. Returns B200SEG_E_BADARG when the shape is not eligible (caller falls back to the
 // generic per-tap kernel). The statistics partials are [grid][2][roundup16(cout)].
-int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
-                        const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
-                        const void* addend, int addend_ld, int emit_stats, cudaStream_t stream) {
-  if (cin % 8 || in_ld % 8 || out_ld % 8 || cout % 16) return B200SEG_E_BADARG;
-  HaloParams p;
+// Tiling / shared-memory / occupancy decisions of one launch (host only; also reported by b200seg_conv2d_plan_info).
+static int halo_plan(int n, int h, int w, int cin, int cout, HaloParams& p, size_t& smem_bytes, int& grid, int& occ) {
+  if (cin % 8 || cout % 16) return B200SEG_E_BADARG;
   p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
   p.cchunks = (cin + 63) / 64;
   const int rem = cin - (p.cchunks - 1) * 64;
@@ -386,39 +413,41 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   p.BN = ((cout + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;
   p.cout_pad = (cout + 15) / 16 * 16;
   p.total_tiles = m_tiles * p.n_tiles;
-  p.y_ld = out_ld; p.has_bias = bias != nullptr; p.emit_stats = emit_stats; p.addend_ld = addend_ld;
   p.b_tile_bytes = (p.BN * 128 + 1023) / 1024 * 1024;
   p.acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
   p.tmem_cols = 2 * p.acc_stride;
-  const size_t fixed = 1024 + (2 * kMaxASlots + 2 * kMaxBSlots2 + 4) * 8 + 16 + (size_t)4 * 2 * p.cout_pad * 4;
-  const size_t resident_bytes = (size_t)9 * p.cchunks * p.b_tile_bytes;
   { const char* e = getenv("B200SEG_DBG"); p.dbg = e ? atoi(e) : 0; }
-  size_t smem_bytes = 0;
-  int occ = (halo_coresident_enabled() && p.BN <= 128) ? 2 : 1;
-  for (; occ >= 1; --occ) {
-    const size_t budget = (occ == 2 ? kHalfSmBudget : (size_t)227 * 1024) - fixed;
-    p.resident = (p.n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) ? 1 : 0;
-    if (p.resident) {
-      int as_ = (int)((budget - resident_bytes) / kASlotBytes);
-      p.a_slots = as_ > kMaxASlots ? kMaxASlots : as_;
-      p.b_slots = 0;
-      smem_bytes = fixed + resident_bytes + (size_t)p.a_slots * kASlotBytes;
-      break;
-    }
-    p.a_slots = 2;
-    if (budget < 2 * (size_t)kASlotBytes + 2 * (size_t)p.b_tile_bytes) continue;      // try the full SM
-    int bs = (int)((budget - 2 * (size_t)kASlotBytes) / p.b_tile_bytes);
-    if (bs > kMaxBSlots2) bs = kMaxBSlots2;
-    if (occ == 2 && bs < 4) continue;          // a two-deep weight ring starves the tensor pipe: take the whole SM instead
-    p.b_slots = bs;
-    smem_bytes = fixed + 2 * (size_t)kASlotBytes + (size_t)bs * p.b_tile_bytes;
-    break;
-  }
+  HaloSmem L;
+  occ = halo_smem_layout(p.BN, p.n_tiles, p.cchunks, p.cout_pad, L);
+  if (occ >= 1) { p.resident = L.resident; p.a_slots = L.a_slots; p.b_slots = L.b_slots; smem_bytes = L.bytes; }
   if (occ < 1) return B200SEG_E_BADARG;
   // one CTA per SM unless the co-resident configuration was chosen (occupancy is bounded by shared memory and registers)
   if (occ == 1 && smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   const int slots = occ == 2 ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
-  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  grid = p.total_tiles < slots ? p.total_tiles : slots;
+  return 0;
+}
+
+// {kernel 1 = halo, BN, n_tiles, grid, smem bytes, ring depth (A slots), CTAs per SM, TMEM columns, resident weights, B slots}
+int conv3x3_halo_plan_info(int n, int h, int w, int cin, int cout, int32_t* out) {
+  HaloParams p;
+  size_t smem_bytes;
+  int grid, occ;
+  if (int rc = halo_plan(n, h, w, cin, cout, p, smem_bytes, grid, occ)) return rc;
+  out[0] = 1; out[1] = p.BN; out[2] = p.n_tiles; out[3] = grid; out[4] = (int32_t)smem_bytes; out[5] = p.a_slots;
+  out[6] = occ; out[7] = p.tmem_cols; out[8] = p.resident; out[9] = p.b_slots;
+  return 0;
+}
+
+int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
+                        const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
+                        const void* addend, int addend_ld, int emit_stats, cudaStream_t stream) {
+  if (in_ld % 8 || out_ld % 8) return B200SEG_E_BADARG;
+  HaloParams p;
+  size_t smem_bytes;
+  int grid, occ;
+  if (int rc = halo_plan(n, h, w, cin, cout, p, smem_bytes, grid, occ)) return rc;
+  p.y_ld = out_ld; p.has_bias = bias != nullptr; p.emit_stats = emit_stats; p.addend_ld = addend_ld;
   if (stats_grid) *stats_grid = grid;
   if (!in || !wts || !out) return B200SEG_E_BADARG;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(wts) & 15) ||

@@ -329,8 +329,8 @@ static int plan_geom(const LaunchGeom& g, ConvPlan* pl) {
       if (BN > 256) continue;
       if ((cout16 + BN - 1) / BN != nt) continue;
       const long long tiles = (long long)m_tiles * nt;
-      const long long slots = (coresident_enabled() && BN <= 128) ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
-      const double waves = (double)((tiles + slots - 1) / slots);
+      // rounds per SM (co-resident CTAs share the tensor pipe: latency hiding, not throughput)
+      const double waves = (double)((tiles + B200SEG_MAX_CTAS - 1) / B200SEG_MAX_CTAS);
       const double cost = waves * k16 * (64.0 + BN / 2) + 8.0 * BN + 2000.0 + 64.0 * nt;
       if (best_nt == 0 || cost < best) { best = cost; best_nt = nt; }
       if (BN <= 16) break;
@@ -462,6 +462,7 @@ static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const 
 int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
                         const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
                         const void* addend, int addend_ld, int emit_stats, cudaStream_t stream);
+int conv3x3_halo_plan_info(int n, int h, int w, int cin, int cout, int32_t* out);
 
 }  // namespace b200seg
 
@@ -471,6 +472,28 @@ extern "C" size_t b200seg_conv2d_stats_elems(const b200seg_conv_desc* d) {
   ConvPlan pl;
   if (conv_plan(d, &pl) != 0) return 0;
   return (size_t)B200SEG_MAX_GRID * 2 * ((d->cout + 15) / 16 * 16);   // [grid <= 296][2][roundup16(cout)]
+}
+
+// Host-only: the launch plan of a forward (which = 0) or stride-1 data-gradient (which = 1) convolution, for tests and
+// tuning scripts. out[10] = {kernel (1 halo / 0 per-tap), BN, n_tiles, grid, dynamic smem bytes, ring depth, CTAs per SM,
+// TMEM columns, resident weights (halo), weight slots (halo)}.
+extern "C" int b200seg_conv2d_plan_info(const b200seg_conv_desc* d, int32_t which, int32_t* out) {
+  if (!desc_ok(d) || !out || which < 0 || which > 1) return B200SEG_E_BADARG;
+  if (which == 1 && d->stride != 1) return B200SEG_E_BADARG;
+  const bool halo_fwd = d->ksize == 3 && d->stride == 1 && !d->out_fp32 && d->cout % 16 == 0 && d->reserved == 0;
+  const bool halo_bwd = d->ksize == 3 && d->cin % 16 == 0 && d->reserved == 0;
+  if (which == 0 && halo_fwd) return conv3x3_halo_plan_info(d->n, d->h, d->w, d->cin, d->cout, out);
+  if (which == 1 && halo_bwd) return conv3x3_halo_plan_info(d->n, d->h, d->w, (d->cout + 7) / 8 * 8, d->cin, out);
+  LaunchGeom g = fwd_geom(d);
+  if (which == 1) {          // same GEMM shape with the channel roles swapped (taps and lattice as the forward)
+    g.in_c = (d->cout + 7) / 8 * 8; g.in_ld = g.in_c; g.out_c = d->cin; g.out_ld = d->cin;
+    g.out_fp32 = 0; g.has_bias = 0; g.emit_stats = 0;
+  }
+  ConvPlan pl;
+  if (int rc = plan_geom(g, &pl)) return rc;
+  out[0] = 0; out[1] = pl.BN; out[2] = pl.n_tiles; out[3] = pl.grid; out[4] = (int32_t)pl.smem_bytes; out[5] = pl.nstages;
+  out[6] = pl.occ; out[7] = pl.tmem_cols; out[8] = 0; out[9] = 0;
+  return 0;
 }
 
 extern "C" int b200seg_conv2d_fwd(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
