@@ -474,6 +474,9 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
     if (e != cudaSuccess) return (int)e;
+    // two CTAs per SM need (almost) the whole 228 KB as shared memory: ask for the maximum carve-out explicitly
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   cudaError_t e =

@@ -448,6 +448,9 @@ static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const 
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
     if (e != cudaSuccess) return (int)e;
+    // two CTAs per SM need (almost) the whole 228 KB as shared memory: ask for the maximum carve-out explicitly
+    e = cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   if (stats_grid) *stats_grid = pl.grid;
