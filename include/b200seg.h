@@ -57,6 +57,10 @@ typedef struct b200seg_conv_desc {
  * bytes, ring depth, CTAs per SM, TMEM columns, resident weights, weight slots}. Returns 0 or a negative error. */
 int b200seg_conv2d_plan_info(const b200seg_conv_desc* d, int32_t which, int32_t* out);
 
+/* Diagnostics (needs a GPU): CTAs per SM the runtime grants kernel (1 = halo-tile 3x3, 0 = per-tap) in its
+ * co-resident (occ_variant 2) or full-SM (1) build with smem_bytes of dynamic shared memory; negative = error. */
+int32_t b200seg_debug_occupancy(int32_t kernel, int32_t occ_variant, int32_t smem_bytes);
+
 /* Number of fp32 elements the stats partial buffer must hold: B200SEG_MAX_GRID * 2 * cout_padded. */
 size_t b200seg_conv2d_stats_elems(const b200seg_conv_desc* d);
 

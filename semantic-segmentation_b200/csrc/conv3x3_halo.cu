@@ -487,4 +487,25 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   return e == cudaSuccess ? 0 : (int)e;
 }
 
+
+// Diagnostics: CTAs per SM the runtime grants the co-resident (OCC = 2) and the full-SM (OCC = 1) build of the two
+// convolution kernels for a given dynamic shared-memory size (registers, shared-memory carve-out, barriers all included).
+int conv_igemm_occupancy(int occ_variant, int smem_bytes);
+int conv3x3_halo_occupancy(int occ_variant, int smem_bytes) {
+  int nb = -1;
+  cudaFuncSetAttribute(conv3x3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
+  cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = occ_variant == 2
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv3x3_halo_kernel<2>, kHThreads, (size_t)smem_bytes)
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv3x3_halo_kernel<1>, kHThreads, (size_t)smem_bytes);
+  return e == cudaSuccess ? nb : -(int)e;
+}
+
 }  // namespace b200seg
+
+extern "C" int32_t b200seg_debug_occupancy(int32_t kernel, int32_t occ_variant, int32_t smem_bytes) {
+  if (occ_variant != 1 && occ_variant != 2) return B200SEG_E_BADARG;
+  return kernel == 1 ? b200seg::conv3x3_halo_occupancy(occ_variant, smem_bytes)
+                     : b200seg::conv_igemm_occupancy(occ_variant, smem_bytes);
+}
