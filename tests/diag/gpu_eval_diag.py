@@ -1,7 +1,7 @@
 """Layer-by-layer eval-mode comparison of the B200 path against the bf16-emulating oracle (debug aid).
-usage: python tools/gpu_eval_diag.py [arch]"""
+usage: python tests/diag/gpu_eval_diag.py [arch]"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "semantic-segmentation_b200"))
 import torch
 from oracle import seg_oracle as O

@@ -1,6 +1,6 @@
 """RMI head debug: pooled maps, pooled-probability gradient and final logit gradient against torch autograd (fp64)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "semantic-segmentation_b200"))
 import torch, torch.nn.functional as F
 from b200seg import raw

@@ -4,6 +4,10 @@ convolution class (kind, shape), launches, measured time, roofline time and thei
 inside a step, so the expected kernel-name sequence is rotated onto the observed one first.
 
     python -O tools/conv_classes.py profiles/r1_launches_v2.csv.gz
+    python -O tools/conv_classes.py gpurun_out/abi_launches.csv --abi gpurun_out/abi_calls.json
+
+With --abi (the log tools/gpu_abi_log.py wrote in the SAME run as the launch list) nothing is guessed: the k-th b200seg
+kernel of the list belongs to the ABI call whose cumulative launch count covers k.
 """
 import collections
 import csv
@@ -48,8 +52,59 @@ def load_trace():
     return exp
 
 
+def open_text(path):
+    return gzip.open(path, "rt") if path.endswith(".gz") else open(path, "rt")
+
+
+def join_with_abi_log(csv_path, abi_path):
+    import json
+    with open(abi_path) as f:
+        log = json.load(f)
+    rows = list(csv.reader(open_text(csv_path)))
+    for i, r in enumerate(rows):
+        if "Kernel Name" in r:
+            hdr, start = r, i
+            break
+    ki, mi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    dur = []
+    for r in rows[start + 2:]:
+        if len(r) > mi and "b200seg::" in r[ki]:
+            try:
+                dur.append(float(r[mi].replace(",", "")) / 1000.0)
+            except ValueError:
+                pass
+    calls = log["calls"]
+    total = sum(c[4] for c in calls)
+    print("ABI log: %d calls, %d kernels; launch list: %d b200seg kernels" % (len(calls), total, len(dur)))
+    if total != len(dur):
+        print("COUNT MISMATCH: the two files are not from the same run (or a launch count passed to check() is wrong)")
+    first = log["step_starts"][-1]           # the last logged step (allocator warm, kernels loaded)
+    k = sum(c[4] for c in calls[:first])
+    agg, per_entry = collections.OrderedDict(), collections.OrderedDict()
+    for name, detail, flops, nbytes, launches in calls[first:]:
+        t = sum(dur[k:k + launches])
+        k += launches
+        if launches == 0:
+            continue
+        roof = max(flops / P, nbytes / B) * 1e6
+        for key, table in (((name, detail), agg), ((name, ""), per_entry)):
+            a = table.setdefault(key, [0, 0, 0.0, 0.0])
+            a[0] += 1; a[1] += launches; a[2] += t; a[3] += roof
+    for title, table in (("per entry point", per_entry), ("per convolution class", agg)):
+        print("\n%s\n%-18s %-30s %6s %8s %10s %10s %8s" % (title, "entry point", "shape", "calls", "kernels", "meas ms",
+                                                         "roof ms", "ratio"))
+        tot = [0.0, 0.0]
+        for (name, detail), (c, l, t, rt) in sorted(table.items(), key=lambda kv: -kv[1][2]):
+            if table is agg and not detail:
+                continue
+            print("%-18s %-30s %6d %8d %10.3f %10.3f %8.1f" % (name, detail, c, l, t / 1e3, rt / 1e3, t / max(rt, 1e-9)))
+            tot[0] += t; tot[1] += rt
+        print("%-18s %-30s %6s %8s %10.3f %10.3f %8.1f" % ("sum", "", "", "", tot[0] / 1e3, tot[1] / 1e3,
+                                                          tot[0] / max(tot[1], 1e-9)))
+
+
 def load_launches(path):
-    rows = list(csv.reader(gzip.open(path, "rt")))
+    rows = list(csv.reader(open_text(path)))
     for i, r in enumerate(rows):
         if "Kernel Name" in r:
             hdr, start = r, i
@@ -70,6 +125,9 @@ def load_launches(path):
 
 
 def main():
+    if "--abi" in sys.argv:
+        join_with_abi_log(sys.argv[1], sys.argv[sys.argv.index("--abi") + 1])
+        return
     exp = load_trace()
     obs = load_launches(sys.argv[1])
     print("expected %d tensor-core launches per step, launch list holds %d" % (len(exp), len(obs)))
