@@ -26,7 +26,8 @@ extern "C" {
 
 #define B200SEG_E_BADARG (-1)      /* shape / alignment not supported by the kernel */
 #define B200SEG_E_NODRIVER (-100)  /* cuTensorMapEncodeTiled entry point unavailable */
-#define B200SEG_MAX_CTAS 148       /* persistent grids never exceed one CTA per SM */
+#define B200SEG_MAX_CTAS 148       /* SMs of a B200 */
+#define B200SEG_MAX_GRID 296       /* persistent grids: at most two co-resident CTAs per SM (narrow Cout tiles) */
 
 /* ABI / build identification. */
 int b200seg_abi_version(void);
@@ -51,7 +52,16 @@ typedef struct b200seg_conv_desc {
   int32_t reserved;
 } b200seg_conv_desc;
 
-/* Number of fp32 elements the stats partial buffer must hold: B200SEG_MAX_CTAS * 2 * cout_padded. */
+/* Host-only introspection of the launch plan (tests, tuning): which = 0 forward, 1 stride-1 data gradient.
+ * out[10] = {kernel (1 = halo-tile 3x3, 0 = per-tap implicit GEMM), Cout tile, Cout tiles, grid, dynamic shared memory
+ * bytes, ring depth, CTAs per SM, TMEM columns, resident weights, weight slots}. Returns 0 or a negative error. */
+int b200seg_conv2d_plan_info(const b200seg_conv_desc* d, int32_t which, int32_t* out);
+
+/* Diagnostics (needs a GPU): CTAs per SM the runtime grants kernel (1 = halo-tile 3x3, 0 = per-tap) in its
+ * co-resident (occ_variant 2) or full-SM (1) build with smem_bytes of dynamic shared memory; negative = error. */
+int32_t b200seg_debug_occupancy(int32_t kernel, int32_t occ_variant, int32_t smem_bytes);
+
+/* Number of fp32 elements the stats partial buffer must hold: B200SEG_MAX_GRID * 2 * cout_padded. */
 size_t b200seg_conv2d_stats_elems(const b200seg_conv_desc* d);
 
 /* y[n,ho,wo,co] = sum_{kh,kw,ci} x[n, ho*s+kh-p, wo*s+kw-p, ci] * w[co,kh,kw,ci] (+ bias[co]).

@@ -143,7 +143,7 @@ def conv2d_fwd(x, w_ohwi, bias=None, stride=1, out=None, out_fp32=False, emit_st
     check(lib().b200seg_conv2d_fwd(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out), ptr(stats),
                                    ctypes.byref(grid), stream_ptr()), "conv2d_fwd")
     if emit_stats:
-        cout_pad = nelem // (148 * 2)
+        cout_pad = (cout + 15) // 16 * 16
         return out, (stats, grid.value, cout_pad)
     return out
 

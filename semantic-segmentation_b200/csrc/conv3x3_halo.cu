@@ -36,6 +36,7 @@ struct HaloParams {
   int resident;                // weights stay in smem for the CTA lifetime
   int a_slots, b_slots;        // ring depths (b_slots unused when resident)
   int b_tile_bytes;            // BN * 128 rounded to 1024
+  int acc_stride, tmem_cols;   // TMEM: two accumulator buffers of acc_stride = pow2 >= BN columns (tmem_cols = 2 * acc_stride)
   int dbg;                     // B200SEG_DBG=8: block 0 records a per-role ns timeline behind the statistics partials
 };
 
@@ -69,7 +70,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define DBG_TS(role, it)                                                                                      \
   do {                                                                                                        \
     if ((p.dbg & 8) && blockIdx.x == 0 && (it) < 16)                                                          \
-      reinterpret_cast<unsigned long long*>(stats_partials + 148 * 2 * 1024)[(role) * 16 + (it)] = gtime();  \
+      reinterpret_cast<unsigned long long*>(stats_partials + B200SEG_MAX_GRID * 2 * 1024)[(role) * 16 + (it)] = gtime();  \
   } while (0)
 #else
 #define DBG_TS(role, it) do { } while (0)
@@ -90,7 +91,8 @@ __device__ __forceinline__ void halo_issue9(uint32_t d_tmem, uint64_t adesc, uin
   }
 }
 
-__global__ void __launch_bounds__(kHThreads, 1)
+template <int OCC>     // CTAs per SM the register budget allows: 2 -> 80 registers (co-resident narrow tiles), 1 -> 168
+__global__ void __launch_bounds__(kHThreads, OCC)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const HaloParams p, __nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
                     float* __restrict__ stats_partials, const __nv_bfloat16* __restrict__ addend) {
@@ -117,25 +119,30 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  if (warp == 2) { tmem_alloc(tmem_ptr_smem, p.tmem_cols); tmem_relinquish(); }
   if (p.emit_stats)
     for (int i = threadIdx.x; i < 4 * 2 * p.cout_pad; i += kHThreads) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
+  // Resident weights are static for the whole step (written by the pack kernels, which never trigger a programmatic
+  // launch): fetch them while the previous kernel on the stream is still draining.
+  if (warp == 0 && p.resident) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&b_full[0], 9 * p.cchunks * p.b_tile_bytes);
+      for (int cc = 0; cc < p.cchunks; ++cc)
+        for (int t = 0; t < 9; ++t)
+          tma_load_3d(&tmB, &b_full[0], b_base + (size_t)(cc * 9 + t) * p.b_tile_bytes, cc * 64, t, 0);
+    }
+    __syncwarp();
+  }
+  pdl_sync();   // everything above overlapped the previous kernel's tail; activations are touched only below
   if (threadIdx.x == 0) DBG_TS(6, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one elected lane)
     if (elect_one()) {
-      if (p.resident) {   // all weight tiles of this CTA's (single) Cout tile, once
-        mbar_arrive_expect_tx(&b_full[0], 9 * p.cchunks * p.b_tile_bytes);
-        for (int cc = 0; cc < p.cchunks; ++cc)
-          for (int t = 0; t < 9; ++t)
-            tma_load_3d(&tmB, &b_full[0], b_base + (size_t)(cc * 9 + t) * p.b_tile_bytes, cc * 64, t, 0);
-      }
       int a_slot = 0, b_slot = 0;
       uint32_t a_phase = 0, b_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -179,7 +186,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int as = it & 1;
         mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * 256;
+        const uint32_t d_tmem = tmem_base + as * p.acc_stride;
         for (int cc = 0; cc <= last; ++cc) {
           mbar_wait(&a_full[a_slot], a_phase);
           tc_fence_after();
@@ -243,7 +250,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull[as], (it >> 1) & 1);
       tc_fence_after();
       if (warp == 4 && lane == 0) DBG_TS(3, it);
-      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * 256;
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * p.acc_stride;
 
       // one 16-column group: bias, gradient addend, bf16 store, batch statistics of the stored values
       auto epi16 = [&](const uint32_t* r, int c0) {
@@ -325,18 +332,58 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = threadIdx.x; i < 2 * p.cout_pad; i += kHThreads)
       out[i] = (s_stats[i] + s_stats[2 * p.cout_pad + i]) + (s_stats[4 * p.cout_pad + i] + s_stats[6 * p.cout_pad + i]);
   }
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
 // Cout tile width: minimise (waves x per-tile clocks) with per-tile clocks = max(tensor issue, L2->smem fill).
 // A narrow tile costs ~32 clocks per MMA regardless of N (the A operand read from shared memory bounds it).
+// Two CTAs may share an SM when their Cout tile needs at most 128 accumulator columns per buffer (2 x 128 of the 512 TMEM
+// columns), 80 registers x 384 threads and half of the shared memory: CTAs of DIFFERENT launches (the 0.5x and 1.0x
+// passes, the HRNet branch streams, a PDL successor's prologue) then overlap their fill/drain latencies on one SM, and a
+// 256-tile layer runs as one round of 296 slots instead of two rounds of 148. B200SEG_CORESIDENT=0 restores one CTA/SM.
+static bool halo_coresident_enabled() {
+  static const bool on = []() { const char* e = getenv("B200SEG_CORESIDENT"); return !(e && e[0] == '0'); }();
+  return on;
+}
+constexpr size_t kHalfSmBudget = 115712;   // (228 KB - 2 x 1 KB reserved) / 2
+
+// Shared-memory layout of a CTA for a given Cout tile: returns the CTAs per SM it allows (2, 1, or 0 = does not fit).
+struct HaloSmem { int resident, a_slots, b_slots; size_t bytes; };
+static int halo_smem_layout(int BN, int n_tiles, int cchunks, int cout_pad, HaloSmem& L) {
+  const size_t b_tile = (size_t)(BN * 128 + 1023) / 1024 * 1024;
+  const size_t fixed = 1024 + (2 * kMaxASlots + 2 * kMaxBSlots2 + 4) * 8 + 16 + (size_t)4 * 2 * cout_pad * 4;
+  const size_t resident_bytes = (size_t)9 * cchunks * b_tile;
+  for (int occ = (halo_coresident_enabled() && BN <= 128) ? 2 : 1; occ >= 1; --occ) {
+    const size_t budget = (occ == 2 ? kHalfSmBudget : (size_t)227 * 1024) - fixed;
+    if (n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) {
+      const int as_ = (int)((budget - resident_bytes) / kASlotBytes);
+      L.resident = 1; L.a_slots = as_ > kMaxASlots ? kMaxASlots : as_; L.b_slots = 0;
+      L.bytes = fixed + resident_bytes + (size_t)L.a_slots * kASlotBytes;
+      return occ;
+    }
+    if (budget < 2 * (size_t)kASlotBytes + 2 * b_tile) continue;
+    int bs = (int)((budget - 2 * (size_t)kASlotBytes) / b_tile);
+    if (bs > kMaxBSlots2) bs = kMaxBSlots2;
+    if (occ == 2 && bs < 4) continue;        // a two-deep weight ring starves the tensor pipe: take the whole SM instead
+    L.resident = 0; L.a_slots = 2; L.b_slots = bs;
+    L.bytes = fixed + 2 * (size_t)kASlotBytes + (size_t)bs * b_tile;
+    return occ;
+  }
+  return 0;
+}
+
 static int halo_pick_ntiles(int m_tiles, int cout, int cchunks, int k16) {
   int best_nt = 0;
   double best = 0;
+  const int cout_pad = (cout + 15) / 16 * 16;
   for (int nt = 1; nt <= 16; ++nt) {
     const int BN = ((cout + nt - 1) / nt + 15) / 16 * 16;
     if (BN > 256) continue;
     if ((cout + BN - 1) / BN != nt) continue;          // same split as a smaller nt
+    HaloSmem L;
+    if (halo_smem_layout(BN, nt, cchunks, cout_pad, L) == 0) continue;
+    // Rounds are counted per SM, not per CTA slot: two co-resident CTAs share one tensor pipe and one L2->smem path, so
+    // co-residency hides latency but adds no throughput; the tiling is the one measured with one CTA per SM.
     const long long tiles = (long long)m_tiles * nt;
     const double waves = (double)((tiles + B200SEG_MAX_CTAS - 1) / B200SEG_MAX_CTAS);
     const double mma = (double)k16 * (BN / 2 > 32 ? BN / 2 : 32);
@@ -351,11 +398,9 @@ static int halo_pick_ntiles(int m_tiles, int cout, int cchunks, int k16) {
 // Host launcher shared by forward and stride-1 data gradient. `in` is the A-operand tensor [n,h,w,cin_ext] (pitch in_ld),
 // w is [cout][9][cin_ext] bf16. Returns B200SEG_E_BADARG when the shape is not eligible (caller falls back to the
 // generic per-tap kernel). The statistics partials are [grid][2][roundup16(cout)].
-int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
-                        const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
-                        const void* addend, int addend_ld, int emit_stats, cudaStream_t stream) {
-  if (cin % 8 || in_ld % 8 || out_ld % 8 || cout % 16) return B200SEG_E_BADARG;
-  HaloParams p;
+// Tiling / shared-memory / occupancy decisions of one launch (host only; also reported by b200seg_conv2d_plan_info).
+static int halo_plan(int n, int h, int w, int cin, int cout, HaloParams& p, size_t& smem_bytes, int& grid, int& occ) {
+  if (cin % 8 || cout % 16) return B200SEG_E_BADARG;
   p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
   p.cchunks = (cin + 63) / 64;
   const int rem = cin - (p.cchunks - 1) * 64;
@@ -368,29 +413,41 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   p.BN = ((cout + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;
   p.cout_pad = (cout + 15) / 16 * 16;
   p.total_tiles = m_tiles * p.n_tiles;
-  p.y_ld = out_ld; p.has_bias = bias != nullptr; p.emit_stats = emit_stats; p.addend_ld = addend_ld;
   p.b_tile_bytes = (p.BN * 128 + 1023) / 1024 * 1024;
-  const size_t fixed = 1024 + (2 * kMaxASlots + 2 * kMaxBSlots2 + 4) * 8 + 16 + (size_t)4 * 2 * p.cout_pad * 4;
-  const size_t budget = 227 * 1024 - fixed;
-  const size_t resident_bytes = (size_t)9 * p.cchunks * p.b_tile_bytes;
+  p.acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
+  p.tmem_cols = 2 * p.acc_stride;
   { const char* e = getenv("B200SEG_DBG"); p.dbg = e ? atoi(e) : 0; }
-  p.resident = (p.n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) ? 1 : 0;
+  HaloSmem L;
+  occ = halo_smem_layout(p.BN, p.n_tiles, p.cchunks, p.cout_pad, L);
+  if (occ >= 1) { p.resident = L.resident; p.a_slots = L.a_slots; p.b_slots = L.b_slots; smem_bytes = L.bytes; }
+  if (occ < 1) return B200SEG_E_BADARG;
+  // one CTA per SM unless the co-resident configuration was chosen (occupancy is bounded by shared memory and registers)
+  if (occ == 1 && smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
+  const int slots = occ == 2 ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
+  grid = p.total_tiles < slots ? p.total_tiles : slots;
+  return 0;
+}
+
+// {kernel 1 = halo, BN, n_tiles, grid, smem bytes, ring depth (A slots), CTAs per SM, TMEM columns, resident weights, B slots}
+int conv3x3_halo_plan_info(int n, int h, int w, int cin, int cout, int32_t* out) {
+  HaloParams p;
   size_t smem_bytes;
-  if (p.resident) {
-    int as_ = (int)((budget - resident_bytes) / kASlotBytes);
-    p.a_slots = as_ > kMaxASlots ? kMaxASlots : as_;
-    p.b_slots = 0;
-    smem_bytes = fixed + resident_bytes + (size_t)p.a_slots * kASlotBytes;
-  } else {
-    p.a_slots = 2;
-    int bs = (int)((budget - 2 * (size_t)kASlotBytes) / p.b_tile_bytes);
-    if (bs > kMaxBSlots2) bs = kMaxBSlots2;
-    if (bs < 2) return B200SEG_E_BADARG;
-    p.b_slots = bs;
-    smem_bytes = fixed + 2 * (size_t)kASlotBytes + (size_t)bs * p.b_tile_bytes;
-  }
-  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM: each allocates all 512 TMEM columns
-  const int grid = p.total_tiles < B200SEG_MAX_CTAS ? p.total_tiles : B200SEG_MAX_CTAS;
+  int grid, occ;
+  if (int rc = halo_plan(n, h, w, cin, cout, p, smem_bytes, grid, occ)) return rc;
+  out[0] = 1; out[1] = p.BN; out[2] = p.n_tiles; out[3] = grid; out[4] = (int32_t)smem_bytes; out[5] = p.a_slots;
+  out[6] = occ; out[7] = p.tmem_cols; out[8] = p.resident; out[9] = p.b_slots;
+  return 0;
+}
+
+int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
+                        const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
+                        const void* addend, int addend_ld, int emit_stats, cudaStream_t stream) {
+  if (in_ld % 8 || out_ld % 8) return B200SEG_E_BADARG;
+  HaloParams p;
+  size_t smem_bytes;
+  int grid, occ;
+  if (int rc = halo_plan(n, h, w, cin, cout, p, smem_bytes, grid, occ)) return rc;
+  p.y_ld = out_ld; p.has_bias = bias != nullptr; p.emit_stats = emit_stats; p.addend_ld = addend_ld;
   if (stats_grid) *stats_grid = grid;
   if (!in || !wts || !out) return B200SEG_E_BADARG;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(wts) & 15) ||
@@ -413,13 +470,42 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
+    if (e != cudaSuccess) return (int)e;
+    // two CTAs per SM need (almost) the whole 228 KB as shared memory: ask for the maximum carve-out explicitly
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  cudaError_t e = launch_k(conv3x3_halo_kernel, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, p,
-                           (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend);
+  cudaError_t e =
+      occ == 2 ? launch_k(conv3x3_halo_kernel<2>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, p,
+                          (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend)
+               : launch_k(conv3x3_halo_kernel<1>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, p,
+                          (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
+
+// Diagnostics: CTAs per SM the runtime grants the co-resident (OCC = 2) and the full-SM (OCC = 1) build of the two
+// convolution kernels for a given dynamic shared-memory size (registers, shared-memory carve-out, barriers all included).
+int conv_igemm_occupancy(int occ_variant, int smem_bytes);
+int conv3x3_halo_occupancy(int occ_variant, int smem_bytes) {
+  int nb = -1;
+  cudaFuncSetAttribute(conv3x3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
+  cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = occ_variant == 2
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv3x3_halo_kernel<2>, kHThreads, (size_t)smem_bytes)
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv3x3_halo_kernel<1>, kHThreads, (size_t)smem_bytes);
+  return e == cudaSuccess ? nb : -(int)e;
+}
+
 }  // namespace b200seg
+
+extern "C" int32_t b200seg_debug_occupancy(int32_t kernel, int32_t occ_variant, int32_t smem_bytes) {
+  if (occ_variant != 1 && occ_variant != 2) return B200SEG_E_BADARG;
+  return kernel == 1 ? b200seg::conv3x3_halo_occupancy(occ_variant, smem_bytes)
+                     : b200seg::conv_igemm_occupancy(occ_variant, smem_bytes);
+}

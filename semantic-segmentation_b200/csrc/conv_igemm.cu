@@ -16,6 +16,7 @@
 //               per TMEM lane quarter, half of the accumulator columns each).
 //   Launch:     programmatic dependent launch (launch.h): the prologue overlaps the previous kernel's tail.
 #include "ptx.cuh"
+#include <cstdlib>
 #include "tma_host.h"
 #include "launch.h"
 #include "../../include/b200seg.h"
@@ -36,11 +37,12 @@ struct ConvKParams {
   int y_ld, out_fp32, has_bias, emit_stats, cout_pad, addend_ld;
   int layout_type, sbo;
   int a_bytes, b_bytes, stage_bytes, nstages;
+  int acc_stride, tmem_cols;    // two TMEM accumulator buffers of acc_stride = pow2 >= BN columns
 };
 
 constexpr int kThreads = 384;
 constexpr int kMaxStages = 8;
-constexpr int kAccCols = 256;   // TMEM columns per accumulator stage
+constexpr size_t kHalfSmBudget = 115712;   // (228 KB - 2 x 1 KB reserved) / 2: two CTAs per SM (see conv3x3_halo.cu)
 
 // Sum v[0..15] over the 32 lanes of the warp: afterwards v[0] holds the total for channel (lane & 15).
 __device__ __forceinline__ void butterfly16(float (&v)[16], uint32_t lane) {
@@ -57,7 +59,8 @@ __device__ __forceinline__ void butterfly16(float (&v)[16], uint32_t lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int OCC>     // CTAs per SM the register budget allows (2: co-resident narrow tiles)
+__global__ void __launch_bounds__(kThreads, OCC)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ConvKParams p, void* __restrict__ y, const float* __restrict__ bias,
                   float* __restrict__ stats_partials, const __nv_bfloat16* __restrict__ addend) {
@@ -86,7 +89,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_alloc(tmem_ptr_smem, p.tmem_cols);
     tmem_relinquish();
   }
   if (p.emit_stats) {
@@ -140,7 +143,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kAccCols;
+        const uint32_t d_tmem = tmem_base + as * p.acc_stride;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -183,7 +186,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * kAccCols;
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * p.acc_stride;
 
       auto epi16 = [&](const uint32_t* r, int c0) {
         float v[16];
@@ -273,7 +276,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -286,6 +289,11 @@ struct LaunchGeom {
   int ntaps, tap_dh[9], tap_dw[9], tap_w[9], wtaps;   // wtaps = taps dimension of the weight tensor
   int out_fp32, has_bias, emit_stats, force_kc;
 };
+
+static bool coresident_enabled() {
+  static const bool on = []() { const char* e = getenv("B200SEG_CORESIDENT"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 static int plan_geom(const LaunchGeom& g, ConvPlan* pl) {
   if (g.n <= 0 || g.sub_h <= 0 || g.sub_w <= 0) return B200SEG_E_BADARG;
@@ -321,6 +329,7 @@ static int plan_geom(const LaunchGeom& g, ConvPlan* pl) {
       if (BN > 256) continue;
       if ((cout16 + BN - 1) / BN != nt) continue;
       const long long tiles = (long long)m_tiles * nt;
+      // rounds per SM (co-resident CTAs share the tensor pipe: latency hiding, not throughput)
       const double waves = (double)((tiles + B200SEG_MAX_CTAS - 1) / B200SEG_MAX_CTAS);
       const double cost = waves * k16 * (64.0 + BN / 2) + 8.0 * BN + 2000.0 + 64.0 * nt;
       if (best_nt == 0 || cost < best) { best = cost; best_nt = nt; }
@@ -331,17 +340,29 @@ static int plan_geom(const LaunchGeom& g, ConvPlan* pl) {
     pl->cout_pad = cout16;     // row pitch of the statistics partials (independent of the tiling)
   }
   pl->total_tiles = g.n * pl->tiles_h * pl->tiles_w * pl->n_tiles;
-  pl->grid = pl->total_tiles < B200SEG_MAX_CTAS ? pl->total_tiles : B200SEG_MAX_CTAS;
   pl->a_bytes = 128 * KC * 2;
   pl->b_bytes = pl->BN * KC * 2;
   pl->stage_bytes = (pl->a_bytes + pl->b_bytes + 1023) / 1024 * 1024;
+  pl->acc_stride = pl->BN <= 32 ? 32 : (pl->BN <= 64 ? 64 : (pl->BN <= 128 ? 128 : 256));
+  pl->tmem_cols = 2 * pl->acc_stride;
   size_t fixed = 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16 + (size_t)4 * 2 * pl->cout_pad * 4;
-  int nst = (int)((227 * 1024 - fixed) / pl->stage_bytes);
-  if (nst > kMaxStages) nst = kMaxStages;
-  if (nst < 2) return B200SEG_E_BADARG;
+  // two CTAs per SM for narrow Cout tiles (TMEM 2 x <=128 columns, 80 registers, half of the shared memory each), so that
+  // CTAs of different launches overlap their fill / drain latencies on one SM; else one CTA with the deepest ring
+  int occ = (coresident_enabled() && pl->BN <= 128) ? 2 : 1;
+  int nst = 0;
+  for (; occ >= 1; --occ) {
+    const size_t budget = (occ == 2 ? kHalfSmBudget : (size_t)227 * 1024) - fixed;
+    nst = (int)(budget / pl->stage_bytes);
+    if (nst > kMaxStages) nst = kMaxStages;
+    if (nst >= (occ == 2 ? 3 : 2)) break;
+  }
+  if (occ < 1) return B200SEG_E_BADARG;
   pl->nstages = nst;
+  pl->occ = occ;
   pl->smem_bytes = fixed + (size_t)nst * pl->stage_bytes;
-  if (pl->smem_bytes < 120 * 1024) pl->smem_bytes = 120 * 1024;   // keep one CTA per SM: each allocates all 512 TMEM columns
+  if (occ == 1 && pl->smem_bytes < 120 * 1024) pl->smem_bytes = 120 * 1024;   // one CTA per SM
+  const int slots = occ == 2 ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
+  pl->grid = pl->total_tiles < slots ? pl->total_tiles : slots;
   return 0;
 }
 
@@ -419,22 +440,43 @@ static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const 
   p.layout_type = pl.KC == 64 ? 2 : (pl.KC == 32 ? 4 : 6);
   p.sbo = 8 * pl.KC * 2;
   p.a_bytes = pl.a_bytes; p.b_bytes = pl.b_bytes; p.stage_bytes = pl.stage_bytes; p.nstages = pl.nstages;
+  p.acc_stride = pl.acc_stride; p.tmem_cols = pl.tmem_cols;
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
+    if (e != cudaSuccess) return (int)e;
+    // two CTAs per SM need (almost) the whole 228 KB as shared memory: ask for the maximum carve-out explicitly
+    e = cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   if (stats_grid) *stats_grid = pl.grid;
-  cudaError_t e = launch_k(conv_igemm_kernel, dim3(pl.grid), dim3(kThreads), pl.smem_bytes, stream, tmA, tmB, p, out,
-                           bias, stats_partials, (const __nv_bfloat16*)addend);
+  cudaError_t e =
+      pl.occ == 2 ? launch_k(conv_igemm_kernel<2>, dim3(pl.grid), dim3(kThreads), pl.smem_bytes, stream, tmA, tmB, p, out,
+                             bias, stats_partials, (const __nv_bfloat16*)addend)
+                  : launch_k(conv_igemm_kernel<1>, dim3(pl.grid), dim3(kThreads), pl.smem_bytes, stream, tmA, tmB, p, out,
+                             bias, stats_partials, (const __nv_bfloat16*)addend);
   return e == cudaSuccess ? 0 : (int)e;
+}
+
+int conv_igemm_occupancy(int occ_variant, int smem_bytes) {
+  int nb = -1;
+  cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
+  cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = occ_variant == 2
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_igemm_kernel<2>, kThreads, (size_t)smem_bytes)
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_igemm_kernel<1>, kThreads, (size_t)smem_bytes);
+  return e == cudaSuccess ? nb : -(int)e;
 }
 
 int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
                         const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
                         const void* addend, int addend_ld, int emit_stats, cudaStream_t stream);
+int conv3x3_halo_plan_info(int n, int h, int w, int cin, int cout, int32_t* out);
 
 }  // namespace b200seg
 
@@ -443,7 +485,29 @@ using namespace b200seg;
 extern "C" size_t b200seg_conv2d_stats_elems(const b200seg_conv_desc* d) {
   ConvPlan pl;
   if (conv_plan(d, &pl) != 0) return 0;
-  return (size_t)B200SEG_MAX_CTAS * 2 * ((d->cout + 15) / 16 * 16);   // [grid <= 148][2][roundup16(cout)]
+  return (size_t)B200SEG_MAX_GRID * 2 * ((d->cout + 15) / 16 * 16);   // [grid <= 296][2][roundup16(cout)]
+}
+
+// Host-only: the launch plan of a forward (which = 0) or stride-1 data-gradient (which = 1) convolution, for tests and
+// tuning scripts. out[10] = {kernel (1 halo / 0 per-tap), BN, n_tiles, grid, dynamic smem bytes, ring depth, CTAs per SM,
+// TMEM columns, resident weights (halo), weight slots (halo)}.
+extern "C" int b200seg_conv2d_plan_info(const b200seg_conv_desc* d, int32_t which, int32_t* out) {
+  if (!desc_ok(d) || !out || which < 0 || which > 1) return B200SEG_E_BADARG;
+  if (which == 1 && d->stride != 1) return B200SEG_E_BADARG;
+  const bool halo_fwd = d->ksize == 3 && d->stride == 1 && !d->out_fp32 && d->cout % 16 == 0 && d->reserved == 0;
+  const bool halo_bwd = d->ksize == 3 && d->cin % 16 == 0 && d->reserved == 0;
+  if (which == 0 && halo_fwd) return conv3x3_halo_plan_info(d->n, d->h, d->w, d->cin, d->cout, out);
+  if (which == 1 && halo_bwd) return conv3x3_halo_plan_info(d->n, d->h, d->w, (d->cout + 7) / 8 * 8, d->cin, out);
+  LaunchGeom g = fwd_geom(d);
+  if (which == 1) {          // same GEMM shape with the channel roles swapped (taps and lattice as the forward)
+    g.in_c = (d->cout + 7) / 8 * 8; g.in_ld = g.in_c; g.out_c = d->cin; g.out_ld = d->cin;
+    g.out_fp32 = 0; g.has_bias = 0; g.emit_stats = 0;
+  }
+  ConvPlan pl;
+  if (int rc = plan_geom(g, &pl)) return rc;
+  out[0] = 0; out[1] = pl.BN; out[2] = pl.n_tiles; out[3] = pl.grid; out[4] = (int32_t)pl.smem_bytes; out[5] = pl.nstages;
+  out[6] = pl.occ; out[7] = pl.tmem_cols; out[8] = 0; out[9] = 0;
+  return 0;
 }
 
 extern "C" int b200seg_conv2d_fwd(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,

@@ -39,7 +39,9 @@ __global__ void direct_conv_kernel(const __nv_bfloat16* __restrict__ x, const __
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, int K, __nv_bfloat16* __restrict__ ohwi,
                                    __nv_bfloat16* __restrict__ dgrad, int Opad) {
-  pdl_sync();
+  // No programmatic trigger here: the convolution kernels read their (static) weights BEFORE griddepcontrol.wait, so a
+  // kernel that writes weights must be fully complete before any successor starts (plain stream order).
+  pdl_wait();
   const int taps = K * K;
   const size_t total = (size_t)O * I * taps;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -51,6 +53,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, in
     if (ohwi) ohwi[((size_t)o * taps + t) * I + i] = v;
     if (dgrad) dgrad[((size_t)i * taps + (taps - 1 - t)) * Opad + o] = v;   // pad columns stay zero (caller memset)
   }
+  __threadfence();   // the packed weights are device-visible before this block exits (successors read them pre-wait)
 }
 
 // All weights of the model in ONE launch: block b repacks kPackChunk consecutive OIHW elements of item blk_item[b]
@@ -59,7 +62,7 @@ constexpr int kPackChunk = 4096;
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const b200seg_pack_item* __restrict__ items, const int32_t* __restrict__ blk_item,
                     const int32_t* __restrict__ blk_start, int which) {
-  pdl_sync();
+  pdl_wait();     // no programmatic trigger: see pack_weight_kernel
   const b200seg_pack_item it = items[blk_item[blockIdx.x]];
   const float* __restrict__ w = reinterpret_cast<const float*>(it.w_oihw);
   __nv_bfloat16* __restrict__ ohwi = (which & 1) ? reinterpret_cast<__nv_bfloat16*>(it.w_ohwi) : nullptr;
@@ -78,6 +81,7 @@ pack_weights_kernel(const b200seg_pack_item* __restrict__ items, const int32_t* 
     if (ohwi) ohwi[((size_t)o * taps + t) * Id + i] = v;
     if (dgrad) dgrad[((size_t)i * taps + (taps - 1 - t)) * it.o_pad + o] = v;
   }
+  __threadfence();
 }
 
 }  // namespace b200seg

@@ -78,7 +78,7 @@ def test_conv_planner_rejects_bad_shapes():
     d = _lib.ConvDesc()
     d.n, d.h, d.w, d.cin, d.cout, d.ksize, d.stride, d.pad, d.x_ld, d.y_ld = 1, 32, 32, 48, 48, 3, 1, 1, 48, 48
     d.emit_stats = 1
-    assert L.b200seg_conv2d_stats_elems(ctypes.byref(d)) == 148 * 2 * 48
+    assert L.b200seg_conv2d_stats_elems(ctypes.byref(d)) == 296 * 2 * 48
     assert L.b200seg_conv2d_wgrad_ws_bytes(ctypes.byref(d)) > 0
     d.cin = 50                                                          # not a multiple of 8
     assert L.b200seg_conv2d_stats_elems(ctypes.byref(d)) == 0

@@ -14,13 +14,13 @@ x = torch.randn((1, h, w, c), device="cuda").to(torch.bfloat16)
 wt = torch.randn((c, c, 3, 3), device="cuda") * 0.05
 w_f, _ = raw.pack_weight(wt)
 y = torch.empty_like(x)
-stats = torch.zeros(148 * 2 * 1024 + 4096, device="cuda")
+stats = torch.zeros(296 * 2 * 1024 + 4096, device="cuda")
 d = conv_desc(1, h, w, c, c, 3, 1, c, c, False, False, bool(stats_on), 0)
 g = ctypes.c_int32(0)
 for _ in range(5):
     assert L.b200seg_conv2d_fwd(ctypes.byref(d), ptr(x), ptr(w_f), None, ptr(y), ptr(stats), ctypes.byref(g), stream_ptr()) == 0
 torch.cuda.synchronize()
-ts = stats[148 * 2 * 1024:148 * 2 * 1024 + 2 * 7 * 16].view(torch.int64).cpu().view(7, 16)
+ts = stats[296 * 2 * 1024:296 * 2 * 1024 + 2 * 7 * 16].view(torch.int64).cpu().view(7, 16)
 t0 = int(ts[6, 0])
 names = ["prod A issued", "mma a_full seen", "mma issued+commit", "epi tfull seen", "epi done", "epi tmem loaded", "misc(start,end)"]
 print("shape", h, w, c, "stats", stats_on)
