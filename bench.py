@@ -57,8 +57,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-gpu-baseline", action="store_true",
-                    help="also time the reference algorithm through stock PyTorch (ATen / cuDNN, autocast bf16 and fp32) on "
-                         "this GPU: the practical kernel to beat (BASELINE.md §5); adds `torch_gpu_baseline` to the line")
+                    help="time the reference algorithm through stock PyTorch (ATen / cuDNN, autocast bf16 and fp32) on "
+                         "this GPU: the practical kernel to beat (BASELINE.md §3b step 5); adds `torch_gpu_baseline` and "
+                         "`vs_torch_gpu` to the line. Default at --gpus 1; this flag forces it for N > 1 (rank 0)")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true")
     return ap.parse_args()
 
 
@@ -180,7 +182,7 @@ def cpu_reference_step_time(arch, h, w, steps, warmup=1, budget_s=60.0, criterio
     return sum(times) / len(times), len(times)
 
 
-def torch_gpu_step_time(arch, h, w, autocast, criterion="ce", steps=5, warmup=3):
+def torch_gpu_step_time(arch, h, w, autocast, criterion="ce", steps=4, warmup=2):
     """The reference algorithm (oracle restatement = the reference's own call sequence of F.conv2d / batch_norm /
     interpolate / softmax ...) through stock PyTorch on the current GPU: ATen + cuDNN kernels, NCHW, cudnn.benchmark as
     in train.py:330, optionally under torch.autocast(bf16) (the modern spelling of the reference's apex AMP O1).
@@ -430,20 +432,26 @@ def run_b200(args):
                                 "program (profiles/r1_step_roofline_model.txt)"),
         roofline=roof, clocks=clocks, last_loss=loss_val,
         max_memory_allocated_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
-    if args.torch_gpu_baseline:
+    if (args.torch_gpu_baseline or world == 1) and not args.no_torch_gpu_baseline:
         del net, opt
         torch.cuda.empty_cache()
         tg = {}
         for name, ac in (("autocast_bf16", True), ("fp32_tf32_off", False)):
             try:
-                ms_t = torch_gpu_step_time(args.arch, H, W, ac, args.criterion)
-                tg[name] = dict(ms_per_step=ms_t, value=1000.0 / ms_t, unit="crops/s")
+                ms_t = torch_gpu_step_time(args.arch, H, W, ac, args.criterion, steps=4 if ac else 2,
+                                           warmup=2 if ac else 1)
+                tg[name] = dict(ms_per_step=ms_t, value=B * 1000.0 / ms_t, unit="crops/s")
             except Exception as e:  # noqa
                 tg[name] = dict(error=repr(e))
             torch.cuda.empty_cache()
-        tg["what"] = ("oracle restatement of the reference algorithm through stock PyTorch eager (ATen/cuDNN, NCHW, "
-                      "cudnn.benchmark, torch.optim.SGD), one crop, same GPU, device-resident inputs")
+        tg["what"] = ("the reference algorithm (oracle restatement = the reference's own call sequence) through stock "
+                      "PyTorch eager: ATen/cuDNN, NCHW, cudnn.benchmark, torch.optim.SGD, %d crop, this GPU, "
+                      "device-resident inputs; per-GPU figure" % B)
         line["torch_gpu_baseline"] = tg
+        best = max((v["value"] for v in tg.values() if isinstance(v, dict) and "value" in v), default=None)
+        if best:
+            line["vs_torch_gpu"] = dict(value=(value / world) / best, e2e=(e2e_value / world) / best,
+                                        note="per-GPU crops/s of this path / best stock-PyTorch figure above")
     if not args.no_cpu_baseline:
         try:
             sh, sw = 128, 256
