@@ -350,6 +350,57 @@ def mscale_fwd(ctx, x, hcfg=HRNET_W48, ocfg=OCR_CFG):
                 cls_q=cls, aux_q=aux, attn_q=attn)
 
 
+def mscale_basic_fwd(ctx, x, hcfg=HRNET_W48):
+    """MscaleBasic._fwd (mscale.py:463-470): trunk features -> attention head and seg head, both scale_as()'d to the
+    input size. Same dict keys as mscale_fwd (no auxiliary head)."""
+    size = x.shape[2:]
+    feats = hrnet_forward(ctx, "backbone", x, hcfg)
+    attn = attn_head(ctx, "scale_attn", feats)
+    cls = seg_head(ctx, "cls_head", feats)
+    return dict(cls_out=bilinear(cls, size), aux_out=None, logit_attn=bilinear(attn, size), cls_q=cls, attn_q=attn)
+
+
+def mscale_basic_two_scale(ctx, images, gts=None, criterion=criterion_ce, hcfg=HRNET_W48, lo_scale=0.5,
+                           supervised_mscale_wt=0.0):
+    """MscaleBase.two_scale_forward (mscale.py:182-220) for arch 'mscale.HRNet' (MscaleBasic, mscale.py:450-475)."""
+    x_lo = resize_x(images, lo_scale)
+    lo = mscale_basic_fwd(ctx, x_lo, hcfg)
+    hi = mscale_basic_fwd(ctx, images, hcfg)
+    pred_05x, p_1x, attn = lo["cls_out"], hi["cls_out"], lo["logit_attn"]
+    size = p_1x.shape[2:]
+    joint_pred = bilinear(attn * pred_05x, size) + (1 - bilinear(attn, size)) * p_1x
+    if ctx.training:
+        loss = criterion(joint_pred, gts)
+        if supervised_mscale_wt:
+            loss = loss + supervised_mscale_wt * criterion(bilinear(pred_05x, size), gts, do_rmi=False)
+            loss = loss + supervised_mscale_wt * criterion(p_1x, gts, do_rmi=False)
+        return loss
+    return dict(pred=joint_pred, pred_05x=pred_05x, pred_10x=p_1x, attn_05x=attn)
+
+
+def mscale_basic_nscale(ctx, images, scales, hcfg=HRNET_W48):
+    """MscaleBase.nscale_forward (mscale.py:114-180), eval branch."""
+    assert 1.0 in scales
+    pred = None
+    out = {}
+    for s in sorted(scales, reverse=True):
+        o = mscale_basic_fwd(ctx, resize_x(images, s), hcfg)
+        p, attn = o["cls_out"], o["logit_attn"]
+        out[fmt_scale("pred", s)] = p
+        if s != 2.0:
+            out[fmt_scale("attn", s)] = attn
+        if pred is None:
+            pred = p
+        elif s >= 1.0:
+            pred = attn * p + (1 - attn) * bilinear(pred, p.shape[2:])
+        else:
+            p = bilinear(attn * p, pred.shape[2:])
+            attn = bilinear(attn, pred.shape[2:])
+            pred = p + (1 - attn) * pred
+    out["pred"] = pred
+    return out
+
+
 def mscale_two_scale(ctx, images, gts=None, criterion=criterion_ce, hcfg=HRNET_W48, ocfg=OCR_CFG, lo_scale=0.5,
                      ocr_alpha=0.4, ocr_aux_rmi=False, supervised_mscale_wt=0.0):
     """MscaleOCR.two_scale_forward (ocrnet.py:264-327); MscaleBase twin at mscale.py:182-220."""
@@ -654,6 +705,16 @@ def _conv_names(hcfg, ocfg, arch):
         conv_(s + ".0", bot, high, 3); bn_(s + ".1", bot)
         conv_(s + ".3", bot, bot, 3); bn_(s + ".4", bot)
         conv_(s + ".6", ncls, bot, 1)
+    elif arch == "mscale.HRNet":     # MscaleBasic.__init__ (mscale.py:450-461)
+        bot, ncls = ocfg["segattn_bot_ch"], ocfg["num_classes"]
+        s = "cls_head"
+        conv_(s + ".0", bot, high, 3); bn_(s + ".1", bot)
+        conv_(s + ".3", bot, bot, 3); bn_(s + ".4", bot)
+        conv_(s + ".6", ncls, bot, 1)
+        a = "scale_attn"
+        conv_(a + ".conv0", bot, high, 3); bn_(a + ".bn0", bot)
+        conv_(a + ".conv1", bot, bot, 3); bn_(a + ".bn1", bot)
+        conv_(a + ".conv2", 1, bot, 1)
     else:
         raise ValueError(arch)
     return out

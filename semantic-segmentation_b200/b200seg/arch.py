@@ -18,7 +18,17 @@ HRNET_W48 = dict(
 # config.py:157-159 (OCR), :130 (SEGATTN_BOT_CH), network/ocrnet.py:63 (dropout)
 OCR_DEFAULT = dict(mid_channels=512, key_channels=256, num_classes=19, segattn_bot_ch=256, dropout=0.05)
 
-ARCHS = ("ocrnet.HRNet_Mscale", "ocrnet.HRNet", "basic.HRNet")
+ARCHS = ("ocrnet.HRNet_Mscale", "ocrnet.HRNet", "basic.HRNet", "mscale.HRNet")
+
+
+def is_two_scale(arch):
+    """Architectures whose training forward is the hierarchical two-scale pass (MscaleOCR.two_scale_forward,
+    network/ocrnet.py:264-334; MscaleBase.two_scale_forward, network/mscale.py:182-231)."""
+    return arch in ("ocrnet.HRNet_Mscale", "mscale.HRNet")
+
+
+def has_ocr(arch):
+    return arch in ("ocrnet.HRNet_Mscale", "ocrnet.HRNet")
 
 # network/wider_resnet.py:303-345 (WiderResNetA2, structure "38", dilation=True) — SURVEY.md §8(f) row f2. Only the
 # parameter specification exists so far (checked against the reference's state_dict order); the dilated-convolution /
@@ -186,6 +196,17 @@ def tensor_specs(arch, hcfg=HRNET_W48, ocfg=OCR_DEFAULT):
         conv(s + ".0", bot, high, 3); bn(s + ".1", bot)
         conv(s + ".3", bot, bot, 3); bn(s + ".4", bot)
         conv(s + ".6", ncls, bot, 1)
+    elif arch == "mscale.HRNet":
+        # MscaleBasic.__init__ (network/mscale.py:450-461): backbone, cls_head = make_seg_head, scale_attn = make_attn_head
+        bot, ncls = ocfg["segattn_bot_ch"], ocfg["num_classes"]
+        s = "cls_head"
+        conv(s + ".0", bot, high, 3); bn(s + ".1", bot)
+        conv(s + ".3", bot, bot, 3); bn(s + ".4", bot)
+        conv(s + ".6", ncls, bot, 1)
+        a = "scale_attn"
+        conv(a + ".conv0", bot, high, 3); bn(a + ".bn0", bot)
+        conv(a + ".conv1", bot, bot, 3); bn(a + ".bn1", bot)
+        conv(a + ".conv2", 1, bot, 1)
     else:
         raise ValueError("unsupported arch %r (hot path covers %s)" % (arch, ", ".join(ARCHS)))
     return out

@@ -3,11 +3,13 @@ reference's output assembly in fp32 NCHW on the device.
 
   ocrnet.HRNet_Mscale : MscaleOCR.nscale_forward when cfg.MODEL.N_SCALES is set (network/ocrnet.py:185-262), else the
                         eval branch of two_scale_forward (:264-327)
+  mscale.HRNet        : MscaleBase.nscale_forward / two_scale_forward eval branches (network/mscale.py:114-231)
   ocrnet.HRNet        : OCRNet.forward eval branch (:104-122)
   basic.HRNet         : Basic.forward eval branch (network/basic.py:50-64)
 """
 import torch
 
+from . import arch as A
 from . import model as M
 from . import raw
 from .engine import Engine
@@ -23,8 +25,7 @@ def _pass(module, E, images, size_hw):
     out = M.scale_pass(E, images, size_hw, module.arch, module.hcfg, module.ocfg)
     H, W = size_hw
     res = dict(cls_out=raw.resize_to_nchw(out["cls"].logits, 19, H, W))
-    if out["aux"] is not None:
-        res["aux_out"] = raw.resize_to_nchw(out["aux"].logits, 19, H, W)
+    # the full-resolution auxiliary map only feeds the training loss (network/ocrnet.py:254-259): dead in eval mode
     if out["attn"] is not None:
         res["logit_attn"] = raw.resize_to_nchw(out["attn"].logits, 1, H, W, apply_sigmoid=True)
     return res
@@ -39,33 +40,30 @@ def eval_forward(module, images):
     tensors = {k: v.detach() for k, v in module._tensors().items()}
     E = Engine(tensors, {}, module._packed, False, None)
     arch = module.arch
-    if arch != "ocrnet.HRNet_Mscale":
+    if not A.is_two_scale(arch):
         return {"pred": _pass(module, E, images, (H, W))["cls_out"]}
 
     if module.n_scales:
         scales = sorted([float(s) for s in module.n_scales], reverse=True)
         assert 1.0 in scales, "expected 1.0 to be the target scale"
-        pred = aux = None
+        pred = None
         out = {}
         for s in scales:
             hs, ws = int(H * s), int(W * s)             # ResizeX: floor(in * scale)
             o = _pass(module, E, images, (hs, ws))
-            cls, attn, auxo = o["cls_out"], o["logit_attn"], o["aux_out"]
+            cls, attn = o["cls_out"], o["logit_attn"]
             out[_fmt_scale("pred", s)] = cls
             if s != 2.0:
                 out[_fmt_scale("attn", s)] = attn
             if pred is None:
-                pred, aux = cls, auxo
+                pred = cls
             elif s >= 1.0:
                 pred = raw.blend(attn, cls, raw.resize_nchw(pred, hs, ws), 0)
-                aux = raw.blend(attn, auxo, raw.resize_nchw(aux, hs, ws), 0)
             else:
                 ph, pw = pred.shape[2:]
                 cls_s = raw.resize_nchw(raw.blend(attn, cls, None, 2), ph, pw)
-                aux_s = raw.resize_nchw(raw.blend(attn, auxo, None, 2), ph, pw)
                 attn_s = raw.resize_nchw(attn, ph, pw)
                 pred = raw.blend(attn_s, cls_s, pred, 1)
-                aux = raw.blend(attn_s, aux_s, aux, 1)
         out["pred"] = pred
         return out
 

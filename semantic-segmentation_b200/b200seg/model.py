@@ -4,6 +4,7 @@ Each function mirrors one reference forward (cited), expressed with ``Engine`` f
 """
 import torch
 
+from . import arch as A
 from . import raw
 from .engine import Act, BF16, F32
 
@@ -240,6 +241,8 @@ def scale_pass(E, images, size_hw, arch, hcfg, ocfg):
     feats = hrnet_forward(E, x16, hcfg)
     if arch == "basic.HRNet":
         return dict(cls=seg_head(E, feats), aux=None, attn=None)
+    if arch == "mscale.HRNet":      # MscaleBasic._fwd (network/mscale.py:463-470): both heads read the trunk features
+        return dict(cls=seg_head(E, feats, "cls_head"), aux=None, attn=attn_head(E, feats))
     cls, aux, mid_feats = ocr_block(E, feats, ocfg)
     attn = attn_head(E, mid_feats) if arch == "ocrnet.HRNet_Mscale" else None
     return dict(cls=cls, aux=aux, attn=attn)
@@ -248,6 +251,7 @@ def scale_pass(E, images, size_hw, arch, hcfg, ocfg):
 def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, sup_wt=0.0, ignore_index=255, E_lo=None,
                loss_kind="ce"):
     """Training forward + loss. ocrnet.HRNet_Mscale: MscaleOCR.two_scale_forward (network/ocrnet.py:264-319);
+    mscale.HRNet: MscaleBase.two_scale_forward (network/mscale.py:182-220; one head, no auxiliary loss);
     ocrnet.HRNet: OCRNet.forward (:104-122); basic.HRNet: Basic.forward (network/basic.py:50-64).
     Returns the fp32 loss vector [total, cls, aux, sup_lo, sup_hi, rmi, 0, 0]; pushes the loss backward on the tape.
     loss_kind "ce": CrossEntropyLoss2d (loss/utils.py:133-134); "rmi": RMILoss (loss/rmi.py:70-215) = sigmoid BCE on
@@ -259,7 +263,7 @@ def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, su
     E_lo.stream (a parallel branch of the captured CUDA graph) in forward and in backward; its small kernels fill the
     SMs the full-resolution pass leaves idle."""
     n, _, H, W = images.shape
-    two_scale = arch == "ocrnet.HRNet_Mscale"
+    two_scale = A.is_two_scale(arch)
     lo = None
     main = torch.cuda.current_stream() if images.is_cuda else None
     par = two_scale and E_lo is not None and E_lo.stream is not None
@@ -276,7 +280,7 @@ def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, su
     hi = scale_pass(E, images, (H, W), arch, hcfg, ocfg)
     if par:
         main.wait_stream(E_lo.stream)
-    nheads = 1 if arch == "basic.HRNet" else 2
+    nheads = 2 if A.has_ocr(arch) else 1
     hq, wq = hi["cls"].logits.shape[1:3]
     rmi = loss_kind == "rmi"
     kind = 1 if rmi else 0
@@ -284,7 +288,7 @@ def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, su
         hl, wl = lo["cls"].logits.shape[1:3]
         d = raw.mscale_desc(n, H, W, hq, wq, hm, wm, hl, wl, nheads, 1.0, ocr_alpha, sup_wt, ignore_index, kind)
         lo_attn = lo["attn"].logits
-        mid, mid_sup = raw.mscale_mid_fwd(d, lo["cls"].logits, lo["aux"].logits, lo_attn)
+        mid, mid_sup = raw.mscale_mid_fwd(d, lo["cls"].logits, lo["aux"].logits if nheads > 1 else None, lo_attn)
     else:
         d = raw.mscale_desc(n, H, W, hq, wq, 0, 0, 0, 0, nheads, 1.0, ocr_alpha, 0.0, ignore_index, kind)
         mid = mid_sup = None
@@ -301,9 +305,11 @@ def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, su
         if nheads > 1:
             hi["aux"].dlogits = d_aux
         if two_scale:
-            dl_cls, dl_aux, dl_attn = raw.mscale_lo_bwd(d, g_lo, g_sup, lo["cls"].logits, lo["aux"].logits, lo_attn,
-                                                        mid)
-            lo["cls"].dlogits, lo["aux"].dlogits, lo["attn"].dlogits = dl_cls, dl_aux, dl_attn
+            dl_cls, dl_aux, dl_attn = raw.mscale_lo_bwd(d, g_lo, g_sup, lo["cls"].logits,
+                                                        lo["aux"].logits if nheads > 1 else None, lo_attn, mid)
+            lo["cls"].dlogits, lo["attn"].dlogits = dl_cls, dl_attn
+            if nheads > 1:
+                lo["aux"].dlogits = dl_aux
             if par:
                 # allocated on the main stream, consumed on the low-resolution stream: keep them until the final join
                 E.hold.extend((dl_cls, dl_aux, dl_attn))

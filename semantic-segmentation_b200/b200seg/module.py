@@ -299,7 +299,7 @@ class B200SegModule(nn.Module):
         if self._sync is None:
             from .p2p import SyncBNContext
             chans = {n[: -len(".running_mean")]: shp[0] for n, shp, k in self._specs if k == "bn_rm"}
-            self._sync = SyncBNContext(chans, n_passes=2 if self.arch == "ocrnet.HRNet_Mscale" else 1)
+            self._sync = SyncBNContext(chans, n_passes=2 if A.is_two_scale(self.arch) else 1)
             self._graphs = {}
         return self._sync
 
@@ -312,7 +312,7 @@ class B200SegModule(nn.Module):
         if sync is not None:
             sync.advance()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
-        par = self.parallel_scales and self.arch == "ocrnet.HRNet_Mscale"
+        par = self.parallel_scales and A.is_two_scale(self.arch)
         self._acc_hi.zero_()         # two memsets (45 us each) beat clearing inside the fold's transposed gather
         if par:
             self._acc_lo.zero_()
@@ -338,7 +338,7 @@ class B200SegModule(nn.Module):
             E_lo = Engine(tensors, grads_lo, self._packed, True, drop_mask, side_stream=self._side_stream_lo,
                           bstat=self._bstat_views[0], stream=self._lo_stream, sync=sync, pass_id=0,
                           branch_streams=self._bstreams["lo"], ws_holder=self._ws_holders["lo"])
-        two_pass = self.arch == "ocrnet.HRNet_Mscale"
+        two_pass = A.is_two_scale(self.arch)
         if sync is not None and two_pass and not par:
             raise RuntimeError("SyncBN needs parallel_scales=True for the two-scale step (one engine per pass)")
         E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream,
@@ -359,7 +359,7 @@ class B200SegModule(nn.Module):
 
     def _drop_mask(self, n, device):
         """Dropout2d(0.05) channel mask (network/ocr_utils.py:146) drawn from torch's generator, folded with 1/(1-p)."""
-        if self.arch == "basic.HRNet":
+        if not A.has_ocr(self.arch):
             return None
         p = self.ocfg["dropout"]
         c = self.ocfg["mid_channels"]

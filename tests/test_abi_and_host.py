@@ -64,6 +64,7 @@ def test_factory_contract_and_cpu_refusal():
     net = network.get_model("network.ocrnet.HRNet_Mscale", 19, None)
     assert type(net).__name__ == "B200SegModule" and net.arch == "ocrnet.HRNet_Mscale"
     assert network.get_model("network.basic.HRNet", 19, None).arch == "basic.HRNet"
+    assert network.get_model("network.mscale.HRNet", 19, None).arch == "mscale.HRNet"      # network/mscale.py:473-475
     with pytest.raises((ImportError, ModuleNotFoundError, AttributeError)):
         network.get_model("network.deepv3.DeepV3PlusW38", 19, None)     # outside the hot path: not provided
     net.train()

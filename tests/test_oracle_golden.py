@@ -126,3 +126,63 @@ def test_deepv3_wrn38_matches_reference():
     with torch.no_grad():
         o = O.deepv3_forward(O.Ctx(sd, training=False), images)
     close(O.sample_like(o["pred"]), g["eval_pred"])
+
+
+# ----------------------------------------------------------------------------------------------- mscale.HRNet (MscaleBasic)
+@pytest.fixture(scope="module")
+def golden_mscale():
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    return torch.load(os.path.join(here, "golden", "reference_mscale.pt"), map_location="cpu")
+
+
+@pytest.mark.parametrize("loss_name,sup", [("ce", 0.0), ("ce", 0.05), ("rmi", 0.05)])
+def test_mscale_basic_train_step_matches_reference(golden_mscale, loss_name, sup):
+    """arch 'mscale.HRNet' (network/mscale.py:450-475, two_scale_forward :182-220) against the imported reference."""
+    g = golden_mscale["mscale.HRNet/%s/sup%g/w16" % (loss_name, sup)]
+    hcfg = O.HRNET_W16_TEST
+    sd = O.synth_state_dict("mscale.HRNet", hcfg, seed=3)
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    images, gts = O.synth_batch(2, 64, 128, seed=5)
+    crit = O.criterion_ce if loss_name == "ce" else O.criterion_rmi
+    loss = O.mscale_basic_two_scale(O.Ctx(sd, training=True), images, gts, criterion=crit, hcfg=hcfg,
+                                    supervised_mscale_wt=sup)
+    loss.backward()
+    close(loss.detach(), g["loss"], rtol=1e-5)
+    for name, ref in g["grads"].items():
+        close(O.sample_like(sd[name].grad), ref, rtol=2e-3 if loss_name == "rmi" else 5e-4)
+    close(sd["backbone.bn1.running_mean"].detach(), g["running_mean_bb_bn1"], atol=1e-6)
+    close(sd["scale_attn.bn1.running_var"].detach(), g["running_var_attn"])
+    if "eval_two_scale" not in g:
+        return
+    sd = {k: v.detach() for k, v in sd.items()}
+    ctx = O.Ctx(sd, training=False)
+    with torch.no_grad():
+        o2 = O.mscale_basic_two_scale(ctx, images, hcfg=hcfg)
+        for k, ref in g["eval_two_scale"].items():
+            close(O.sample_like(o2[k]), ref)
+        o3 = O.mscale_basic_nscale(ctx, images, [0.5, 1.0, 2.0], hcfg=hcfg)
+        assert sorted(o3.keys()) == g["eval_three_scale_keys"]
+        for k, ref in g["eval_three_scale"].items():
+            close(O.sample_like(o3[k]), ref)
+
+
+def test_mscale_basic_state_dict_order_matches_reference(golden_mscale):
+    """The B200 module registers the tensors of mscale.HRNet under the reference's names, in its order."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "semantic-segmentation_b200"))
+    from b200seg import arch as A
+    names = [n for n, _s, _k in A.tensor_specs("mscale.HRNet")]
+    assert names == golden_mscale["state_dict_keys_w48"]
+    nparams = 0
+    for _n, shp, kind in A.tensor_specs("mscale.HRNet"):
+        if kind in ("conv_w", "conv_b", "bn_w", "bn_b"):
+            k = 1
+            for s in shp:
+                k *= s
+            nparams += k
+    assert nparams == golden_mscale["nparams_w48"]

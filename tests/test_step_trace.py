@@ -39,3 +39,14 @@ def test_single_scale_architectures_trace():
     assert abs(r["total"][1] - 7.77) <= 0.08, r["total"]                 # 3 x 2.5907 TFLOP
     r = _trace("--arch", "basic.HRNet", "--height", "256", "--width", "512")
     assert abs(r["total"][1] - 0.365) <= 0.01, r["total"]                # cfg1
+
+
+def test_mscale_basic_architecture_traces():
+    """arch 'mscale.HRNet' (MscaleBasic, network/mscale.py:450-475): per 1x forward the trunk (678.3 GMAC) plus two
+    3x3-3x3-1x1 heads on the 720-channel features (295.3 + 294.7 GMAC) = 2.536 TFLOP; train step = 1.25 x forward +
+    2 x (1.25 x forward - the dead 1.0x attention head 0.589 TFLOP)."""
+    r = _trace("--arch", "mscale.HRNet")
+    fwd1 = 2.0 * (678.3 + 295.3 + 294.7) * 1e-3
+    want = 1.25 * fwd1 + 2.0 * (1.25 * fwd1 - 2.0 * 294.7e-3)
+    assert abs(r["total"][1] - want) <= 0.01 * want, (r["total"], want)
+    assert r["conv2d_wgrad"][0] == r["conv2d_fwd"][0] - 3
