@@ -60,6 +60,8 @@ int b200seg_conv2d_plan_info(const b200seg_conv_desc* d, int32_t which, int32_t*
 /* Diagnostics (needs a GPU): CTAs per SM the runtime grants kernel (1 = halo-tile 3x3, 0 = per-tap) in its
  * co-resident (occ_variant 2) or full-SM (1) build with smem_bytes of dynamic shared memory; negative = error. */
 int32_t b200seg_debug_occupancy(int32_t kernel, int32_t occ_variant, int32_t smem_bytes);
+/* prints (stdout) the device limits, the kernels' resource usage and blocks/SM as a function of dynamic shared memory */
+void b200seg_debug_occupancy_report(void);
 
 /* Number of fp32 elements the stats partial buffer must hold: B200SEG_MAX_GRID * 2 * cout_padded. */
 size_t b200seg_conv2d_stats_elems(const b200seg_conv_desc* d);
@@ -116,21 +118,24 @@ int32_t b200seg_conv2d_wgrad_launches(const b200seg_conv_desc* d);
 int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, int32_t dy_ld, float* dw_ohwi,
                          void* workspace, size_t ws_bytes, void* stream);
 
-/* End-of-step gradient fold over ONE flat fp32 buffer layout shared by dst / acc_a / acc_b (element offsets in segs):
- *   conv weights (is_conv): dst[co][ci][tap] (OIHW, the nn.Parameter .grad layout) += acc_a[co][tap][ci] + acc_b[...]
- *   vectors (BN affine, biases; cout = 1, taps = 1, cin = numel): dst[i] += acc_b[i]
- * and, with clear != 0, zeroes what it read from acc_a / acc_b (either may be NULL). One thread block per chunk of
- * b200seg_grad_fold_chunk() consecutive elements of one segment: blk_seg[b] indexes segs, blk_start[b] is the first
- * element of the chunk inside its segment. Replaces autograd's gradient accumulation across the two scale passes
- * (network/ocrnet.py:278-281). */
+/* End-of-step gradient fold: dst and the two accumulators share ONE flat fp32 layout (element offsets in segs):
+ *   conv weights: dst[co][ci][tap] (OIHW, the nn.Parameter .grad layout) (+)= acc_a[co][tap][ci'] + acc_b[co][tap][ci']
+ *                 with ci' running over src_cin >= cin input channels of the accumulator (the stem accumulates on the
+ *                 16-channel padded image: src_cin = 16, cin = 3) starting at src_offset;
+ *   vectors (BN affine, biases; cout = 1, taps = 1, cin = numel): dst[i] (+)= acc_a[i] + acc_b[i].
+ * mode bit 0 (clear): zero what was read from acc_a / acc_b; bit 1 (overwrite): dst = sum instead of dst += sum (dst is
+ * then not read). Either accumulator may be NULL. One thread block per chunk of b200seg_grad_fold_chunk() consecutive
+ * elements of one segment: blk_seg[b] indexes segs, blk_start[b] is the first element of the chunk inside its segment.
+ * Replaces autograd's gradient accumulation across the two scale passes (network/ocrnet.py:278-281). */
 typedef struct b200seg_grad_seg {
-  int64_t offset;          /* first element of the parameter in the flat buffers */
+  int64_t offset;          /* first element of the parameter in dst */
+  int64_t src_offset;      /* first element of its accumulator in acc_a / acc_b */
   int32_t cout, cin, taps; /* conv: [cout][cin][taps]; vector: cout = 1, cin = numel, taps = 1 */
-  int32_t is_conv;
+  int32_t src_cin;         /* input channels per tap in the accumulator (>= cin) */
 } b200seg_grad_seg;
 int32_t b200seg_grad_fold_chunk(void);
 int b200seg_grad_fold(float* dst, float* acc_a, float* acc_b, const b200seg_grad_seg* segs, const int32_t* blk_seg,
-                      const int32_t* blk_start, int32_t n_blocks, int32_t clear, void* stream);
+                      const int32_t* blk_start, int32_t n_blocks, int32_t mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training-mode BatchNorm around the convolutions. Replaces cuDNN/Apex BN behind Norm2d (network/mynn.py:18-24),
@@ -195,6 +200,12 @@ int b200seg_sgd_step(const b200seg_sgd_item* items, const int32_t* blk_item, con
 /* dst[n] += src[n] (fp32, n multiple of 4, 16-byte aligned): folds a scale pass' private parameter-gradient buffer
  * into the step gradient (the passes run concurrently; autograd's accumulation order lo -> hi is kept). */
 int b200seg_accum_f32(float* dst, const float* src, int64_t n, void* stream);
+/* Gradient publish (the step's autograd boundary): dst = (accumulate ? dst : 0) + (*scale_dev * scale_const) * src over n
+ * fp32 elements (n multiple of 4, 16-byte aligned). scale_dev (device pointer, may be NULL = 1) is the upstream gradient
+ * of the loss handed to backward() - amp.scale_loss / loss / accumulation_steps (train.py:499-505) - scale_const the
+ * 1 / world_size of the data-parallel average (network/__init__.py:38-39 apex DDP). */
+int b200seg_publish_grads(float* dst, const float* src, int64_t n, const float* scale_dev, float scale_const,
+                          int32_t accumulate, void* stream);
 /* eval mode: scale/shift from running statistics */
 int b200seg_bn_eval_params(int32_t c, const float* gamma, const float* beta, float eps, const float* running_mean,
                            const float* running_var, float* scale, float* shift, void* stream);

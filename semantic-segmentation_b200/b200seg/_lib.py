@@ -67,6 +67,7 @@ SIGNATURES = {
     "b200seg_conv2d_stats_elems": (c_size_t, [ctypes.POINTER(ConvDesc)]),
     "b200seg_conv2d_plan_info": (c_int32, [ctypes.POINTER(ConvDesc), c_int32, P32]),
     "b200seg_debug_occupancy": (c_int32, [c_int32, c_int32, c_int32]),
+    "b200seg_debug_occupancy_report": (None, []),
     "b200seg_conv2d_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V, P32, V]),
     "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
     "b200seg_pack_weight": (ctypes.c_int, [V, I32, I32, I32, V, V, I32, V]),
@@ -86,6 +87,7 @@ SIGNATURES = {
     "b200seg_p2p_free": (ctypes.c_int, [V]),
     "b200seg_bn_running_update": (ctypes.c_int, [V, V, V, I64, F, V, I32, I32, V]),
     "b200seg_accum_f32": (ctypes.c_int, [V, V, I64, V]),
+    "b200seg_publish_grads": (ctypes.c_int, [V, V, I64, V, F, I32, V]),
     "b200seg_sgd_chunk": (I32, []),
     "b200seg_sgd_step": (ctypes.c_int, [V, V, V, I32, F, F, F, F, I32, I32, V]),
     "b200seg_bn_eval_params": (ctypes.c_int, [I32, V, V, F, V, V, V, V, V]),

@@ -41,22 +41,29 @@ def _criterion_kind(criterion):
     raise NotImplementedError("criterion %s is outside the B200 hot path (CE and RMI are covered)" % name)
 
 
-def allreduce_mean_(flat):
-    """Gradient all-reduce-average of the data-parallel step (collective C1): ONE collective over the flat
-    fp32 gradient buffer (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests). No-op without a process
-    group or with a single rank."""
+def allreduce_sum_(flat):
+    """Gradient all-reduce of the data-parallel step (collective C1): ONE sum over the flat fp32 gradient
+    buffer (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests); returns the world size the caller divides
+    by (folded into the publish kernel). No-op (returns 1) without a process group or with a single rank."""
     if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
-        return flat
+        return 1
     ws = torch.distributed.get_world_size()
     if ws > 1:
         torch.distributed.all_reduce(flat)
+    return ws
+
+
+def allreduce_mean_(flat):
+    """all-reduce-average in place (host-logic helper of the CPU tests; the module folds the 1/world into its publish)."""
+    ws = allreduce_sum_(flat)
+    if ws > 1:
         flat.mul_(1.0 / ws)
     return flat
 
 
 class _PublishGrads(torch.autograd.Function):
-    """Bridges the engine's eagerly computed gradients into autograd: forward returns the loss, backward hands every
-    parameter its slice of the flat gradient buffer."""
+    """Bridges the engine's eagerly computed gradients into autograd: forward returns the loss, backward scales the
+    step's gradient by the upstream gradient it receives and hands every parameter its slice of the flat buffer."""
 
     @staticmethod
     def forward(ctx, module, loss, anchor):
@@ -65,9 +72,9 @@ class _PublishGrads(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        # Gradients were computed for a unit upstream gradient (bf16 needs no loss scaling; the apex.amp shim is a
-        # pass-through), so grad_out is not applied.
-        ctx.module._publish()
+        # grad_out is d(objective)/d(loss): 1 for loss.backward(), 1/k for (loss / k).backward() under gradient
+        # accumulation, the loss scale under amp.scale_loss (train.py:499-505). Applied on the device (no host sync).
+        ctx.module._publish(grad_out)
         return None, None, None
 
 
@@ -82,7 +89,8 @@ class B200SegModule(nn.Module):
         self.hcfg = hcfg or A.HRNET_W48
         self.ocfg = dict(ocfg or A.OCR_DEFAULT)
         self.ocfg["num_classes"] = num_classes
-        assert num_classes == 19, "kernels are instantiated for the 19 Cityscapes classes"
+        if num_classes != 19:
+            raise NotImplementedError("the loss / soft-region kernels are instantiated for the 19 Cityscapes classes")
         self.lo_scale, self.ocr_alpha, self.sup_wt, self.ignore_index = lo_scale, ocr_alpha, supervised_mscale_wt, ignore_index
         self.n_scales = n_scales
         self.use_cuda_graph = use_cuda_graph
@@ -159,7 +167,8 @@ class B200SegModule(nn.Module):
             raise RuntimeError("B200SegModule runs on CUDA only (sm_100a); there is no CPU path - call .cuda() first")
         if self._flat_grad is None or self._flat_grad.device != dev:
             total = sum((p.numel() + 63) // 64 * 64 for _, p in params)
-            self._flat_grad = torch.zeros(total, dtype=F32, device=dev)
+            self._flat_grad = torch.zeros(total, dtype=F32, device=dev)      # published gradients (param.grad views)
+            self._step_flat = torch.zeros(total, dtype=F32, device=dev)      # gradient of the last executed step
             self._grad_views = {}
             off = 0
             for n, p in params:
@@ -174,52 +183,55 @@ class B200SegModule(nn.Module):
                     w_f = torch.zeros((o, k * k, i), dtype=torch.bfloat16, device=dev)
                     w_d = torch.zeros((i, k * k, (o + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
                     self._packed[n[: -len(".weight")]] = (w_f, w_d)
-            self._stem_pad = None
             self._graphs = {}
             self._build_grad_accumulators(params, dev)
         self._ensure_flat_running(dev)
 
     def _build_grad_accumulators(self, params, dev):
-        """Step-private fp32 gradient accumulators sharing the flat layout of ``_flat_grad``:
-          _acc_hi : conv-weight gradients of the main (1.0x / only) pass in the kernels' [O][taps][I] layout (vector
-                    parameters of that pass accumulate straight into ``_flat_grad``);
-          _acc_lo : everything the concurrently executed 0.5x pass produces (conv weights [O][taps][I], vectors as is).
-        They are zeroed at the start of a step; ``raw.grad_fold`` adds them into the OIHW ``_flat_grad`` at its end."""
-        self._acc_hi = torch.zeros_like(self._flat_grad)
-        self._acc_lo = torch.zeros_like(self._flat_grad)
+        """Step-private fp32 gradient accumulators in the flat layout of ``_flat_grad`` (+ a tail for the stem, whose
+        weight gradient accumulates on the 16-channel padded image):
+          _acc_hi : everything the main (1.0x / only) pass produces - conv weights in the kernels' [O][taps][I] layout,
+                    vectors (BN affine, biases) as is;
+          _acc_lo : the same for the concurrently executed 0.5x pass.
+        They are zeroed at the start of a step; ``raw.grad_fold`` sums and transposes them into ``_step_flat`` (OIHW) at
+        its end. Nothing a step computes touches ``_flat_grad`` / ``param.grad`` before ``loss.backward()``."""
+        total = self._flat_grad.numel()
+        tail = 0
+        for n, p in params:
+            if p.dim() == 4 and p.shape[1] == 3:
+                tail += p.shape[0] * p.shape[2] * p.shape[3] * 16
+        self._acc_hi = torch.zeros(total + tail, dtype=F32, device=dev)
+        self._acc_lo = torch.zeros(total + tail, dtype=F32, device=dev)
         self._eng_grads = {"hi": {}, "lo": {}}
         segs = []
-        off = 0
+        off, toff = 0, total
         for n, p in params:
             numel = p.numel()
             if p.dim() == 4:
                 o, i, k, _ = p.shape
-                self._eng_grads["hi"][n] = self._acc_hi[off:off + numel].view(o, k * k, i)
-                self._eng_grads["lo"][n] = self._acc_lo[off:off + numel].view(o, k * k, i)
-                if i != 3:     # the stem accumulates on the 16-channel padded image and is folded separately
-                    segs.append((off, o, i, k * k, 1))
+                if i == 3:
+                    for which, acc in (("hi", self._acc_hi), ("lo", self._acc_lo)):
+                        self._eng_grads[which][n] = acc[toff:toff + o * k * k * 16].view(o, k * k, 16)
+                    segs.append((off, toff, o, i, k * k, 16))
+                    toff += o * k * k * 16
+                else:
+                    for which, acc in (("hi", self._acc_hi), ("lo", self._acc_lo)):
+                        self._eng_grads[which][n] = acc[off:off + numel].view(o, k * k, i)
+                    segs.append((off, off, o, i, k * k, i))
             else:
-                self._eng_grads["hi"][n] = self._grad_views[n]
-                self._eng_grads["lo"][n] = self._acc_lo[off:off + numel].view(p.shape)
-                segs.append((off, 1, numel, 1, 0))
+                for which, acc in (("hi", self._acc_hi), ("lo", self._acc_lo)):
+                    self._eng_grads[which][n] = acc[off:off + numel].view(p.shape)
+                segs.append((off, off, 1, numel, 1, numel))
             off += (numel + 63) // 64 * 64
         self._fold_table = raw.grad_fold_table(segs, dev)
 
     def _engine_grads(self, which="hi"):
-        """name -> fp32 tensor an Engine accumulates into, plus the stem's padded [O][9][16] scratch accumulator."""
-        g = dict(self._eng_grads[which])
-        stem = "backbone.conv1.weight"
-        dev = self._flat_grad.device
-        pad = torch.zeros((g[stem].shape[0], 9, 16), dtype=F32, device=dev)
-        g[stem] = pad
-        return g, pad
+        """name -> fp32 tensor an Engine accumulates into."""
+        return dict(self._eng_grads[which])
 
-    def _fold_grads(self, stem_pads, with_lo):
-        stem = "backbone.conv1.weight"
-        for pad in stem_pads:
-            o = pad.shape[0]
-            self._grad_views[stem].add_(pad[:, :, :3].permute(0, 2, 1).reshape(o, 3, 3, 3))
-        raw.grad_fold(self._flat_grad, self._acc_hi, self._acc_lo if with_lo else None, self._fold_table, clear=False)
+    def _fold_grads(self, with_lo):
+        raw.grad_fold(self._step_flat, self._acc_hi, self._acc_lo if with_lo else None, self._fold_table, clear=False,
+                      overwrite=True)
 
     def _ensure_flat_running(self, dev):
         """BatchNorm running statistics live in ONE flat fp32 buffer ([mean C | var C] per layer) and the module's
@@ -327,14 +339,12 @@ class B200SegModule(nn.Module):
             self._bstreams = {"hi": mk(), "lo": mk()}
             hold = self._sync is None      # reusable slab workspaces go with the keep-alive mode
             self._ws_holders = {"hi": [None] if hold else None, "lo": [None] if hold else None}
-        grads, stem_pad = self._engine_grads("hi")
-        stem_pads = [stem_pad]
+        grads = self._engine_grads("hi")
         E_lo = None
         if par:
             if getattr(self, "_lo_stream", None) is None:
                 self._lo_stream, self._side_stream_lo = torch.cuda.Stream(), torch.cuda.Stream()
-            grads_lo, stem_pad_lo = self._engine_grads("lo")
-            stem_pads.append(stem_pad_lo)
+            grads_lo = self._engine_grads("lo")
             E_lo = Engine(tensors, grads_lo, self._packed, True, drop_mask, side_stream=self._side_stream_lo,
                           bstat=self._bstat_views[0], stream=self._lo_stream, sync=sync, pass_id=0,
                           branch_streams=self._bstreams["lo"], ws_holder=self._ws_holders["lo"])
@@ -350,7 +360,7 @@ class B200SegModule(nn.Module):
         if E_lo is not None:
             E_lo.pre_backward_event = wd_ready
         M.run_backward(E, E_lo)
-        self._fold_grads(stem_pads, par)
+        self._fold_grads(par)
         if par:
             assert E.bn_seen == E_lo.bn_seen and len(E.bn_seen) == len(self._bn_slots), "BN bookkeeping out of sync"
             raw.bn_running_update(self._run_flat, self._bstat[0], self._bstat[1], BN_MOMENTUM, self._nbt_flat, 2)
@@ -375,12 +385,6 @@ class B200SegModule(nn.Module):
         gts = gts.contiguous().long()
         key = (tuple(images.shape), str(images.device))
         mask = self._drop_mask(images.shape[0], images.device)
-        # Gradient accumulation contract: zero the flat buffer only when the caller dropped the gradients
-        # (optimizer.zero_grad(set_to_none=True)); an in-place zero_grad already cleared it through the aliased views,
-        # and live .grad tensors mean the caller wants this step accumulated on top.
-        first = next(self.parameters())
-        if first.grad is None:
-            self._flat_grad.zero_()
         if not self.use_cuda_graph:
             return self._step_eager(images, gts, mask)
         st = self._graphs.get(key)
@@ -404,17 +408,39 @@ class B200SegModule(nn.Module):
         st["graph"].replay()
         return st["loss"]
 
-    def _publish(self):
-        """Called from loss.backward(): aliases every ``param.grad`` to its slice of the flat gradient buffer (or adds
-        into a foreign .grad tensor) and, under the data-parallel shim, averages the buffer across ranks (C1)."""
+    def _publish(self, grad_out=None):
+        """Called from loss.backward(): param.grad (+)= grad_out * (gradient of the last step), averaged across the
+        data-parallel ranks (collective C1) under the DDP shim. Contract, like autograd's: gradients the caller dropped
+        (``zero_grad(set_to_none=True)``) are replaced, live ones are accumulated into. Every ``param.grad`` this creates
+        is a view of ONE flat fp32 buffer (what FusedSGD and the all-reduce work on)."""
+        scale = 1.0
         if self._ddp_allreduce:
-            allreduce_mean_(self._flat_grad)
-        for n, p in self.named_parameters():
-            g = self._grad_views[n]
+            scale = 1.0 / allreduce_sum_(self._step_flat)
+        if grad_out is not None:
+            grad_out = grad_out.detach().reshape(()).to(F32)
+        params = list(self.named_parameters())
+        views = self._grad_views
+        n_none = sum(1 for _, p in params if p.grad is None)
+        if n_none == len(params):
+            raw.publish_grads(self._flat_grad, self._step_flat, grad_out, scale, accumulate=False)
+            for n, p in params:
+                p.grad = views[n]
+            return
+        if n_none == 0 and all(p.grad.data_ptr() == views[n].data_ptr() for n, p in params):
+            raw.publish_grads(self._flat_grad, self._step_flat, grad_out, scale, accumulate=True)
+            return
+        # mixed / foreign .grad tensors (rare: a caller that assigns its own gradient tensors): per-parameter slow path
+        tmp = torch.empty_like(self._step_flat)
+        raw.publish_grads(tmp, self._step_flat, grad_out, scale, accumulate=False)
+        off = 0
+        for n, p in params:
+            t = tmp[off:off + p.numel()].view(p.shape)
             if p.grad is None:
-                p.grad = g
-            elif p.grad.data_ptr() != g.data_ptr():
-                p.grad.add_(g)
+                views[n].copy_(t)
+                p.grad = views[n]
+            else:
+                p.grad.add_(t)
+            off += (p.numel() + 63) // 64 * 64
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, inputs):

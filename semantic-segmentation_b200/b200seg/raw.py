@@ -191,25 +191,35 @@ def ohwi_to_oihw(dw_ohwi, ksize):
 
 
 def grad_fold_table(segs, device):
-    """segs: list of (offset, cout, cin, taps, is_conv) over one flat layout -> device tables for grad_fold."""
+    """segs: list of (dst offset, accumulator offset, cout, cin, taps, accumulator cin) -> device tables for grad_fold."""
     import numpy as np
     chunk = lib().b200seg_grad_fold_chunk()
     blk_seg, blk_start = [], []
-    for si, (_off, cout, cin, taps, _c) in enumerate(segs):
+    for si, (_off, _soff, cout, cin, taps, _scin) in enumerate(segs):
         numel = cout * cin * taps
         for st in range(0, numel, chunk):
             blk_seg.append(si)
             blk_start.append(st)
-    seg_np = np.array(segs, dtype=np.dtype([("offset", "<i8"), ("cout", "<i4"), ("cin", "<i4"), ("taps", "<i4"),
-                                            ("is_conv", "<i4")]))
+    seg_np = np.array(segs, dtype=np.dtype([("offset", "<i8"), ("src_offset", "<i8"), ("cout", "<i4"), ("cin", "<i4"),
+                                            ("taps", "<i4"), ("src_cin", "<i4")]))
     return dict(segs=torch.from_numpy(seg_np.view(np.uint8).copy()).to(device),
                 blk_seg=torch.tensor(blk_seg, dtype=torch.int32, device=device),
                 blk_start=torch.tensor(blk_start, dtype=torch.int32, device=device), n_blocks=len(blk_seg))
 
 
-def grad_fold(dst, acc_a, acc_b, table, clear=True):
+def grad_fold(dst, acc_a, acc_b, table, clear=False, overwrite=False):
     check(lib().b200seg_grad_fold(ptr(dst), ptr(acc_a), ptr(acc_b), ptr(table["segs"]), ptr(table["blk_seg"]),
-                                  ptr(table["blk_start"]), table["n_blocks"], int(clear), stream_ptr()), "grad_fold")
+                                  ptr(table["blk_start"]), table["n_blocks"], int(clear) | (int(overwrite) << 1),
+                                  stream_ptr()), "grad_fold")
+
+
+def publish_grads(dst, src, scale_dev=None, scale_const=1.0, accumulate=False):
+    """dst = (accumulate ? dst : 0) + (*scale_dev * scale_const) * src over flat fp32 buffers of equal size."""
+    assert dst.numel() == src.numel() and dst.dtype == F32 and src.dtype == F32
+    if scale_dev is not None:
+        assert scale_dev.dtype == F32 and scale_dev.numel() == 1 and scale_dev.is_cuda
+    check(lib().b200seg_publish_grads(ptr(dst), ptr(src), dst.numel(), ptr(scale_dev), float(scale_const),
+                                      int(accumulate), stream_ptr()), "publish_grads")
 
 
 # ----------------------------------------------------------------------------------------------- batch norm

@@ -17,6 +17,7 @@
 // that low-resolution layers still spread over the SMs (a 16x32x384 layer has 4 pixel tiles but 6 x 64-wide Cout tiles).
 // Replaces cuDNN fwd/dgrad behind the 3x3 stride-1 convolutions of network/hrnetv2.py:31-34 (BasicBlock), :76
 // (Bottleneck), network/ocrnet.py:54-57 (conv3x3_ocr) and network/utils.py:348-356 (attention head).
+#include <cstdio>
 #include "ptx.cuh"
 #include "tma_host.h"
 #include "launch.h"
@@ -502,7 +503,39 @@ int conv3x3_halo_occupancy(int occ_variant, int smem_bytes) {
   return e == cudaSuccess ? nb : -(int)e;
 }
 
+template <typename K>
+static void occupancy_report_one(const char* name, K kernel, int threads) {
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, kernel) != cudaSuccess) { printf("%s: cudaFuncGetAttributes failed\n", name); return; }
+  printf("%s: regs %d static smem %zu local %zu maxThreads %d maxDynSmem %d carveout %d\n  blocks/SM by dyn smem:", name,
+         a.numRegs, a.sharedSizeBytes, a.localSizeBytes, a.maxThreadsPerBlock, a.maxDynamicSharedSizeBytes,
+         a.preferredShmemCarveout);
+  for (int kb = 0; kb <= 112; kb += 16) {
+    int nb = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, (size_t)kb * 1024);
+    printf(" %dK:%d", kb, nb);
+  }
+  printf("\n");
+}
+void conv_igemm_occupancy_report();
 }  // namespace b200seg
+
+// Diagnostics (stdout): what the runtime knows about the convolution kernels and the SM (tools/gpu_occupancy.py).
+extern "C" void b200seg_debug_occupancy_report(void) {
+  cudaDeviceProp pr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&pr, dev);
+  printf("device %s: SMs %d regs/SM %d regs/block %d smem/SM %zu smem/block optin %zu reserved smem/block %zu "
+         "max blocks/SM %d max threads/SM %d\n", pr.name, pr.multiProcessorCount, pr.regsPerMultiprocessor,
+         pr.regsPerBlock, pr.sharedMemPerMultiprocessor, pr.sharedMemPerBlockOptin, pr.reservedSharedMemPerBlock,
+         pr.maxBlocksPerMultiProcessor, pr.maxThreadsPerMultiProcessor);
+  b200seg::conv3x3_halo_occupancy(2, 1024);     // sets the attributes of both builds
+  b200seg::occupancy_report_one("conv3x3_halo_kernel<2>", b200seg::conv3x3_halo_kernel<2>, b200seg::kHThreads);
+  b200seg::occupancy_report_one("conv3x3_halo_kernel<1>", b200seg::conv3x3_halo_kernel<1>, b200seg::kHThreads);
+  b200seg::conv_igemm_occupancy_report();
+  fflush(stdout);
+}
 
 extern "C" int32_t b200seg_debug_occupancy(int32_t kernel, int32_t occ_variant, int32_t smem_bytes) {
   if (occ_variant != 1 && occ_variant != 2) return B200SEG_E_BADARG;

@@ -15,6 +15,7 @@
 //               barrier waits + unrolled tcgen05.mma issue), warp 2 TMEM allocator, warps 4-11 epilogue (two warps
 //               per TMEM lane quarter, half of the accumulator columns each).
 //   Launch:     programmatic dependent launch (launch.h): the prologue overlaps the previous kernel's tail.
+#include <cstdio>
 #include "ptx.cuh"
 #include <cstdlib>
 #include "tma_host.h"
@@ -471,6 +472,19 @@ int conv_igemm_occupancy(int occ_variant, int smem_bytes) {
       ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_igemm_kernel<2>, kThreads, (size_t)smem_bytes)
       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_igemm_kernel<1>, kThreads, (size_t)smem_bytes);
   return e == cudaSuccess ? nb : -(int)e;
+}
+
+void conv_igemm_occupancy_report() {
+  conv_igemm_occupancy(2, 1024);
+  for (int v = 2; v >= 1; --v) {
+    cudaFuncAttributes a;
+    if (v == 2) cudaFuncGetAttributes(&a, conv_igemm_kernel<2>); else cudaFuncGetAttributes(&a, conv_igemm_kernel<1>);
+    printf("conv_igemm_kernel<%d>: regs %d static smem %zu local %zu maxThreads %d maxDynSmem %d carveout %d\n  blocks/SM by dyn smem:",
+           v, a.numRegs, a.sharedSizeBytes, a.localSizeBytes, a.maxThreadsPerBlock, a.maxDynamicSharedSizeBytes,
+           a.preferredShmemCarveout);
+    for (int kb = 0; kb <= 112; kb += 16) printf(" %dK:%d", kb, conv_igemm_occupancy(v, kb * 1024));
+    printf("\n");
+  }
 }
 
 int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,

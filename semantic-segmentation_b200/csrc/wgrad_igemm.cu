@@ -299,23 +299,25 @@ wgrad_reduce_kernel(const WgradParams p, const float* __restrict__ ws, float* __
   }
 }
 
-// Folds the step's gradient accumulators into the published gradient and clears them (no per-step memsets):
-//   conv weights : dst[co][ci][tap] (OIHW master layout) += acc_a[co][tap][ci] + acc_b[co][tap][ci]   (OHWI accumulators)
-//   vectors      : dst[i] += acc_b[i]                                    (BN affine / bias gradients of the second pass)
-// One block = up to kFoldChunk consecutive elements of one parameter: coalesced read-modify-write of dst, transposed
-// gather from the accumulators (each accumulator element is read, and cleared, by exactly one thread).
+// Folds the step's gradient accumulators into the step gradient (see b200seg_grad_fold in the header):
+//   conv weights : dst[co][ci][tap] (OIHW master layout) (+)= acc_a[co][tap][ci] + acc_b[co][tap][ci]   (OHWI accumulators)
+//   vectors      : dst[i] (+)= acc_a[i] + acc_b[i]
+// One block = up to kFoldChunk consecutive elements of one parameter: coalesced write (or read-modify-write) of dst,
+// transposed gather from the accumulators (each accumulator element is read, and cleared, by exactly one thread).
 constexpr int kFoldChunk = 4096;
 __global__ void __launch_bounds__(256)
 grad_fold_kernel(float* __restrict__ dst, float* __restrict__ acc_a, float* __restrict__ acc_b,
                  const b200seg_grad_seg* __restrict__ segs, const int32_t* __restrict__ blk_seg,
-                 const int32_t* __restrict__ blk_start, int clear) {
+                 const int32_t* __restrict__ blk_start, int mode) {
   pdl_sync();
+  const bool clear = mode & 1, overwrite = mode & 2;
   const b200seg_grad_seg sg = segs[blk_seg[blockIdx.x]];
   const uint32_t numel = (uint32_t)sg.cout * sg.cin * sg.taps;     // a parameter has < 2^31 elements
   const uint32_t j0 = (uint32_t)blk_start[blockIdx.x];
-  const uint32_t len = (uint32_t)(sg.cin * sg.taps), taps = (uint32_t)sg.taps, cin = (uint32_t)sg.cin;
-  float* a = (sg.is_conv && acc_a) ? acc_a + sg.offset : nullptr;
-  float* b = acc_b ? acc_b + sg.offset : nullptr;
+  const uint32_t len = (uint32_t)(sg.cin * sg.taps), taps = (uint32_t)sg.taps, scin = (uint32_t)sg.src_cin;
+  const uint32_t slen = scin * taps;
+  float* a = acc_a ? acc_a + sg.src_offset : nullptr;
+  float* b = acc_b ? acc_b + sg.src_offset : nullptr;
   float* d = dst + sg.offset;
   for (int t0 = threadIdx.x; t0 < kFoldChunk; t0 += 4 * 256) {   // four elements in flight per thread
     uint32_t js[4], srcs[4];
@@ -326,16 +328,16 @@ grad_fold_kernel(float* __restrict__ dst, float* __restrict__ acc_a, float* __re
       const uint32_t j = j0 + t0 + u * 256;
       ok[u] = j < numel;
       uint32_t src = j;
-      if (taps > 1) {
+      if (taps > 1 || scin != (uint32_t)sg.cin) {
         const uint32_t r = j / len;
         const uint32_t jj = j - r * len;
         const uint32_t ci = jj / taps, tap = jj - ci * taps;
-        src = r * len + tap * cin + ci;
+        src = r * slen + tap * scin + ci;
       }
       js[u] = j; srcs[u] = src;
       v[u] = 0.f;
       if (ok[u]) {
-        v[u] = d[j];
+        if (!overwrite) v[u] = d[j];
         if (a) v[u] += a[src];
         if (b) v[u] += b[src];
       }
@@ -352,6 +354,21 @@ grad_fold_kernel(float* __restrict__ dst, float* __restrict__ acc_a, float* __re
         if (b) b[srcs[u]] = 0.f;
       }
     }
+  }
+}
+
+// dst = (accumulate ? dst : 0) + (*scale_dev * scale_const) * src   (gradient publish, see the header)
+__global__ void __launch_bounds__(256)
+publish_grads_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4,
+                     const float* __restrict__ scale_dev, float scale_const, int accumulate) {
+  pdl_sync();
+  const float sc = (scale_dev ? *scale_dev : 1.f) * scale_const;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (accumulate) a = reinterpret_cast<float4*>(dst)[i];
+    a.x += sc * b.x; a.y += sc * b.y; a.z += sc * b.z; a.w += sc * b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
   }
 }
 
@@ -510,10 +527,20 @@ extern "C" int32_t b200seg_conv2d_wgrad_launches(const b200seg_conv_desc* d) {
 extern "C" int32_t b200seg_grad_fold_chunk(void) { return kFoldChunk; }
 
 extern "C" int b200seg_grad_fold(float* dst, float* acc_a, float* acc_b, const b200seg_grad_seg* segs,
-                                 const int32_t* blk_seg, const int32_t* blk_start, int32_t n_blocks, int32_t clear,
+                                 const int32_t* blk_seg, const int32_t* blk_start, int32_t n_blocks, int32_t mode,
                                  void* stream) {
   if (!dst || (!acc_a && !acc_b) || !segs || !blk_seg || !blk_start || n_blocks <= 0) return B200SEG_E_BADARG;
   cudaError_t e = launch_k(grad_fold_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, dst, acc_a, acc_b,
-                           segs, blk_seg, blk_start, (int)clear);
+                           segs, blk_seg, blk_start, (int)mode);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int b200seg_publish_grads(float* dst, const float* src, int64_t n, const float* scale_dev, float scale_const,
+                                     int32_t accumulate, void* stream) {
+  if (!dst || !src || n <= 0 || (n & 3) || (reinterpret_cast<uintptr_t>(dst) & 15) ||
+      (reinterpret_cast<uintptr_t>(src) & 15))
+    return B200SEG_E_BADARG;
+  cudaError_t e = launch_k(publish_grads_kernel, dim3(148 * 8), dim3(256), 0, (cudaStream_t)stream, dst, src,
+                           (long long)(n / 4), scale_dev, scale_const, (int)accumulate);
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -31,6 +31,38 @@ def build(arch, num_classes, criterion):
             raise NotImplementedError("only the default OCR / attention-head configuration is on the hot path")
         if cfg.LOSS.OCR_AUX_RMI:
             raise NotImplementedError("OCR_AUX_RMI is not covered")
+        # cfg.MODEL.BNFUNC (config.py:216-225: apex.parallel.SyncBatchNorm under --syncbn --apex, else BatchNorm2d)
+        # decides whether BatchNorm statistics span the data-parallel group
+        bnfunc = getattr(cfg.MODEL, "BNFUNC", None)
+        kw["syncbn"] = bnfunc is not None and "sync" in getattr(bnfunc, "__name__", str(bnfunc)).lower()
+        checkpoint = getattr(cfg.MODEL, "HRNET_CHECKPOINT", "")
     except ImportError:
-        pass
-    return B200SegModule(arch, num_classes=num_classes, criterion=criterion, **kw)
+        checkpoint = ""
+    if num_classes != 19:
+        raise NotImplementedError("the B200 loss / soft-region kernels are instantiated for the 19 Cityscapes classes "
+                                  "(csrc/mscale_common.cuh NC); got num_classes=%d" % num_classes)
+    net = B200SegModule(arch, num_classes=num_classes, criterion=criterion, **kw)
+    load_backbone_checkpoint(net, checkpoint)
+    return net
+
+
+def load_backbone_checkpoint(net, path):
+    """HighResolutionNet.init_weights (network/hrnetv2.py:451-477): after the N(0, 1e-3) / (1, 0) initialisation the
+    ImageNet-pretrained trunk is loaded into ``backbone.*`` with the reference's key remapping ('last_layer' ->
+    'aux_head', 'model.' stripped; keys the trunk does not own are dropped); an empty path keeps the random init, a
+    non-empty missing path raises like the reference does."""
+    import torch
+    if not path:
+        return 0
+    if not os.path.isfile(path):
+        raise RuntimeError("No such file {}".format(path))
+    pretrained = torch.load(path, map_location="cpu")
+    own = net.state_dict()
+    loaded = 0
+    with torch.no_grad():
+        for k, v in pretrained.items():
+            k = "backbone." + k.replace("last_layer", "aux_head").replace("model.", "")
+            if k in own and tuple(own[k].shape) == tuple(v.shape):
+                own[k].copy_(v)
+                loaded += 1
+    return loaded

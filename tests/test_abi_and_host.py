@@ -103,3 +103,51 @@ def test_deepv3_parameter_spec_matches_reference_order():
                 k *= d
             nparams += k
     assert nparams == g["nparams"]
+
+
+def test_factory_reads_bnfunc_and_backbone_checkpoint(tmp_path):
+    """network/_factory.build honours what the reference constructors read from cfg: BNFUNC (config.py:216-225) decides
+    SyncBN, HRNET_CHECKPOINT (hrnetv2.py:451-477) is loaded into backbone.* with the reference's key remapping, a missing
+    file raises, other class counts are refused loudly."""
+    import types
+    from network import _factory
+    from b200seg.module import B200SegModule
+    net = B200SegModule("basic.HRNet", 19)
+    ck = {"model.conv1.weight": torch.full((64, 3, 3, 3), 0.5), "bn1.bias": torch.full((64,), 0.25),
+          "last_layer.0.weight": torch.zeros(3), "conv2.weight": torch.zeros(1)}       # wrong shape / foreign: dropped
+    path = str(tmp_path / "hrnet.pth")
+    torch.save(ck, path)
+    assert _factory.load_backbone_checkpoint(net, path) == 2
+    assert float(net.backbone.conv1.weight.min()) == 0.5 and float(net.backbone.bn1.bias.max()) == 0.25
+    assert _factory.load_backbone_checkpoint(net, "") == 0
+    with pytest.raises(RuntimeError, match="No such file"):
+        _factory.load_backbone_checkpoint(net, str(tmp_path / "missing.pth"))
+    with pytest.raises(NotImplementedError, match="19"):
+        _factory.build("ocrnet.HRNet", 65, None)
+    # a stand-in for the reference's config module
+    class SyncBatchNorm:    # noqa
+        pass
+    ex = types.SimpleNamespace(**{k: types.SimpleNamespace(NUM_MODULES=1, NUM_BLOCKS=b, NUM_CHANNELS=c) for k, b, c in (
+        ("STAGE1", [1], [32]), ("STAGE2", [1, 1], [16, 32]), ("STAGE3", [1, 1, 1], [16, 32, 64]),
+        ("STAGE4", [1, 1, 1, 1], [16, 32, 64, 128]))})
+    cfg = types.SimpleNamespace(
+        MODEL=types.SimpleNamespace(OCR_EXTRA=ex, OCR=types.SimpleNamespace(MID_CHANNELS=512, KEY_CHANNELS=256),
+                                    SEGATTN_BOT_CH=256, MSCALE_LO_SCALE=0.5, N_SCALES=None, ALIGN_CORNERS=False,
+                                    OCR_ASPP=False, MSCALE_OLDARCH=False, MSCALE_INNER_3x3=True, MSCALE_DROPOUT=False,
+                                    BNFUNC=SyncBatchNorm, HRNET_CHECKPOINT=""),
+        LOSS=types.SimpleNamespace(OCR_ALPHA=0.4, SUPERVISED_MSCALE_WT=0.05, OCR_AUX_RMI=False),
+        DATASET=types.SimpleNamespace(IGNORE_LABEL=255))
+    mod = types.ModuleType("config")
+    mod.cfg = cfg
+    import sys
+    sys.modules["config"] = mod
+    try:
+        net = _factory.build("ocrnet.HRNet_Mscale", 19, None)
+        assert net.syncbn is True and net.sup_wt == 0.05
+        cfg.MODEL.BNFUNC = torch.nn.BatchNorm2d
+        assert _factory.build("basic.HRNet", 19, None).syncbn is False
+        cfg.MODEL.HRNET_CHECKPOINT = str(tmp_path / "missing.pth")
+        with pytest.raises(RuntimeError, match="No such file"):
+            _factory.build("basic.HRNet", 19, None)
+    finally:
+        del sys.modules["config"]

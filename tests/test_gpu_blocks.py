@@ -38,9 +38,8 @@ class Harness:
         self.net = net.cuda().train()
         net._ensure_device_state()
         net._repack()
-        net._flat_grad.zero_()
         tensors = {k: v.detach() for k, v in net._tensors().items()}
-        self.grads, _ = net._engine_grads("hi")     # conv weights: kernel-layout [O][taps][I] accumulators
+        self.grads = net._engine_grads("hi")        # conv weights: kernel-layout [O][taps][I] accumulators
         self.E = Engine(tensors, self.grads, net._packed, True, torch.ones((2, 512), device="cuda"))
 
     def rand_bf16(self, shape, seed, scale=1.0):

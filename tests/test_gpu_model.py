@@ -1,4 +1,4 @@
-"""End-to-end parity of the B200 module (through the C ABI) against the CPU oracle on identical weights and inputs.
+"""End-to-end parity of the B200 module (through the C ABI) against the oracle on identical weights and inputs.
 
 The product computes in bf16 storage / fp32 accumulate while the oracle is fp32, so whole-network comparisons use
 statistical tolerances (loss within a few 1e-2 relative, gradient cosine similarity), as discussed in SURVEY.md §7
@@ -23,7 +23,9 @@ def _oracle_step(O, arch, hcfg, sd, images, gts, sup_wt=0.0, crit=None):
             v.requires_grad_(True)
     ctx = O.Ctx(sd, training=True)
     crit = crit or O.criterion_ce
-    if arch == "ocrnet.HRNet_Mscale":
+    if arch == "mscale.HRNet":
+        loss = O.mscale_basic_two_scale(ctx, images, gts, criterion=crit, hcfg=hcfg, supervised_mscale_wt=sup_wt)
+    elif arch == "ocrnet.HRNet_Mscale":
         loss = O.mscale_two_scale(ctx, images, gts, criterion=crit, hcfg=hcfg, supervised_mscale_wt=sup_wt)
     elif arch == "ocrnet.HRNet":
         loss = O.ocrnet_forward(ctx, images, gts, criterion=crit, hcfg=hcfg)
@@ -34,29 +36,21 @@ def _oracle_step(O, arch, hcfg, sd, images, gts, sup_wt=0.0, crit=None):
 
 
 @pytest.mark.parametrize("arch,sup", [("ocrnet.HRNet_Mscale", 0.0), ("ocrnet.HRNet_Mscale", 0.05),
-                                      ("ocrnet.HRNet", 0.0), ("basic.HRNet", 0.0)])
+                                      ("ocrnet.HRNet", 0.0), ("basic.HRNet", 0.0), ("mscale.HRNet", 0.05)])
 def test_train_step_matches_oracle_w16(arch, sup):
-    """Loss of one fused step vs the oracle (fp32 and bf16-emulating), state bookkeeping, and that every parameter the
-    oracle gives a gradient also gets one here (and vice versa: the dead 1x attention head gets none)."""
+    """One fused step vs the oracle at matched precision (bf16-storage emulation, run on the GPU through stock PyTorch
+    fp32): loss to 5e-3, every per-tensor gradient within the oracle's own one-bf16-ulp noise floor (tests/_parity.py),
+    the same zero pattern (the dead 1x attention head gets no gradient), running statistics, step bookkeeping."""
+    import _parity as P
     O, B200SegModule = _mods()
-    torch.set_num_threads(8)
     hcfg = O.HRNET_W16_TEST
     sd0 = O.synth_state_dict(arch, hcfg, seed=3)
     images, gts = O.synth_batch(2, 64, 128, seed=5)
-    sd_ref, loss_ref = _oracle_step(O, arch, hcfg, sd0, images, gts, sup)
-
-    ocfg = dict(O.OCR_CFG)
-    ocfg["dropout"] = 0.0
-    net = B200SegModule(arch, 19, criterion=None, hcfg=hcfg, ocfg=ocfg, supervised_mscale_wt=sup,
-                        use_cuda_graph=False)
+    sd_ref, loss_ref = P.oracle_train_step(O, arch, hcfg, sd0, images, gts, sup)
+    floor, run_floor = P.noise_floor(O, arch, hcfg, sd0, images, gts, sd_ref, sup)
+    net, lv = P.product_train_step(B200SegModule, O, arch, hcfg, sd0, images, gts, sup)
     assert list(net.state_dict().keys()) == list(sd0.keys())
-    net.load_state_dict(sd0)
-    net = net.cuda().train()
-    loss = net({"images": images.cuda(), "gts": gts.cuda()})
-    loss.backward()
-    torch.cuda.synchronize()
-    lv = float(loss)
-    assert abs(lv - loss_ref) <= 3e-2 * abs(loss_ref), (lv, loss_ref)
+    assert abs(lv - loss_ref) <= 5e-3 * abs(loss_ref), (lv, loss_ref)
     for name, p in net.named_parameters():
         g_ref = sd_ref[name].grad
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
@@ -65,13 +59,14 @@ def test_train_step_matches_oracle_w16(arch, sup):
         if name.endswith(".0.bias") and (".conv3x3_ocr." in name or ".aux_head.0" in name):
             continue    # bias in front of a training-mode BN: analytically zero
         assert ref_zero == ours_zero, (name, ref_zero, ours_zero)
-        if not ref_zero:
-            ratio = float(p.grad.norm().cpu() / g_ref.norm())
-            assert 0.3 < ratio < 3.0, (name, ratio)
+    rep = {k: v for k, v in P.grad_report(net, sd_ref).items()
+           if not (k.endswith(".0.bias") and (".conv3x3_ocr." in k or ".aux_head.0" in k))}
+    bad, summary = P.check_against_floor(rep, floor, P.running_report(net, sd_ref), run_floor)
+    assert not bad, (summary, bad[:8])
+    # the tensors next to the loss see no gate-flip noise from above: tight agreement
+    last = {"basic.HRNet": "seg_head.6.weight", "mscale.HRNet": "cls_head.6.weight"}.get(arch, "ocr.aux_head.2.bias")
+    assert rep[last][0] >= 0.99, (last, rep[last])
     sd_new = net.state_dict()
-    for key in ("backbone.bn1.running_mean", "backbone.stage4.0.branches.3.0.bn2.running_var"):
-        a, b = sd_new[key].cpu(), sd_ref[key]
-        assert (a - b).abs().max() <= 3e-2 * b.abs().max() + 1e-4, key
     assert int(sd_new["backbone.bn1.num_batches_tracked"]) == int(sd_ref["backbone.bn1.num_batches_tracked"])
 
 

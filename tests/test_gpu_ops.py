@@ -84,42 +84,72 @@ def test_conv_fwd_dgrad_wgrad(case):
 
 
 def test_grad_fold_layouts_and_clearing():
-    """End-of-step fold: OHWI accumulators of two passes -> OIHW gradient (+=), vectors of the second pass added,
-    accumulators cleared."""
+    """End-of-step fold: OHWI accumulators of two passes -> OIHW gradient (+= or overwrite), vectors of both passes, the
+    stem accumulating on 16 padded input channels at its own accumulator offset, accumulators cleared on request."""
     import numpy as np
     raw = _setup()
-    shapes = [(48, 32, 3, 3), (19, 512, 1, 1), (96,), (64, 16, 3, 3), (7,), (96, 96, 3, 3)]
+    shapes = [(48, 32, 3, 3), (19, 512, 1, 1), (96,), (64, 16, 3, 3), (7,), (96, 96, 3, 3), (64, 3, 3, 3)]
     offs, off = [], 0
     for shp in shapes:
         offs.append(off)
         off += (int(np.prod(shp)) + 63) // 64 * 64
+    stem_src = off                        # padded stem accumulator [64][9][16] behind the flat layout
+    acc_len = off + 64 * 9 * 16
     g = torch.Generator(device="cuda").manual_seed(0)
-    dst = torch.randn(off, generator=g, device="cuda")
-    a = torch.randn(off, generator=g, device="cuda")
-    b = torch.randn(off, generator=g, device="cuda")
-    want = dst.clone()
-    segs = []
-    for shp, o_ in zip(shapes, offs):
-        n = int(np.prod(shp))
-        if len(shp) == 4:
-            co, ci, k, _ = shp
-            src = (a[o_:o_ + n] + b[o_:o_ + n]).view(co, k * k, ci)
-            want[o_:o_ + n] += src.permute(0, 2, 1).reshape(-1)
-            segs.append((o_, co, ci, k * k, 1))
-        else:
-            want[o_:o_ + n] += b[o_:o_ + n]
-            segs.append((o_, 1, n, 1, 0))
-    table = raw.grad_fold_table(segs, "cuda")
-    a_vec_before = a[offs[2]:offs[2] + 96].clone()
-    raw.grad_fold(dst, a, b, table)
-    torch.cuda.synchronize()
-    for shp, o_ in zip(shapes, offs):
-        n = int(np.prod(shp))
-        assert torch.allclose(dst[o_:o_ + n], want[o_:o_ + n], rtol=0, atol=1e-6), shp
-        assert float(b[o_:o_ + n].abs().max()) == 0.0
-        if len(shp) == 4:
-            assert float(a[o_:o_ + n].abs().max()) == 0.0
-    assert torch.equal(a[offs[2]:offs[2] + 96], a_vec_before)     # vectors never live in the first accumulator
+    for overwrite in (False, True):
+        dst = torch.randn(off, generator=g, device="cuda")
+        a = torch.randn(acc_len, generator=g, device="cuda")
+        b = torch.randn(acc_len, generator=g, device="cuda")
+        want = torch.zeros_like(dst) if overwrite else dst.clone()
+        untouched = dst.clone()
+        segs = []
+        for shp, o_ in zip(shapes, offs):
+            n = int(np.prod(shp))
+            if len(shp) == 4 and shp[1] == 3:
+                co, ci, k, _ = shp
+                src = (a[stem_src:] + b[stem_src:]).view(co, k * k, 16)[:, :, :ci]
+                want[o_:o_ + n] += src.permute(0, 2, 1).reshape(-1)
+                segs.append((o_, stem_src, co, ci, k * k, 16))
+            elif len(shp) == 4:
+                co, ci, k, _ = shp
+                src = (a[o_:o_ + n] + b[o_:o_ + n]).view(co, k * k, ci)
+                want[o_:o_ + n] += src.permute(0, 2, 1).reshape(-1)
+                segs.append((o_, o_, co, ci, k * k, ci))
+            else:
+                want[o_:o_ + n] += a[o_:o_ + n] + b[o_:o_ + n]
+                segs.append((o_, o_, 1, n, 1, n))
+        table = raw.grad_fold_table(segs, "cuda")
+        a0 = a.clone()
+        raw.grad_fold(dst, a, b, table, clear=False, overwrite=overwrite)
+        torch.cuda.synchronize()
+        assert torch.equal(a, a0)                                           # not cleared unless asked
+        for shp, o_ in zip(shapes, offs):
+            n = int(np.prod(shp))
+            assert torch.allclose(dst[o_:o_ + n], want[o_:o_ + n], rtol=0, atol=2e-6), (shp, overwrite)
+            pad_end = o_ + (n + 63) // 64 * 64
+            assert torch.equal(dst[o_ + n:pad_end], untouched[o_ + n:pad_end])   # alignment gaps are not written
+        raw.grad_fold(dst, a, b, table, clear=True, overwrite=True)
+        torch.cuda.synchronize()
+        for shp, o_ in zip(shapes, offs):
+            n = int(np.prod(shp))
+            if not (len(shp) == 4 and shp[1] == 3):
+                assert float(a[o_:o_ + n].abs().max()) == 0.0 and float(b[o_:o_ + n].abs().max()) == 0.0
+        assert float(a[stem_src:].view(64, 9, 16)[:, :, :3].abs().max()) == 0.0
+
+
+def test_publish_grads_scales_and_accumulates():
+    """Gradient publish: dst = (accumulate ? dst : 0) + (*scale_dev * scale_const) * src."""
+    raw = _setup()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n = 64 * 1000 + 64
+    src = torch.randn(n, generator=g, device="cuda")
+    dst = torch.randn(n, generator=g, device="cuda")
+    d0 = dst.clone()
+    sc = torch.tensor(0.25, device="cuda")
+    raw.publish_grads(dst, src, sc, 0.5, accumulate=True)
+    assert torch.allclose(dst, d0 + 0.125 * src, rtol=0, atol=1e-6)
+    raw.publish_grads(dst, src, None, 1.0, accumulate=False)
+    assert torch.equal(dst, src)
 
 
 def test_conv_logit_head_fp32_and_padded_grads():

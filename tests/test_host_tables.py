@@ -15,17 +15,18 @@ def _cover(table, numels):
 def test_grad_fold_table_covers_every_element_once():
     from b200seg import raw, _lib
     chunk = _lib.lib().b200seg_grad_fold_chunk()
-    segs = [(0, 48, 32, 9, 1), (13824, 1, 96, 1, 0), (13952, 19, 512, 1, 1), (23680, 96, 96, 9, 1)]
+    segs = [(0, 0, 48, 32, 9, 32), (13824, 13824, 1, 96, 1, 96), (13952, 13952, 19, 512, 1, 512),
+            (23680, 23680, 96, 96, 9, 96), (106624, 200000, 64, 3, 9, 16)]
     tab = raw.grad_fold_table(segs, "cpu")
-    numels = [s[1] * s[2] * s[3] for s in segs]
+    numels = [s[2] * s[3] * s[4] for s in segs]
     items, starts, seen = _cover(tab, numels)
     assert tab["n_blocks"] == len(items) == sum((n + chunk - 1) // chunk for n in numels)
     for it, st in zip(items, starts):
         seen[it][st:st + chunk] += 1
     assert all((s == 1).all() for s in seen)
     raw_segs = np.frombuffer(tab["segs"].numpy().tobytes(), dtype=np.dtype(
-        [("offset", "<i8"), ("cout", "<i4"), ("cin", "<i4"), ("taps", "<i4"), ("is_conv", "<i4")]))
-    assert [tuple(int(v) for v in r) for r in raw_segs] == segs          # 24-byte records, C layout
+        [("offset", "<i8"), ("src_offset", "<i8"), ("cout", "<i4"), ("cin", "<i4"), ("taps", "<i4"), ("src_cin", "<i4")]))
+    assert [tuple(int(v) for v in r) for r in raw_segs] == segs          # 32-byte records, C layout
 
 
 def test_pack_table_records_pointers_and_blocks():

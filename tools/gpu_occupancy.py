@@ -29,3 +29,4 @@ for case in T._hrnet_shapes(1024, 2048) + T._hrnet_shapes(512, 1024):
     got = L.b200seg_debug_occupancy(kern, occ, smem)
     print("%-5s planned occ %d  smem %6d B  BN %3d  -> runtime grants %d CTA/SM %s" %
           ("halo" if kern else "igemm", occ, smem, bn, got, "" if got >= occ else "  <-- LESS THAN PLANNED"))
+L.b200seg_debug_occupancy_report()
