@@ -145,6 +145,55 @@ def test_sgd_on_fixed_batch_tracks_oracle():
     assert curve[0] - curve[-1] > 0.5 * drop_ref, (curve, ref_curve)
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_backward_applies_upstream_gradient_and_accumulates(use_graph):
+    """The autograd boundary (train.py:499-505): (k * loss).backward() publishes k * gradient (amp.scale_loss, loss /
+    accumulation steps), live .grad tensors are accumulated into, dropped ones replaced, a foreign .grad tensor receives
+    the step's contribution, and a forward without backward leaves param.grad alone."""
+    O, B200SegModule = _mods()
+    arch, hcfg = "ocrnet.HRNet_Mscale", O.HRNET_W16_TEST
+    sd0 = O.synth_state_dict(arch, hcfg, seed=3)
+    ocfg = dict(O.OCR_CFG)
+    ocfg["dropout"] = 0.0
+    net = B200SegModule(arch, 19, hcfg=hcfg, ocfg=ocfg, use_cuda_graph=use_graph)
+    net.load_state_dict(sd0)
+    net = net.cuda().train()
+    images, gts = O.synth_batch(2, 64, 128, seed=5)
+    batch = {"images": images.cuda(), "gts": gts.cuda()}
+
+    def flat():
+        return torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
+
+    rel = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+    for _ in range(3 if use_graph else 1):          # eager warm-up, capture, replay
+        net.zero_grad(set_to_none=True)
+        net(batch).backward()
+    g1 = flat()
+    assert float(g1.norm()) > 0
+    net.zero_grad(set_to_none=True)
+    (net(batch) * 0.25).backward()                   # scaled loss
+    assert rel(flat(), 0.25 * g1) <= 1e-5
+    net(batch).backward()                            # live gradients: accumulate on top
+    assert rel(flat(), 1.25 * g1) <= 1e-5
+    before = flat()
+    net(batch)                                       # forward only: nothing is published
+    torch.cuda.synchronize()
+    assert torch.equal(flat(), before)
+    net.zero_grad(set_to_none=False)                 # in-place zeroing keeps the aliased views
+    net(batch).backward()
+    assert rel(flat(), g1) <= 1e-5
+    names = [n for n, _ in net.named_parameters()]
+    pieces = dict(zip(names, torch.split(g1, [p.numel() for p in net.parameters()])))
+    p0 = net.get_parameter("ocr.cls_head.weight")    # a caller-owned gradient tensor
+    own = torch.full_like(p0, 2.0)
+    p0.grad = own
+    (net(batch) * 2.0).backward()
+    assert p0.grad is own
+    assert rel(own, 2.0 + 2.0 * pieces["ocr.cls_head.weight"].view_as(p0)) <= 1e-5
+    for n in ("backbone.conv1.weight", "scale_attn.conv0.weight", "ocr.aux_head.2.bias"):
+        assert rel(net.get_parameter(n).grad.flatten(), 3.0 * pieces[n]) <= 1e-5, n     # 1 (previous) + 2 (this step)
+
+
 def test_cuda_graph_replay_equals_eager():
     O, B200SegModule = _mods()
     hcfg = O.HRNET_W16_TEST
@@ -185,7 +234,8 @@ def _condition_eval_weights(sd0):
 
 
 @pytest.mark.parametrize("arch,n_scales", [("ocrnet.HRNet_Mscale", None), ("ocrnet.HRNet_Mscale", [0.5, 1.0, 2.0]),
-                                           ("ocrnet.HRNet", None), ("basic.HRNet", None)])
+                                           ("ocrnet.HRNet", None), ("basic.HRNet", None),
+                                           ("mscale.HRNet", None), ("mscale.HRNet", [0.5, 1.0, 2.0])])
 def test_eval_forward_matches_oracle(arch, n_scales):
     """Eval mode (running-stat BN: no batch-statistics chaos) against the oracle with bf16-storage emulation: same dict
     keys as the reference (network/ocrnet.py:234-262,319-327), fp32 NCHW maps, argmax agreement."""
@@ -209,6 +259,9 @@ def test_eval_forward_matches_oracle(arch, n_scales):
         if arch == "ocrnet.HRNet_Mscale":
             ref = O.mscale_nscale(ctx, images.cuda(), n_scales, hcfg=hcfg) if n_scales else \
                 O.mscale_two_scale(ctx, images.cuda(), hcfg=hcfg)
+        elif arch == "mscale.HRNet":
+            ref = O.mscale_basic_nscale(ctx, images.cuda(), n_scales, hcfg=hcfg) if n_scales else \
+                O.mscale_basic_two_scale(ctx, images.cuda(), hcfg=hcfg)
         elif arch == "ocrnet.HRNet":
             ref = O.ocrnet_forward(ctx, images.cuda(), hcfg=hcfg)
         else:

@@ -81,3 +81,35 @@ for a, b, n in busiest:
 print("kernels on the busiest stream:")
 for n, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
     print("  %-48s n=%5d total %8.3f ms" % (n, c, d / 1e6))
+
+# union coverage per kernel class: share of the step during which at least one kernel of the class is in flight, and the
+# summed durations (a class whose union ~ its sum runs serialised; a sum far above the union overlaps with itself)
+def union(iv):
+    iv = sorted(iv)
+    tot, cur_a, cur_b = 0, None, None
+    for a, b in iv:
+        if cur_b is None or a > cur_b:
+            if cur_b is not None:
+                tot += cur_b - cur_a
+            cur_a, cur_b = a, b
+        else:
+            cur_b = max(cur_b, b)
+    if cur_b is not None:
+        tot += cur_b - cur_a
+    return tot
+
+
+classes = {"tensor-core conv (halo/igemm/wgrad)": ("conv3x3_halo", "conv_igemm", "wgrad_igemm"),
+           "wgrad_reduce": ("wgrad_reduce",), "batchnorm": ("bn_",), "resample/fuse": ("fuse_fwd", "upsample", "masked_accum"),
+           "everything": ("",)}
+print("%-40s %8s %10s %10s" % ("class", "kernels", "sum ms", "union ms"))
+for cname, keys in classes.items():
+    iv = [(a, b) for _, a, b, n in ev if any(k in n for k in keys)]
+    print("%-40s %8d %10.3f %10.3f" % (cname, len(iv), sum(b - a for a, b in iv) / 1e6, union(iv) / 1e6))
+byname = defaultdict(lambda: [0, 0])
+for _, a, b, n in ev:
+    byname[n][0] += 1
+    byname[n][1] += b - a
+print("per kernel (all streams):")
+for n, (c, d) in sorted(byname.items(), key=lambda kv: -kv[1][1])[:16]:
+    print("  %-48s n=%5d total %8.3f ms avg %6.1f us" % (n, c, d / 1e6, d / c / 1e3))
