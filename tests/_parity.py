@@ -103,20 +103,28 @@ def noise_floor(O, arch, hcfg, sd0, images, gts, sd_ref, sup_wt=0.0, crit=None):
     return floor, run
 
 
-def check_against_floor(rep, floor, run_rep, run_floor, slack=2.0, abs_slack=0.1, med_slack=1.25):
-    """rep / floor: name -> (cos, rel[, norm]). Returns a list of violations (empty = pass)."""
-    bad = []
+def check_against_floor(rep, floor, run_rep, run_floor, slack=2.0, abs_slack=0.1, med_slack=1.25, outliers=0.02):
+    """rep / floor: name -> (cos, rel[, norm]). Criteria: the median relative distance to the oracle stays within
+    med_slack of the floor's median; per tensor rel <= slack * floor + abs_slack for all but a fraction `outliers` of the
+    tensors (gate-flip noise is lumpy for small tensors: a 2-sigma tensor is expected among hundreds) and never beyond
+    1.6 (= anti-correlated). Returns (violations, summary); empty violations = pass."""
+    bad, over = [], []
     names = [n for n in rep if n in floor]
     assert len(names) >= 0.9 * len(rep)
     for n in names:
-        if rep[n][1] > slack * floor[n][1] + abs_slack:
-            bad.append(("grad", n, rep[n][1], floor[n][1]))
+        if rep[n][1] > 1.6 and rep[n][1] > slack * floor[n][1] + abs_slack:
+            bad.append(("grad-hard", n, rep[n][1], floor[n][1]))
+        elif rep[n][1] > slack * floor[n][1] + abs_slack:
+            over.append(("grad", n, rep[n][1], floor[n][1]))
+    if len(over) > max(1, int(outliers * len(names))):
+        bad.extend(over)
     med = lambda xs: sorted(xs)[len(xs) // 2]
     m_po, m_fl = med([rep[n][1] for n in names]), med([floor[n][1] for n in names])
     if m_po > med_slack * m_fl + 0.02:
         bad.append(("grad-median", "", m_po, m_fl))
-    for k, v in run_rep.items():
-        if v > slack * run_floor.get(k, 0.0) + 2e-2:
-            bad.append(("running", k, v, run_floor.get(k)))
-    return bad, dict(median_rel=m_po, median_rel_floor=m_fl,
+    run_over = [("running", k, v, run_floor.get(k)) for k, v in run_rep.items()
+                if v > slack * run_floor.get(k, 0.0) + 2e-2]
+    if len(run_over) > max(1, int(outliers * max(1, len(run_rep)))):
+        bad.extend(run_over)
+    return bad, dict(median_rel=m_po, median_rel_floor=m_fl, outliers=len(over), running_outliers=len(run_over),
                      median_cos=med([rep[n][0] for n in names]), median_cos_floor=med([floor[n][0] for n in names]))
