@@ -17,6 +17,7 @@ def _worker(rank, world, port, use_graph, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")     # no lazy kernel loading while a GPU spins on its peer
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method="env://", rank=rank, world_size=world)
     from oracle import seg_oracle as O
@@ -105,7 +106,7 @@ def test_two_gpu_data_parallel_gradients_are_the_rank_mean(tmp_path):
     mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
     res = torch.load(out)
     assert res["rel"] <= 1e-5, res               # same kernels on the same data; only the all-reduce's sum order differs
-    assert res["loss"] == res["loss_single"], res
+    assert abs(res["loss"] - res["loss_single"]) <= 1e-6 * abs(res["loss_single"]), res
 
 
 @pytest.mark.timeout(420)
