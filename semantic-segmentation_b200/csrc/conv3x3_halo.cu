@@ -39,12 +39,14 @@ struct HaloParams {
   int b_tile_bytes;            // BN * 128 rounded to 1024
   int acc_stride, tmem_cols;   // TMEM: two accumulator buffers of acc_stride = pow2 >= BN columns (tmem_cols = 2 * acc_stride)
   int dbg;                     // B200SEG_DBG=8: block 0 records a per-role ns timeline behind the statistics partials
+  int stage_bytes;             // FAST epilogue: two 16 KB output staging tiles behind the operand buffers, else 0
 };
 
 constexpr int kHThreads = 384;
 constexpr int kASlotBytes = 24576;     // 180 halo rows x 128 B = 23040, padded to a 1024 multiple
 constexpr int kHaloW = 10, kHaloH = 18, kTW = 8, kTH = 16;
 constexpr int kMaxASlots = 4, kMaxBSlots2 = 8;
+constexpr int kStageTile = 128 * 128;  // 128 output pixels x 128 B (64 bf16 channels), SWIZZLE_128B like the operand tiles
 
 // Sum v[0..15] over the 32 lanes of the warp: afterwards v[0] holds the total for channel (lane & 15).
 __device__ __forceinline__ void h_butterfly16(float (&v)[16], uint32_t lane) {
@@ -92,17 +94,25 @@ __device__ __forceinline__ void halo_issue9(uint32_t d_tmem, uint64_t adesc, uin
   }
 }
 
-template <int OCC>     // CTAs per SM the register budget allows: 2 -> 80 registers (co-resident narrow tiles), 1 -> 168
+// OCC: CTAs per SM the register budget allows: 2 -> 80 registers (co-resident narrow tiles), 1 -> full register file.
+// FAST (narrow layers: one Cout tile of at most 64 channels, the HBM-bound ones; OCC = 1 only): the epilogue
+//   * stages the bf16 tile in shared memory (swizzled, conflict-free 16-byte stores) and writes it with ONE TMA store per
+//     tile (coalesced, clipped at the image edge by the tensor map) instead of 32-byte pieces at a 96-byte pitch per thread;
+//   * keeps the batch statistics of its pixel slot in registers across all tiles of the persistent CTA and reduces them
+//     across the warp ONCE at the end (two 16-way butterflies per 16 channels per TILE were ~1/2 of the epilogue time).
+template <int OCC, bool FAST>
 __global__ void __launch_bounds__(kHThreads, OCC)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const HaloParams p, __nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
-                    float* __restrict__ stats_partials, const __nv_bfloat16* __restrict__ addend) {
+                    const __grid_constant__ CUtensorMap tmY, const HaloParams p, __nv_bfloat16* __restrict__ y,
+                    const float* __restrict__ bias, float* __restrict__ stats_partials,
+                    const __nv_bfloat16* __restrict__ addend) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_base = smem;
   uint8_t* b_base = smem + (size_t)p.a_slots * kASlotBytes;
   const int b_tiles_total = p.resident ? 9 * p.cchunks : p.b_slots;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)b_tiles_total * p.b_tile_bytes);
+  uint8_t* stage_base = b_base + (size_t)b_tiles_total * p.b_tile_bytes;      // 1024-aligned (all tiles are)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + p.stage_bytes);
   uint64_t* a_full = bars;                         // [kMaxASlots]
   uint64_t* a_empty = bars + kMaxASlots;
   uint64_t* b_full = bars + 2 * kMaxASlots;        // [kMaxBSlots2] (resident: only [0])
@@ -113,7 +123,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [4 lane quarters][2][cout_pad]
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (FAST) tma_prefetch_desc(&tmY);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kMaxBSlots2; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -238,6 +252,94 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ch_begin = half ? (nchunks + 1) / 2 : 0;
     const int ch_end = half ? nchunks : (nchunks + 1) / 2;
     int it = 0;
+    if constexpr (FAST) {
+      // n_tiles == 1, BN <= 64: this warp owns 16-column groups {2*half, 2*half+1} of its 32 pixels
+      float acc1[2][16], acc2[2][16];
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { acc1[k][j] = 0.f; acc2[k][j] = 0.f; }
+      const bool issuer = (warp == 4) && (lane == 0);
+      const uint32_t sw = (uint32_t)m & 7u;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const int tw_i = tile % p.tiles_w;
+        const int th_i = (tile / p.tiles_w) % p.tiles_h;
+        const int img = tile / (p.tiles_w * p.tiles_h);
+        const int ho = th_i * kTH + th, wo = tw_i * kTW + tw;
+        const bool valid = (ho < p.H) && (wo < p.W);
+        const size_t pix = ((size_t)img * p.H + ho) * p.W + wo;
+        uint8_t* srow = stage_base + (size_t)as * kStageTile + (size_t)m * 128;
+        mbar_wait(&tfull[as], (it >> 1) & 1);
+        tc_fence_after();
+        if (warp == 4 && lane == 0) DBG_TS(3, it);
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * p.acc_stride;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c0 = ((int)half * 2 + k) * 16;
+          if (c0 < p.BN) {                        // warp-uniform
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.has_bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.Cout) ? __ldg(bias + c0 + j) : 0.f;
+            }
+            if (addend != nullptr && valid && c0 + 16 <= p.Cout) {
+              const __nv_bfloat16* ap = addend + pix * p.addend_ld + c0;
+              float a0[8], a1[8];
+              load8(ap, a0);
+              load8(ap + 8, a1);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            const uint32_t lc = (uint32_t)c0 >> 3;               // logical 16-byte chunk inside the 128-byte pixel row
+            st_shared_v4(srow + ((lc ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(srow + (((lc + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+            if (p.emit_stats && valid) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
+                acc1[k][2 * j] += lo;          acc1[k][2 * j + 1] += hi;
+                acc2[k][2 * j] += lo * lo;     acc2[k][2 * j + 1] += hi * hi;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);       // the accumulator buffer is free: the next tile's MMAs may start
+        fence_proxy_async();                            // my st.shared -> visible to the TMA (async proxy)
+        if (issuer) tma_store_wait_read<0>();           // the previous tile's store has drained the OTHER staging buffer
+        named_barrier_sync(1, 256);
+        if (issuer) {
+          tma_store_4d(&tmY, stage_base + (size_t)as * kStageTile, 0, tw_i * kTW, th_i * kTH, img);
+          tma_store_commit();
+          DBG_TS(4, it);
+        }
+      }
+      if (issuer) tma_store_wait_all<0>();
+      if (p.emit_stats) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c0 = ((int)half * 2 + k) * 16;
+          if (c0 < p.BN) {
+            h_butterfly16(acc1[k], lane);
+            h_butterfly16(acc2[k], lane);
+            if (lane < 16) {
+              my_stats[c0 + lane] += acc1[k][0];
+              my_stats[p.cout_pad + c0 + lane] += acc2[k][0];
+            }
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
@@ -350,11 +452,13 @@ constexpr size_t kHalfSmBudget = 115712;   // (228 KB - 2 x 1 KB reserved) / 2
 
 // Shared-memory layout of a CTA for a given Cout tile: returns the CTAs per SM it allows (2, 1, or 0 = does not fit).
 struct HaloSmem { int resident, a_slots, b_slots; size_t bytes; };
-static int halo_smem_layout(int BN, int n_tiles, int cchunks, int cout_pad, HaloSmem& L) {
+static int halo_smem_layout(int BN, int n_tiles, int cchunks, int cout_pad, HaloSmem& L, int stage_bytes = 0) {
   const size_t b_tile = (size_t)(BN * 128 + 1023) / 1024 * 1024;
-  const size_t fixed = 1024 + (2 * kMaxASlots + 2 * kMaxBSlots2 + 4) * 8 + 16 + (size_t)4 * 2 * cout_pad * 4;
+  const size_t fixed = 1024 + (2 * kMaxASlots + 2 * kMaxBSlots2 + 4) * 8 + 16 + (size_t)4 * 2 * cout_pad * 4 +
+                       (size_t)stage_bytes;
   const size_t resident_bytes = (size_t)9 * cchunks * b_tile;
-  for (int occ = (halo_coresident_enabled() && BN <= 128) ? 2 : 1; occ >= 1; --occ) {
+  // the staged epilogue (stage_bytes != 0) is built for one CTA per SM only
+  for (int occ = (halo_coresident_enabled() && BN <= 128 && stage_bytes == 0) ? 2 : 1; occ >= 1; --occ) {
     const size_t budget = (occ == 2 ? kHalfSmBudget : (size_t)227 * 1024) - fixed;
     if (n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) {
       const int as_ = (int)((budget - resident_bytes) / kASlotBytes);
@@ -417,9 +521,14 @@ static int halo_plan(int n, int h, int w, int cin, int cout, HaloParams& p, size
   p.b_tile_bytes = (p.BN * 128 + 1023) / 1024 * 1024;
   p.acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
   p.tmem_cols = 2 * p.acc_stride;
+  // staged TMA-store epilogue with register-resident statistics for the narrow (HBM-bound) layers; B200SEG_HALO_FAST=0
+  // switches it off (A/B measurements). It needs the full register file, so it runs one CTA per SM.
+  static const bool fast_enabled = []() { const char* e = getenv("B200SEG_HALO_FAST"); return !(e && e[0] == '0'); }();
+  const bool fast = fast_enabled && p.n_tiles == 1 && p.BN <= 64;
+  p.stage_bytes = fast ? 2 * kStageTile : 0;
   { const char* e = getenv("B200SEG_DBG"); p.dbg = e ? atoi(e) : 0; }
   HaloSmem L;
-  occ = halo_smem_layout(p.BN, p.n_tiles, p.cchunks, p.cout_pad, L);
+  occ = halo_smem_layout(p.BN, p.n_tiles, p.cchunks, p.cout_pad, L, p.stage_bytes);
   if (occ >= 1) { p.resident = L.resident; p.a_slots = L.a_slots; p.b_slots = L.b_slots; smem_bytes = L.bytes; }
   if (occ < 1) return B200SEG_E_BADARG;
   // one CTA per SM unless the co-resident configuration was chosen (occupancy is bounded by shared memory and registers)
@@ -454,13 +563,22 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(wts) & 15) ||
       (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15) || (addend && addend_ld % 8))
     return B200SEG_E_BADARG;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmY;
   {
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     uint64_t strides[3] = {(uint64_t)in_ld * 2, (uint64_t)w * in_ld * 2, (uint64_t)h * w * in_ld * 2};
     uint32_t box[4] = {64, (uint32_t)kHaloW, (uint32_t)kHaloH, 1};
     int rc = encode_bf16(&tmA, in, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+  }
+  if (p.stage_bytes) {   // output tile: 64 channels x 8 x 16 pixels, clipped to [cout, w, h] by the tensor map
+    uint64_t dims[4] = {(uint64_t)cout, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    uint64_t strides[3] = {(uint64_t)out_ld * 2, (uint64_t)w * out_ld * 2, (uint64_t)h * w * out_ld * 2};
+    uint32_t box[4] = {64, (uint32_t)kTW, (uint32_t)kTH, 1};
+    int rc = encode_bf16(&tmY, out, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else {
+    tmY = tmA;   // unused
   }
   {
     uint64_t dims[3] = {(uint64_t)cin, 9, (uint64_t)cout};
@@ -471,20 +589,24 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
     if (e != cudaSuccess) return (int)e;
     // two CTAs per SM need (almost) the whole 228 KB as shared memory: ask for the maximum carve-out explicitly
-    e = cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   cudaError_t e =
-      occ == 2 ? launch_k(conv3x3_halo_kernel<2>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, p,
-                          (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend)
-               : launch_k(conv3x3_halo_kernel<1>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, p,
-                          (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend);
+      p.stage_bytes ? launch_k(conv3x3_halo_kernel<1, true>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, tmY, p,
+                               (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend)
+      : occ == 2    ? launch_k(conv3x3_halo_kernel<2, false>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, tmY, p,
+                               (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend)
+                    : launch_k(conv3x3_halo_kernel<1, false>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, tmY, p,
+                               (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -494,12 +616,12 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
 int conv_igemm_occupancy(int occ_variant, int smem_bytes);
 int conv3x3_halo_occupancy(int occ_variant, int smem_bytes) {
   int nb = -1;
-  cudaFuncSetAttribute(conv3x3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
-  cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(conv3x3_halo_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv3x3_halo_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmBudget);
+  cudaFuncSetAttribute(conv3x3_halo_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaError_t e = occ_variant == 2
-      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv3x3_halo_kernel<2>, kHThreads, (size_t)smem_bytes)
-      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv3x3_halo_kernel<1>, kHThreads, (size_t)smem_bytes);
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv3x3_halo_kernel<2, false>, kHThreads, (size_t)smem_bytes)
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv3x3_halo_kernel<1, false>, kHThreads, (size_t)smem_bytes);
   return e == cudaSuccess ? nb : -(int)e;
 }
 
@@ -531,8 +653,8 @@ extern "C" void b200seg_debug_occupancy_report(void) {
          pr.regsPerBlock, pr.sharedMemPerMultiprocessor, pr.sharedMemPerBlockOptin, pr.reservedSharedMemPerBlock,
          pr.maxBlocksPerMultiProcessor, pr.maxThreadsPerMultiProcessor);
   b200seg::conv3x3_halo_occupancy(2, 1024);     // sets the attributes of both builds
-  b200seg::occupancy_report_one("conv3x3_halo_kernel<2>", b200seg::conv3x3_halo_kernel<2>, b200seg::kHThreads);
-  b200seg::occupancy_report_one("conv3x3_halo_kernel<1>", b200seg::conv3x3_halo_kernel<1>, b200seg::kHThreads);
+  b200seg::occupancy_report_one("conv3x3_halo_kernel<2>", b200seg::conv3x3_halo_kernel<2, false>, b200seg::kHThreads);
+  b200seg::occupancy_report_one("conv3x3_halo_kernel<1>", b200seg::conv3x3_halo_kernel<1, false>, b200seg::kHThreads);
   b200seg::conv_igemm_occupancy_report();
   fflush(stdout);
 }
