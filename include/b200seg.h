@@ -72,6 +72,31 @@ size_t b200seg_conv2d_stats_elems(const b200seg_conv_desc* d);
 int b200seg_conv2d_fwd(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias, void* y,
                        float* stats_partials, int32_t* stats_grid, void* stream);
 
+/* The same convolution with the training-mode BatchNorm statistics FINALISED inside the launch (no partial table, no
+ * bn_finalize launch): every CTA adds its per-channel sums to `accum` (fp64), the last CTA to finish writes
+ * scale / shift / mean / invstd (and the batch statistics / running statistics exactly like b200seg_bn_finalize) and
+ * clears `accum` / `counter` again. accum: [2][roundup16(cout)] fp64 and counter: uint32, both owned by the caller,
+ * zero before the first use and private to one (layer, scale pass) - launches that share them must be stream ordered.
+ * Per-GPU statistics only (SyncBN uses b200seg_conv2d_fwd + b200seg_bn_finalize, whose exchange needs its own kernel). */
+typedef struct b200seg_bn_fold {
+  double* accum;
+  uint32_t* counter;
+  const float* gamma;            /* may be NULL (1) */
+  const float* beta;             /* may be NULL (0) */
+  float* scale;
+  float* shift;
+  float* mean;
+  float* invstd;
+  float* batch_stats_out;        /* [2*c] = [mean | unbiased var] or NULL */
+  float* running_mean;           /* NULL with batch_stats_out (deferred b200seg_bn_running_update) */
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float eps, momentum, count;    /* count = n * ho * wo */
+  int32_t c;
+} b200seg_bn_fold;
+int b200seg_conv2d_fwd_bn(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias, void* y,
+                          const b200seg_bn_fold* fold, void* stream);
+
 /* Slow, obviously-correct CUDA-core direct convolution with identical numerics contract (fp32 accumulate, one rounding).
  * Used by the GPU test-suite as an on-device cross-check and for shapes the GEMM path does not take. */
 int b200seg_conv2d_fwd_direct(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
@@ -222,6 +247,13 @@ int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* mask, int32
 /* dgamma += sum g*xhat, dbeta += sum g (accumulating), c1 = sum g / count, c2 = sum g*xhat / count */
 int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int32_t c, float count, float* dgamma, float* dbeta,
                             float* c1, float* c2, const b200seg_bn_sync* sync, void* stream);
+/* bn_bwd_reduce with the finalisation folded into the launch (per-GPU statistics; csrc/bn_fold.cuh pattern): CTAs add
+ * their sums to accum ([2][c] fp64, zero between launches, private to one layer and scale pass), the last CTA adds
+ * dgamma / dbeta, writes c1 = sum(g)/npix, c2 = sum(g*xhat)/npix and clears accum / counter. */
+int b200seg_bn_bwd_reduce_finalize(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld,
+                                   const float* post_scale, const void* y, int32_t y_ld, const float* mean,
+                                   const float* invstd, int64_t npix, int32_t hw, int32_t c, double* accum,
+                                   uint32_t* counter, float* dgamma, float* dbeta, float* c1, float* c2, void* stream);
 /* dy = gamma*invstd*(g - c1 - xhat*c2); optionally g_out (=|+=) g for the residual / identity branch */
 int b200seg_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld, const float* post_scale,
                          const void* y, int32_t y_ld, const float* mean, const float* invstd, const float* gamma,

@@ -46,6 +46,14 @@ class BnSync(ctypes.Structure):
                 ("reserved", c_int32), ("beacon", c_void_p)]
 
 
+class BnFold(ctypes.Structure):
+    _fields_ = [("accum", c_void_p), ("counter", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+                ("scale", c_void_p), ("shift", c_void_p), ("mean", c_void_p), ("invstd", c_void_p),
+                ("batch_stats_out", c_void_p), ("running_mean", c_void_p), ("running_var", c_void_p),
+                ("num_batches_tracked", c_void_p), ("eps", c_float), ("momentum", c_float), ("count", c_float),
+                ("c", c_int32)]
+
+
 class ProbeOperand(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "rows", "cols", "box_cols", "box_rows", "nboxes", "c0", "r0", "dcol", "drow", "smem_stride",
@@ -69,6 +77,7 @@ SIGNATURES = {
     "b200seg_debug_occupancy": (c_int32, [c_int32, c_int32, c_int32]),
     "b200seg_debug_occupancy_report": (None, []),
     "b200seg_conv2d_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V, P32, V]),
+    "b200seg_conv2d_fwd_bn": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, ctypes.POINTER(BnFold), V]),
     "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
     "b200seg_pack_weight": (ctypes.c_int, [V, I32, I32, I32, V, V, I32, V]),
     "b200seg_pack_chunk": (I32, []),
@@ -95,6 +104,8 @@ SIGNATURES = {
     "b200seg_bn_bwd_grid": (I32, [I64, I32]),
     "b200seg_bn_bwd_reduce": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, I64, I32, I32, V, V]),
     "b200seg_bn_bwd_finalize": (ctypes.c_int, [V, I32, I32, F, V, V, V, V, ctypes.POINTER(BnSync), V]),
+    "b200seg_bn_bwd_reduce_finalize": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, I64, I32, I32, V, V, V, V, V, V,
+                                                      V]),
     "b200seg_bn_bwd_apply": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, V, V, V, V, I32, V, I32, I32, I64, I32,
                                             I32, V]),
     "b200seg_masked_accum": (ctypes.c_int, [V, I32, V, I32, V, I32, I32, I64, I32, V]),

@@ -44,7 +44,7 @@ class HeadRec:
 
 class Engine:
     def __init__(self, params, grads, packed, training, drop_mask=None, side_stream=None, bstat=None, stream=None,
-                 sync=None, pass_id=0, branch_streams=None, ws_holder=None):
+                 sync=None, pass_id=0, branch_streams=None, ws_holder=None, bnfold=None):
         """params: name -> tensor (weights, BN buffers); grads: name -> fp32 tensor accumulated into (training);
         packed: name -> (w_fwd, w_dgrad) bf16 operand caches; drop_mask: fp32 [N, mid] post-ReLU multiplier;
         bstat: BN layer name -> fp32 [2*C] slot receiving the batch [mean | unbiased var] (the running statistics are
@@ -52,6 +52,8 @@ class Engine:
         stream: the stream this engine's program is enqueued on when it runs concurrently with another engine (the
         low-resolution pass of the two-scale step), None = the caller's current stream;
         sync / pass_id: SyncBNContext (p2p.py) and this engine's pass index in its exchange table (data parallel);
+        bnfold: BN layer name -> (fp64 accumulator, int32 ticket) cells: the BatchNorm statistics are finalised inside
+        the convolution launch (raw.conv2d_fwd_bn) instead of by a bn_finalize launch (per-GPU statistics only);
         branch_streams: up to three extra streams for the parallel branches of a HighResolutionModule (branch 0 stays
         on the engine's own stream); ws_holder: reusable weight-gradient slab workspace of the side stream."""
         self.p = params
@@ -65,6 +67,7 @@ class Engine:
         self.pass_id = pass_id
         self.bstreams = list(branch_streams or [])
         self.ws_holder = ws_holder
+        self.bnfold = bnfold if sync is None else None
         self._ctx = None         # stream of the branch section being recorded (None = the engine's own stream)
         self.pre_backward_event = None   # e.g. "data-gradient weight operands packed" (recorded on another stream)
         self.tape = []
@@ -173,7 +176,19 @@ class Engine:
         rec.x, rec.cname, rec.bname, rec.ksize, rec.stride, rec.has_bias = x, cname, bname, ksize, stride, bias
         rec.cout = w_f.shape[0]
         b = self.p[cname + ".bias"] if bias else None
-        if self.training:
+        if self.training and self.bnfold is not None:
+            acc, ticket = self.bnfold[bname]
+            if self.bstat is not None:
+                self.bn_seen.add(bname)
+                y, par = raw.conv2d_fwd_bn(x.t, w_f, b, stride, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
+                                           BN_MOMENTUM, acc, ticket, batch_out=self.bstat[bname])
+            else:
+                y, par = raw.conv2d_fwd_bn(x.t, w_f, b, stride, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
+                                           BN_MOMENTUM, acc, ticket, running_mean=self.p[bname + ".running_mean"],
+                                           running_var=self.p[bname + ".running_var"],
+                                           nbt=self.p[bname + ".num_batches_tracked"])
+            rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], par[2], par[3]
+        elif self.training:
             y, stats = raw.conv2d_fwd(x.t, w_f, b, stride=stride, emit_stats=True)
             n, ho, wo, _ = y.shape
             if self.bstat is not None:
@@ -201,7 +216,8 @@ class Engine:
         """Backward of BN(conv(x)) given the gradient w.r.t. the BN output (dz, optionally ReLU-masked by `mask`)."""
         dy = raw.bn_bwd(dz, mask, post_scale, rec.y, rec.mean, rec.invstd, self.p[rec.bname + ".weight"],
                         self.g[rec.bname + ".weight"], self.g[rec.bname + ".bias"], g_out=g_out,
-                        g_accumulate=g_accumulate, sync=self._sync(rec.bname, 1))
+                        g_accumulate=g_accumulate, sync=self._sync(rec.bname, 1),
+                        fold=self.bnfold[rec.bname] if self.bnfold is not None else None)
         x = rec.x
         self.wgrad(x.t, dy, self.g[rec.cname + ".weight"], rec.cout, rec.ksize, rec.stride)
         # a conv bias in front of a training-mode BN has an exactly zero gradient (BN removes the mean): left at 0

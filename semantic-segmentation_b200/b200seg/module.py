@@ -100,6 +100,10 @@ class B200SegModule(nn.Module):
         # NVLink peer memory (needs torch.distributed, world > 1); None / False = per-GPU statistics. Opt-in for now: the
         # exchange was validated on 2 GPUs only.
         self.syncbn = syncbn
+        # BatchNorm statistics finalised inside the convolution launch (csrc/bn_fold.cuh); B200SEG_FUSED_BN=0 restores the
+        # separate bn_finalize launches (A/B measurements); SyncBN always uses the separate finaliser (its exchange)
+        import os
+        self.fused_bn_finalize = os.environ.get("B200SEG_FUSED_BN", "1") != "0"
         self._sync = None
         self._run_flat = None
         self._specs = A.tensor_specs(arch, self.hcfg, self.ocfg)
@@ -264,6 +268,19 @@ class B200SegModule(nn.Module):
                 self._bn_slots[b] = (off, c)
                 off += 2 * c
         self._run_flat, self._nbt_flat = flat, nbt_flat
+        # self-clearing reduction cells of the in-launch BatchNorm finalisation (raw.conv2d_fwd_bn), one set per pass
+        self._bnfold = []
+        for _pass in range(2):
+            cells = {}
+            acc = torch.zeros(sum(2 * ((c_ + 15) // 16 * 16) for _o, c_ in self._bn_slots.values()), dtype=torch.float64,
+                              device=dev)
+            tickets = torch.zeros(len(self._bn_slots), dtype=torch.int32, device=dev)
+            o = 0
+            for li, (b, (_o, c_)) in enumerate(self._bn_slots.items()):
+                cp = (c_ + 15) // 16 * 16
+                cells[b] = (acc[o:o + 2 * cp], tickets[li:li + 1])
+                o += 2 * cp
+            self._bnfold.append(cells)
         self._bstat = [torch.zeros(total, dtype=F32, device=dev) for _ in range(2)]
         self._bstat_views = [{b: t[o_:o_ + 2 * c_] for b, (o_, c_) in self._bn_slots.items()} for t in self._bstat]
         self._graphs = {}
@@ -347,13 +364,15 @@ class B200SegModule(nn.Module):
             grads_lo = self._engine_grads("lo")
             E_lo = Engine(tensors, grads_lo, self._packed, True, drop_mask, side_stream=self._side_stream_lo,
                           bstat=self._bstat_views[0], stream=self._lo_stream, sync=sync, pass_id=0,
-                          branch_streams=self._bstreams["lo"], ws_holder=self._ws_holders["lo"])
+                          branch_streams=self._bstreams["lo"], ws_holder=self._ws_holders["lo"],
+                          bnfold=self._bnfold[0] if self.fused_bn_finalize else None)
         two_pass = A.is_two_scale(self.arch)
         if sync is not None and two_pass and not par:
             raise RuntimeError("SyncBN needs parallel_scales=True for the two-scale step (one engine per pass)")
         E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream,
                    bstat=self._bstat_views[1] if par else None, sync=sync, pass_id=1 if two_pass else 0,
-                   branch_streams=self._bstreams["hi"], ws_holder=self._ws_holders["hi"])
+                   branch_streams=self._bstreams["hi"], ws_holder=self._ws_holders["hi"],
+                   bnfold=self._bnfold[1] if self.fused_bn_finalize else None)
         loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,
                             self.ignore_index, E_lo=E_lo, loss_kind=self.loss_kind)
         E.pre_backward_event = wd_ready

@@ -279,12 +279,22 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+struct BnBwdFold {          // in-launch finalisation of bn_bwd_reduce (accum == nullptr: partial table + bn_bwd_finalize)
+  double* accum;            // [2][C] fp64, zero between launches
+  unsigned* counter;
+  float* dgamma;
+  float* dbeta;
+  float* c1;
+  float* c2;
+  float count;
+};
+
 // Thread (r, cg): r-th pixel row of the block, 8-channel group cg. blockDim.x = groups * rows.
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv_bfloat16* __restrict__ mask,
                      int mask_ld, const float* __restrict__ post_scale, const __nv_bfloat16* __restrict__ y, int y_ld,
                      const float* __restrict__ mean, const float* __restrict__ invstd, long long npix, int hw, int C,
-                     int rows, float* __restrict__ partials) {
+                     int rows, float* __restrict__ partials, const BnBwdFold fold) {
   pdl_sync();
   extern __shared__ float s_red[];   // [rows][groups][16]
   const int groups = C >> 3;
@@ -326,8 +336,29 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv
     float acc = 0.f;
     for (int rr = 0; rr < rows; ++rr) acc += s_red[((size_t)rr * groups + g_) * 16 + k];
     const int c = g_ * 8 + (k & 7);
-    partials[(size_t)blockIdx.x * 2 * C + (k >> 3) * C + c] = acc;
+    if (fold.accum != nullptr) atomicAdd(fold.accum + (k >> 3) * C + c, (double)acc);
+    else partials[(size_t)blockIdx.x * 2 * C + (k >> 3) * C + c] = acc;
   }
+  if (fold.accum == nullptr) return;
+  // In-launch finalisation (per-GPU statistics): the last CTA to finish turns the fp64 totals into dgamma / dbeta
+  // (accumulated) and the two mean terms of the input gradient, and clears the cells (see bn_fold.cuh for the pattern).
+  __shared__ unsigned s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(fold.counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double s1 = __ldcg(fold.accum + c), s2 = __ldcg(fold.accum + C + c);
+    fold.accum[c] = 0.0;
+    fold.accum[C + c] = 0.0;
+    if (fold.dbeta) fold.dbeta[c] += (float)s1;
+    if (fold.dgamma) fold.dgamma[c] += (float)s2;
+    fold.c1[c] = (float)(s1 / (double)fold.count);
+    fold.c2[c] = (float)(s2 / (double)fold.count);
+  }
+  if (threadIdx.x == 0) *fold.counter = 0u;
 }
 
 __global__ void __launch_bounds__(32 * kFinSlices)
@@ -543,11 +574,11 @@ extern "C" int32_t b200seg_bn_bwd_grid(int64_t npix, int32_t c) {
   return (int32_t)(b < cap ? b : cap);
 }
 
-extern "C" int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld,
-                                     const float* post_scale, const void* y, int32_t y_ld, const float* mean,
-                                     const float* invstd, int64_t npix, int32_t hw, int32_t c, float* partials,
-                                     void* stream) {
-  if (!dz || !y || !mean || !invstd || !partials || c % 8 || c > 2048) return B200SEG_E_BADARG;
+static int bn_bwd_reduce_launch(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld,
+                                const float* post_scale, const void* y, int32_t y_ld, const float* mean,
+                                const float* invstd, int64_t npix, int32_t hw, int32_t c, float* partials,
+                                const BnBwdFold& fold, void* stream) {
+  if (!dz || !y || !mean || !invstd || (!partials && !fold.accum) || c % 8 || c > 2048) return B200SEG_E_BADARG;
   int rows, threads;
   reduce_shape(c, &rows, &threads);
   if (threads > 256) return B200SEG_E_BADARG;
@@ -555,8 +586,31 @@ extern "C" int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* 
   const size_t smem = (size_t)rows * (c / 8) * 16 * sizeof(float);
   launch_k(bn_bwd_reduce_kernel, dim3(grid), dim3(threads), smem, (cudaStream_t)stream, (const __nv_bfloat16*)dz,
            dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y, y_ld, mean, invstd, npix,
-           hw, c, rows, partials);
+           hw, c, rows, partials, fold);
   CHECK_LAUNCH();
+}
+
+extern "C" int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld,
+                                     const float* post_scale, const void* y, int32_t y_ld, const float* mean,
+                                     const float* invstd, int64_t npix, int32_t hw, int32_t c, float* partials,
+                                     void* stream) {
+  BnBwdFold fold;
+  memset(&fold, 0, sizeof(fold));
+  return bn_bwd_reduce_launch(dz, dz_ld, mask, mask_ld, post_scale, y, y_ld, mean, invstd, npix, hw, c, partials, fold,
+                              stream);
+}
+
+extern "C" int b200seg_bn_bwd_reduce_finalize(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld,
+                                              const float* post_scale, const void* y, int32_t y_ld, const float* mean,
+                                              const float* invstd, int64_t npix, int32_t hw, int32_t c, double* accum,
+                                              uint32_t* counter, float* dgamma, float* dbeta, float* c1, float* c2,
+                                              void* stream) {
+  if (!accum || !counter || !c1 || !c2 || (reinterpret_cast<uintptr_t>(accum) & 7)) return B200SEG_E_BADARG;
+  BnBwdFold fold;
+  fold.accum = accum; fold.counter = counter; fold.dgamma = dgamma; fold.dbeta = dbeta; fold.c1 = c1; fold.c2 = c2;
+  fold.count = (float)npix;
+  return bn_bwd_reduce_launch(dz, dz_ld, mask, mask_ld, post_scale, y, y_ld, mean, invstd, npix, hw, c, nullptr, fold,
+                              stream);
 }
 
 extern "C" int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int32_t c, float count, float* dgamma,

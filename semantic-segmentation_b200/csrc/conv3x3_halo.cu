@@ -19,6 +19,7 @@
 // (Bottleneck), network/ocrnet.py:54-57 (conv3x3_ocr) and network/utils.py:348-356 (attention head).
 #include <cstdio>
 #include "ptx.cuh"
+#include "bn_fold.cuh"
 #include "tma_host.h"
 #include "launch.h"
 #include "../../include/b200seg.h"
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kHThreads, OCC)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const HaloParams p, __nv_bfloat16* __restrict__ y,
                     const float* __restrict__ bias, float* __restrict__ stats_partials,
-                    const __nv_bfloat16* __restrict__ addend) {
+                    const __nv_bfloat16* __restrict__ addend, const BnFoldDev fold) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_base = smem;
@@ -431,9 +432,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (p.emit_stats) {
-    float* out = stats_partials + (size_t)blockIdx.x * 2 * p.cout_pad;
-    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += kHThreads)
-      out[i] = (s_stats[i] + s_stats[2 * p.cout_pad + i]) + (s_stats[4 * p.cout_pad + i] + s_stats[6 * p.cout_pad + i]);
+    if (fold.accum != nullptr) {
+      bn_fold_tail(fold, s_stats, p.cout_pad, tmem_ptr_smem + 1);          // statistics finalised by the last CTA of this launch
+    } else {
+      float* out = stats_partials + (size_t)blockIdx.x * 2 * p.cout_pad;
+      for (int i = threadIdx.x; i < 2 * p.cout_pad; i += kHThreads)
+        out[i] = (s_stats[i] + s_stats[2 * p.cout_pad + i]) + (s_stats[4 * p.cout_pad + i] + s_stats[6 * p.cout_pad + i]);
+    }
   }
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
@@ -549,10 +554,15 @@ int conv3x3_halo_plan_info(int n, int h, int w, int cin, int cout, int32_t* out)
   return 0;
 }
 
+int make_bn_fold(const b200seg_bn_fold* f, int cout, BnFoldDev* out);
 int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
                         const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
-                        const void* addend, int addend_ld, int emit_stats, cudaStream_t stream) {
+                        const void* addend, int addend_ld, int emit_stats, cudaStream_t stream,
+                        const b200seg_bn_fold* fold) {
   if (in_ld % 8 || out_ld % 8) return B200SEG_E_BADARG;
+  BnFoldDev fd;
+  if (int frc = make_bn_fold(emit_stats ? fold : nullptr, cout, &fd)) return frc;
+  if (emit_stats && !stats_partials && !fold) return B200SEG_E_BADARG;
   HaloParams p;
   size_t smem_bytes;
   int grid, occ;
@@ -602,11 +612,11 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
   }
   cudaError_t e =
       p.stage_bytes ? launch_k(conv3x3_halo_kernel<1, true>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, tmY, p,
-                               (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend)
+                               (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend, fd)
       : occ == 2    ? launch_k(conv3x3_halo_kernel<2, false>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, tmY, p,
-                               (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend)
+                               (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend, fd)
                     : launch_k(conv3x3_halo_kernel<1, false>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, tmY, p,
-                               (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend);
+                               (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend, fd);
   return e == cudaSuccess ? 0 : (int)e;
 }
 

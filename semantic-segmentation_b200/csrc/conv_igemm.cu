@@ -16,12 +16,14 @@
 //               per TMEM lane quarter, half of the accumulator columns each).
 //   Launch:     programmatic dependent launch (launch.h): the prologue overlaps the previous kernel's tail.
 #include <cstdio>
+#include <cstring>
 #include "ptx.cuh"
 #include <cstdlib>
 #include "tma_host.h"
 #include "launch.h"
 #include "../../include/b200seg.h"
 #include "conv_common.h"
+#include "bn_fold.cuh"
 #include "vec.cuh"
 
 namespace b200seg {
@@ -64,7 +66,7 @@ template <int OCC>     // CTAs per SM the register budget allows (2: co-resident
 __global__ void __launch_bounds__(kThreads, OCC)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ConvKParams p, void* __restrict__ y, const float* __restrict__ bias,
-                  float* __restrict__ stats_partials, const __nv_bfloat16* __restrict__ addend) {
+                  float* __restrict__ stats_partials, const __nv_bfloat16* __restrict__ addend, const BnFoldDev fold) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A|B] (1024-aligned) | barriers | tmem ptr | stats[4][2][cout_pad]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -270,9 +272,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (p.emit_stats) {
-    float* out = stats_partials + (size_t)blockIdx.x * 2 * p.cout_pad;
-    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += kThreads) {
-      out[i] = (s_stats[i] + s_stats[2 * p.cout_pad + i]) + (s_stats[4 * p.cout_pad + i] + s_stats[6 * p.cout_pad + i]);
+    if (fold.accum != nullptr) {
+      bn_fold_tail(fold, s_stats, p.cout_pad, tmem_ptr_smem + 1);          // statistics finalised by the last CTA of this launch
+    } else {
+      float* out = stats_partials + (size_t)blockIdx.x * 2 * p.cout_pad;
+      for (int i = threadIdx.x; i < 2 * p.cout_pad; i += kThreads) {
+        out[i] = (s_stats[i] + s_stats[2 * p.cout_pad + i]) + (s_stats[4 * p.cout_pad + i] + s_stats[6 * p.cout_pad + i]);
+      }
     }
   }
   if (warp == 2) {
@@ -397,15 +403,33 @@ int conv_plan(const b200seg_conv_desc* d, ConvPlan* pl) {
   return plan_geom(fwd_geom(d), pl);
 }
 
+int make_bn_fold(const b200seg_bn_fold* f, int cout, BnFoldDev* out) {
+  BnFoldDev d;
+  memset(&d, 0, sizeof(d));
+  if (f) {
+    if (!f->accum || !f->counter || !f->scale || !f->shift || !f->mean || !f->invstd || f->c != cout || f->count <= 0.f ||
+        (reinterpret_cast<uintptr_t>(f->accum) & 7))
+      return B200SEG_E_BADARG;
+    d.accum = f->accum; d.counter = f->counter; d.gamma = f->gamma; d.beta = f->beta;
+    d.scale = f->scale; d.shift = f->shift; d.mean = f->mean; d.invstd = f->invstd; d.batch_out = f->batch_stats_out;
+    d.running_mean = f->running_mean; d.running_var = f->running_var; d.nbt = (long long*)f->num_batches_tracked;
+    d.eps = f->eps; d.momentum = f->momentum; d.count = f->count; d.C = f->c;
+  }
+  *out = d;
+  return 0;
+}
+
 static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const float* bias, void* out,
                        float* stats_partials, int32_t* stats_grid, const void* addend, int addend_ld,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const b200seg_bn_fold* fold = nullptr) {
   ConvPlan pl;
   int rc = plan_geom(g, &pl);
   if (rc) return rc;
   if (!a || !w || !out) return B200SEG_E_BADARG;
   if (g.has_bias && !bias) return B200SEG_E_BADARG;
-  if (g.emit_stats && (!stats_partials || g.out_fp32)) return B200SEG_E_BADARG;
+  if (g.emit_stats && ((!stats_partials && !fold) || g.out_fp32)) return B200SEG_E_BADARG;
+  BnFoldDev fd;
+  if (int frc = make_bn_fold(g.emit_stats ? fold : nullptr, g.out_c, &fd)) return frc;
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
       (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15))
     return B200SEG_E_BADARG;
@@ -457,9 +481,9 @@ static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const 
   if (stats_grid) *stats_grid = pl.grid;
   cudaError_t e =
       pl.occ == 2 ? launch_k(conv_igemm_kernel<2>, dim3(pl.grid), dim3(kThreads), pl.smem_bytes, stream, tmA, tmB, p, out,
-                             bias, stats_partials, (const __nv_bfloat16*)addend)
+                             bias, stats_partials, (const __nv_bfloat16*)addend, fd)
                   : launch_k(conv_igemm_kernel<1>, dim3(pl.grid), dim3(kThreads), pl.smem_bytes, stream, tmA, tmB, p, out,
-                             bias, stats_partials, (const __nv_bfloat16*)addend);
+                             bias, stats_partials, (const __nv_bfloat16*)addend, fd);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -489,7 +513,8 @@ void conv_igemm_occupancy_report() {
 
 int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
                         const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
-                        const void* addend, int addend_ld, int emit_stats, cudaStream_t stream);
+                        const void* addend, int addend_ld, int emit_stats, cudaStream_t stream,
+                        const b200seg_bn_fold* fold = nullptr);
 int conv3x3_halo_plan_info(int n, int h, int w, int cin, int cout, int32_t* out);
 
 }  // namespace b200seg
@@ -534,6 +559,15 @@ extern "C" int b200seg_conv2d_fwd(const b200seg_conv_desc* d, const void* x, con
                                d->y_ld, stats_partials, stats_grid, nullptr, 0, d->emit_stats, (cudaStream_t)stream);
   }
   return launch_geom(fwd_geom(d), x, w_ohwi, bias, y, stats_partials, stats_grid, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int b200seg_conv2d_fwd_bn(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
+                                     void* y, const b200seg_bn_fold* fold, void* stream) {
+  if (!desc_ok(d) || !fold || !d->emit_stats || d->out_fp32) return B200SEG_E_BADARG;
+  if (d->ksize == 3 && d->stride == 1 && d->cout % 16 == 0 && d->reserved == 0)
+    return conv3x3_halo_launch(d->n, d->h, d->w, d->cin, d->x_ld, x, d->cout, w_ohwi, d->has_bias ? bias : nullptr, y,
+                               d->y_ld, nullptr, nullptr, nullptr, 0, 1, (cudaStream_t)stream, fold);
+  return launch_geom(fwd_geom(d), x, w_ohwi, bias, y, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream, fold);
 }
 
 // Data gradient. d describes the FORWARD convolution. dx[n,h,w,cin] = sum_taps dy[...] * W  (+ addend).

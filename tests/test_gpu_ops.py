@@ -83,6 +83,54 @@ def test_conv_fwd_dgrad_wgrad(case):
         close(raw.ohwi_to_oihw(dw, k), 2 * wr.grad, 2e-3, "wgrad")
 
 
+@pytest.mark.parametrize("case", [(1, 64, 96, 48, 48, 3, 1, False), (2, 40, 72, 64, 64, 3, 1, False),
+                                  (1, 32, 64, 720, 512, 3, 1, True), (1, 32, 64, 96, 48, 1, 1, False),
+                                  (1, 64, 128, 48, 96, 3, 2, False), (1, 19, 1, 512, 256, 1, 1, False),
+                                  (1, 256, 512, 48, 48, 3, 1, False)])
+def test_conv_with_in_launch_bn_finalize(case):
+    """b200seg_conv2d_fwd_bn (statistics finalised by the last CTA, csrc/bn_fold.cuh) against the two-launch path
+    (conv2d_fwd partials + bn_finalize): same output bits, same scale / shift / mean / invstd / batch statistics /
+    running statistics, reduction cells left clean (three launches in a row share them), and against F.batch_norm."""
+    raw = _setup()
+    n, h, w, cin, cout, k, s, bias = case
+    x = rnd((n, h, w, cin), 1)
+    wt = rnd((cout, cin, k, k), 2, scale=(cin * k * k) ** -0.5, dtype=torch.float32).contiguous()
+    b = rnd((cout,), 3, dtype=torch.float32) if bias else None
+    gamma = 1.0 + 0.1 * rnd((cout,), 4, dtype=torch.float32)
+    beta = 0.1 * rnd((cout,), 5, dtype=torch.float32)
+    w_f, _ = raw.pack_weight(wt, want_dgrad=False)
+    y0, stats = raw.conv2d_fwd(x, w_f, b, stride=s, emit_stats=True)
+    npix = y0.shape[0] * y0.shape[1] * y0.shape[2]
+    rm0, rv0 = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+    nbt0 = torch.zeros((), dtype=torch.long, device="cuda")
+    par0 = raw.bn_finalize(stats, npix, gamma, beta, 1e-5, 0.1, rm0, rv0, nbt0, cout)
+    cpad = (cout + 15) // 16 * 16
+    acc = torch.zeros(2 * cpad, dtype=torch.float64, device="cuda")
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rm1, rv1 = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+    nbt1 = torch.zeros((), dtype=torch.long, device="cuda")
+    for rep in range(3):
+        batch = torch.zeros(2 * cout, device="cuda")
+        if rep == 0:
+            y1, par1 = raw.conv2d_fwd_bn(x, w_f, b, s, gamma, beta, 1e-5, 0.1, acc, ticket, running_mean=rm1,
+                                         running_var=rv1, nbt=nbt1)
+        else:
+            y1, par1 = raw.conv2d_fwd_bn(x, w_f, b, s, gamma, beta, 1e-5, 0.1, acc, ticket, batch_out=batch)
+        torch.cuda.synchronize()
+        assert torch.equal(y1, y0)
+        assert float(acc.abs().max()) == 0.0 and int(ticket) == 0, rep
+        for i, name in enumerate(("scale", "shift", "mean", "invstd")):
+            close(par1[i], par0[i], 2e-6, name)
+        if rep:
+            close(batch[:cout], par0[2], 2e-6, "batch mean")
+    close(rm1, rm0, 2e-6, "running mean")
+    close(rv1, rv0, 2e-6, "running var")
+    assert int(nbt1) == int(nbt0) == 1
+    yr = y0.float().reshape(-1, cout)
+    ref = F.batch_norm(yr, None, None, gamma, beta, training=True, eps=1e-5)
+    close(yr * par1[0] + par1[1], ref, 2e-5, "affine vs F.batch_norm")
+
+
 def test_grad_fold_layouts_and_clearing():
     """End-of-step fold: OHWI accumulators of two passes -> OIHW gradient (+= or overwrite), vectors of both passes, the
     stem accumulating on 16 padded input channels at its own accumulator offset, accumulators cleared on request."""
@@ -221,6 +269,18 @@ def test_batchnorm_train_fwd_bwd(c, res, relu):
     close(dbeta, b_t.grad, 5e-3, "dbeta")
     if res:
         close(g_out, rr.grad.permute(0, 2, 3, 1), BF16_TOL, "residual grad")
+    # the in-launch finalisation of the reduce (no bn_bwd_finalize launch) gives the same gradients and leaves its
+    # reduction cells clean (two launches in a row share them)
+    acc = torch.zeros(2 * ((c + 15) // 16 * 16), dtype=torch.float64, device="cuda")
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        dgamma2, dbeta2 = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+        dy2 = raw.bn_bwd(dz, z if relu else None, ps, y, par[2], par[3], gamma, dgamma2, dbeta2, fold=(acc, ticket))
+        torch.cuda.synchronize()
+        close(dy2, dy, 2.0 ** -8, "fused dx")            # the mean terms may differ in the last fp32 bit -> <= 1 bf16 ulp
+        close(dgamma2, dgamma, 1e-5, "fused dgamma")
+        close(dbeta2, dbeta, 1e-5, "fused dbeta")
+        assert float(acc.abs().max()) == 0.0 and int(ticket) == 0
 
 
 def test_fuse_and_upsample_adjoint():

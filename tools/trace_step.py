@@ -84,6 +84,8 @@ def main():
                     help="sustained dense bf16 TFLOP/s (MEASURED_PEAKS.json)")
     ap.add_argument("--gbs", type=float, default=pk["hbm_gbs"], help="HBM copy bandwidth GB/s (MEASURED_PEAKS.json)")
     ap.add_argument("--top", type=int, default=0, help="also list the N largest launches by roofline time")
+    ap.add_argument("--separate-bn-finalize", action="store_true",
+                    help="trace the program with bn_finalize launches (SyncBN mode) instead of the in-launch finalisation")
     args = ap.parse_args()
     if __debug__:
         sys.exit("run with python -O (the wrappers assert is_cuda)")
@@ -111,7 +113,12 @@ def main():
     images = torch.empty((1, 3, args.height, args.width), dtype=torch.float32, device=dev)
     gts = torch.empty((1, args.height, args.width), dtype=torch.long, device=dev)
     mask = torch.empty((1, net.ocfg["mid_channels"]), dtype=torch.float32, device=dev)
-    E = EN.Engine(tensors, grads, packed, True, mask)
+    bnfold = None
+    if not args.separate_bn_finalize:
+        bnfold = {n[: -len(".running_mean")]: (torch.empty(2 * ((v.shape[0] + 15) // 16 * 16), dtype=torch.float64, device=dev),
+                                               torch.empty(1, dtype=torch.int32, device=dev))
+                  for n, v in tensors.items() if n.endswith(".running_mean")}
+    E = EN.Engine(tensors, grads, packed, True, mask, bnfold=bnfold)
     M.train_loss(E, images, gts, args.arch, net.hcfg, net.ocfg)
     n_fwd = len(EVENTS)
     M.run_backward(E)
