@@ -18,10 +18,6 @@ import time
 # The SyncBN exchange spins inside kernels of two concurrent streams per GPU: give every stream its own hardware work
 # queue (the default 8 connections can alias streams and turn a peer wait into a false cross-stream dependency).
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-if "--syncbn" in sys.argv:
-    # Lazy module loading may synchronise the context when a kernel is launched for the first time; a host thread
-    # blocked there while its GPU spins on a peer is the documented lazy-loading deadlock. Load everything up front.
-    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "semantic-segmentation_b200")):

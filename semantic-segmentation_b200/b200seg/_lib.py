@@ -77,6 +77,7 @@ SIGNATURES = {
     "b200seg_debug_occupancy": (c_int32, [c_int32, c_int32, c_int32]),
     "b200seg_debug_occupancy_report": (None, []),
     "b200seg_conv2d_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V, P32, V]),
+    "b200seg_set_smem_reserve": (ctypes.c_int, [I32]),
     "b200seg_conv2d_fwd_bn": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, ctypes.POINTER(BnFold), V]),
     "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
     "b200seg_pack_weight": (ctypes.c_int, [V, I32, I32, I32, V, V, I32, V]),

@@ -66,13 +66,23 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
   return v;
 }
 
-// Called by ALL threads of a finaliser block (blockDim = 32 channels x kFinSlices); threads with slice == 0 and c < C
-// carry the local sums in (s1, s2) and receive the global sums.
-__device__ __forceinline__ void sync_exchange(const SyncArgs& sy, int C, int c, int slice, double& s1, double& s2) {
+// The exchange is split over two kernels so that NOTHING that waits for a peer holds more than one warp of an SM:
+//   sync_post  (tail of the finaliser, 512-thread blocks): store my sums into every peer's mailbox, publish the flags,
+//              exit - never waits;
+//   sync_wait_fold (bn_sync_finish_kernel / bn_bwd_sync_finish_kernel: ONE WARP per 32 channels, no shared memory):
+//              poll my own flags, fold the ranks in rank order, write the layer's parameters.
+// Why: a persistent tensor-core convolution takes a whole SM per CTA (up to 60 K registers, 226 KB of shared memory) and
+// owns its tiles statically. A 512-thread spinning finaliser (27 K registers + 8 KB) on one SM keeps that SM's CTA of a
+// convolution on ANOTHER stream from starting, so that convolution never completes - and when the peer is waiting for
+// exactly that convolution's statistics while its own spinner blocks the convolution this rank waits for, the two GPUs
+// deadlock (observed at 1024x2048: rank 0 spinning in the 1.0x stem exchange, rank 1 in the 0.5x attention head's).
+// A one-warp waiter (<= 1.3 K registers, 1 KB reserved shared memory) fits next to any CTA of the library (the
+// planners leave B200SEG_SYNC_SMEM_RESERVE bytes free per SM in SyncBN mode), so every launched kernel whose stream
+// predecessors are done can always be scheduled, which is what the ordering argument in DESIGN.md needs.
+__device__ __forceinline__ void sync_post(const SyncArgs& sy, int C, int c, bool owner, double s1, double s2) {
   const unsigned step = *sy.step;
   const long long base = (long long)(step & 1u) * sy.parity_stride + sy.mail_off;
-  const bool owner = slice == 0 && c < C;
-  if (sy.beacon && blockIdx.x == 0 && threadIdx.x == 0) {   // post-mortem aid: which exchange this rank entered last
+  if (sy.beacon && blockIdx.x == 0 && threadIdx.x == 0) {   // post-mortem aid: which exchange this rank posted last
     sy.beacon[0] = sy.flag_off;
     sy.beacon[1] = (int)step;
   }
@@ -89,67 +99,53 @@ __device__ __forceinline__ void sync_exchange(const SyncArgs& sy, int C, int c, 
   if (threadIdx.x == 0)
     for (int r = 0; r < sy.world; ++r)
       st_release_sys(sy.flag_peers[r] + sy.flag_off + sy.rank * nblk + blockIdx.x, step);
-  if (owner) {
-    const unsigned* myflags = sy.flag_peers[sy.rank] + sy.flag_off + blockIdx.x;
-    const double* mymail = sy.mail_peers[sy.rank] + base;
-    double t1 = 0.0, t2 = 0.0;
-    for (int r = 0; r < sy.world; ++r) {
-      unsigned spins = 0;
-      unsigned long long t0 = 0;
-      // flags are monotonic step numbers: a peer that is already one step ahead (it wrote step + 1 into the OTHER parity
-      // half) must not be waited for, so compare by order, not by equality
-      while ((int)(ld_acquire_sys(myflags + r * nblk) - step) < 0) {
-        if ((++spins & 0xFFFFu) == 0) {            // a lost peer traps after 180 s instead of hanging the GPU
-          unsigned long long now;
-          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-          if (t0 == 0) t0 = now;
-          else if (now - t0 > 180000000000ull) __trap();
-        }
+}
+
+// One warp, lane = channel blockIdx.x * 32 + lane. Returns the sums over all ranks (rank order: bitwise identical on
+// every GPU) for lanes with c < C.
+__device__ __forceinline__ void sync_wait_fold(const SyncArgs& sy, int C, int c, double& s1, double& s2) {
+  const unsigned step = *sy.step;
+  const long long base = (long long)(step & 1u) * sy.parity_stride + sy.mail_off;
+  const int nblk = gridDim.x;
+  const unsigned* myflags = sy.flag_peers[sy.rank] + sy.flag_off + blockIdx.x;
+  const double* mymail = sy.mail_peers[sy.rank] + base;
+  const int lane = threadIdx.x;
+  // lane r < world polls rank r's flag; flags are monotonic step numbers: a peer that is already one step ahead (it wrote
+  // step + 1 into the OTHER parity half) must not be waited for, so compare by order, not by equality
+  if (lane < sy.world) {
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    while ((int)(ld_acquire_sys(myflags + lane * nblk) - step) < 0) {
+      if ((++spins & 0xFFFFu) == 0) {            // a lost peer traps after 180 s instead of hanging the GPU
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 180000000000ull) __trap();
       }
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+  double t1 = 0.0, t2 = 0.0;
+  if (c < C) {
+    for (int r = 0; r < sy.world; ++r) {
       t1 += ld_volatile_f64(mymail + (long long)r * 2 * C + c);
       t2 += ld_volatile_f64(mymail + (long long)r * 2 * C + C + c);
     }
-    s1 = t1;
-    s2 = t2;
   }
-  if (sy.beacon && blockIdx.x == 0 && threadIdx.x == 0) {   // ... and which one it left last
+  s1 = t1;
+  s2 = t2;
+  if (sy.beacon && blockIdx.x == 0 && lane == 0) {   // ... and which one it completed last
     sy.beacon[4] = sy.flag_off;
     sy.beacon[5] = (int)step;
   }
 }
 
-__global__ void __launch_bounds__(32 * kFinSlices)
-bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int Cpad, float count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
-                                   float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out, float* __restrict__ batch_stats_out,
-                                   const SyncArgs sy) {
-  // Dependents are released only AFTER the cross-GPU exchange: a successor that became resident early (PDL) would hold
-  // its SMs / TMEM while this kernel spins on a peer, and two ranks doing that on different streams deadlock.
-  pdl_wait();
-  if (sy.world <= 1) pdl_launch();
-  // block = 32 channels x 16 slices of the G partial rows (coalesced 128-byte reads, four independent rows in flight per
-  // thread: the kernel is a pure latency chain otherwise), then a fixed-order fold -> deterministic
-  __shared__ double sh1[kFinSlices][32], sh2[kFinSlices][32];
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  double a1 = 0.0, a2 = 0.0;
-  if (c < C) fold_rows(partials, G, 2 * Cpad, Cpad, c, slice, a1, a2);
-  sh1[slice][lane] = a1;
-  sh2[slice][lane] = a2;
-  __syncthreads();
-  double s1 = 0.0, s2 = 0.0;
-  if (slice == 0 && c < C)
-    for (int k = 0; k < kFinSlices; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
-  if (sy.world > 1) {            // SyncBN: statistics of the global batch (equal pixel counts on every rank)
-    sync_exchange(sy, C, c, slice, s1, s2);
-    count *= (float)sy.world;
-    pdl_launch();
-  }
-  if (slice != 0 || c >= C) return;
+// scale / shift / mean / invstd (+ running statistics or the deferred batch statistics) of channel c from the totals
+__device__ __forceinline__ void bn_write_params(double s1, double s2, float count, int c, int C, const float* gamma,
+                                                const float* beta, float eps, float momentum, float* running_mean,
+                                                float* running_var, float* scale, float* shift, float* mean_out,
+                                                float* invstd_out, float* batch_stats_out) {
   const double mean = s1 / count;
   double var = s2 / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -168,6 +164,57 @@ bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int Cpad, f
     batch_stats_out[c] = (float)mean;
     batch_stats_out[C + c] = (float)unbiased;
   }
+}
+
+// SyncBN, second half: one warp per 32 channels waits for every rank's sums and writes the layer's parameters. Its
+// dependents (the BN apply pass ...) are released only AFTER the exchange: a successor that became resident early (PDL)
+// would hold registers / shared memory on many SMs while this warp waits for a peer.
+__global__ void __launch_bounds__(32)
+bn_sync_finish_kernel(int C, float count, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                      float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                      float* __restrict__ invstd_out, float* __restrict__ batch_stats_out, const SyncArgs sy) {
+  pdl_wait();
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s1, s2;
+  sync_wait_fold(sy, C, c, s1, s2);
+  pdl_launch();
+  if (c < C)
+    bn_write_params(s1, s2, count * (float)sy.world, c, C, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                    shift, mean_out, invstd_out, batch_stats_out);
+}
+
+__global__ void __launch_bounds__(32 * kFinSlices)
+bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int Cpad, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, float* __restrict__ batch_stats_out,
+                                   const SyncArgs sy) {
+  pdl_wait();
+  pdl_launch();     // the only dependent in SyncBN mode is the one-warp bn_sync_finish_kernel (it never blocks anything)
+  // block = 32 channels x 16 slices of the G partial rows (coalesced 128-byte reads, four independent rows in flight per
+  // thread: the kernel is a pure latency chain otherwise), then a fixed-order fold -> deterministic
+  __shared__ double sh1[kFinSlices][32], sh2[kFinSlices][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C) fold_rows(partials, G, 2 * Cpad, Cpad, c, slice, a1, a2);
+  sh1[slice][lane] = a1;
+  sh2[slice][lane] = a2;
+  __syncthreads();
+  double s1 = 0.0, s2 = 0.0;
+  if (slice == 0 && c < C)
+    for (int k = 0; k < kFinSlices; ++k) { s1 += sh1[k][lane]; s2 += sh2[k][lane]; }
+  if (sy.world > 1) {            // SyncBN: post my sums to every rank; bn_sync_finish_kernel completes the layer
+    sync_post(sy, C, c, slice == 0 && c < C, s1, s2);
+    return;
+  }
+  if (slice != 0 || c >= C) return;
+  bn_write_params(s1, s2, count, c, C, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean_out,
+                  invstd_out, batch_stats_out);
 }
 
 // Running-statistics update of ALL BatchNorm layers of a step in one pass. The scale passes of the multi-scale step run
@@ -365,8 +412,8 @@ __global__ void __launch_bounds__(32 * kFinSlices)
 bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, float count,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
                        float* __restrict__ c2, const SyncArgs sy) {
-  pdl_wait();                       // see bn_finalize_kernel: dependents are released after the exchange
-  if (sy.world <= 1) pdl_launch();
+  pdl_wait();
+  pdl_launch();                     // SyncBN: the dependent is the one-warp bn_bwd_sync_finish_kernel
   __shared__ double sh1[kFinSlices][32], sh2[kFinSlices][32];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -382,14 +429,27 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, float c
     if (dbeta) dbeta[c] += (float)s1;
     if (dgamma) dgamma[c] += (float)s2;
   }
-  if (sy.world > 1) {            // SyncBN backward: the mean terms run over the global batch
-    sync_exchange(sy, C, c, slice, s1, s2);
-    count *= (float)sy.world;
-    pdl_launch();
+  if (sy.world > 1) {            // SyncBN backward: the mean terms run over the global batch (bn_bwd_sync_finish_kernel)
+    sync_post(sy, C, c, slice == 0 && c < C, s1, s2);
+    return;
   }
   if (slice != 0 || c >= C) return;
   c1[c] = (float)(s1 / count);
   c2[c] = (float)(s2 / count);
+}
+
+__global__ void __launch_bounds__(32)
+bn_bwd_sync_finish_kernel(int C, float count, float* __restrict__ c1, float* __restrict__ c2, const SyncArgs sy) {
+  pdl_wait();
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s1, s2;
+  sync_wait_fold(sy, C, c, s1, s2);
+  pdl_launch();
+  if (c < C) {
+    const double n = (double)count * (double)sy.world;
+    c1[c] = (float)(s1 / n);
+    c2[c] = (float)(s2 / n);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -519,6 +579,12 @@ extern "C" int b200seg_bn_finalize(const float* partials, int32_t grid, int32_t 
   launch_k(bn_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinSlices), 0, (cudaStream_t)stream, partials, grid, c,
            cpad, count, gamma, beta, eps, momentum, running_mean, running_var, (long long*)num_batches_tracked, scale,
            shift, mean, invstd, batch_stats_out, sy);
+  if (sy.world > 1) {
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) return (int)e0;
+    launch_k(bn_sync_finish_kernel, dim3((c + 31) / 32), dim3(32), 0, (cudaStream_t)stream, (int)c, count, gamma, beta,
+             eps, momentum, running_mean, running_var, scale, shift, mean, invstd, batch_stats_out, sy);
+  }
   CHECK_LAUNCH();
 }
 
@@ -620,6 +686,11 @@ extern "C" int b200seg_bn_bwd_finalize(const float* partials, int32_t grid, int3
   if (int rc = make_sync(sync, &sy)) return rc;
   launch_k(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinSlices), 0, (cudaStream_t)stream, partials,
            grid, c, count, dgamma, dbeta, c1, c2, sy);
+  if (sy.world > 1) {
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) return (int)e0;
+    launch_k(bn_bwd_sync_finish_kernel, dim3((c + 31) / 32), dim3(32), 0, (cudaStream_t)stream, (int)c, count, c1, c2, sy);
+  }
   CHECK_LAUNCH();
 }
 

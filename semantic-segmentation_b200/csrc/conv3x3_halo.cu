@@ -20,6 +20,7 @@
 #include <cstdio>
 #include "ptx.cuh"
 #include "bn_fold.cuh"
+#include "conv_common.h"
 #include "tma_host.h"
 #include "launch.h"
 #include "../../include/b200seg.h"
@@ -464,7 +465,7 @@ static int halo_smem_layout(int BN, int n_tiles, int cchunks, int cout_pad, Halo
   const size_t resident_bytes = (size_t)9 * cchunks * b_tile;
   // the staged epilogue (stage_bytes != 0) is built for one CTA per SM only
   for (int occ = (halo_coresident_enabled() && BN <= 128 && stage_bytes == 0) ? 2 : 1; occ >= 1; --occ) {
-    const size_t budget = (occ == 2 ? kHalfSmBudget : (size_t)227 * 1024) - fixed;
+    const size_t budget = (occ == 2 ? kHalfSmBudget : (size_t)227 * 1024) - fixed - (size_t)smem_reserve() / occ;
     if (n_tiles == 1 && resident_bytes + 2 * (size_t)kASlotBytes <= budget) {
       const int as_ = (int)((budget - resident_bytes) / kASlotBytes);
       L.resident = 1; L.a_slots = as_ > kMaxASlots ? kMaxASlots : as_; L.b_slots = 0;

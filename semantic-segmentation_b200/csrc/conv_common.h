@@ -13,4 +13,7 @@ struct ConvPlan {
   size_t smem_bytes;
 };
 int conv_plan(const b200seg_conv_desc* d, ConvPlan* pl);
+// Shared memory per SM the tensor-core kernels leave unused (b200seg_set_smem_reserve): in SyncBN mode a few one-warp
+// waiter CTAs (1 KB of reserved shared memory each) must fit next to ANY convolution CTA, see bn_kernels.cu.
+int smem_reserve();
 }  // namespace b200seg

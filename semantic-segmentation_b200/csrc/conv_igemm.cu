@@ -358,7 +358,7 @@ static int plan_geom(const LaunchGeom& g, ConvPlan* pl) {
   int occ = (coresident_enabled() && pl->BN <= 128) ? 2 : 1;
   int nst = 0;
   for (; occ >= 1; --occ) {
-    const size_t budget = (occ == 2 ? kHalfSmBudget : (size_t)227 * 1024) - fixed;
+    const size_t budget = (occ == 2 ? kHalfSmBudget : (size_t)227 * 1024) - fixed - (size_t)smem_reserve() / occ;
     nst = (int)(budget / pl->stage_bytes);
     if (nst > kMaxStages) nst = kMaxStages;
     if (nst >= (occ == 2 ? 3 : 2)) break;
@@ -397,6 +397,9 @@ static bool desc_ok(const b200seg_conv_desc* d) {
   if (d->stride != 1 && d->stride != 2) return false;
   return true;
 }
+
+static int g_smem_reserve = 0;
+int smem_reserve() { return g_smem_reserve; }
 
 int conv_plan(const b200seg_conv_desc* d, ConvPlan* pl) {
   if (!desc_ok(d)) return B200SEG_E_BADARG;
@@ -559,6 +562,12 @@ extern "C" int b200seg_conv2d_fwd(const b200seg_conv_desc* d, const void* x, con
                                d->y_ld, stats_partials, stats_grid, nullptr, 0, d->emit_stats, (cudaStream_t)stream);
   }
   return launch_geom(fwd_geom(d), x, w_ohwi, bias, y, stats_partials, stats_grid, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int b200seg_set_smem_reserve(int32_t bytes) {
+  if (bytes < 0 || bytes > 64 * 1024) return B200SEG_E_BADARG;
+  g_smem_reserve = (bytes + 1023) / 1024 * 1024;
+  return 0;
 }
 
 extern "C" int b200seg_conv2d_fwd_bn(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,

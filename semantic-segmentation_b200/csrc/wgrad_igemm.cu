@@ -20,6 +20,7 @@
 #include "ptx.cuh"
 #include "tma_host.h"
 #include "launch.h"
+#include "conv_common.h"
 #include "../../include/b200seg.h"
 
 namespace b200seg {
@@ -473,7 +474,7 @@ extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, c
     if (reinterpret_cast<uintptr_t>(workspace) & 15) return B200SEG_E_BADARG;
   }
   const size_t fixed = 1024 + 2 * (size_t)p.a_slot_bytes + (4 + 2 * kMaxBSlots + 2) * 8 + 16;
-  int bs = (int)((227 * 1024 - fixed) / p.b_slot_bytes);
+  int bs = (int)((227 * 1024 - smem_reserve() - fixed) / p.b_slot_bytes);
   if (bs > kMaxBSlots) bs = kMaxBSlots;
   if (bs < 2) return B200SEG_E_BADARG;
   p.b_slots = bs;

@@ -114,9 +114,6 @@ def test_two_gpu_data_parallel_gradients_are_the_rank_mean(tmp_path):
 def test_two_gpu_syncbn_step_equals_single_gpu_batch(tmp_path, use_graph):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if os.environ.get("B200SEG_TEST_SYNCBN") != "1":
-        pytest.skip("SyncBN exchange not re-validated after the multi-stream changes (DESIGN.md §6): "
-                    "set B200SEG_TEST_SYNCBN=1 to run it")
     import torch.multiprocessing as mp
     out = str(tmp_path / "res.pt")
     port = 29500 + (os.getpid() % 1000) + (1 if use_graph else 0)
