@@ -348,6 +348,12 @@ def run_b200(args):
     #     i+1 is already running (what a training loop that logs asynchronously does);
     # (b) blocking read: loss.item() right after every step (the reference's train.py:499-512 pattern) - this also
     #     exposes the launch latency of the ~6 000-node graph on an idle GPU every step.
+    from b200seg.prefetch import DevicePrefetcher
+
+    def host_batches(n):
+        for _ in range(n):
+            yield {"images": images_h, "gts": gts_h}      # pinned host tensors: every step's inputs cross PCIe again
+
     pin = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     evts = [torch.cuda.Event() for _ in range(2)]
     t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -355,10 +361,8 @@ def run_b200(args):
     t_e0.record()
     prev = None
     loss_val = float("nan")
-    for i in range(args.steps):
-        im = images_h.cuda(non_blocking=True)
-        gt = gts_h.cuda(non_blocking=True)
-        loss = step(im, gt)
+    for i, batch in enumerate(DevicePrefetcher(host_batches(args.steps))):   # H2D of step i+1 on a copy stream under step i
+        loss = step(batch["images"], batch["gts"])
         slot = i % 2
         pin[slot].copy_(loss.detach().reshape(1), non_blocking=True)
         evts[slot].record()
@@ -413,8 +417,10 @@ def run_b200(args):
                     model_tflop_per_crop=TFLOP_PER_CROP[args.arch]),
         e2e=dict(value=e2e_value, unit="crops/s", ms_per_step=ms_e2e / args.steps,
                  h2d_bytes_per_step=int(images_h.numel() * 4 + gts_h.numel() * 8), d2h_bytes_per_step=4,
-                 api="net({'images','gts'}) -> loss.backward() -> optimizer.step() from pinned host tensors; the loss of "
-                     "every step is copied to pinned host memory and read while the next step runs",
+                 api="b200seg.prefetch.DevicePrefetcher(pinned host batches) -> net({'images','gts'}) -> loss.backward() -> "
+                     "optimizer.step(); every step's inputs are copied host->device (copy stream, double buffer, "
+                     "overlapping the previous step), the loss of every step is copied to pinned host memory and read while "
+                     "the next step runs",
                  blocking_read=dict(value=crops / (ms_e2e_block * 1e-3), ms_per_step=ms_e2e_block / args.steps,
                                     note="loss.item() immediately after every step (exposes the graph-launch latency "
                                          "on an idle GPU each step)")),

@@ -316,3 +316,24 @@ def test_eval_minibatch_device_tail_matches_host_scoring():
     assert int((res["hist"] - ref_hist).abs().sum()) <= 4
     assert res["hist"].sum() == mask.sum()
     assert iou_from_hist(res["hist"]).shape == (19,)
+
+
+def test_device_prefetcher_double_buffer_keeps_batches_intact():
+    """b200seg.prefetch.DevicePrefetcher: batches arrive on the device unchanged and in order while a slow consumer runs on
+    the compute stream (the copy of batch i+1 may only overwrite a slot after the step that used it has finished)."""
+    from b200seg.prefetch import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    host = [{"images": torch.randn((1, 3, 64, 128), generator=g).pin_memory(),
+             "gts": torch.randint(0, 19, (1, 64, 128), generator=g).pin_memory()} for _ in range(7)]
+    big = torch.randn((4096, 4096), device="cuda")
+    sums = []
+    for i, b in enumerate(DevicePrefetcher(host)):
+        assert b["images"].is_cuda and b["gts"].dtype == torch.long
+        for _ in range(3):
+            big = (big @ big).tanh_()                 # keep the compute stream busy after the batch was handed out
+        sums.append((b["images"].double().sum() + b["gts"].double().sum()).clone())
+    torch.cuda.synchronize()
+    assert len(sums) == 7
+    for i, s in enumerate(sums):
+        want = host[i]["images"].double().sum() + host[i]["gts"].double().sum()
+        assert abs(float(s) - float(want)) <= 1e-6 * abs(float(want)) + 1e-6, i
