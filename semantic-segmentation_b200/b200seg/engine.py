@@ -71,6 +71,7 @@ class Engine:
         self._ctx = None         # stream of the branch section being recorded (None = the engine's own stream)
         self.pre_backward_event = None   # e.g. "data-gradient weight operands packed" (recorded on another stream)
         self.tape = []
+        self.on_mark = None      # callable(engine, tag): fired in backward when everything recorded after mark(tag) has run
         self.bn_seen = set()
         self.hold = []      # tensors handed across streams: kept alive until the step's final join
         # Weight gradients do not feed the rest of the backward chain: they run on a side stream (a parallel branch of
@@ -93,6 +94,9 @@ class Engine:
                 else:
                     with torch.cuda.stream(st):
                         fn()
+            elif kind == "mark":
+                if self.on_mark is not None:
+                    self.on_mark(self, fn)
             elif kind == "join":          # forward joined k branches here: backward forks them
                 self._fork_streams(fn)
             else:                          # forward forked here: backward joins
@@ -140,6 +144,13 @@ class Engine:
                 yield
         finally:
             self._ctx = prev
+
+    def mark(self, tag):
+        """Checkpoint on the main chain of the program: in backward, on_mark(self, tag) fires once the gradients of
+        everything recorded AFTER this point are enqueued (used to hand finished parameter-gradient buckets to the
+        data-parallel all-reduce while the rest of the backward still runs)."""
+        if self.training:
+            self.tape.append(("mark", tag, None))
 
     def finish(self):
         """After every stream of the step has been joined: drop the cross-stream keep-alive references."""

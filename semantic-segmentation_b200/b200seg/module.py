@@ -228,6 +228,18 @@ class B200SegModule(nn.Module):
                 segs.append((off, off, 1, numel, 1, numel))
             off += (numel + 63) // 64 * 64
         self._fold_table = raw.grad_fold_table(segs, dev)
+        # Gradient buckets for the overlapped data-parallel all-reduce, contiguous in the flat layout (= registration
+        # order) and listed in the order the backward completes them: heads, transition3 + stage4, everything before.
+        names = [n for n, _ in params]
+        i1 = next((i for i, n in enumerate(names) if n.startswith("backbone.transition3.")), 0)
+        i2 = next((i for i, n in enumerate(names) if not n.startswith("backbone.")), len(names))
+        i1 = min(i1, i2)
+        self._buckets = []
+        for tag, (a, b) in (("heads", (i2, len(names))), ("stage4", (i1, i2)), ("rest", (0, i1))):
+            if b > a:
+                lo = segs[a][0]
+                hi = segs[b - 1][0] + (segs[b - 1][2] * segs[b - 1][3] * segs[b - 1][4] + 63) // 64 * 64
+                self._buckets.append(dict(tag=tag, lo=lo, hi=hi, table=raw.grad_fold_table(segs[a:b], dev)))
 
     def _engine_grads(self, which="hi"):
         """name -> fp32 tensor an Engine accumulates into."""
@@ -378,13 +390,70 @@ class B200SegModule(nn.Module):
         E.pre_backward_event = wd_ready
         if E_lo is not None:
             E_lo.pre_backward_event = wd_ready
-        M.run_backward(E, E_lo)
-        self._fold_grads(par)
+        bucketed = self._bucketed_allreduce()
+        self._reduced_in_step = bucketed
+        if bucketed:
+            self._run_backward_bucketed(E, E_lo, par)
+        else:
+            M.run_backward(E, E_lo)
+            self._fold_grads(par)
         if par:
             assert E.bn_seen == E_lo.bn_seen and len(E.bn_seen) == len(self._bn_slots), "BN bookkeeping out of sync"
             raw.bn_running_update(self._run_flat, self._bstat[0], self._bstat[1], BN_MOMENTUM, self._nbt_flat, 2)
         raw.KEEP = None
         return loss
+
+    def _bucketed_allreduce(self):
+        """Data-parallel step: fold and all-reduce finished gradient buckets while the backward still runs."""
+        import os
+        if not self._ddp_allreduce or os.environ.get("B200SEG_BUCKET_ALLREDUCE", "1") == "0":
+            return False
+        d = torch.distributed
+        return d.is_available() and d.is_initialized() and d.get_world_size() > 1
+
+    def _run_backward_bucketed(self, E, E_lo, par):
+        """Collective C1 overlapped with the backward (the reference's apex DDP overlaps its buckets the same way,
+        network/__init__.py:38-39): when the tapes of all scale passes have passed a bucket's marker, a communication
+        stream folds that bucket's accumulators into the step gradient (OIHW) and NCCL all-reduces its slice, while the
+        compute streams continue with the earlier layers. Inside the captured graph this is a side branch that joins at
+        the end of the step; the 1 / world_size average is applied by the publish kernel."""
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream()
+        comm = self._comm_stream
+        engines = [E] + ([E_lo] if E_lo is not None else [])
+        seen = {}
+        works = []
+        by_tag = {b["tag"]: b for b in self._buckets}
+
+        def launch(bucket, events):
+            with torch.cuda.stream(comm):
+                for ev in events:
+                    comm.wait_event(ev)
+                raw.grad_fold(self._step_flat, self._acc_hi, self._acc_lo if par else None, bucket["table"], clear=False,
+                              overwrite=True)
+                works.append(torch.distributed.all_reduce(self._step_flat[bucket["lo"]:bucket["hi"]], async_op=True))
+
+        def on_mark(eng, tag):
+            if tag not in by_tag:
+                return
+            cur = torch.cuda.current_stream()
+            evs = [cur.record_event()]
+            if eng.side is not None:
+                evs.append(eng.side.record_event())
+            seen.setdefault(tag, []).extend(evs)
+            seen[tag + "#n"] = seen.get(tag + "#n", 0) + 1
+            if seen[tag + "#n"] == len(engines):
+                launch(by_tag[tag], seen[tag])
+
+        for eng in engines:
+            eng.on_mark = on_mark
+        M.run_backward(E, E_lo)                      # joins every compute stream on the current one at its end
+        if "rest" in by_tag:
+            launch(by_tag["rest"], [torch.cuda.current_stream().record_event()])
+        with torch.cuda.stream(comm):
+            for w in works:
+                w.wait()
+        torch.cuda.current_stream().wait_stream(comm)
 
     def _drop_mask(self, n, device):
         """Dropout2d(0.05) channel mask (network/ocr_utils.py:146) drawn from torch's generator, folded with 1/(1-p)."""
@@ -434,7 +503,10 @@ class B200SegModule(nn.Module):
         is a view of ONE flat fp32 buffer (what FusedSGD and the all-reduce work on)."""
         scale = 1.0
         if self._ddp_allreduce:
-            scale = 1.0 / allreduce_sum_(self._step_flat)
+            if getattr(self, "_reduced_in_step", False):       # the step all-reduced its buckets while it ran
+                scale = 1.0 / torch.distributed.get_world_size()
+            else:
+                scale = 1.0 / allreduce_sum_(self._step_flat)
         if grad_out is not None:
             grad_out = grad_out.detach().reshape(()).to(F32)
         params = list(self.named_parameters())

@@ -56,18 +56,22 @@ def wrap_network_in_dataparallel(net, use_apex_data_parallel=False):
     only a thin container that keeps the ``module.`` state_dict prefix train.py / logx.save_model expect."""
     if use_apex_data_parallel:
         return FlatGradDataParallel(net)
-    raise NotImplementedError("single-process nn.DataParallel replication is outside the B200 hot path; launch one "
-                              "process per GPU (torch.distributed.launch / torchrun) with --apex")
+    if torch.cuda.device_count() <= 1:
+        # torch.nn.DataParallel on a single device calls the module directly (network/__init__.py:41): keep the
+        # `module.` state_dict prefix the checkpoint code expects, no collective
+        return FlatGradDataParallel(net, allreduce=False)
+    raise NotImplementedError("single-process nn.DataParallel replication over several GPUs is outside the B200 hot "
+                              "path; launch one process per GPU (torch.distributed.launch / torchrun) with --apex")
 
 
 class FlatGradDataParallel(torch.nn.Module):
     """Stands in for apex.parallel.DistributedDataParallel(net) (collective C1 of SURVEY.md §2b)."""
 
-    def __init__(self, module):
+    def __init__(self, module, allreduce=True):
         super().__init__()
         self.module = module
-        module._ddp_allreduce = True
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        module._ddp_allreduce = bool(allreduce)
+        if allreduce and torch.distributed.is_available() and torch.distributed.is_initialized():
             # replicate rank 0's initial weights like DDP does at construction
             for t in list(module.parameters()) + list(module.buffers()):
                 torch.distributed.broadcast(t.data, src=0)

@@ -35,7 +35,9 @@ def build(arch, num_classes, criterion):
         # decides whether BatchNorm statistics span the data-parallel group
         bnfunc = getattr(cfg.MODEL, "BNFUNC", None)
         kw["syncbn"] = bnfunc is not None and "sync" in getattr(bnfunc, "__name__", str(bnfunc)).lower()
-        checkpoint = getattr(cfg.MODEL, "HRNET_CHECKPOINT", "")
+        # cfg.MODEL.HRNET_CHECKPOINT hangs off the hard-coded cfg.ASSETS_PATH (config.py:52,147) users edit in their
+        # checkout; B200SEG_HRNET_CHECKPOINT overrides it without touching the reference ("" = random initialisation)
+        checkpoint = os.environ.get("B200SEG_HRNET_CHECKPOINT", getattr(cfg.MODEL, "HRNET_CHECKPOINT", ""))
     except ImportError:
         checkpoint = ""
     if num_classes != 19:
