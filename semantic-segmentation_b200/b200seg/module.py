@@ -406,7 +406,11 @@ class B200SegModule(nn.Module):
     def _bucketed_allreduce(self):
         """Data-parallel step: fold and all-reduce finished gradient buckets while the backward still runs."""
         import os
-        if not self._ddp_allreduce or os.environ.get("B200SEG_BUCKET_ALLREDUCE", "1") == "0":
+        # Opt-in (B200SEG_BUCKET_ALLREDUCE=1): NCCL's kernels wait for their peers while holding whole SMs, and every
+        # persistent convolution CTA owns its tiles statically - a convolution that shares the GPU with an all-reduce
+        # stalls until the collective leaves its SMs, and under SyncBN (compute that waits for the peer's compute) the
+        # combination can deadlock, so SyncBN mode never overlaps. Default: one all-reduce at gradient-publish time.
+        if not self._ddp_allreduce or self._sync is not None or os.environ.get("B200SEG_BUCKET_ALLREDUCE", "0") != "1":
             return False
         d = torch.distributed
         return d.is_available() and d.is_initialized() and d.get_world_size() > 1
