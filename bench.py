@@ -32,7 +32,69 @@ FWD_TFLOP_1X = 3.0546
 # Launch-level roofline of one train step per 1024x2048 crop: sum over the step's launches of max(FLOPs / sustained bf16
 # peak, bytes / HBM copy bandwidth), from the static trace of the real step program (tools/trace_step.py,
 # profiles/r1_step_roofline_model.txt; peaks of MEASURED_PEAKS.json: 1386.7 TFLOP/s, 6572.9 GB/s)
-STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.10, "ocrnet.HRNet": 11.34}
+STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.02, "ocrnet.HRNet": 11.34}
+# the same model per kernel class (profiles/r2_step_roofline_model.txt): class -> (kernel-name fragments, roofline ms)
+KERNEL_CLASSES = {
+    "conv fwd+dgrad (tcgen05)": (("conv3x3_halo", "conv_igemm"), 2.960 + 2.954 + 0.135),
+    "conv wgrad (tcgen05 + slab reduce)": (("wgrad_igemm", "wgrad_reduce"), 3.127),
+    "batchnorm passes": (("bn_",), 2.405 + 1.672 + 1.225),
+    "resample / fuse / accumulate": (("fuse_fwd", "upsample_adjoint", "masked_accum", "image_prep"), 0.359),
+    "loss + OCR softmaxes": (("loss_fwd", "_bwd_kernel", "mid_fwd", "softmax", "spatial_", "count_valid", "colsum",
+                              "cast_rows", "transpose_pad", "rmi_"), 0.19),
+    "weights / gradients / optimizer": (("pack_weights", "grad_fold", "publish_grads", "sgd_step", "running_update"), 0.27 + 0.8),
+}
+
+
+def kernel_class_table(step_fn, ms_per_step):
+    """One extra step under Kineto/CUPTI: per kernel class the launches, the summed kernel durations, their share of all
+    kernel time, the union (wall-clock during which at least one kernel of the class runs) and the launch-level roofline
+    time of the class. Durations come from the profiler run (a few % slower than the timed loop), shares are what matter."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step_fn()
+        torch.cuda.synchronize()
+    ev = []
+    for e in prof.profiler.kineto_results.events():
+        try:
+            if "cuda" not in str(e.device_type()).lower():
+                continue
+            t0 = e.start_ns() if hasattr(e, "start_ns") else e.start_us() * 1000
+            d = e.duration_ns() if hasattr(e, "duration_ns") else e.duration_us() * 1000
+            ev.append((int(t0), int(t0 + d), e.name()))
+        except Exception:
+            continue
+    if not ev:
+        return None
+
+    def union(iv):
+        tot, a0, b0 = 0, None, None
+        for a, b in sorted(iv):
+            if b0 is None or a > b0:
+                if b0 is not None:
+                    tot += b0 - a0
+                a0, b0 = a, b
+            else:
+                b0 = max(b0, b)
+        return tot + ((b0 - a0) if b0 is not None else 0)
+
+    total = sum(b - a for a, b, _ in ev)
+    span = max(b for _, b, _ in ev) - min(a for a, _, _ in ev)
+    out, used = {}, set()
+    for cname, (keys, roof_ms) in KERNEL_CLASSES.items():
+        idx = [i for i, (_, _, n) in enumerate(ev) if i not in used and any(k in n for k in keys)]
+        used.update(idx)
+        iv = [(ev[i][0], ev[i][1]) for i in idx]
+        sm = sum(b - a for a, b in iv) / 1e6
+        out[cname] = dict(launches=len(iv), sum_ms=round(sm, 3), share_of_kernel_time=round(sm * 1e6 / max(total, 1), 4),
+                          union_ms=round(union(iv) / 1e6, 3), roofline_ms=round(roof_ms, 3),
+                          roofline_frac=round(roof_ms / sm, 3) if sm > 0 else None)
+    rest = [(a, b) for i, (a, b, _) in enumerate(ev) if i not in used]
+    out["other (ATen fills, NCCL ...)"] = dict(launches=len(rest), sum_ms=round(sum(b - a for a, b in rest) / 1e6, 3))
+    out["_step"] = dict(kernels=len(ev), span_ms=round(span / 1e6, 3), all_kernels_union_ms=round(union([(a, b) for a, b, _ in ev]) / 1e6, 3),
+                        all_kernels_sum_ms=round(total / 1e6, 3), timed_ms_per_step=round(ms_per_step, 3))
+    return out
+
 
 
 def parse():
@@ -57,6 +119,7 @@ def parse():
                          "this GPU: the practical kernel to beat (BASELINE.md §3b step 5); adds `torch_gpu_baseline` and "
                          "`vs_torch_gpu` to the line. Default at --gpus 1; this flag forces it for N > 1 (rank 0)")
     ap.add_argument("--no-torch-gpu-baseline", action="store_true")
+    ap.add_argument("--no-recipe", action="store_true", help="skip the second (RMI + supervised multi-scale) measurement")
     return ap.parse_args()
 
 
@@ -271,7 +334,11 @@ def dominant_kernel_roofline(pk):
                                        "BN statistics in the epilogue)",
                 achieved=achieved, peak=pk["tf_burst"], unit="TFLOP/s", frac=achieved / pk["tf_burst"],
                 peak_source=pk["src"] + " bf16_tflops (burst: kernel timed alone)", ms_per_launch=t,
-                traffic=296.26e6, traffic_unit="bytes/launch (ncu dram read+write)", algorithmic_bytes=algo_bytes)
+                traffic=296.26e6, traffic_unit="bytes/launch (ncu dram read+write)",
+                traffic_source="profiles/r1_ncu_full_prof_ocr.txt (one ncu --set full capture of this launch; not "
+                               "re-measured in this run)", algorithmic_bytes=algo_bytes,
+                note="the largest single launch (1.4 % of the step); whole-step figures: model_flops_utilisation, "
+                     "step_roofline and kernel_classes")
 
 
 def run_b200(args):
@@ -398,6 +465,10 @@ def run_b200(args):
     e2e_value = crops / (ms_e2e * 1e-3)
     pk = peaks()
     roof = dominant_kernel_roofline(pk)
+    try:
+        classes = kernel_class_table(lambda: step(images_d, gts_d), ms / args.steps)
+    except Exception as e:  # noqa
+        classes = dict(error=repr(e))
     step_tflops = TFLOP_PER_CROP[args.arch] * (H * W) / (1024.0 * 2048.0) * B / (ms / args.steps * 1e-3) / 1e0
     kernels_per_step = getattr(net, "kernels_per_step", 0)
     line = dict(
@@ -432,10 +503,49 @@ def run_b200(args):
                            frac=STEP_ROOFLINE_MS[args.arch] * (H * W) / (1024.0 * 2048.0) * B / (ms / args.steps),
                            what="sum over the step's launches of max(FLOPs/P, bytes/B), static trace of the step "
                                 "program (profiles/r1_step_roofline_model.txt)"),
-        roofline=roof, clocks=clocks, last_loss=loss_val,
+        roofline=roof, kernel_classes=classes, clocks=clocks, last_loss=loss_val,
         max_memory_allocated_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
+    if world == 1 and not args.no_recipe and args.criterion == "ce" and args.sup_wt == 0.0:
+        # second reported number: the loss recipe of scripts/train_cityscapes.yml (rmi_loss: true,
+        # supervised_mscale_loss_wt: 0.05) on the same crop
+        try:
+            del net, opt
+            torch.cuda.empty_cache()
+            net2 = B200SegModule(args.arch, 19, criterion="rmi", supervised_mscale_wt=0.05,
+                                 use_cuda_graph=not args.no_graph).cuda().train()
+            with torch.no_grad():
+                for n_, p_ in net2.named_parameters():
+                    if p_.dim() == 4 and n_.startswith("backbone"):
+                        p_.normal_(0, (2.0 / (p_.shape[1] * p_.shape[2] * p_.shape[3])) ** 0.5)
+            from b200seg.optim import FusedSGD as _SGD
+            opt2 = _SGD(net2.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+
+            def step2():
+                opt2.zero_grad(set_to_none=True)
+                l2 = net2({"images": images_d, "gts": gts_d})
+                l2.backward()
+                opt2.step()
+                return l2
+
+            for _ in range(4):
+                step2()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            r0.record()
+            for _ in range(10):
+                l2 = step2()
+            r1.record()
+            torch.cuda.synchronize()
+            ms2 = r0.elapsed_time(r1) / 10
+            line["train_recipe_rmi_sup"] = dict(value=B * 1000.0 / ms2, unit="crops/s", ms_per_step=ms2, steps=10,
+                                                loss=float(l2), what="same step with criterion RMILoss and "
+                                                "supervised_mscale_loss_wt 0.05 (scripts/train_cityscapes.yml:21-24)")
+            del net2, opt2
+        except Exception as e:  # noqa
+            line["train_recipe_rmi_sup"] = dict(error=repr(e))
+        net = opt = None
     if (args.torch_gpu_baseline or world == 1) and not args.no_torch_gpu_baseline:
-        del net, opt
+        net = opt = None
         torch.cuda.empty_cache()
         tg = {}
         for name, ac in (("autocast_bf16", True), ("fp32_tf32_off", False)):
