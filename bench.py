@@ -544,6 +544,58 @@ def run_b200(args):
         except Exception as e:  # noqa
             line["train_recipe_rmi_sup"] = dict(error=repr(e))
         net = opt = None
+    if world == 1 and not args.no_recipe and args.criterion == "ce" and args.sup_wt == 0.0 and (H, W) == (1024, 2048):
+        # the other single-GPU configurations of BASELINE.json, measured in the same run (bf16 arithmetic throughout)
+        extra = {}
+        try:   # cfg2: ocrnet.HRNet (single scale) 1024x2048, 2 crops per step
+            torch.cuda.empty_cache()
+            net3 = B200SegModule("ocrnet.HRNet", 19, criterion="ce", use_cuda_graph=not args.no_graph).cuda().train()
+            from b200seg.optim import FusedSGD as _SGD3
+            opt3 = _SGD3(net3.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+            im2, gt2 = synth_batch(2, H, W, 7, "cpu")
+            im2, gt2 = im2.cuda(), gt2.cuda()
+            for it in range(3 + 8):
+                if it == 3:
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    c0.record()
+                opt3.zero_grad(set_to_none=True)
+                l3 = net3({"images": im2, "gts": gt2})
+                l3.backward()
+                opt3.step()
+            c1.record()
+            torch.cuda.synchronize()
+            ms3 = c0.elapsed_time(c1) / 8
+            extra["cfg2_ocrnet_HRNet_bs2_train"] = dict(
+                value=2 * 1000.0 / ms3, unit="crops/s", ms_per_step=ms3, tflops=2 * 7.77 / (ms3 * 1e-3),
+                what="ocrnet.HRNet single-scale train step, 2 x 1024x2048 crops per step, CE, bf16 storage / fp32 accumulate "
+                     "(BASELINE cfg2 names fp16: this path has one precision policy, bf16)")
+            del net3, opt3, im2, gt2
+        except Exception as e:  # noqa
+            extra["cfg2_ocrnet_HRNet_bs2_train"] = dict(error=repr(e))
+        try:   # cfg5: 3-scale inference {0.5, 1.0, 2.0} of a 1024x2048 frame (the 2.0x pass runs at 2048x4096)
+            torch.cuda.empty_cache()
+            net4 = B200SegModule(args.arch, 19, n_scales=[0.5, 1.0, 2.0]).cuda().eval()
+            from b200seg.evaltail import eval_minibatch
+            with torch.no_grad():
+                for it in range(2 + 5):
+                    if it == 2:
+                        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        torch.cuda.synchronize()
+                        c0.record()
+                    res = eval_minibatch(net4, images_d, gts_d, scales=(1.0,), do_flip=False)
+                c1.record()
+                torch.cuda.synchronize()
+            ms4 = c0.elapsed_time(c1) / 5
+            extra["cfg5_three_scale_inference"] = dict(
+                value=1000.0 / ms4, unit="frames/s", ms_per_frame=ms4, tflops=16.04 / (ms4 * 1e-3),
+                what="ocrnet.HRNet_Mscale nscale_forward {0.5,1.0,2.0} on a 1024x2048 frame + device-side argmax / "
+                     "confusion matrix (evaltail.eval_minibatch), eager launches, BatchNorm from running statistics")
+            del net4, res
+        except Exception as e:  # noqa
+            extra["cfg5_three_scale_inference"] = dict(error=repr(e))
+        line["other_configs"] = extra
+        torch.cuda.empty_cache()
     if (args.torch_gpu_baseline or world == 1) and not args.no_torch_gpu_baseline:
         net = opt = None
         torch.cuda.empty_cache()
