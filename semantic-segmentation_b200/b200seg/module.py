@@ -79,7 +79,10 @@ class B200SegModule(nn.Module):
         self.arch = arch
         self.criterion = criterion
         self.loss_kind = _criterion_kind(criterion)
-        self.hcfg = hcfg or A.HRNET_W48
+        self.is_deepv3 = arch == "deepv3.DeepV3PlusW38"
+        self.hcfg = hcfg or (A.WRN38 if self.is_deepv3 else A.HRNET_W48)
+        self._stem = "backbone.mod1.conv1.weight" if self.is_deepv3 else "backbone.conv1.weight"
+        self.wrn_dropout_scale = 1.0     # tests set 0.0 for a dropout-free step
         self.ocfg = dict(ocfg or A.OCR_DEFAULT)
         self.ocfg["num_classes"] = num_classes
         assert num_classes == 19, "kernels are instantiated for the 19 Cityscapes classes"
@@ -122,7 +125,14 @@ class B200SegModule(nn.Module):
             in_backbone = parts[0] == "backbone"
             if kind == "conv_w":
                 w = torch.empty(shape)
-                if in_backbone:
+                if self.is_deepv3:
+                    # WRN-38 trunk: nn.Conv2d default; ASPP / bot_* / final: initialize_weights = kaiming_normal_
+                    # (network/deepv3.py:66-69, network/mynn.py:27-39)
+                    if in_backbone:
+                        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+                    else:
+                        nn.init.kaiming_normal_(w)
+                elif in_backbone:
                     nn.init.normal_(w, std=0.001)
                 else:
                     nn.init.kaiming_uniform_(w, a=math.sqrt(5))
@@ -208,14 +218,14 @@ class B200SegModule(nn.Module):
     def _engine_grads(self, which="hi"):
         """name -> fp32 tensor an Engine accumulates into, plus the stem's padded [O][9][16] scratch accumulator."""
         g = dict(self._eng_grads[which])
-        stem = "backbone.conv1.weight"
+        stem = self._stem
         dev = self._flat_grad.device
         pad = torch.zeros((g[stem].shape[0], 9, 16), dtype=F32, device=dev)
         g[stem] = pad
         return g, pad
 
     def _fold_grads(self, stem_pads, with_lo):
-        stem = "backbone.conv1.weight"
+        stem = self._stem
         for pad in stem_pads:
             o = pad.shape[0]
             self._grad_views[stem].add_(pad[:, :, :3].permute(0, 2, 1).reshape(o, 3, 3, 3))
@@ -361,6 +371,15 @@ class B200SegModule(nn.Module):
 
     def _drop_mask(self, n, device):
         """Dropout2d(0.05) channel mask (network/ocr_utils.py:146) drawn from torch's generator, folded with 1/(1-p)."""
+        if self.is_deepv3:
+            # WRN-38 mod6 / mod7: Dropout2d(0.3) / Dropout2d(0.5) in front of conv3 (network/wider_resnet.py:302 patches
+            # nn.Dropout to Dropout2d; :336-338). One flat fp32 buffer, [n, c] per block in A.wrn_drop_layout order.
+            parts = []
+            for _bp, c, p in A.wrn_drop_layout(self.hcfg):
+                p = p * self.wrn_dropout_scale
+                keep = torch.bernoulli(torch.full((n * c,), 1.0 - p, dtype=F32, device=device))
+                parts.append(keep / (1.0 - p))
+            return torch.cat(parts) if parts else None
         if self.arch == "basic.HRNet":
             return None
         p = self.ocfg["dropout"]
