@@ -18,6 +18,10 @@ import time
 # The SyncBN exchange spins inside kernels of two concurrent streams per GPU: give every stream its own hardware work
 # queue (the default 8 connections can alias streams and turn a peer wait into a false cross-stream dependency).
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+if "--syncbn" in sys.argv:
+    # Lazy module loading may synchronise the context when a kernel is launched for the first time; a host thread
+    # blocked there while its GPU spins on a peer is the documented lazy-loading deadlock. Load everything up front.
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "semantic-segmentation_b200")):
@@ -29,6 +33,10 @@ import torch  # noqa: E402
 # Algorithmic work per 1024x2048 crop (SURVEY.md §8d / BASELINE.md §2, conv FLOPs = 2*MAC)
 TFLOP_PER_CROP = {"ocrnet.HRNet_Mscale": 10.53, "ocrnet.HRNet": 7.77}
 FWD_TFLOP_1X = 3.0546
+# Launch-level roofline of one train step per 1024x2048 crop: sum over the step's launches of max(FLOPs / sustained bf16
+# peak, bytes / HBM copy bandwidth), from the static trace of the real step program (tools/trace_step.py,
+# profiles/r1_step_roofline_model.txt; peaks of MEASURED_PEAKS.json: 1386.7 TFLOP/s, 6572.9 GB/s)
+STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.10, "ocrnet.HRNet": 11.34}
 
 
 def parse():
@@ -48,6 +56,9 @@ def parse():
     ap.add_argument("--torch-sgd", action="store_true", help="torch.optim.SGD instead of b200seg.optim.FusedSGD")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-gpu-baseline", action="store_true",
+                    help="also time the reference algorithm through stock PyTorch (ATen / cuDNN, autocast bf16 and fp32) on "
+                         "this GPU: the practical kernel to beat (BASELINE.md §5); adds `torch_gpu_baseline` to the line")
     return ap.parse_args()
 
 
@@ -122,6 +133,12 @@ def usable_cores():
     return max(1, min(n, 64))
 
 
+def workload_name(args):
+    """config.workload, identical for both arms (the driver pairs their lines)."""
+    return ("%s two-scale {0.5,1.0} train step (zero_grad, fwd+bwd, SGD momentum + weight decay), %dx%d crops, "
+            "%d crop/GPU, %s loss" % (args.arch, args.height, args.width, args.batch_per_gpu, args.criterion.upper()))
+
+
 def synth_batch(n, h, w, seed, device):
     g = torch.Generator().manual_seed(seed)
     images = torch.randn((n, 3, h, w), generator=g)
@@ -163,6 +180,43 @@ def cpu_reference_step_time(arch, h, w, steps, warmup=1, budget_s=60.0, criterio
     return sum(times) / len(times), len(times)
 
 
+def torch_gpu_step_time(arch, h, w, autocast, criterion="ce", steps=5, warmup=3):
+    """The reference algorithm (oracle restatement = the reference's own call sequence of F.conv2d / batch_norm /
+    interpolate / softmax ...) through stock PyTorch on the current GPU: ATen + cuDNN kernels, NCHW, cudnn.benchmark as
+    in train.py:330, optionally under torch.autocast(bf16) (the modern spelling of the reference's apex AMP O1).
+    Baseline measurement only, rank 0, never on the product path. Returns milliseconds per step (CUDA events)."""
+    from oracle import seg_oracle as O
+    torch.backends.cudnn.benchmark = True
+    sd = {k: v.cuda() for k, v in O.synth_state_dict(arch, O.HRNET_W48, seed=0).items()}
+    params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    images, gts = O.synth_batch(1, h, w, seed=1)
+    images, gts = images.cuda(), gts.cuda()
+    crit = O.criterion_rmi if criterion == "rmi" else O.criterion_ce
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            ctx = O.Ctx(sd, training=True)
+            if arch == "ocrnet.HRNet_Mscale":
+                loss = O.mscale_two_scale(ctx, images, gts, criterion=crit)
+            else:
+                loss = O.ocrnet_forward(ctx, images, gts, criterion=crit)
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -178,8 +232,7 @@ def run_reference(args):
     line = dict(metric="1024x2048 crops/sec fwd+bwd HRNet-OCR-MScale", value=value, unit="crops/s", impl="reference",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 / value,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32", data="synthetic",
-                config=dict(workload="%s two-scale train step (fwd+bwd+SGD), %dx%d crop, bs1, %s loss" %
-                            (args.arch, args.height, args.width, args.criterion.upper())),
+                config=dict(workload=workload_name(args)),
                 cpu_baseline=dict(value=value, unit="crops/s", cores=cores, kind="port",
                                   sample="%d timed step(s) of the full algorithm at %dx%d (1/%d of the pixels, 90 s "
                                          "budget), rescaled by the pixel ratio" % (timed, sh, sw, round(1 / ratio))),
@@ -349,12 +402,13 @@ def run_b200(args):
         metric="1024x2048 crops/sec fwd+bwd HRNet-OCR-MScale", value=value, unit="crops/s", n_gpus=world,
         steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-        config=dict(workload="%s two-scale {0.5,1.0} train step (zero_grad, fused fwd+bwd, grad publish%s, SGD "
-                             "momentum + weight decay), %dx%d crops, %d crop/GPU, %s loss, %s" %
-                             (args.arch, "+NCCL all-reduce" if world > 1 else "", H, W, B, args.criterion.upper(),
-                              "SyncBN: per-layer statistics exchanged through NVLink peer memory inside the BN "
-                              "finalisers" if (world > 1 and args.syncbn) else
-                              "BatchNorm statistics local to each GPU (SyncBN is opt-in: --syncbn)"),
+        config=dict(workload=workload_name(args),
+                    step="fused fwd+bwd through the C ABI inside one CUDA graph, gradient publish%s, %s" %
+                         (" + one NCCL all-reduce over the flat gradient buffer" if world > 1 else "",
+                          "torch.optim.SGD" if args.torch_sgd else "b200seg FusedSGD"),
+                    batchnorm="SyncBN: per-layer statistics exchanged through NVLink peer memory inside the BN finalisers"
+                              if (world > 1 and args.syncbn) else
+                              "statistics local to each GPU (SyncBN is opt-in: --syncbn)",
                     global_batch=B * world, parallelism="dp%d" % world, cuda_graph=not args.no_graph,
                     l2_policy="per-step working set (>4 GB of activations) far exceeds the 126 MB L2; the "
                               "single-kernel roofline run flushes L2 with a 256 MB write between iterations",
@@ -370,8 +424,26 @@ def run_b200(args):
         gpu_launches_note="%d b200seg kernels per step (inside one CUDA graph replay), three timed loops" % kernels_per_step,
         model_flops_utilisation=dict(achieved_tflops=step_tflops / 1.0, peak=pk["tf_sust"],
                                      frac=step_tflops / pk["tf_sust"], peak_source=pk["src"] + " sustained bf16"),
+        step_roofline=dict(model_ms_per_step=STEP_ROOFLINE_MS[args.arch] * (H * W) / (1024.0 * 2048.0) * B,
+                           frac=STEP_ROOFLINE_MS[args.arch] * (H * W) / (1024.0 * 2048.0) * B / (ms / args.steps),
+                           what="sum over the step's launches of max(FLOPs/P, bytes/B), static trace of the step "
+                                "program (profiles/r1_step_roofline_model.txt)"),
         roofline=roof, clocks=clocks, last_loss=loss_val,
         max_memory_allocated_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
+    if args.torch_gpu_baseline:
+        del net, opt
+        torch.cuda.empty_cache()
+        tg = {}
+        for name, ac in (("autocast_bf16", True), ("fp32_tf32_off", False)):
+            try:
+                ms_t = torch_gpu_step_time(args.arch, H, W, ac, args.criterion)
+                tg[name] = dict(ms_per_step=ms_t, value=1000.0 / ms_t, unit="crops/s")
+            except Exception as e:  # noqa
+                tg[name] = dict(error=repr(e))
+            torch.cuda.empty_cache()
+        tg["what"] = ("oracle restatement of the reference algorithm through stock PyTorch eager (ATen/cuDNN, NCHW, "
+                      "cudnn.benchmark, torch.optim.SGD), one crop, same GPU, device-resident inputs")
+        line["torch_gpu_baseline"] = tg
     if not args.no_cpu_baseline:
         try:
             sh, sw = 128, 256

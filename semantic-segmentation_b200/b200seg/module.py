@@ -322,8 +322,6 @@ class B200SegModule(nn.Module):
         if sync is not None:
             sync.advance()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
-        if getattr(self, "_side_stream", None) is None:
-            self._side_stream = torch.cuda.Stream()
         par = self.parallel_scales and self.arch == "ocrnet.HRNet_Mscale"
         self._acc_hi.zero_()         # two memsets (45 us each) beat clearing inside the fold's transposed gather
         if par:

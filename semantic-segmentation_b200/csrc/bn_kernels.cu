@@ -96,7 +96,9 @@ __device__ __forceinline__ void sync_exchange(const SyncArgs& sy, int C, int c, 
     for (int r = 0; r < sy.world; ++r) {
       unsigned spins = 0;
       unsigned long long t0 = 0;
-      while (ld_acquire_sys(myflags + r * nblk) != step) {
+      // flags are monotonic step numbers: a peer that is already one step ahead (it wrote step + 1 into the OTHER parity
+      // half) must not be waited for, so compare by order, not by equality
+      while ((int)(ld_acquire_sys(myflags + r * nblk) - step) < 0) {
         if ((++spins & 0xFFFFu) == 0) {            // a lost peer traps after 180 s instead of hanging the GPU
           unsigned long long now;
           asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));

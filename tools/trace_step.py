@@ -73,8 +73,16 @@ def main():
     ap.add_argument("--arch", default="ocrnet.HRNet_Mscale")
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--width", type=int, default=2048)
-    ap.add_argument("--tflops", type=float, default=1386.7, help="sustained dense bf16 TFLOP/s (MEASURED_PEAKS.json)")
-    ap.add_argument("--gbs", type=float, default=6650.0, help="HBM copy bandwidth GB/s (MEASURED_PEAKS.json)")
+    pk = dict(bf16_tflops_sustained=1386.7, hbm_gbs=6572.9)       # this pool's measured values; refreshed from the file
+    try:
+        import json
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk.update(json.load(f))
+    except (OSError, ValueError):
+        pass
+    ap.add_argument("--tflops", type=float, default=pk["bf16_tflops_sustained"],
+                    help="sustained dense bf16 TFLOP/s (MEASURED_PEAKS.json)")
+    ap.add_argument("--gbs", type=float, default=pk["hbm_gbs"], help="HBM copy bandwidth GB/s (MEASURED_PEAKS.json)")
     ap.add_argument("--top", type=int, default=0, help="also list the N largest launches by roofline time")
     args = ap.parse_args()
     if __debug__:
