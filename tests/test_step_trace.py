@@ -39,7 +39,6 @@ def test_single_scale_architectures_trace():
     assert abs(r["total"][1] - 7.77) <= 0.08, r["total"]                 # 3 x 2.5907 TFLOP
     r = _trace("--arch", "basic.HRNet", "--height", "256", "--width", "512")
     assert abs(r["total"][1] - 0.365) <= 0.01, r["total"]                # cfg1
-<<<<<<< HEAD
 
 
 def test_deepv3_wrn38_program_traces():
@@ -47,5 +46,3 @@ def test_deepv3_wrn38_program_traces():
     assert abs(r["total"][1] - 34.95) <= 0.35, r["total"]                # 3 x 11.65 TFLOP
     assert r["maxpool3x3s2_fwd"][0] == 2 and r["maxpool3x3s2_bwd"][0] == 2
     assert r["conv2d_fwd"][0] + r["conv2d_fwd_add"][0] == r["conv2d_wgrad"][0]
-=======
->>>>>>> main
