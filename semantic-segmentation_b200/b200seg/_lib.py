@@ -20,7 +20,7 @@ P32 = ctypes.POINTER(c_int32)
 class ConvDesc(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "n", "h", "w", "cin", "cout", "ksize", "stride", "pad", "x_ld", "y_ld",
-        "out_fp32", "has_bias", "emit_stats", "reserved")]
+        "out_fp32", "has_bias", "emit_stats", "reserved", "dilation")]
 
 
 class FuseTerm(ctypes.Structure):
@@ -79,6 +79,7 @@ SIGNATURES = {
     "b200seg_conv2d_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V, P32, V]),
     "b200seg_set_smem_reserve": (ctypes.c_int, [I32]),
     "b200seg_conv2d_fwd_bn": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, ctypes.POINTER(BnFold), V]),
+    "b200seg_conv2d_fwd_add": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, I32, V, V, P32, V]),
     "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
     "b200seg_pack_weight": (ctypes.c_int, [V, I32, I32, I32, V, V, I32, V]),
     "b200seg_pack_chunk": (I32, []),
@@ -134,6 +135,13 @@ SIGNATURES = {
     "b200seg_resize_to_nchw": (ctypes.c_int, [V, I32, I32, I32, I32, I32, I32, V, I32, I32, V]),
     "b200seg_resize_nchw": (ctypes.c_int, [V, I32, I32, I32, V, I32, I32, V]),
     "b200seg_blend": (ctypes.c_int, [V, V, V, V, I32, I32, I64, I32, V]),
+    "b200seg_maxpool3x3s2_fwd": (ctypes.c_int, [V, I32, I32, I32, I32, I32, V, I32, V]),
+    "b200seg_maxpool3x3s2_bwd": (ctypes.c_int, [V, I32, V, I32, I32, I32, I32, I32, V, I32, I32, V]),
+    "b200seg_channel_stats_grid": (I32, [I64, I32]),
+    "b200seg_channel_stats": (ctypes.c_int, [V, I32, I64, I32, V, V]),
+    "b200seg_spatial_sum_splits": (I32, [I32]),
+    "b200seg_spatial_sum": (ctypes.c_int, [V, I32, I32, I32, I32, F, V, V, I32, I32, V]),
+    "b200seg_broadcast_pixels": (ctypes.c_int, [V, I32, I32, I32, I32, F, V, I32, I32, V]),
     "b200seg_accum_pred": (ctypes.c_int, [V, V, I32, I32, I32, I32, I32, I32, V]),
     "b200seg_argmax_hist": (ctypes.c_int, [V, I32, I32, I64, F, V, V, V, V, V]),
 }

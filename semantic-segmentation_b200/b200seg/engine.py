@@ -24,17 +24,19 @@ BN_MOMENTUM = 0.1   # network/hrnetv2.py:25 and the nn.BatchNorm2d default
 
 
 class Act:
-    __slots__ = ("t", "grad", "needs_grad")
+    __slots__ = ("t", "grad", "needs_grad", "stats")
 
     def __init__(self, t, needs_grad=True):
         self.t = t
         self.grad = None
         self.needs_grad = needs_grad
+        self.stats = None      # (partials, grid, cpad) batch statistics of t when a pre-activation BatchNorm follows
 
 
 class ConvBNRec:
     """A convolution + batch-statistics record whose affine/activation is applied later (bn_act or inside a fuse)."""
-    __slots__ = ("x", "y", "cname", "bname", "ksize", "stride", "cout", "scale", "shift", "mean", "invstd", "has_bias")
+    __slots__ = ("x", "y", "cname", "bname", "ksize", "stride", "cout", "scale", "shift", "mean", "invstd", "has_bias",
+                 "dil")
 
 
 class HeadRec:
@@ -156,16 +158,16 @@ class Engine:
         """After every stream of the step has been joined: drop the cross-stream keep-alive references."""
         self.hold.clear()
 
-    def wgrad(self, x_t, dy, dw, cout, ksize, stride):
+    def wgrad(self, x_t, dy, dw, cout, ksize, stride, dilation=1):
         """dw += wgrad(x, dy) on the side stream. Operands are kept alive until the streams are joined (the caching
         allocator must not hand their memory to main-stream allocations while the side stream still reads them)."""
         if self.side is None:
-            raw.conv2d_wgrad(x_t, dy, dw, cout, ksize, stride)
+            raw.conv2d_wgrad(x_t, dy, dw, cout, ksize, stride, dilation=dilation)
             return
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            ws = raw.conv2d_wgrad(x_t, dy, dw, cout, ksize, stride, ws_holder=self.ws_holder)
+            ws = raw.conv2d_wgrad(x_t, dy, dw, cout, ksize, stride, ws_holder=self.ws_holder, dilation=dilation)
         self._keepalive.append((x_t, dy, ws))
 
     def _push(self, fn):
@@ -181,26 +183,27 @@ class Engine:
             new_grad_fn(act.grad)
 
     # ------------------------------------------------------------------------------------------ conv + BN
-    def conv_stats(self, x, cname, bname, ksize, stride=1, bias=False):
+    def conv_stats(self, x, cname, bname, ksize, stride=1, bias=False, dilation=1):
         w_f, _ = self.packed[cname]
         rec = ConvBNRec()
         rec.x, rec.cname, rec.bname, rec.ksize, rec.stride, rec.has_bias = x, cname, bname, ksize, stride, bias
         rec.cout = w_f.shape[0]
+        rec.dil = dilation
         b = self.p[cname + ".bias"] if bias else None
         if self.training and self.bnfold is not None:
             acc, ticket = self.bnfold[bname]
             if self.bstat is not None:
                 self.bn_seen.add(bname)
                 y, par = raw.conv2d_fwd_bn(x.t, w_f, b, stride, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
-                                           BN_MOMENTUM, acc, ticket, batch_out=self.bstat[bname])
+                                           BN_MOMENTUM, acc, ticket, batch_out=self.bstat[bname], dilation=dilation)
             else:
                 y, par = raw.conv2d_fwd_bn(x.t, w_f, b, stride, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
                                            BN_MOMENTUM, acc, ticket, running_mean=self.p[bname + ".running_mean"],
                                            running_var=self.p[bname + ".running_var"],
-                                           nbt=self.p[bname + ".num_batches_tracked"])
+                                           nbt=self.p[bname + ".num_batches_tracked"], dilation=dilation)
             rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], par[2], par[3]
         elif self.training:
-            y, stats = raw.conv2d_fwd(x.t, w_f, b, stride=stride, emit_stats=True)
+            y, stats = raw.conv2d_fwd(x.t, w_f, b, stride=stride, emit_stats=True, dilation=dilation)
             n, ho, wo, _ = y.shape
             if self.bstat is not None:
                 self.bn_seen.add(bname)
@@ -213,7 +216,7 @@ class Engine:
                                       self.p[bname + ".num_batches_tracked"], rec.cout, sync=self._sync(bname, 0))
             rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], par[2], par[3]
         else:
-            y = raw.conv2d_fwd(x.t, w_f, b, stride=stride)
+            y = raw.conv2d_fwd(x.t, w_f, b, stride=stride, dilation=dilation)
             par = raw.bn_eval_params(self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
                                      self.p[bname + ".running_mean"], self.p[bname + ".running_var"])
             rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], None, None
@@ -230,14 +233,15 @@ class Engine:
                         g_accumulate=g_accumulate, sync=self._sync(rec.bname, 1),
                         fold=self.bnfold[rec.bname] if self.bnfold is not None else None)
         x = rec.x
-        self.wgrad(x.t, dy, self.g[rec.cname + ".weight"], rec.cout, rec.ksize, rec.stride)
+        self.wgrad(x.t, dy, self.g[rec.cname + ".weight"], rec.cout, rec.ksize, rec.stride, rec.dil)
         # a conv bias in front of a training-mode BN has an exactly zero gradient (BN removes the mean): left at 0
         if x.needs_grad:
             _, w_d = self.packed[rec.cname]
             if x.grad is None:
-                x.grad = raw.conv2d_dgrad(dy, w_d, tuple(x.t.shape), rec.ksize, rec.stride)
+                x.grad = raw.conv2d_dgrad(dy, w_d, tuple(x.t.shape), rec.ksize, rec.stride, dilation=rec.dil)
             else:
-                raw.conv2d_dgrad(dy, w_d, tuple(x.t.shape), rec.ksize, rec.stride, addend=x.grad, out=x.grad)
+                raw.conv2d_dgrad(dy, w_d, tuple(x.t.shape), rec.ksize, rec.stride, addend=x.grad, out=x.grad,
+                                 dilation=rec.dil)
 
     def bn_act(self, rec, relu=True, residual=None, out=None, post_scale=None):
         z = raw.bn_apply(rec.y, rec.scale, rec.shift, residual.t if residual is not None else None, post_scale, relu,
@@ -261,9 +265,133 @@ class Engine:
         return za
 
     def conv_bn(self, x, cname, bname, ksize, stride=1, relu=True, residual=None, out=None, bias=False,
-                post_scale=None):
-        rec = self.conv_stats(x, cname, bname, ksize, stride, bias)
+                post_scale=None, dilation=1):
+        rec = self.conv_stats(x, cname, bname, ksize, stride, bias, dilation)
         return self.bn_act(rec, relu, residual, out, post_scale)
+
+    # ------------------------------------------------------------------------------------------ pre-activation networks
+    def _add_grad(self, act, g):
+        """act.grad += g with copy semantics (g may still be read by a weight-gradient kernel on the side stream)."""
+        if not act.needs_grad:
+            return
+        if act.grad is None:
+            act.grad = raw._new(g.shape, dtype=BF16, device=g.device)
+            raw.masked_accum(g, None, act.grad, False)
+        else:
+            raw.masked_accum(g, None, act.grad, True)
+
+    def conv_sum(self, x, cname, ksize, stride=1, dilation=1, addend=None, want_stats=False, out=None):
+        """y = conv(x) (+ addend) with no normalisation behind it; the epilogue can emit the batch statistics of y for a
+        pre-activation BatchNorm further down (IdentityResidualBlock, network/wider_resnet.py:170-183). y may have any
+        number of consumers: its producer's backward runs after all of theirs."""
+        w_f, _ = self.packed[cname]
+        cout = w_f.shape[0]
+        stats = None
+        res = raw.conv2d_fwd(x.t, w_f, None, stride=stride, emit_stats=want_stats and self.training, dilation=dilation,
+                             addend=addend.t if addend is not None else None, out=out)
+        if want_stats and self.training:
+            y, stats = res
+        else:
+            y = res
+        ya = Act(y)
+        ya.stats = stats
+
+        def bwd():
+            dy = ya.grad
+            if dy is None:
+                return
+            self.wgrad(x.t, dy, self.g[cname + ".weight"], cout, ksize, stride, dilation)
+            if x.needs_grad:
+                _, w_d = self.packed[cname]
+                if x.grad is None:
+                    x.grad = raw.conv2d_dgrad(dy, w_d, tuple(x.t.shape), ksize, stride, dilation=dilation)
+                else:
+                    raw.conv2d_dgrad(dy, w_d, tuple(x.t.shape), ksize, stride, addend=x.grad, out=x.grad,
+                                     dilation=dilation)
+            if addend is not None:
+                self._add_grad(addend, dy)
+            ya.grad = None
+        self._push(bwd)
+        return ya
+
+    def preact(self, x, bname, post_scale=None):
+        """a = relu(BN(x)) for an activation whose batch statistics are already known (x.stats)."""
+        c = x.t.shape[3]
+        if self.training:
+            assert x.stats is not None, "pre-activation BN needs the batch statistics of its input"
+            n, h, w, _ = x.t.shape
+            par = raw.bn_finalize(x.stats, n * h * w, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
+                                  BN_MOMENTUM, self.p[bname + ".running_mean"], self.p[bname + ".running_var"],
+                                  self.p[bname + ".num_batches_tracked"], c, sync=self._sync(bname, 0))
+        else:
+            par = raw.bn_eval_params(self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
+                                     self.p[bname + ".running_mean"], self.p[bname + ".running_var"])
+        a = raw.bn_apply(x.t, par[0], par[1], None, post_scale, True)
+        aa = Act(a)
+
+        def bwd():
+            dz = aa.grad
+            if dz is None:
+                return
+            dy = raw.bn_bwd(dz, a, post_scale, x.t, par[2], par[3], self.p[bname + ".weight"],
+                            self.g[bname + ".weight"], self.g[bname + ".bias"], sync=self._sync(bname, 1))
+            if x.needs_grad:
+                if x.grad is None:
+                    x.grad = dy                  # fresh tensor, no other reader
+                else:
+                    raw.masked_accum(dy, None, x.grad, True)
+            aa.grad = None
+        self._push(bwd)
+        return aa
+
+    def maxpool(self, x):
+        """nn.MaxPool2d(3, 2, 1) (+ the batch statistics of the pooled map for the pre-activation BN behind it)."""
+        y = raw.maxpool3x3s2(x.t)
+        ya = Act(y)
+        if self.training:
+            ya.stats = raw.channel_stats(y)
+
+        def bwd():
+            if ya.grad is None or not x.needs_grad:
+                return
+            if x.grad is None:
+                x.grad = raw.maxpool3x3s2_bwd(x.t, ya.grad)
+            else:
+                raw.maxpool3x3s2_bwd(x.t, ya.grad, out=x.grad, accumulate=True)
+            ya.grad = None
+        self._push(bwd)
+        return ya
+
+    def image_pool(self, x):
+        """nn.AdaptiveAvgPool2d(1): [n,h,w,c] -> [n,1,1,c]."""
+        n, h, w, c = x.t.shape
+        va = Act(raw.spatial_sum(x.t, 1.0 / (h * w)))
+
+        def bwd():
+            if va.grad is None or not x.needs_grad:
+                return
+            if x.grad is None:
+                x.grad = raw.broadcast_pixels(va.grad, h, w, scale=1.0 / (h * w))
+            else:
+                raw.broadcast_pixels(va.grad, h, w, out=x.grad, scale=1.0 / (h * w), accumulate=True)
+            va.grad = None
+        self._push(bwd)
+        return va
+
+    def broadcast(self, v, h, w, out):
+        """Upsample of a 1x1 map into (a channel slice of) an [n,h,w,*] buffer."""
+        oa = Act(raw.broadcast_pixels(v.t, h, w, out=out))
+
+        def bwd():
+            if oa.grad is None:
+                return
+            if v.grad is None:
+                v.grad = raw.spatial_sum(oa.grad, 1.0)
+            else:
+                raw.spatial_sum(oa.grad, 1.0, out=v.grad, accumulate=True)
+            oa.grad = None
+        self._push(bwd)
+        return oa
 
     # ------------------------------------------------------------------------------------------ fuse / resample
     def fuse(self, out_shape, terms, relu=True, out=None):

@@ -6,6 +6,7 @@ reference's output assembly in fp32 NCHW on the device.
   mscale.HRNet        : MscaleBase.nscale_forward / two_scale_forward eval branches (network/mscale.py:114-231)
   ocrnet.HRNet        : OCRNet.forward eval branch (:104-122)
   basic.HRNet         : Basic.forward eval branch (network/basic.py:50-64)
+  deepv3.DeepV3PlusW38: DeepV3Plus.forward eval branch (network/deepv3.py:73-96)
 """
 import torch
 
@@ -40,6 +41,9 @@ def eval_forward(module, images):
     tensors = {k: v.detach() for k, v in module._tensors().items()}
     E = Engine(tensors, {}, module._packed, False, None)
     arch = module.arch
+    if arch == "deepv3.DeepV3PlusW38":          # DeepV3Plus.forward eval branch (network/deepv3.py:73-96)
+        head = M.deepv3_pass(E, images, module.hcfg)
+        return {"pred": raw.resize_to_nchw(head.logits, 19, H, W)}
     if not A.is_two_scale(arch):
         return {"pred": _pass(module, E, images, (H, W))["cls_out"]}
 

@@ -86,7 +86,10 @@ class B200SegModule(nn.Module):
         self.arch = arch
         self.criterion = criterion
         self.loss_kind = _criterion_kind(criterion)
-        self.hcfg = hcfg or A.HRNET_W48
+        self.is_deepv3 = arch == "deepv3.DeepV3PlusW38"
+        self.hcfg = hcfg or (A.WRN38 if self.is_deepv3 else A.HRNET_W48)
+        self._stem = "backbone.mod1.conv1.weight" if self.is_deepv3 else "backbone.conv1.weight"
+        self.wrn_dropout_scale = 1.0     # tests set 0.0 for a dropout-free step
         self.ocfg = dict(ocfg or A.OCR_DEFAULT)
         self.ocfg["num_classes"] = num_classes
         if num_classes != 19:
@@ -134,7 +137,14 @@ class B200SegModule(nn.Module):
             in_backbone = parts[0] == "backbone"
             if kind == "conv_w":
                 w = torch.empty(shape)
-                if in_backbone:
+                if self.is_deepv3:
+                    # WRN-38 trunk: nn.Conv2d default; ASPP / bot_* / final: initialize_weights = kaiming_normal_
+                    # (network/deepv3.py:66-69, network/mynn.py:27-39)
+                    if in_backbone:
+                        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+                    else:
+                        nn.init.kaiming_normal_(w)
+                elif in_backbone:
                     nn.init.normal_(w, std=0.001)
                 else:
                     nn.init.kaiming_uniform_(w, a=math.sqrt(5))
@@ -461,6 +471,15 @@ class B200SegModule(nn.Module):
 
     def _drop_mask(self, n, device):
         """Dropout2d(0.05) channel mask (network/ocr_utils.py:146) drawn from torch's generator, folded with 1/(1-p)."""
+        if self.is_deepv3:
+            # WRN-38 mod6 / mod7: Dropout2d(0.3) / Dropout2d(0.5) in front of conv3 (network/wider_resnet.py:302 patches
+            # nn.Dropout to Dropout2d; :336-338). One flat fp32 buffer, [n, c] per block in A.wrn_drop_layout order.
+            parts = []
+            for _bp, c, p in A.wrn_drop_layout(self.hcfg):
+                p = p * self.wrn_dropout_scale
+                keep = torch.bernoulli(torch.full((n * c,), 1.0 - p, dtype=F32, device=device))
+                parts.append(keep / (1.0 - p))
+            return torch.cat(parts) if parts else None
         if not A.has_ocr(self.arch):
             return None
         p = self.ocfg["dropout"]

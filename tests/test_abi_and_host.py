@@ -65,8 +65,9 @@ def test_factory_contract_and_cpu_refusal():
     assert type(net).__name__ == "B200SegModule" and net.arch == "ocrnet.HRNet_Mscale"
     assert network.get_model("network.basic.HRNet", 19, None).arch == "basic.HRNet"
     assert network.get_model("network.mscale.HRNet", 19, None).arch == "mscale.HRNet"      # network/mscale.py:473-475
+    assert network.get_model("network.deepv3.DeepV3PlusW38", 19, None).arch == "deepv3.DeepV3PlusW38"
     with pytest.raises((ImportError, ModuleNotFoundError, AttributeError)):
-        network.get_model("network.deepv3.DeepV3PlusW38", 19, None)     # outside the hot path: not provided
+        network.get_model("network.deepv3.DeepV3PlusSRNX50V3PlusD_m1", 19, None)   # other trunks: not provided
     net.train()
     with pytest.raises(RuntimeError, match="CUDA only"):                 # no CPU fallback
         net({"images": torch.zeros(1, 3, 64, 64), "gts": torch.zeros(1, 64, 64, dtype=torch.long)})

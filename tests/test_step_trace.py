@@ -58,3 +58,10 @@ def test_mscale_basic_architecture_traces():
     want = 1.25 * fwd1 + 2.0 * (1.25 * fwd1 - 2.0 * 294.7e-3)
     assert abs(r["total"][1] - want) <= 0.01 * want, (r["total"], want)
     assert r["conv2d_wgrad"][0] == r["conv2d_fwd"][0] + r["conv2d_fwd_bn"][0] - 3
+
+
+def test_deepv3_wrn38_program_traces():
+    r = _trace("--arch", "deepv3.DeepV3PlusW38")
+    assert abs(r["total"][1] - 34.95) <= 0.35, r["total"]                # 3 x 11.65 TFLOP
+    assert r["maxpool3x3s2_fwd"][0] == 2 and r["maxpool3x3s2_bwd"][0] == 2
+    assert r["conv2d_fwd"][0] + r.get("conv2d_fwd_bn", (0,))[0] + r["conv2d_fwd_add"][0] == r["conv2d_wgrad"][0]

@@ -112,7 +112,11 @@ def main():
             grads[n] = torch.empty(p.shape, dtype=torch.float32, device=dev)
     images = torch.empty((1, 3, args.height, args.width), dtype=torch.float32, device=dev)
     gts = torch.empty((1, args.height, args.width), dtype=torch.long, device=dev)
-    mask = torch.empty((1, net.ocfg["mid_channels"]), dtype=torch.float32, device=dev)
+    if args.arch.startswith("deepv3."):
+        from b200seg import arch as A
+        mask = torch.empty((sum(c for _b, c, _p in A.wrn_drop_layout(net.hcfg)),), dtype=torch.float32, device=dev)
+    else:
+        mask = torch.empty((1, net.ocfg["mid_channels"]), dtype=torch.float32, device=dev)
     bnfold = None
     if not args.separate_bn_finalize:
         bnfold = {n[: -len(".running_mean")]: (torch.empty(2 * ((v.shape[0] + 15) // 16 * 16), dtype=torch.float64, device=dev),
