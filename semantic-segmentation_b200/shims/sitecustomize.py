@@ -18,6 +18,16 @@ if sys.argv and os.path.basename(sys.argv[0]) == "train.py":
     if not have and "LOCAL_RANK" in os.environ:
         argv += ["--local_rank", os.environ["LOCAL_RANK"]]
     sys.argv[1:] = argv
+    # `python train.py` puts the script's own directory (the reference checkout, with its network/ package) in FRONT of
+    # PYTHONPATH, after this module has run: bind the overlay's `network` package now, while the overlay directory
+    # (first on PYTHONPATH) still wins, so that train.py's `import network` finds it in sys.modules.
+    if os.environ.get("B200SEG_OVERLAY", "1") != "0":
+        try:
+            import network as _network  # noqa: F401
+            if "semantic-segmentation_b200" not in os.path.abspath(_network.__file__):
+                del sys.modules["network"]
+        except Exception as _e:  # noqa
+            print("b200seg sitecustomize: could not pre-import the overlay network package: %r" % (_e,), file=sys.stderr)
     try:
         import numpy as _np
         if not hasattr(_np, "int"):
