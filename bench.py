@@ -34,7 +34,7 @@ FWD_TFLOP_1X = 3.0546
 # profiles/r1_step_roofline_model.txt; peaks of MEASURED_PEAKS.json: 1386.7 TFLOP/s, 6572.9 GB/s)
 # SyncBN at --gpus N > 1 unless --no-syncbn (every reference script trains with syncbn: true)
 SYNCBN_DEFAULT = False
-STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.02, "ocrnet.HRNet": 11.34}
+STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.12, "ocrnet.HRNet": 11.34}
 # the same model per kernel class (profiles/r2_step_roofline_model.txt): class -> (kernel-name fragments, roofline ms)
 KERNEL_CLASSES = {
     "conv fwd+dgrad (tcgen05)": (("conv3x3_halo", "conv_igemm"), 2.960 + 2.954 + 0.135),

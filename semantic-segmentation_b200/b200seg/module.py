@@ -100,10 +100,12 @@ class B200SegModule(nn.Module):
         # NVLink peer memory (needs torch.distributed, world > 1); None / False = per-GPU statistics. Opt-in for now: the
         # exchange was validated on 2 GPUs only.
         self.syncbn = syncbn
-        # BatchNorm statistics finalised inside the convolution launch (csrc/bn_fold.cuh); B200SEG_FUSED_BN=0 restores the
-        # separate bn_finalize launches (A/B measurements); SyncBN always uses the separate finaliser (its exchange)
+        # BatchNorm statistics finalised inside the producing launches (csrc/bn_fold.cuh): 1262 launches fewer per step,
+        # but measured 0.9 ms SLOWER on the device (40.18 vs 39.3 ms, alternating runs on one box: the tail of every
+        # convolution grows by ~4 us while the removed finalisers ran on a handful of SMs next to other work) with no
+        # clear end-to-end gain, so it is opt-in (B200SEG_FUSED_BN=1); SyncBN always uses the separate finaliser.
         import os
-        self.fused_bn_finalize = os.environ.get("B200SEG_FUSED_BN", "1") != "0"
+        self.fused_bn_finalize = os.environ.get("B200SEG_FUSED_BN", "0") == "1"
         self._sync = None
         self._run_flat = None
         self._specs = A.tensor_specs(arch, self.hcfg, self.ocfg)
