@@ -461,6 +461,12 @@ def run_b200(args):
     barrier()
     ms_e2e_block = b_e0.elapsed_time(b_e1)
     clocks = sampler.stop() if rank == 0 else None
+    # one extra (collective) step under the profiler on EVERY rank: a step contains the all-reduce / SyncBN exchanges
+    try:
+        classes = kernel_class_table(lambda: step(images_d, gts_d), ms / args.steps)
+    except Exception as e:  # noqa
+        classes = dict(error=repr(e))
+    barrier()
     if dist is not None:
         t = torch.tensor([ms, ms_e2e, ms_e2e_block], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -472,10 +478,6 @@ def run_b200(args):
     e2e_value = crops / (ms_e2e * 1e-3)
     pk = peaks()
     roof = dominant_kernel_roofline(pk)
-    try:
-        classes = kernel_class_table(lambda: step(images_d, gts_d), ms / args.steps)
-    except Exception as e:  # noqa
-        classes = dict(error=repr(e))
     step_tflops = TFLOP_PER_CROP[args.arch] * (H * W) / (1024.0 * 2048.0) * B / (ms / args.steps * 1e-3) / 1e0
     kernels_per_step = getattr(net, "kernels_per_step", 0)
     line = dict(

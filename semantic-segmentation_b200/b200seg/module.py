@@ -350,8 +350,13 @@ class B200SegModule(nn.Module):
         if getattr(self, "_side_stream", None) is None:
             self._side_stream = torch.cuda.Stream()
         sync = self._sync
-        # under SyncBN keep the validated stream structure: everything of the repack on the main stream
-        wd_ready = self._repack(side=self._side_stream if sync is None else None)
+        # SyncBN: B200SEG_SYNCBN_BRANCH_STREAMS=0 restores the two-chain structure (one stream per scale pass + its side
+        # stream, repack on the main stream); the default runs the same 21-stream program as per-GPU statistics - the
+        # one-warp waiter kernels never keep another kernel from being scheduled (csrc/bn_kernels.cu), so up to eight
+        # exchanges (four branches x two passes) are in flight and hide each other's NVLink round trips.
+        import os
+        wide = sync is None or os.environ.get("B200SEG_SYNCBN_BRANCH_STREAMS", "1") != "0"
+        wd_ready = self._repack(side=self._side_stream if wide else None)
         if sync is not None:
             sync.advance()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
@@ -359,17 +364,13 @@ class B200SegModule(nn.Module):
         self._acc_hi.zero_()         # two memsets (45 us each) beat clearing inside the fold's transposed gather
         if par:
             self._acc_lo.zero_()
-        # every allocation of the step stays referenced until its final join (raw.py); SyncBN mode keeps the stream /
-        # allocation structure that was validated on 2 GPUs (no branch streams, no keep-alive, fresh wgrad workspaces)
-        raw.KEEP = [] if sync is None else None
+        # every allocation of the step stays referenced until its final join (raw.py)
+        raw.KEEP = [] if wide else None
         if getattr(self, "_bstreams", None) is None:
-            # SyncBN spins on peers inside the BN finalisers: keep the validated stream structure (one stream per scale
-            # pass + its side stream) there; branch-level streams are a single-GPU-statistics optimisation for now
-            use_b = self.parallel_branches and self._sync is None
+            use_b = self.parallel_branches and wide
             mk = lambda: [torch.cuda.Stream() for _ in range(3)] if use_b else []
             self._bstreams = {"hi": mk(), "lo": mk()}
-            hold = self._sync is None      # reusable slab workspaces go with the keep-alive mode
-            self._ws_holders = {"hi": [None] if hold else None, "lo": [None] if hold else None}
+            self._ws_holders = {"hi": [None] if wide else None, "lo": [None] if wide else None}
         grads = self._engine_grads("hi")
         E_lo = None
         if par:
