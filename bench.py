@@ -32,7 +32,9 @@ FWD_TFLOP_1X = 3.0546
 # Launch-level roofline of one train step per 1024x2048 crop: sum over the step's launches of max(FLOPs / sustained bf16
 # peak, bytes / HBM copy bandwidth), from the static trace of the real step program (tools/trace_step.py,
 # profiles/r1_step_roofline_model.txt; peaks of MEASURED_PEAKS.json: 1386.7 TFLOP/s, 6572.9 GB/s)
-STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.02, "ocrnet.HRNet": 11.34}
+# SyncBN at --gpus N > 1 unless --no-syncbn (every reference script trains with syncbn: true)
+SYNCBN_DEFAULT = False
+STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.12, "ocrnet.HRNet": 11.34}
 # the same model per kernel class (profiles/r2_step_roofline_model.txt): class -> (kernel-name fragments, roofline ms)
 KERNEL_CLASSES = {
     "conv fwd+dgrad (tcgen05)": (("conv3x3_halo", "conv_igemm"), 2.960 + 2.954 + 0.135),
@@ -109,8 +111,10 @@ def parse():
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--sup-wt", type=float, default=0.0)
     ap.add_argument("--criterion", default="ce", choices=["ce", "rmi"])
-    ap.add_argument("--syncbn", action="store_true",
-                    help="synchronise BatchNorm statistics across the GPUs (NVLink peer-memory exchange; validated at N=2)")
+    ap.add_argument("--syncbn", dest="syncbn", action="store_true", default=None,
+                    help="synchronise BatchNorm statistics across the GPUs through NVLink peer memory (syncbn: true in every "
+                         "reference script); the default for --gpus N > 1")
+    ap.add_argument("--no-syncbn", dest="syncbn", action="store_false", help="per-GPU BatchNorm statistics at N > 1")
     ap.add_argument("--torch-sgd", action="store_true", help="torch.optim.SGD instead of b200seg.optim.FusedSGD")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -355,8 +359,11 @@ def run_b200(args):
     from b200seg import _lib
 
     torch.manual_seed(0)
+    if args.syncbn is None:
+        args.syncbn = SYNCBN_DEFAULT
+    args.syncbn = bool(args.syncbn and world > 1)
     net = B200SegModule(args.arch, 19, criterion=args.criterion, supervised_mscale_wt=args.sup_wt,
-                        use_cuda_graph=not args.no_graph, syncbn=bool(args.syncbn and world > 1)).cuda().train()
+                        use_cuda_graph=not args.no_graph, syncbn=args.syncbn).cuda().train()
     net._ddp_allreduce = world > 1
     # well-scaled weights (the reference's default N(0,1e-3) init underflows activations after a few BN-free paths)
     with torch.no_grad():
@@ -454,6 +461,12 @@ def run_b200(args):
     barrier()
     ms_e2e_block = b_e0.elapsed_time(b_e1)
     clocks = sampler.stop() if rank == 0 else None
+    # one extra (collective) step under the profiler on EVERY rank: a step contains the all-reduce / SyncBN exchanges
+    try:
+        classes = kernel_class_table(lambda: step(images_d, gts_d), ms / args.steps)
+    except Exception as e:  # noqa
+        classes = dict(error=repr(e))
+    barrier()
     if dist is not None:
         t = torch.tensor([ms, ms_e2e, ms_e2e_block], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -465,10 +478,6 @@ def run_b200(args):
     e2e_value = crops / (ms_e2e * 1e-3)
     pk = peaks()
     roof = dominant_kernel_roofline(pk)
-    try:
-        classes = kernel_class_table(lambda: step(images_d, gts_d), ms / args.steps)
-    except Exception as e:  # noqa
-        classes = dict(error=repr(e))
     step_tflops = TFLOP_PER_CROP[args.arch] * (H * W) / (1024.0 * 2048.0) * B / (ms / args.steps * 1e-3) / 1e0
     kernels_per_step = getattr(net, "kernels_per_step", 0)
     line = dict(
@@ -479,9 +488,9 @@ def run_b200(args):
                     step="fused fwd+bwd through the C ABI inside one CUDA graph, gradient publish%s, %s" %
                          (" + one NCCL all-reduce over the flat gradient buffer" if world > 1 else "",
                           "torch.optim.SGD" if args.torch_sgd else "b200seg FusedSGD"),
-                    batchnorm="SyncBN: per-layer statistics exchanged through NVLink peer memory inside the BN finalisers"
-                              if (world > 1 and args.syncbn) else
-                              "statistics local to each GPU (SyncBN is opt-in: --syncbn)",
+                    batchnorm="SyncBN: per-layer statistics exchanged through NVLink peer memory (non-blocking post in the "
+                              "finaliser, one-warp waiter kernels)" if (world > 1 and args.syncbn) else
+                              "statistics local to each GPU" + (" (--no-syncbn)" if world > 1 else ""),
                     global_batch=B * world, parallelism="dp%d" % world, cuda_graph=not args.no_graph,
                     l2_policy="per-step working set (>4 GB of activations) far exceeds the 126 MB L2; the "
                               "single-kernel roofline run flushes L2 with a 256 MB write between iterations",

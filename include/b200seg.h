@@ -66,7 +66,7 @@ int32_t b200seg_debug_occupancy(int32_t kernel, int32_t occ_variant, int32_t sme
 void b200seg_debug_occupancy_report(void);
 
 /* Process-wide planner setting: bytes of shared memory per SM every tensor-core kernel leaves unused (default 0).
- * SyncBN mode sets 4096: the one-warp kernels that wait for a peer GPU's BatchNorm statistics (1 KB of reserved shared
+ * SyncBN mode sets 12288: the one-warp kernels that wait for a peer GPU's BatchNorm statistics (1 KB of reserved shared
  * memory each) must fit on an SM next to ANY convolution CTA, otherwise a waiting warp can keep a persistent
  * convolution of another stream from completing and two GPUs wait for each other forever. */
 int b200seg_set_smem_reserve(int32_t bytes);

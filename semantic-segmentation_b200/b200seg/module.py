@@ -103,10 +103,12 @@ class B200SegModule(nn.Module):
         # NVLink peer memory (needs torch.distributed, world > 1); None / False = per-GPU statistics. Opt-in for now: the
         # exchange was validated on 2 GPUs only.
         self.syncbn = syncbn
-        # BatchNorm statistics finalised inside the convolution launch (csrc/bn_fold.cuh); B200SEG_FUSED_BN=0 restores the
-        # separate bn_finalize launches (A/B measurements); SyncBN always uses the separate finaliser (its exchange)
+        # BatchNorm statistics finalised inside the producing launches (csrc/bn_fold.cuh): 1262 launches fewer per step,
+        # but measured 0.9 ms SLOWER on the device (40.18 vs 39.3 ms, alternating runs on one box: the tail of every
+        # convolution grows by ~4 us while the removed finalisers ran on a handful of SMs next to other work) with no
+        # clear end-to-end gain, so it is opt-in (B200SEG_FUSED_BN=1); SyncBN always uses the separate finaliser.
         import os
-        self.fused_bn_finalize = os.environ.get("B200SEG_FUSED_BN", "1") != "0"
+        self.fused_bn_finalize = os.environ.get("B200SEG_FUSED_BN", "0") == "1"
         self._sync = None
         self._run_flat = None
         self._specs = A.tensor_specs(arch, self.hcfg, self.ocfg)
@@ -358,8 +360,13 @@ class B200SegModule(nn.Module):
         if getattr(self, "_side_stream", None) is None:
             self._side_stream = torch.cuda.Stream()
         sync = self._sync
-        # under SyncBN keep the validated stream structure: everything of the repack on the main stream
-        wd_ready = self._repack(side=self._side_stream if sync is None else None)
+        # SyncBN: B200SEG_SYNCBN_BRANCH_STREAMS=0 restores the two-chain structure (one stream per scale pass + its side
+        # stream, repack on the main stream); the default runs the same 21-stream program as per-GPU statistics - the
+        # one-warp waiter kernels never keep another kernel from being scheduled (csrc/bn_kernels.cu), so up to eight
+        # exchanges (four branches x two passes) are in flight and hide each other's NVLink round trips.
+        import os
+        wide = sync is None or os.environ.get("B200SEG_SYNCBN_BRANCH_STREAMS", "1") != "0"
+        wd_ready = self._repack(side=self._side_stream if wide else None)
         if sync is not None:
             sync.advance()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
@@ -367,17 +374,13 @@ class B200SegModule(nn.Module):
         self._acc_hi.zero_()         # two memsets (45 us each) beat clearing inside the fold's transposed gather
         if par:
             self._acc_lo.zero_()
-        # every allocation of the step stays referenced until its final join (raw.py); SyncBN mode keeps the stream /
-        # allocation structure that was validated on 2 GPUs (no branch streams, no keep-alive, fresh wgrad workspaces)
-        raw.KEEP = [] if sync is None else None
+        # every allocation of the step stays referenced until its final join (raw.py)
+        raw.KEEP = [] if wide else None
         if getattr(self, "_bstreams", None) is None:
-            # SyncBN spins on peers inside the BN finalisers: keep the validated stream structure (one stream per scale
-            # pass + its side stream) there; branch-level streams are a single-GPU-statistics optimisation for now
-            use_b = self.parallel_branches and self._sync is None
+            use_b = self.parallel_branches and wide
             mk = lambda: [torch.cuda.Stream() for _ in range(3)] if use_b else []
             self._bstreams = {"hi": mk(), "lo": mk()}
-            hold = self._sync is None      # reusable slab workspaces go with the keep-alive mode
-            self._ws_holders = {"hi": [None] if hold else None, "lo": [None] if hold else None}
+            self._ws_holders = {"hi": [None] if wide else None, "lo": [None] if wide else None}
         grads = self._engine_grads("hi")
         E_lo = None
         if par:
@@ -567,5 +570,32 @@ class B200SegModule(nn.Module):
             if self._anchor is None or self._anchor.device != loss5.device:
                 self._anchor = torch.zeros(1, device=loss5.device, requires_grad=True)
             return _PublishGrads.apply(self, loss5[0], self._anchor)
+        return self._eval_forward(images)
+
+    def _eval_forward(self, images):
+        """Eval mode: the first call for an input shape runs eagerly, the second is captured into a CUDA graph (about a
+        thousand launches per scale pass), later calls replay it. The returned maps are fresh tensors (copies of the
+        graph's static outputs), so callers may keep them across calls like the reference's."""
         from .evalpath import eval_forward
-        return eval_forward(self, images)
+        if not self.use_cuda_graph or not images.is_cuda:
+            return eval_forward(self, images)
+        self._ensure_device_state()
+        images = images.contiguous().float()
+        key = ("eval", tuple(images.shape), str(images.device), tuple(self.n_scales or ()))
+        st = self._graphs.get(key)
+        if st is None:
+            st = dict(images=images.clone(), calls=0, graph=None, out=None)
+            self._graphs[key] = st
+        st["calls"] += 1
+        if st["graph"] is None:
+            if st["calls"] < 2:
+                return eval_forward(self, images)
+            st["images"].copy_(images)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["out"] = eval_forward(self, st["images"])
+            st["graph"] = g
+        st["images"].copy_(images)
+        st["graph"].replay()
+        return {k: v.clone() for k, v in st["out"].items()}

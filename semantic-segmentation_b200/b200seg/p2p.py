@@ -38,8 +38,9 @@ class SyncBNContext:
         self.names = list(bn_channels)
         self.n_passes = n_passes
         dev = torch.device("cuda", torch.cuda.current_device())
-        # the one-warp waiter kernels must fit next to any convolution CTA (csrc/bn_kernels.cu sync_wait_fold)
-        check(lib().b200seg_set_smem_reserve(4096), "set_smem_reserve", 0)
+        # the one-warp waiter kernels (1 KB of reserved shared memory each, up to 2 passes x 4 branches in flight, several
+        # blocks per exchange) must fit next to any convolution CTA (csrc/bn_kernels.cu sync_wait_fold)
+        check(lib().b200seg_set_smem_reserve(12288), "set_smem_reserve", 0)
         self.mail_off, self.flag_off, moff, foff = exchange_layout(bn_channels, self.world, n_passes)
         self.parity_stride = moff
         L = lib()

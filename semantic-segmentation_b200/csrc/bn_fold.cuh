@@ -36,7 +36,9 @@ __device__ __forceinline__ void bn_fold_tail(const BnFoldDev& f, const float* s_
     const float v = (s_stats[i] + s_stats[2 * cout_pad + i]) + (s_stats[4 * cout_pad + i] + s_stats[6 * cout_pad + i]);
     atomicAdd(f.accum + i, (double)v);
   }
-  __threadfence();
+  // Only the threads that added to the accumulator fence (their adds must be visible before the ticket is drawn): a
+  // fence in the epilogue threads would also wait for their outstanding output stores, which nobody here depends on.
+  if ((int)threadIdx.x < 2 * cout_pad) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) *s_ticket_p = atomicAdd(f.counter, 1u);
   __syncthreads();

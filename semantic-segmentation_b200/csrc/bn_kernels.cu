@@ -298,30 +298,47 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const float* __re
   __syncthreads();
   const int groups = C >> 3;
   const long long total = npix * groups;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long pix = idx / groups;
-    const int c0 = (int)(idx - pix * groups) << 3;
-    float v[8];
-    load8(y + pix * y_ld + c0, v);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = 4;               // 16-byte vectors in flight per thread and tensor (the pass is pure latency otherwise)
+  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += U * stride) {
+    uint4 yv[U], rv[U];
+    long long pix[U];
+    int c0[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = v[j] * s_par[c0 + j] + s_par[C + c0 + j];
-    if (res) {
-      float r[8];
-      load8(res + pix * res_ld + c0, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    for (int u = 0; u < U; ++u) {
+      const long long idx = base + u * stride;
+      const long long pp = idx / groups;
+      pix[u] = pp;
+      c0[u] = (int)(idx - pp * groups) << 3;
+      if (idx < total) {
+        yv[u] = *reinterpret_cast<const uint4*>(y + pp * y_ld + c0[u]);
+        if (res) rv[u] = *reinterpret_cast<const uint4*>(res + pp * res_ld + c0[u]);
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-    }
-    if (post_scale) {
-      const float* ps = post_scale + (pix / hw) * C + c0;
+    for (int u = 0; u < U; ++u) {
+      if (base + u * stride >= total) break;
+      float v[8];
+      unpack8(yv[u], v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= ps[j];
+      for (int j = 0; j < 8; ++j) v[j] = v[j] * s_par[c0[u] + j] + s_par[C + c0[u] + j];
+      if (res) {
+        float r[8];
+        unpack8(rv[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += r[j];
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (post_scale) {
+        const float* ps = post_scale + (pix[u] / hw) * C + c0[u];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= ps[j];
+      }
+      store8(z + pix[u] * z_ld + c0[u], v);
     }
-    store8(z + pix * z_ld + c0, v);
   }
 }
 
@@ -351,25 +368,42 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv
 #pragma unroll
   for (int j = 0; j < 8; ++j) { m[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; s1[j] = 0.f; s2[j] = 0.f; }
   if (r < rows) {
-    for (long long pix = (long long)blockIdx.x * rows + r; pix < npix; pix += (long long)gridDim.x * rows) {
-      float g[8], yv[8];
-      load8(dz + pix * dz_ld + c0, g);
-      if (post_scale) {
-        const float* ps = post_scale + (pix / hw) * C + c0;
+    constexpr int U = 4;             // pixels in flight per thread (three 16-byte loads each): the pass is latency bound otherwise
+    const long long pstride = (long long)gridDim.x * rows;
+    for (long long p0 = (long long)blockIdx.x * rows + r; p0 < npix; p0 += U * pstride) {
+      uint4 gq[U], mq[U], yq[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= ps[j];
+      for (int u = 0; u < U; ++u) {
+        const long long pix = p0 + u * pstride;
+        if (pix < npix) {
+          gq[u] = *reinterpret_cast<const uint4*>(dz + pix * dz_ld + c0);
+          if (mask) mq[u] = *reinterpret_cast<const uint4*>(mask + pix * mask_ld + c0);
+          yq[u] = *reinterpret_cast<const uint4*>(y + pix * y_ld + c0);
+        }
       }
-      if (mask) {
-        float mk[8];
-        load8(mask + pix * mask_ld + c0, mk);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = mk[j] > 0.f ? g[j] : 0.f;
-      }
-      load8(y + pix * y_ld + c0, yv);
+      for (int u = 0; u < U; ++u) {
+        const long long pix = p0 + u * pstride;
+        if (pix >= npix) break;
+        float g[8], yv[8];
+        unpack8(gq[u], g);
+        if (post_scale) {
+          const float* ps = post_scale + (pix / hw) * C + c0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += g[j];
-        s2[j] += g[j] * (yv[j] - m[j]) * is[j];
+          for (int j = 0; j < 8; ++j) g[j] *= ps[j];
+        }
+        if (mask) {
+          float mk[8];
+          unpack8(mq[u], mk);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = mk[j] > 0.f ? g[j] : 0.f;
+        }
+        unpack8(yq[u], yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += g[j];
+          s2[j] += g[j] * (yv[j] - m[j]) * is[j];
+        }
       }
     }
     float* dst = s_red + ((size_t)r * groups + cg) * 16;
@@ -470,38 +504,59 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv_
   __syncthreads();
   const int groups = C >> 3;
   const long long total = npix * groups;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long pix = idx / groups;
-    const int c0 = (int)(idx - pix * groups) << 3;
-    float g[8], yv[8], o[8];
-    load8(dz + pix * dz_ld + c0, g);
-    if (post_scale) {
-      const float* ps = post_scale + (pix / hw) * C + c0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = 3;               // 16-byte vectors in flight per thread and tensor
+  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += U * stride) {
+    uint4 gq[U], mq[U], yq[U], oq[U];
+    long long pixs[U];
+    int c0s[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] *= ps[j];
-    }
-    if (mask) {
-      float mk[8];
-      load8(mask + pix * mask_ld + c0, mk);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = mk[j] > 0.f ? g[j] : 0.f;
-    }
-    load8(y + pix * y_ld + c0, yv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xhat = (yv[j] - s_par[c0 + j]) * s_par[C + c0 + j];
-      o[j] = s_par[2 * C + c0 + j] * (g[j] - s_par[3 * C + c0 + j] - xhat * s_par[4 * C + c0 + j]);
-    }
-    store8(dy + pix * dy_ld + c0, o);
-    if (g_out) {
-      if (g_accumulate) {
-        float old[8];
-        load8(g_out + pix * g_ld + c0, old);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += old[j];
+    for (int u = 0; u < U; ++u) {
+      const long long idx = base + u * stride;
+      const long long pix = idx / groups;
+      pixs[u] = pix;
+      c0s[u] = (int)(idx - pix * groups) << 3;
+      if (idx < total) {
+        gq[u] = *reinterpret_cast<const uint4*>(dz + pix * dz_ld + c0s[u]);
+        if (mask) mq[u] = *reinterpret_cast<const uint4*>(mask + pix * mask_ld + c0s[u]);
+        yq[u] = *reinterpret_cast<const uint4*>(y + pix * y_ld + c0s[u]);
+        if (g_out && g_accumulate) oq[u] = *reinterpret_cast<const uint4*>(g_out + pix * g_ld + c0s[u]);
       }
-      store8(g_out + pix * g_ld + c0, g);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * stride >= total) break;
+      const long long pix = pixs[u];
+      const int c0 = c0s[u];
+      float g[8], yv[8], o[8];
+      unpack8(gq[u], g);
+      if (post_scale) {
+        const float* ps = post_scale + (pix / hw) * C + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] *= ps[j];
+      }
+      if (mask) {
+        float mk[8];
+        unpack8(mq[u], mk);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = mk[j] > 0.f ? g[j] : 0.f;
+      }
+      unpack8(yq[u], yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = (yv[j] - s_par[c0 + j]) * s_par[C + c0 + j];
+        o[j] = s_par[2 * C + c0 + j] * (g[j] - s_par[3 * C + c0 + j] - xhat * s_par[4 * C + c0 + j]);
+      }
+      store8(dy + pix * dy_ld + c0, o);
+      if (g_out) {
+        if (g_accumulate) {
+          float old[8];
+          unpack8(oq[u], old);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += old[j];
+        }
+        store8(g_out + pix * g_ld + c0, g);
+      }
     }
   }
 }

@@ -527,9 +527,11 @@ static int halo_plan(int n, int h, int w, int cin, int cout, HaloParams& p, size
   p.b_tile_bytes = (p.BN * 128 + 1023) / 1024 * 1024;
   p.acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
   p.tmem_cols = 2 * p.acc_stride;
-  // staged TMA-store epilogue with register-resident statistics for the narrow (HBM-bound) layers; B200SEG_HALO_FAST=0
-  // switches it off (A/B measurements). It needs the full register file, so it runs one CTA per SM.
-  static const bool fast_enabled = []() { const char* e = getenv("B200SEG_HALO_FAST"); return !(e && e[0] == '0'); }();
+  // staged TMA-store epilogue with register-resident statistics for the narrow (HBM-bound) layers (opt-in).
+  // Measured (round 2, whole step): the staged epilogue is faster per launch but needs the full register file, i.e. one
+  // CTA per SM, and the 48 / 64-channel layers it applies to gain more from two co-resident CTAs per SM (39.4 vs
+  // 40.3 ms per step) - it is therefore OFF unless B200SEG_HALO_FAST=1.
+  static const bool fast_enabled = []() { const char* e = getenv("B200SEG_HALO_FAST"); return e && e[0] == '1'; }();
   const bool fast = fast_enabled && p.n_tiles == 1 && p.BN <= 64;
   p.stage_bytes = fast ? 2 * kStageTile : 0;
   { const char* e = getenv("B200SEG_DBG"); p.dbg = e ? atoi(e) : 0; }

@@ -337,3 +337,33 @@ def test_device_prefetcher_double_buffer_keeps_batches_intact():
     for i, s in enumerate(sums):
         want = host[i]["images"].double().sum() + host[i]["gts"].double().sum()
         assert abs(float(s) - float(want)) <= 1e-6 * abs(float(want)) + 1e-6, i
+
+
+@pytest.mark.parametrize("n_scales", [None, [0.5, 1.0, 2.0]])
+def test_eval_graph_replay_equals_eager(n_scales):
+    """Eval mode: eager first call, captured second call, replays - identical maps, fresh output tensors, new weights and
+    new inputs are picked up by the replay."""
+    O, B200SegModule = _mods()
+    arch, hcfg = "ocrnet.HRNet_Mscale", O.HRNET_W16_TEST
+    sd0 = O.synth_state_dict(arch, hcfg, seed=3)
+    _condition_eval_weights(sd0)
+    net = B200SegModule(arch, 19, hcfg=hcfg, n_scales=n_scales)
+    net.load_state_dict(sd0)
+    net = net.cuda().eval()
+    ims = [O.synth_batch(2, 64, 128, seed=s)[0].cuda() for s in (5, 6)]
+    eager = [net({"images": ims[0]})]                       # call 1: eager
+    outs = [net({"images": ims[0]}), net({"images": ims[0]})]   # capture + replay
+    for o in outs:
+        assert sorted(o.keys()) == sorted(eager[0].keys())
+        for k in o:
+            assert torch.equal(o[k], eager[0][k]), k
+    assert outs[0]["pred"].data_ptr() != outs[1]["pred"].data_ptr()
+    ref_net = B200SegModule(arch, 19, hcfg=hcfg, n_scales=n_scales, use_cuda_graph=False)
+    ref_net.load_state_dict(sd0)
+    ref_net = ref_net.cuda().eval()
+    with torch.no_grad():                                   # new weights + new input through the replay
+        for p in list(net.parameters()) + list(ref_net.parameters()):
+            p.mul_(1.01)
+    a, b = net({"images": ims[1]}), ref_net({"images": ims[1]})
+    for k in a:
+        assert torch.equal(a[k], b[k]), k

@@ -226,10 +226,14 @@ def test_conv_logit_head_fp32_and_padded_grads():
     close(db, dl[..., :19].float().sum((0, 1, 2)), 1e-3, "bias grad")
 
 
-@pytest.mark.parametrize("c,res,relu", [(48, True, True), (96, False, True), (720, False, False), (256, True, True)])
-def test_batchnorm_train_fwd_bwd(c, res, relu):
+@pytest.mark.parametrize("c,res,relu,size", [(48, True, True, (2, 24, 40)), (96, False, True, (2, 24, 40)),
+                                             (720, False, False, (2, 24, 40)), (256, True, True, (2, 24, 40)),
+                                             # many pixels per thread: the multi-vector (unrolled) paths of the passes
+                                             (48, True, True, (1, 256, 512)), (96, False, True, (1, 131, 257)),
+                                             (192, True, False, (2, 64, 128))])
+def test_batchnorm_train_fwd_bwd(c, res, relu, size):
     raw = _setup()
-    n, h, w = 2, 24, 40
+    n, h, w = size
     x = rnd((n, h, w, 64), 1)
     wt = rnd((c, 64, 1, 1), 2, scale=0.2, dtype=torch.float32).contiguous()
     w_f, _ = raw.pack_weight(wt, want_dgrad=False)

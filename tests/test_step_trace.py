@@ -25,20 +25,17 @@ def test_two_scale_step_flops_and_launch_structure():
     r = _trace("--arch", "ocrnet.HRNet_Mscale")
     total = r["total"]
     assert abs(total[1] - 10.53) <= 0.01 * 10.53 + 0.05, total           # TFLOP per 1024x2048 crop
-    # convolutions followed by a training-mode BatchNorm finalise its statistics inside their own launch (conv2d_fwd_bn);
-    # the logit heads / OCR products go through conv2d_fwd
-    fwd_bn, fwd_plain, dgrad, wgrad = r["conv2d_fwd_bn"], r["conv2d_fwd"], r["conv2d_dgrad"], r["conv2d_wgrad"]
-    assert fwd_bn[0] == 2 * 316 and "bn_finalize" not in r              # 316 BatchNorm layers per scale pass
-    n_fwd = fwd_bn[0] + fwd_plain[0]
-    assert n_fwd == 2 * 322                                              # 322 convolutions per scale pass
+    fwd, dgrad, wgrad = r["conv2d_fwd"], r["conv2d_dgrad"], r["conv2d_wgrad"]
+    assert fwd[0] == 2 * 322                                             # 322 convolutions per scale pass
     # the 1.0x attention head (3 convolutions) has no backward; the two stem convolutions need no data gradient
-    assert wgrad[0] == n_fwd - 3 and dgrad[0] == n_fwd - 3 - 2
-    assert abs(fwd_bn[1] + fwd_plain[1] - 1.25 * 3.0546) <= 0.02         # 1.25 x one full-resolution _fwd
-    assert "bn_bwd_finalize" not in r and r["bn_bwd_reduce_finalize"][0] == r["bn_bwd_apply"][0]
-    s = _trace("--arch", "ocrnet.HRNet_Mscale", "--separate-bn-finalize")     # the SyncBN program shape
-    assert s["bn_finalize"][0] == 2 * 316 and s["conv2d_fwd"][0] == 2 * 322
-    assert s["bn_bwd_finalize"][0] == s["bn_bwd_reduce"][0] == s["bn_bwd_apply"][0]
-    assert s["total"][0] - r["total"][0] == 2 * 316 + s["bn_bwd_finalize"][0]     # launches the fused finalisers save
+    assert wgrad[0] == fwd[0] - 3 and dgrad[0] == fwd[0] - 3 - 2
+    assert abs(fwd[1] - 1.25 * 3.0546) <= 0.02                           # 1.25 x one full-resolution _fwd
+    assert r["bn_finalize"][0] == 2 * 316 and r["bn_bwd_finalize"][0] == r["bn_bwd_reduce"][0] == r["bn_bwd_apply"][0]
+    # opt-in program (B200SEG_FUSED_BN=1): statistics finalised inside the producing launches
+    f = _trace("--arch", "ocrnet.HRNet_Mscale", "--fused-bn")
+    assert f["conv2d_fwd_bn"][0] == 2 * 316 and "bn_finalize" not in f and "bn_bwd_finalize" not in f
+    assert f["conv2d_fwd_bn"][0] + f["conv2d_fwd"][0] == 2 * 322
+    assert r["total"][0] - f["total"][0] == 2 * 316 + r["bn_bwd_finalize"][0]     # launches the fused finalisers save
     assert 60.0 < total[2] < 90.0                                        # GB of tensors handed to kernels per crop
 
 
@@ -57,7 +54,7 @@ def test_mscale_basic_architecture_traces():
     fwd1 = 2.0 * (678.3 + 295.3 + 294.7) * 1e-3
     want = 1.25 * fwd1 + 2.0 * (1.25 * fwd1 - 2.0 * 294.7e-3)
     assert abs(r["total"][1] - want) <= 0.01 * want, (r["total"], want)
-    assert r["conv2d_wgrad"][0] == r["conv2d_fwd"][0] + r["conv2d_fwd_bn"][0] - 3
+    assert r["conv2d_wgrad"][0] == r["conv2d_fwd"][0] - 3
 
 
 def test_deepv3_wrn38_program_traces():

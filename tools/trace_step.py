@@ -84,8 +84,9 @@ def main():
                     help="sustained dense bf16 TFLOP/s (MEASURED_PEAKS.json)")
     ap.add_argument("--gbs", type=float, default=pk["hbm_gbs"], help="HBM copy bandwidth GB/s (MEASURED_PEAKS.json)")
     ap.add_argument("--top", type=int, default=0, help="also list the N largest launches by roofline time")
-    ap.add_argument("--separate-bn-finalize", action="store_true",
-                    help="trace the program with bn_finalize launches (SyncBN mode) instead of the in-launch finalisation")
+    ap.add_argument("--fused-bn", action="store_true",
+                    help="trace the opt-in program with the BatchNorm finalisation inside the producing launches "
+                         "(B200SEG_FUSED_BN=1) instead of the default bn_finalize / bn_bwd_finalize launches")
     args = ap.parse_args()
     if __debug__:
         sys.exit("run with python -O (the wrappers assert is_cuda)")
@@ -118,7 +119,7 @@ def main():
     else:
         mask = torch.empty((1, net.ocfg["mid_channels"]), dtype=torch.float32, device=dev)
     bnfold = None
-    if not args.separate_bn_finalize:
+    if args.fused_bn:
         bnfold = {n[: -len(".running_mean")]: (torch.empty(2 * ((v.shape[0] + 15) // 16 * 16), dtype=torch.float64, device=dev),
                                                torch.empty(1, dtype=torch.int32, device=dev))
                   for n, v in tensors.items() if n.endswith(".running_mean")}
