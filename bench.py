@@ -417,6 +417,10 @@ def run_b200(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    if os.environ.get("B200SEG_TIME_ONLY") == "1":              # A/B runs of a switch: the device-timed figure only
+        if rank == 0:
+            print(json.dumps(dict(ms_per_step=ms / args.steps, steps=args.steps, time_only=True)))
+        return
     # ---- end-to-end timing: pinned host inputs -> H2D every step, loss read back every step.
     # (a) pipelined read: the loss of step i is copied to pinned memory asynchronously and read on the host while step
     #     i+1 is already running (what a training loop that logs asynchronously does);

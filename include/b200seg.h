@@ -111,11 +111,6 @@ int b200seg_conv2d_fwd_add(const b200seg_conv_desc* d, const void* x, const void
                            const void* addend, int32_t addend_ld, void* y, float* stats_partials, int32_t* stats_grid,
                            void* stream);
 
-/* Slow, obviously-correct CUDA-core direct convolution with identical numerics contract (fp32 accumulate, one rounding).
- * Used by the GPU test-suite as an on-device cross-check and for shapes the GEMM path does not take. */
-int b200seg_conv2d_fwd_direct(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
-                              void* y, void* stream);
-
 /* Repack fp32 OIHW master weights (the nn.Parameter layout the reference checkpoints use) into the kernel layouts:
  *   w_ohwi  bf16 [O][kh*kw][I]            forward operand
  *   w_dgrad bf16 [I][kh*kw (flipped)][o_pad]  data-gradient operand (may be NULL); o_pad >= O is a multiple of 8 and

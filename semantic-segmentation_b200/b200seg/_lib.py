@@ -80,7 +80,6 @@ SIGNATURES = {
     "b200seg_set_smem_reserve": (ctypes.c_int, [I32]),
     "b200seg_conv2d_fwd_bn": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, ctypes.POINTER(BnFold), V]),
     "b200seg_conv2d_fwd_add": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, I32, V, V, P32, V]),
-    "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
     "b200seg_pack_weight": (ctypes.c_int, [V, I32, I32, I32, V, V, I32, V]),
     "b200seg_pack_chunk": (I32, []),
     "b200seg_pack_weights": (ctypes.c_int, [V, V, V, I32, I32, V]),
@@ -145,8 +144,9 @@ SIGNATURES = {
     "b200seg_accum_pred": (ctypes.c_int, [V, V, I32, I32, I32, I32, I32, I32, V]),
     "b200seg_argmax_hist": (ctypes.c_int, [V, I32, I32, I64, F, V, V, V, V, V]),
 }
-# test-only probe entry point (csrc/probe.h), not part of include/b200seg.h
+# test-only entry points (csrc/probe.h, libb200seg_test.so), not part of include/b200seg.h / the product library
 PROBE_SIGNATURES = {
+    "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
     "b200seg_umma_probe": (ctypes.c_int, [ctypes.POINTER(ProbeDesc), V, V, V, V]),
 }
 
@@ -166,13 +166,31 @@ def lib():
                 "libb200seg.so not found at %s - run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU / PyTorch fallback for the hot path)" % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
-        for table in (SIGNATURES, PROBE_SIGNATURES):
-            for name, (res, args) in table.items():
-                fn = getattr(L, name)
-                fn.restype = res
-                fn.argtypes = args
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
         _lib = L
     return _lib
+
+
+TEST_LIB_PATH = os.path.join(_HERE, "lib", "libb200seg_test.so")
+_test_lib = None
+
+
+def test_lib():
+    """The test-only library (direct cross-check convolution, descriptor probe); never loaded by the product path."""
+    global _test_lib
+    if _test_lib is None:
+        if not os.path.exists(TEST_LIB_PATH):
+            raise B200SegError("libb200seg_test.so not found at %s (make -C csrc)" % TEST_LIB_PATH)
+        L = ctypes.CDLL(TEST_LIB_PATH)
+        for name, (res, args) in PROBE_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _test_lib = L
+    return _test_lib
 
 
 KERNEL_LAUNCHES = 0   # running count of kernels launched through the ABI by this process (bench.py reports it)

@@ -134,7 +134,8 @@ def conv2d_fwd(x, w_ohwi, bias=None, stride=1, out=None, out_fp32=False, emit_st
     d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(out), out_fp32, bias is not None, emit_stats,
                   force_kc, dilation)
     if direct:
-        check(lib().b200seg_conv2d_fwd_direct(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out),
+        from ._lib import test_lib        # test-only library (tests/test_gpu_ops.py cross-check)
+        check(test_lib().b200seg_conv2d_fwd_direct(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out),
                                               stream_ptr()), "conv2d_fwd_direct")
         return out
     stats = None

@@ -28,6 +28,10 @@ def test_library_exports_every_declared_symbol():
         assert s in _lib.SIGNATURES, "ctypes table lacks %s" % s
     for s in _lib.SIGNATURES:
         assert s in syms, "%s is bound but not declared in include/b200seg.h" % s
+    # the test-only kernels live in their own library: the product library does not export them
+    T = _lib.test_lib()
+    for s in _lib.PROBE_SIGNATURES:
+        assert hasattr(T, s) and not hasattr(L, s), s
 
 
 def test_no_torch_types_in_the_abi():
