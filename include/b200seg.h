@@ -105,6 +105,11 @@ typedef struct b200seg_bn_fold {
 int b200seg_conv2d_fwd_bn(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias, void* y,
                           const b200seg_bn_fold* fold, void* stream);
 
+/* Deferred variant (fold->counter == NULL; only accum and c are read): the launch adds its statistics to the cells and
+ * nothing else - the BatchNorm apply pass that consumes the layer finalises them in its prologue (b200seg_bn_apply_cells),
+ * so no finaliser launch and no last-CTA tail sits between the convolution and its consumer. The caller zeroes the cells
+ * once per step. */
+
 /* The same with a residual addend: y = conv(x) (+ bias) + addend[n,ho,wo,cout] (bf16, pitch addend_ld); the statistics
  * are those of the stored sum (pre-activation residual networks: network/wider_resnet.py:170-183). bf16 output only. */
 int b200seg_conv2d_fwd_add(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
@@ -248,6 +253,12 @@ int b200seg_bn_eval_params(int32_t c, const float* gamma, const float* beta, flo
 int b200seg_bn_apply(const void* y, int32_t y_ld, const float* scale, const float* shift, const void* res,
                      int32_t res_ld, const float* post_scale, int32_t relu, void* z, int32_t z_ld, int64_t npix,
                      int32_t hw, int32_t c, void* stream);
+/* The same pass as the consumer of a convolution launched in deferred mode (b200seg_conv2d_fwd_bn with counter == NULL):
+ * every block derives scale / shift from f->accum (fp64 [2][roundup16(c)] sums), block 0 writes f->scale / shift / mean /
+ * invstd (+ batch or running statistics exactly like b200seg_bn_finalize). f->counter is ignored. */
+int b200seg_bn_apply_cells(const void* y, int32_t y_ld, const b200seg_bn_fold* f, const void* res, int32_t res_ld,
+                           const float* post_scale, int32_t relu, void* z, int32_t z_ld, int64_t npix, int32_t hw,
+                           int32_t c, void* stream);
 /* backward: g = dz * post_scale * (mask > 0); partials[grid][2][c] of (sum g, sum g*xhat), grid from _bn_bwd_grid */
 int32_t b200seg_bn_bwd_grid(int64_t npix, int32_t c);
 int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld, const float* post_scale,
@@ -267,6 +278,13 @@ int b200seg_bn_bwd_reduce_finalize(const void* dz, int32_t dz_ld, const void* ma
 int b200seg_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld, const float* post_scale,
                          const void* y, int32_t y_ld, const float* mean, const float* invstd, const float* gamma,
                          const float* c1, const float* c2, void* dy, int32_t dy_ld, void* g_out, int32_t g_ld,
+                         int32_t g_accumulate, int64_t npix, int32_t hw, int32_t c, void* stream);
+/* reduce + gradient pass with deferred finalisation (two launches): the reduction adds its sums to cells ([2][c] fp64,
+ * zeroed by the caller once per step), the gradient pass folds them in its prologue and accumulates dgamma / dbeta
+ * (either may be NULL). Per-GPU statistics only (SyncBN: _reduce + _finalize + _apply). */
+int b200seg_bn_bwd_cells(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld, const float* post_scale,
+                         const void* y, int32_t y_ld, const float* mean, const float* invstd, const float* gamma,
+                         float* dgamma, float* dbeta, double* cells, void* dy, int32_t dy_ld, void* g_out, int32_t g_ld,
                          int32_t g_accumulate, int64_t npix, int32_t hw, int32_t c, void* stream);
 /* dst (=|+=) src * (mask > 0) */
 int b200seg_masked_accum(const void* src, int32_t src_ld, const void* mask, int32_t mask_ld, void* dst, int32_t dst_ld,

@@ -36,7 +36,7 @@ class Act:
 class ConvBNRec:
     """A convolution + batch-statistics record whose affine/activation is applied later (bn_act or inside a fuse)."""
     __slots__ = ("x", "y", "cname", "bname", "ksize", "stride", "cout", "scale", "shift", "mean", "invstd", "has_bias",
-                 "dil")
+                 "dil", "pending", "par")
 
 
 class HeadRec:
@@ -46,7 +46,7 @@ class HeadRec:
 
 class Engine:
     def __init__(self, params, grads, packed, training, drop_mask=None, side_stream=None, bstat=None, stream=None,
-                 sync=None, pass_id=0, branch_streams=None, ws_holder=None, bnfold=None):
+                 sync=None, pass_id=0, branch_streams=None, ws_holder=None, bnfold=None, bncells=None):
         """params: name -> tensor (weights, BN buffers); grads: name -> fp32 tensor accumulated into (training);
         packed: name -> (w_fwd, w_dgrad) bf16 operand caches; drop_mask: fp32 [N, mid] post-ReLU multiplier;
         bstat: BN layer name -> fp32 [2*C] slot receiving the batch [mean | unbiased var] (the running statistics are
@@ -56,6 +56,9 @@ class Engine:
         sync / pass_id: SyncBNContext (p2p.py) and this engine's pass index in its exchange table (data parallel);
         bnfold: BN layer name -> (fp64 accumulator, int32 ticket) cells: the BatchNorm statistics are finalised inside
         the convolution launch (raw.conv2d_fwd_bn) instead of by a bn_finalize launch (per-GPU statistics only);
+        bncells: BN layer name -> (fp64 forward cells [2*roundup16(c)], fp64 backward cells [2*c]), all zero at the start
+        of the step: deferred finalisation - the convolution / the backward reduction only add their sums to the cells
+        and the consuming apply pass folds them in its prologue (no finaliser launch on the chain; per-GPU statistics);
         branch_streams: up to three extra streams for the parallel branches of a HighResolutionModule (branch 0 stays
         on the engine's own stream); ws_holder: reusable weight-gradient slab workspace of the side stream."""
         self.p = params
@@ -70,6 +73,7 @@ class Engine:
         self.bstreams = list(branch_streams or [])
         self.ws_holder = ws_holder
         self.bnfold = bnfold if sync is None else None
+        self.bncells = bncells if (sync is None and self.bnfold is None) else None
         self._ctx = None         # stream of the branch section being recorded (None = the engine's own stream)
         self.pre_backward_event = None   # e.g. "data-gradient weight operands packed" (recorded on another stream)
         self.tape = []
@@ -183,13 +187,24 @@ class Engine:
             new_grad_fn(act.grad)
 
     # ------------------------------------------------------------------------------------------ conv + BN
-    def conv_stats(self, x, cname, bname, ksize, stride=1, bias=False, dilation=1):
+    def conv_stats(self, x, cname, bname, ksize, stride=1, bias=False, dilation=1, defer=False):
+        """defer: the caller applies the BatchNorm with bn_act right away (conv_bn): with deferred finalisation the
+        parameters of the layer exist only once that apply pass has run."""
         w_f, _ = self.packed[cname]
         rec = ConvBNRec()
         rec.x, rec.cname, rec.bname, rec.ksize, rec.stride, rec.has_bias = x, cname, bname, ksize, stride, bias
         rec.cout = w_f.shape[0]
         rec.dil = dilation
+        rec.pending = rec.par = None
         b = self.p[cname + ".bias"] if bias else None
+        if self.training and defer and self.bncells is not None:
+            if self.bstat is not None:
+                self.bn_seen.add(bname)
+            rec.pending = self.bncells[bname][0]
+            rec.y = raw.conv2d_fwd_cells(x.t, w_f, b, stride, rec.pending, dilation=dilation)
+            par = rec.par = raw._new((4, rec.cout), dtype=F32, device=x.t.device)
+            rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], par[2], par[3]
+            return rec
         if self.training and self.bnfold is not None:
             acc, ticket = self.bnfold[bname]
             if self.bstat is not None:
@@ -231,7 +246,8 @@ class Engine:
         dy = raw.bn_bwd(dz, mask, post_scale, rec.y, rec.mean, rec.invstd, self.p[rec.bname + ".weight"],
                         self.g[rec.bname + ".weight"], self.g[rec.bname + ".bias"], g_out=g_out,
                         g_accumulate=g_accumulate, sync=self._sync(rec.bname, 1),
-                        fold=self.bnfold[rec.bname] if self.bnfold is not None else None)
+                        fold=self.bnfold[rec.bname] if self.bnfold is not None else None,
+                        cells=self.bncells[rec.bname][1] if self.bncells is not None else None)
         x = rec.x
         self.wgrad(x.t, dy, self.g[rec.cname + ".weight"], rec.cout, rec.ksize, rec.stride, rec.dil)
         # a conv bias in front of a training-mode BN has an exactly zero gradient (BN removes the mean): left at 0
@@ -244,8 +260,18 @@ class Engine:
                                  dilation=rec.dil)
 
     def bn_act(self, rec, relu=True, residual=None, out=None, post_scale=None):
-        z = raw.bn_apply(rec.y, rec.scale, rec.shift, residual.t if residual is not None else None, post_scale, relu,
-                         out=out)
+        if rec.pending is not None:       # deferred finalisation: this pass turns the cells into the layer's parameters
+            bn = rec.bname
+            kw = dict(batch_out=self.bstat[bn]) if self.bstat is not None else dict(
+                running_mean=self.p[bn + ".running_mean"], running_var=self.p[bn + ".running_var"],
+                nbt=self.p[bn + ".num_batches_tracked"])
+            z = raw.bn_apply_cells(rec.y, rec.pending, rec.par, self.p[bn + ".weight"], self.p[bn + ".bias"], BN_EPS,
+                                   BN_MOMENTUM, residual.t if residual is not None else None, post_scale, relu, out=out,
+                                   **kw)
+            rec.pending = None
+        else:
+            z = raw.bn_apply(rec.y, rec.scale, rec.shift, residual.t if residual is not None else None, post_scale,
+                             relu, out=out)
         za = Act(z)
 
         def bwd():
@@ -266,7 +292,7 @@ class Engine:
 
     def conv_bn(self, x, cname, bname, ksize, stride=1, relu=True, residual=None, out=None, bias=False,
                 post_scale=None, dilation=1):
-        rec = self.conv_stats(x, cname, bname, ksize, stride, bias, dilation)
+        rec = self.conv_stats(x, cname, bname, ksize, stride, bias, dilation, defer=True)
         return self.bn_act(rec, relu, residual, out, post_scale)
 
     # ------------------------------------------------------------------------------------------ pre-activation networks
@@ -334,7 +360,8 @@ class Engine:
             if dz is None:
                 return
             dy = raw.bn_bwd(dz, a, post_scale, x.t, par[2], par[3], self.p[bname + ".weight"],
-                            self.g[bname + ".weight"], self.g[bname + ".bias"], sync=self._sync(bname, 1))
+                            self.g[bname + ".weight"], self.g[bname + ".bias"], sync=self._sync(bname, 1),
+                            cells=self.bncells[bname][1] if self.bncells is not None else None)
             if x.needs_grad:
                 if x.grad is None:
                     x.grad = dy                  # fresh tensor, no other reader

@@ -109,6 +109,10 @@ class B200SegModule(nn.Module):
         # clear end-to-end gain, so it is opt-in (B200SEG_FUSED_BN=1); SyncBN always uses the separate finaliser.
         import os
         self.fused_bn_finalize = os.environ.get("B200SEG_FUSED_BN", "0") == "1"
+        # Deferred finalisation (default): the convolution / the backward reduction add their sums to per-layer fp64
+        # cells and the consuming apply pass folds them in its prologue - no finaliser launch and no last-CTA tail on
+        # the chain conv -> BN -> conv (B200SEG_BN_CELLS=0: separate bn_finalize / bn_bwd_finalize launches).
+        self.bn_cells = os.environ.get("B200SEG_BN_CELLS", "1") == "1" and not self.fused_bn_finalize
         self._sync = None
         self._run_flat = None
         self._specs = A.tensor_specs(arch, self.hcfg, self.ocfg)
@@ -305,6 +309,19 @@ class B200SegModule(nn.Module):
                 cells[b] = (acc[o:o + 2 * cp], tickets[li:li + 1])
                 o += 2 * cp
             self._bnfold.append(cells)
+        # deferred BatchNorm finalisation (csrc/bn_fold.cuh, counter == NULL): per pass and layer a forward cell pair
+        # [2 * roundup16(c)] and a backward one [2 * c], one fp64 arena zeroed at the start of every step
+        n_cells = sum(2 * ((c_ + 15) // 16 * 16) + 2 * c_ for _o, c_ in self._bn_slots.values())
+        self._bncell_arena = torch.zeros(2 * n_cells, dtype=torch.float64, device=dev)
+        self._bncells = []
+        o = 0
+        for _pass in range(2):
+            cells = {}
+            for b, (_o, c_) in self._bn_slots.items():
+                cp = (c_ + 15) // 16 * 16
+                cells[b] = (self._bncell_arena[o:o + 2 * cp], self._bncell_arena[o + 2 * cp:o + 2 * cp + 2 * c_])
+                o += 2 * cp + 2 * c_
+            self._bncells.append(cells)
         self._bstat = [torch.zeros(total, dtype=F32, device=dev) for _ in range(2)]
         self._bstat_views = [{b: t[o_:o_ + 2 * c_] for b, (o_, c_) in self._bn_slots.items()} for t in self._bstat]
         self._graphs = {}
@@ -371,6 +388,10 @@ class B200SegModule(nn.Module):
             sync.advance()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
         par = self.parallel_scales and A.is_two_scale(self.arch)
+        # (one engine per scale pass, or a single pass: a layer's cells are used once per step)
+        use_cells = self.bn_cells and sync is None and (par or not A.is_two_scale(self.arch))
+        if use_cells:
+            self._bncell_arena.zero_()
         self._acc_hi.zero_()         # two memsets (45 us each) beat clearing inside the fold's transposed gather
         if par:
             self._acc_lo.zero_()
@@ -390,14 +411,16 @@ class B200SegModule(nn.Module):
             E_lo = Engine(tensors, grads_lo, self._packed, True, drop_mask, side_stream=self._side_stream_lo,
                           bstat=self._bstat_views[0], stream=self._lo_stream, sync=sync, pass_id=0,
                           branch_streams=self._bstreams["lo"], ws_holder=self._ws_holders["lo"],
-                          bnfold=self._bnfold[0] if self.fused_bn_finalize else None)
+                          bnfold=self._bnfold[0] if self.fused_bn_finalize else None,
+                          bncells=self._bncells[0] if use_cells else None)
         two_pass = A.is_two_scale(self.arch)
         if sync is not None and two_pass and not par:
             raise RuntimeError("SyncBN needs parallel_scales=True for the two-scale step (one engine per pass)")
         E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream,
                    bstat=self._bstat_views[1] if par else None, sync=sync, pass_id=1 if two_pass else 0,
                    branch_streams=self._bstreams["hi"], ws_holder=self._ws_holders["hi"],
-                   bnfold=self._bnfold[1] if self.fused_bn_finalize else None)
+                   bnfold=self._bnfold[1] if self.fused_bn_finalize else None,
+                   bncells=self._bncells[1] if use_cells else None)
         loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,
                             self.ignore_index, E_lo=E_lo, loss_kind=self.loss_kind)
         E.pre_backward_event = wd_ready

@@ -183,6 +183,51 @@ def conv2d_fwd_bn(x, w_ohwi, bias, stride, gamma, beta, eps, momentum, accum, co
     return out, par
 
 
+def _cells_fold(cells, par, gamma, beta, eps, momentum, count, c, batch_out, running_mean, running_var, nbt):
+    f = BnFold()
+    f.accum, f.counter = ptr(cells), None          # counter NULL = deferred finalisation (csrc/bn_fold.cuh)
+    f.gamma, f.beta = ptr(gamma), ptr(beta)
+    f.scale, f.shift, f.mean, f.invstd = ptr(par[0]), ptr(par[1]), ptr(par[2]), ptr(par[3])
+    f.batch_stats_out = ptr(batch_out)
+    f.running_mean, f.running_var, f.num_batches_tracked = ptr(running_mean), ptr(running_var), ptr(nbt)
+    f.eps, f.momentum, f.count, f.c = eps, momentum, float(count), c
+    return f
+
+
+def conv2d_fwd_cells(x, w_ohwi, bias, stride, cells, out=None, dilation=1):
+    """Convolution whose epilogue adds the batch statistics of the stored output to `cells` (fp64 [2*roundup16(cout)],
+    zero at the start of the step) and nothing else: the consuming bn_apply_cells finalises them. Returns y."""
+    assert x.is_cuda and x.dtype == BF16
+    cout, taps, cin = w_ohwi.shape
+    assert cin == x.shape[3], (cin, x.shape)
+    ksize = 3 if taps == 9 else 1
+    n, h, w, _ = x.shape
+    ho, wo = out_hw(h, w, ksize, stride, dilation)
+    if out is None:
+        out = _new((n, ho, wo, cout), dtype=BF16, device=x.device)
+    d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(out), False, bias is not None, True,
+                  dilation=dilation)
+    f = BnFold()
+    f.accum, f.counter, f.c = ptr(cells), None, cout
+    check(lib().b200seg_conv2d_fwd_bn(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out), ctypes.byref(f),
+                                      stream_ptr()), "conv2d_fwd_bn(cells)")
+    return out
+
+
+def bn_apply_cells(y, cells, par, gamma, beta, eps, momentum, res=None, post_scale=None, relu=True, out=None,
+                   batch_out=None, running_mean=None, running_var=None, nbt=None):
+    """bn_apply as the consumer of conv2d_fwd_cells: finalises the statistics in its prologue and fills par (fp32
+    [4, c] = scale, shift, mean, invstd) and the batch / running statistics."""
+    n, h, w, c = y.shape
+    if out is None:
+        out = _new((n, h, w, c), dtype=BF16, device=y.device)
+    f = _cells_fold(cells, par, gamma, beta, eps, momentum, n * h * w, c, batch_out, running_mean, running_var, nbt)
+    check(lib().b200seg_bn_apply_cells(ptr(y), _ld(y), ctypes.byref(f), ptr(res), _ld(res) if res is not None else 0,
+                                       ptr(post_scale), int(relu), ptr(out), _ld(out), n * h * w, h * w, c,
+                                       stream_ptr()), "bn_apply_cells")
+    return out
+
+
 def conv2d_dgrad(dy, w_dgrad, x_shape, ksize, stride, addend=None, out=None, force_kc=0, dilation=1):
     """dy: [N,Ho,Wo,roundup8(Cout)] bf16; w_dgrad: [Cin][k*k][roundup8(Cout)]; x_shape = (N,H,W,Cin)."""
     n, h, w, cin = x_shape
@@ -309,12 +354,20 @@ def bn_apply(y, scale, shift, res=None, post_scale=None, relu=True, out=None):
 
 
 def bn_bwd(dz, mask, post_scale, y, mean, invstd, gamma, dgamma, dbeta, g_out=None, g_accumulate=False, dy_out=None,
-           sync=None, fold=None):
+           sync=None, fold=None, cells=None):
     """Returns dy (gradient w.r.t. the BN input). dgamma/dbeta (fp32 views) are accumulated into. fold = (fp64
-    accumulator [2*c], int32 ticket): finalise inside the reduce launch (per-GPU statistics, no bn_bwd_finalize)."""
+    accumulator [2*c], int32 ticket): finalise inside the reduce launch (per-GPU statistics, no bn_bwd_finalize).
+    cells (fp64 [2*c], zero at the start of the step): deferred finalisation inside the gradient pass (two launches)."""
     n, h, w, c = y.shape
     npix = n * h * w
     L = lib()
+    if cells is not None and sync is None:
+        dy = dy_out if dy_out is not None else _new((n, h, w, c), dtype=BF16, device=y.device)
+        check(L.b200seg_bn_bwd_cells(ptr(dz), _ld(dz), ptr(mask), _ld(mask) if mask is not None else 0, ptr(post_scale),
+                                     ptr(y), _ld(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(dgamma), ptr(dbeta),
+                                     ptr(cells), ptr(dy), _ld(dy), ptr(g_out), _ld(g_out) if g_out is not None else 0,
+                                     int(g_accumulate), npix, h * w, c, stream_ptr()), "bn_bwd_cells", launches=2)
+        return dy
     cc = _new((2, c), dtype=F32, device=y.device)
     if fold is not None and sync is None:
         check(L.b200seg_bn_bwd_reduce_finalize(ptr(dz), _ld(dz), ptr(mask), _ld(mask) if mask is not None else 0,

@@ -542,7 +542,7 @@ static int halo_plan(int n, int h, int w, int cin, int cout, HaloParams& p, size
   // one CTA per SM unless the co-resident configuration was chosen (occupancy is bounded by shared memory and registers)
   if (occ == 1 && smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   const int slots = occ == 2 ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
-  grid = p.total_tiles < slots ? p.total_tiles : slots;
+  grid = conv_grid_for(p.total_tiles, slots, (double)k16 * (p.BN / 2 > 32 ? p.BN / 2 : 32));
   return 0;
 }
 

@@ -369,7 +369,10 @@ static int plan_geom(const LaunchGeom& g, ConvPlan* pl) {
   pl->smem_bytes = fixed + (size_t)nst * pl->stage_bytes;
   if (occ == 1 && pl->smem_bytes < 120 * 1024) pl->smem_bytes = 120 * 1024;   // one CTA per SM
   const int slots = occ == 2 ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
-  pl->grid = pl->total_tiles < slots ? pl->total_tiles : slots;
+  {
+    const int k16 = g.ntaps * pl->cchunks * (KC / 16);
+    pl->grid = conv_grid_for(pl->total_tiles, slots, (double)k16 * (64.0 + pl->BN / 2));
+  }
   return 0;
 }
 
@@ -409,6 +412,30 @@ static bool desc_ok(const b200seg_conv_desc* d) {
 static int g_smem_reserve = 0;
 int smem_reserve() { return g_smem_reserve; }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+const Tune& tune() {
+  static const Tune t = {env_int("B200SEG_CONV_MIN_CLK", 0),    env_int("B200SEG_WGRAD_MIN_CLK", 0),
+                         env_int("B200SEG_EW_ITEMS", 8),        env_int("B200SEG_EW_CTAS_PER_SM", 8),
+                         env_int("B200SEG_RED_ITEMS", 4),       env_int("B200SEG_RED_CTAS_PER_SM", 2),
+                         env_int("B200SEG_RS_ITEMS", 1)};
+  return t;
+}
+// grid of a persistent convolution launch: every CTA gets at least conv_min_clk modelled clocks of tiles
+static int conv_grid(long long total_tiles, int slots, double tile_clk) {
+  long long g = total_tiles < slots ? total_tiles : slots;
+  const int min_clk = tune().conv_min_clk;
+  if (min_clk > 0) {
+    long long want = (long long)((double)total_tiles * tile_clk / (double)min_clk + 0.999);
+    if (want < 1) want = 1;
+    if (want < g) g = want;
+  }
+  return (int)g;
+}
+int conv_grid_for(long long total_tiles, int slots, double tile_clk) { return conv_grid(total_tiles, slots, tile_clk); }
+
 int conv_plan(const b200seg_conv_desc* d, ConvPlan* pl) {
   if (!desc_ok(d)) return B200SEG_E_BADARG;
   return plan_geom(fwd_geom(d), pl);
@@ -418,9 +445,9 @@ int make_bn_fold(const b200seg_bn_fold* f, int cout, BnFoldDev* out) {
   BnFoldDev d;
   memset(&d, 0, sizeof(d));
   if (f) {
-    if (!f->accum || !f->counter || !f->scale || !f->shift || !f->mean || !f->invstd || f->c != cout || f->count <= 0.f ||
-        (reinterpret_cast<uintptr_t>(f->accum) & 7))
-      return B200SEG_E_BADARG;
+    if (!f->accum || f->c != cout || (reinterpret_cast<uintptr_t>(f->accum) & 7)) return B200SEG_E_BADARG;
+    // counter == NULL: deferred mode, only the cells are touched (see bn_fold.cuh)
+    if (f->counter && (!f->scale || !f->shift || !f->mean || !f->invstd || f->count <= 0.f)) return B200SEG_E_BADARG;
     d.accum = f->accum; d.counter = f->counter; d.gamma = f->gamma; d.beta = f->beta;
     d.scale = f->scale; d.shift = f->shift; d.mean = f->mean; d.invstd = f->invstd; d.batch_out = f->batch_stats_out;
     d.running_mean = f->running_mean; d.running_var = f->running_var; d.nbt = (long long*)f->num_batches_tracked;

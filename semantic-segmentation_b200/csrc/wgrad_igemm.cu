@@ -421,13 +421,18 @@ static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
       int sp_max = B200SEG_MAX_CTAS / items;
       if (sp_max > p.pix_tiles) sp_max = p.pix_tiles;
       if (sp_max < 1) sp_max = 1;
+      const double mma = (double)tpg * 8.0 * (Nmax / 2 > 32 ? Nmax / 2 : 32);
+      const double bytes = (a_two ? 32768.0 : 16384.0) + (p.halo ? nblk * 23040.0 : (double)tpg * nblk * 16384.0);
+      const double per_tile = mma > bytes / 64.0 ? mma : bytes / 64.0;
+      if (tune().wgrad_min_clk > 0) {     // every unit reduces at least wgrad_min_clk modelled clocks of pixel tiles
+        int sp_w = (int)((double)p.pix_tiles * per_tile / (double)tune().wgrad_min_clk);
+        if (sp_w < 1) sp_w = 1;
+        if (sp_w < sp_max) sp_max = sp_w;
+      }
       for (int pass = 0; pass < 2; ++pass) {
         const int splits = pass == 0 ? 1 : sp_max;
         if (pass == 1 && sp_max == 1) break;
         const double tiles_per_unit = (double)((p.pix_tiles + splits - 1) / splits);
-        const double mma = (double)tpg * 8.0 * (Nmax / 2 > 32 ? Nmax / 2 : 32);
-        const double bytes = (a_two ? 32768.0 : 16384.0) + (p.halo ? nblk * 23040.0 : (double)tpg * nblk * 16384.0);
-        const double per_tile = mma > bytes / 64.0 ? mma : bytes / 64.0;
         const double unit = tiles_per_unit * per_tile + (double)tpg * Nmax * 4.0 + 1500.0;
         const double waves = (double)(((long long)items * splits + B200SEG_MAX_CTAS - 1) / B200SEG_MAX_CTAS);
         double cost = waves * unit;

@@ -28,9 +28,7 @@ def oracle_step(sd0, images, gts, emulate=True, dev="cuda"):
     return sd, float(loss)
 
 
-def main():
-    sd0 = O.synth_state_dict(ARCH, WRN_TEST, seed=3)
-    images, gts = O.synth_batch(2, 128, 256, seed=5)
+def run_variant(tag, sd0, images, gts):
     sd_ref, l_ref = oracle_step(sd0, images, gts)
     sd_p, l_p = oracle_step(sd0, P.ulp_perturbed(images), gts)
     sd_32, l_32 = oracle_step(sd0, images, gts, emulate=False)
@@ -41,7 +39,7 @@ def main():
     loss = net({"images": images.cuda(), "gts": gts.cuda()})
     loss.backward()
     torch.cuda.synchronize()
-    print("loss product %.6f oracle(bf16) %.6f oracle(ulp) %.6f oracle(fp32) %.6f" % (float(loss), l_ref, l_p, l_32))
+    print("[%s] loss product %.6f oracle(bf16) %.6f oracle(ulp) %.6f oracle(fp32) %.6f" % (tag, float(loss), l_ref, l_p, l_32))
     rows = []
     for name, p in net.named_parameters():
         g = sd_ref[name].grad
@@ -51,10 +49,32 @@ def main():
         cf, rf = P.cos_rel(sd_p[name].grad, g)
         c3, r3 = P.cos_rel(sd_32[name].grad, g)
         rows.append((name, r, c, rf, cf, r3, float(g.norm()), float(p.grad.norm())))
-    print("%-52s %8s %8s | %8s %8s | %8s | %10s %10s" % ("tensor", "rel", "cos", "floor", "cosfl", "rel fp32", "|ref|", "|prod|"))
-    for row in rows:
-        print("%-52s %8.4f %8.4f | %8.4f %8.4f | %8.4f | %10.3e %10.3e" % row)
-    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "deepv3_diag.json"), "w"))
+    med = lambda xs: sorted(xs)[len(xs) // 2]
+    for part, sel in (("trunk", lambda n: n.startswith("backbone")), ("head", lambda n: not n.startswith("backbone"))):
+        rr = [r for r in rows if sel(r[0])]
+        print("[%s] %-5s n=%3d  median rel product %.4f floor %.4f fp32 %.4f | max rel product %.4f floor %.4f | median cos product %.4f floor %.4f"
+              % (tag, part, len(rr), med([r[1] for r in rr]), med([r[3] for r in rr]), med([r[5] for r in rr]),
+                 max(r[1] for r in rr), max(r[3] for r in rr), med([r[2] for r in rr]), med([r[4] for r in rr])))
+    rep = {r[0]: (r[2], r[1], r[6]) for r in rows}
+    floor = {r[0]: (r[4], r[3]) for r in rows}
+    bad, summ = P.check_against_floor(rep, floor, {}, {})
+    print("[%s] check_against_floor: %d violations %s %s" % (tag, len(bad), summ, bad[:6]))
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "deepv3_diag_%s.json" % tag), "w"))
+    with open(os.path.join(ROOT, "gpurun_out", "deepv3_diag_%s.txt" % tag), "w") as f:
+        for row in rows:
+            f.write("%-52s %8.4f %8.4f | %8.4f %8.4f | %8.4f | %10.3e %10.3e\n" % row)
+
+
+def main():
+    sd0 = O.synth_state_dict(ARCH, WRN_TEST, seed=3)
+    images, gts = O.synth_batch(2, 128, 256, seed=5)
+    run_variant("base", sd0, images, gts)
+    sd1 = {k: v.clone() for k, v in sd0.items()}
+    sd1["aspp.img_conv.1.weight"].zero_()          # the image-pooling branch feeds no gradient to the trunk
+    run_variant("imgzero", sd1, images, gts)
+    images4, gts4 = O.synth_batch(4, 96, 192, seed=6)
+    run_variant("n4", sd0, images4, gts4)
+    run_variant("n4_imgzero", sd1, images4, gts4)
 
 
 if __name__ == "__main__":
