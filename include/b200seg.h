@@ -116,6 +116,14 @@ int b200seg_conv2d_fwd_add(const b200seg_conv_desc* d, const void* x, const void
                            const void* addend, int32_t addend_ld, void* y, float* stats_partials, int32_t* stats_grid,
                            void* stream);
 
+/* Evaluation mode: BatchNorm from running statistics, the residual sum and the ReLU folded into the convolution epilogue:
+ *   y = relu?(conv(x) * scale[co] + shift[co] (+ addend[n,ho,wo,co]))      (network/hrnetv2.py:50-66,86-106 in one launch)
+ * scale / shift: fp32 [cout] (b200seg_bn_eval_params; a convolution bias is folded into shift by the caller), bf16 output,
+ * d->has_bias = d->emit_stats = d->out_fp32 = 0. */
+int b200seg_conv2d_fwd_affine(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* scale,
+                              const float* shift, int32_t relu, const void* addend, int32_t addend_ld, void* y,
+                              void* stream);
+
 /* Repack fp32 OIHW master weights (the nn.Parameter layout the reference checkpoints use) into the kernel layouts:
  *   w_ohwi  bf16 [O][kh*kw][I]            forward operand
  *   w_dgrad bf16 [I][kh*kw (flipped)][o_pad]  data-gradient operand (may be NULL); o_pad >= O is a multiple of 8 and

@@ -74,6 +74,7 @@ class Engine:
         self.ws_holder = ws_holder
         self.bnfold = bnfold if sync is None else None
         self.bncells = bncells if (sync is None and self.bnfold is None) else None
+        self.eval_bn = None      # evaluation: BN layer name -> (scale, shift) from the running statistics (evalpath.py)
         self._ctx = None         # stream of the branch section being recorded (None = the engine's own stream)
         self.pre_backward_event = None   # e.g. "data-gradient weight operands packed" (recorded on another stream)
         self.tape = []
@@ -232,8 +233,9 @@ class Engine:
             rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], par[2], par[3]
         else:
             y = raw.conv2d_fwd(x.t, w_f, b, stride=stride, dilation=dilation)
-            par = raw.bn_eval_params(self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
-                                     self.p[bname + ".running_mean"], self.p[bname + ".running_var"])
+            par = self.eval_bn[bname] if self.eval_bn is not None else raw.bn_eval_params(
+                self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS, self.p[bname + ".running_mean"],
+                self.p[bname + ".running_var"])
             rec.scale, rec.shift, rec.mean, rec.invstd = par[0], par[1], None, None
         rec.y = y
         return rec
@@ -292,6 +294,15 @@ class Engine:
 
     def conv_bn(self, x, cname, bname, ksize, stride=1, relu=True, residual=None, out=None, bias=False,
                 post_scale=None, dilation=1):
+        if not self.training and self.eval_bn is not None and post_scale is None:
+            # evaluation: BatchNorm (running statistics), residual sum and ReLU in the convolution epilogue - one launch
+            w_f, _ = self.packed[cname]
+            scale, shift = self.eval_bn[bname]
+            if bias:                 # (conv + b) * s + t = conv * s + (b * s + t)
+                shift = shift + self.p[cname + ".bias"].float() * scale
+            z = raw.conv2d_fwd_affine(x.t, w_f, scale, shift, relu, stride=stride,
+                                      addend=residual.t if residual is not None else None, out=out, dilation=dilation)
+            return Act(z)
         rec = self.conv_stats(x, cname, bname, ksize, stride, bias, dilation, defer=True)
         return self.bn_act(rec, relu, residual, out, post_scale)
 
@@ -349,6 +360,8 @@ class Engine:
             par = raw.bn_finalize(x.stats, n * h * w, self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
                                   BN_MOMENTUM, self.p[bname + ".running_mean"], self.p[bname + ".running_var"],
                                   self.p[bname + ".num_batches_tracked"], c, sync=self._sync(bname, 0))
+        elif self.eval_bn is not None:
+            par = self.eval_bn[bname]
         else:
             par = raw.bn_eval_params(self.p[bname + ".weight"], self.p[bname + ".bias"], BN_EPS,
                                      self.p[bname + ".running_mean"], self.p[bname + ".running_var"])

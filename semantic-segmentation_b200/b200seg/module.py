@@ -326,6 +326,28 @@ class B200SegModule(nn.Module):
         self._bstat_views = [{b: t[o_:o_ + 2 * c_] for b, (o_, c_) in self._bn_slots.items()} for t in self._bstat]
         self._graphs = {}
 
+    def _eval_bn_params(self):
+        """Evaluation: scale / shift of EVERY BatchNorm layer from the running statistics in a handful of launches
+        (instead of one bn_eval_params launch per layer and pass): name -> (scale, shift) fp32 views."""
+        dev = self._run_flat.device
+        names = list(self._bn_slots)
+        if getattr(self, "_eval_idx", None) is None or self._eval_idx[0].device != dev:
+            im, iv, spans, o = [], [], {}, 0
+            for b in names:
+                off, c = self._bn_slots[b]
+                im.append(torch.arange(off, off + c))
+                iv.append(torch.arange(off + c, off + 2 * c))
+                spans[b] = (o, o + c)
+                o += c
+            self._eval_idx = (torch.cat(im).to(dev), torch.cat(iv).to(dev), spans)
+        im, iv, spans = self._eval_idx
+        t = self._tensors()
+        gamma = torch.cat([t[b + ".weight"].detach().reshape(-1) for b in names]).float()
+        beta = torch.cat([t[b + ".bias"].detach().reshape(-1) for b in names]).float()
+        scale = gamma * torch.rsqrt(self._run_flat[iv] + BN_EPS)
+        shift = beta - self._run_flat[im] * scale
+        return {b: (scale[a:z], shift[a:z]) for b, (a, z) in spans.items()}
+
     def _repack(self, side=None):
         """fp32 OIHW master weights -> bf16 kernel layouts, one launch for the whole model (inside the captured step:
         the weights change every optimizer step). With `side` (a stream) the data-gradient operands, which nothing

@@ -183,6 +183,23 @@ def conv2d_fwd_bn(x, w_ohwi, bias, stride, gamma, beta, eps, momentum, accum, co
     return out, par
 
 
+def conv2d_fwd_affine(x, w_ohwi, scale, shift, relu, stride=1, addend=None, out=None, dilation=1):
+    """Evaluation: y = relu?(conv(x) * scale + shift (+ addend)) in one launch (BatchNorm from running statistics)."""
+    assert x.is_cuda and x.dtype == BF16
+    cout, taps, cin = w_ohwi.shape
+    assert cin == x.shape[3], (cin, x.shape)
+    ksize = 3 if taps == 9 else 1
+    n, h, w, _ = x.shape
+    ho, wo = out_hw(h, w, ksize, stride, dilation)
+    if out is None:
+        out = _new((n, ho, wo, cout), dtype=BF16, device=x.device)
+    d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(out), dilation=dilation)
+    check(lib().b200seg_conv2d_fwd_affine(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(scale), ptr(shift), int(relu),
+                                          ptr(addend), _ld(addend) if addend is not None else 0, ptr(out),
+                                          stream_ptr()), "conv2d_fwd_affine")
+    return out
+
+
 def _cells_fold(cells, par, gamma, beta, eps, momentum, count, c, batch_out, running_mean, running_var, nbt):
     f = BnFold()
     f.accum, f.counter = ptr(cells), None          # counter NULL = deferred finalisation (csrc/bn_fold.cuh)

@@ -30,7 +30,11 @@ struct BnFoldDev {
   long long* nbt;
   float eps, momentum, count;
   int C;
+  int relu;                 // affine-epilogue mode only (below)
 };
+// Affine-epilogue mode (evaluation: BatchNorm from running statistics folded into the convolution, accum == nullptr and
+// scale != nullptr): the epilogue stores relu?(acc * scale[c] + shift[c] (+ addend)) - one launch per conv + BN (+ residual)
+// + ReLU instead of three (b200seg_conv2d_fwd_affine). A convolution bias is folded into shift by the caller.
 
 // Called by ALL threads of the CTA after its last tile (s_stats = [4 quarters][2][cout_pad] per-CTA sums in shared memory,
 // already synchronised; s_ticket_p = one free word of the CTA's dynamic shared memory). Returns after the layer's parameters are written if this CTA drew the last ticket.

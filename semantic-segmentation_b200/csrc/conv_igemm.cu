@@ -199,6 +199,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.Cout) ? __ldg(bias + c0 + j) : 0.f;
         }
+        const bool affine = fold.accum == nullptr && fold.scale != nullptr;   // evaluation: BN folded into the epilogue
+        if (affine) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.Cout) v[j] = v[j] * __ldg(fold.scale + c0 + j) + __ldg(fold.shift + c0 + j);
+        }
         if (addend != nullptr && valid && c0 + 16 <= p.Cout) {
           const __nv_bfloat16* ap = addend + pix * p.addend_ld + c0;
           float a0[8], a1[8];
@@ -206,6 +212,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           load8(ap + 8, a1);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
+        }
+        if (affine && fold.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (p.out_fp32) {
           if (valid) {
@@ -459,7 +469,7 @@ int make_bn_fold(const b200seg_bn_fold* f, int cout, BnFoldDev* out) {
 
 static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const float* bias, void* out,
                        float* stats_partials, int32_t* stats_grid, const void* addend, int addend_ld,
-                       cudaStream_t stream, const b200seg_bn_fold* fold = nullptr) {
+                       cudaStream_t stream, const b200seg_bn_fold* fold = nullptr, const BnFoldDev* affine = nullptr) {
   ConvPlan pl;
   int rc = plan_geom(g, &pl);
   if (rc) return rc;
@@ -468,6 +478,10 @@ static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const 
   if (g.emit_stats && ((!stats_partials && !fold) || g.out_fp32)) return B200SEG_E_BADARG;
   BnFoldDev fd;
   if (int frc = make_bn_fold(g.emit_stats ? fold : nullptr, g.out_c, &fd)) return frc;
+  if (affine) {                       // evaluation: BatchNorm folded into the epilogue (no statistics)
+    if (g.emit_stats) return B200SEG_E_BADARG;
+    fd = *affine;
+  }
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
       (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15))
     return B200SEG_E_BADARG;
@@ -552,7 +566,7 @@ void conv_igemm_occupancy_report() {
 int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
                         const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
                         const void* addend, int addend_ld, int emit_stats, cudaStream_t stream,
-                        const b200seg_bn_fold* fold = nullptr);
+                        const b200seg_bn_fold* fold = nullptr, const BnFoldDev* affine = nullptr);
 int conv3x3_halo_plan_info(int n, int h, int w, int cin, int cout, int32_t* out);
 
 }  // namespace b200seg
@@ -626,6 +640,25 @@ extern "C" int b200seg_conv2d_fwd_add(const b200seg_conv_desc* d, const void* x,
     return conv3x3_halo_launch(d->n, d->h, d->w, d->cin, d->x_ld, x, d->cout, w_ohwi, d->has_bias ? bias : nullptr, y,
                                d->y_ld, stats_partials, stats_grid, addend, addend_ld, d->emit_stats, (cudaStream_t)stream);
   return launch_geom(fwd_geom(d), x, w_ohwi, bias, y, stats_partials, stats_grid, addend, addend_ld, (cudaStream_t)stream);
+}
+
+// Evaluation: y = relu?(conv(x) * scale[co] + shift[co] (+ addend)) in the convolution epilogue (BatchNorm from running
+// statistics, residual sum and ReLU of network/hrnetv2.py:50-66,86-106 in one launch). bf16 output, no statistics.
+extern "C" int b200seg_conv2d_fwd_affine(const b200seg_conv_desc* d, const void* x, const void* w_ohwi,
+                                         const float* scale, const float* shift, int32_t relu, const void* addend,
+                                         int32_t addend_ld, void* y, void* stream) {
+  if (!desc_ok(d) || !scale || !shift || d->out_fp32 || d->emit_stats || d->has_bias) return B200SEG_E_BADARG;
+  BnFoldDev fd;
+  memset(&fd, 0, sizeof(fd));
+  fd.scale = const_cast<float*>(scale);
+  fd.shift = const_cast<float*>(shift);
+  fd.relu = relu ? 1 : 0;
+  fd.C = d->cout;
+  if (d->ksize == 3 && d->stride == 1 && d->cout % 16 == 0 && d->reserved == 0 && conv_dil(d) == 1)
+    return conv3x3_halo_launch(d->n, d->h, d->w, d->cin, d->x_ld, x, d->cout, w_ohwi, nullptr, y, d->y_ld, nullptr,
+                               nullptr, addend, addend_ld, 0, (cudaStream_t)stream, nullptr, &fd);
+  return launch_geom(fwd_geom(d), x, w_ohwi, nullptr, y, nullptr, nullptr, addend, addend_ld, (cudaStream_t)stream,
+                     nullptr, &fd);
 }
 
 // Data gradient. d describes the FORWARD convolution. dx[n,h,w,cin] = sum_taps dy[...] * W  (+ addend).
