@@ -27,14 +27,14 @@ for p in (ROOT, os.path.join(ROOT, "semantic-segmentation_b200")):
 import torch  # noqa: E402
 
 # Algorithmic work per 1024x2048 crop (SURVEY.md §8d / BASELINE.md §2, conv FLOPs = 2*MAC)
-TFLOP_PER_CROP = {"ocrnet.HRNet_Mscale": 10.53, "ocrnet.HRNet": 7.77}
+TFLOP_PER_CROP = {"ocrnet.HRNet_Mscale": 10.53, "ocrnet.HRNet": 7.77, "deepv3.DeepV3PlusW38": 34.95}
 FWD_TFLOP_1X = 3.0546
 # Launch-level roofline of one train step per 1024x2048 crop: sum over the step's launches of max(FLOPs / sustained bf16
 # peak, bytes / HBM copy bandwidth), from the static trace of the real step program (tools/trace_step.py,
 # profiles/r1_step_roofline_model.txt; peaks of MEASURED_PEAKS.json: 1386.7 TFLOP/s, 6572.9 GB/s)
 # SyncBN at --gpus N > 1 unless --no-syncbn (every reference script trains with syncbn: true)
 SYNCBN_DEFAULT = False
-STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.12, "ocrnet.HRNet": 11.34}
+STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.12, "ocrnet.HRNet": 11.34, "deepv3.DeepV3PlusW38": 30.8}
 # the same model per kernel class (profiles/r2_step_roofline_model.txt): class -> (kernel-name fragments, roofline ms)
 KERNEL_CLASSES = {
     "conv fwd+dgrad (tcgen05)": (("conv3x3_halo", "conv_igemm"), 2.960 + 2.954 + 0.135),
@@ -200,8 +200,9 @@ def usable_cores():
 
 def workload_name(args):
     """config.workload, identical for both arms (the driver pairs their lines)."""
-    return ("%s two-scale {0.5,1.0} train step (zero_grad, fwd+bwd, SGD momentum + weight decay), %dx%d crops, "
-            "%d crop/GPU, %s loss" % (args.arch, args.height, args.width, args.batch_per_gpu, args.criterion.upper()))
+    kind = "two-scale {0.5,1.0}" if args.arch in ("ocrnet.HRNet_Mscale", "mscale.HRNet") else "single-scale"
+    return ("%s %s train step (zero_grad, fwd+bwd, SGD momentum + weight decay), %dx%d crops, "
+            "%d crop/GPU, %s loss" % (args.arch, kind, args.height, args.width, args.batch_per_gpu, args.criterion.upper()))
 
 
 def synth_batch(n, h, w, seed, device):
@@ -417,6 +418,10 @@ def run_b200(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    if os.environ.get("B200SEG_TIME_ONLY") == "1":              # A/B runs of a switch: the device-timed figure only
+        if rank == 0:
+            print(json.dumps(dict(ms_per_step=ms / args.steps, steps=args.steps, time_only=True)))
+        return
     # ---- end-to-end timing: pinned host inputs -> H2D every step, loss read back every step.
     # (a) pipelined read: the loss of step i is copied to pinned memory asynchronously and read on the host while step
     #     i+1 is already running (what a training loop that logs asynchronously does);
@@ -603,6 +608,31 @@ def run_b200(args):
             del net4, res
         except Exception as e:  # noqa
             extra["cfg5_three_scale_inference"] = dict(error=repr(e))
+        try:   # cfg4: deepv3.DeepV3PlusW38 (WideResNet-38 trunk, dilated ASPP) train step, 1 crop per GPU
+            torch.cuda.empty_cache()
+            net5 = B200SegModule("deepv3.DeepV3PlusW38", 19, criterion="ce", use_cuda_graph=not args.no_graph).cuda().train()
+            from b200seg.optim import FusedSGD as _SGD5
+            opt5 = _SGD5(net5.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+            for it in range(3 + 6):
+                if it == 3:
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    c0.record()
+                opt5.zero_grad(set_to_none=True)
+                l5 = net5({"images": images_d, "gts": gts_d})
+                l5.backward()
+                opt5.step()
+            c1.record()
+            torch.cuda.synchronize()
+            ms5 = c0.elapsed_time(c1) / 6
+            extra["cfg4_deepv3_w38_train"] = dict(
+                value=1000.0 / ms5, unit="crops/s", ms_per_step=ms5, tflops=34.95 / (ms5 * 1e-3), loss=float(l5),
+                what="deepv3.DeepV3PlusW38 train step (WRN-38 trunk at output stride 8, dilations 2/4, ASPP 12/24/36, "
+                     "decoder; Dropout2d of mod6/mod7 on), one 1024x2048 crop, CE, bf16 storage / fp32 accumulate, "
+                     "34.95 TFLOP per crop (SURVEY 8d)")
+            del net5, opt5
+        except Exception as e:  # noqa
+            extra["cfg4_deepv3_w38_train"] = dict(error=repr(e))
         line["other_configs"] = extra
         torch.cuda.empty_cache()
     if (args.torch_gpu_baseline or world == 1) and not args.no_torch_gpu_baseline:

@@ -43,13 +43,15 @@ typedef struct b200seg_conv_desc {
   int32_t cin, cout;       /* cin multiple of 8 */
   int32_t ksize;           /* 1 or 3 (square) */
   int32_t stride;          /* 1 or 2 */
-  int32_t pad;             /* 0 for 1x1, 1 for 3x3 */
+  int32_t pad;             /* 0 for 1x1, 1 for 3x3 (= dilation for dilated 3x3) */
   int32_t x_ld;            /* input pixel pitch (elements) */
   int32_t y_ld;            /* output pixel pitch (elements) */
   int32_t out_fp32;        /* 0: bf16 output, 1: fp32 output (logit heads) */
   int32_t has_bias;        /* bias[cout] fp32 added before rounding */
   int32_t emit_stats;      /* write per-CTA per-channel sum / sum-of-squares partials of the stored output */
   int32_t reserved;
+  int32_t dilation;        /* 0 or 1: dense; d > 1: 3x3 taps d pixels apart, pad must equal d (WideResNet-38 mod5-7, ASPP:
+                              network/wider_resnet.py:322-330, network/utils.py:176-192) */
 } b200seg_conv_desc;
 
 /* Host-only introspection of the launch plan (tests, tuning): which = 0 forward, 1 stride-1 data gradient.
@@ -103,10 +105,24 @@ typedef struct b200seg_bn_fold {
 int b200seg_conv2d_fwd_bn(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias, void* y,
                           const b200seg_bn_fold* fold, void* stream);
 
-/* Slow, obviously-correct CUDA-core direct convolution with identical numerics contract (fp32 accumulate, one rounding).
- * Used by the GPU test-suite as an on-device cross-check and for shapes the GEMM path does not take. */
-int b200seg_conv2d_fwd_direct(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
-                              void* y, void* stream);
+/* Deferred variant (fold->counter == NULL; only accum and c are read): the launch adds its statistics to the cells and
+ * nothing else - the BatchNorm apply pass that consumes the layer finalises them in its prologue (b200seg_bn_apply_cells),
+ * so no finaliser launch and no last-CTA tail sits between the convolution and its consumer. The caller zeroes the cells
+ * once per step. */
+
+/* The same with a residual addend: y = conv(x) (+ bias) + addend[n,ho,wo,cout] (bf16, pitch addend_ld); the statistics
+ * are those of the stored sum (pre-activation residual networks: network/wider_resnet.py:170-183). bf16 output only. */
+int b200seg_conv2d_fwd_add(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
+                           const void* addend, int32_t addend_ld, void* y, float* stats_partials, int32_t* stats_grid,
+                           void* stream);
+
+/* Evaluation mode: BatchNorm from running statistics, the residual sum and the ReLU folded into the convolution epilogue:
+ *   y = relu?(conv(x) * scale[co] + shift[co] (+ addend[n,ho,wo,co]))      (network/hrnetv2.py:50-66,86-106 in one launch)
+ * scale / shift: fp32 [cout] (b200seg_bn_eval_params; a convolution bias is folded into shift by the caller), bf16 output,
+ * d->has_bias = d->emit_stats = d->out_fp32 = 0. */
+int b200seg_conv2d_fwd_affine(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* scale,
+                              const float* shift, int32_t relu, const void* addend, int32_t addend_ld, void* y,
+                              void* stream);
 
 /* Repack fp32 OIHW master weights (the nn.Parameter layout the reference checkpoints use) into the kernel layouts:
  *   w_ohwi  bf16 [O][kh*kw][I]            forward operand
@@ -245,6 +261,12 @@ int b200seg_bn_eval_params(int32_t c, const float* gamma, const float* beta, flo
 int b200seg_bn_apply(const void* y, int32_t y_ld, const float* scale, const float* shift, const void* res,
                      int32_t res_ld, const float* post_scale, int32_t relu, void* z, int32_t z_ld, int64_t npix,
                      int32_t hw, int32_t c, void* stream);
+/* The same pass as the consumer of a convolution launched in deferred mode (b200seg_conv2d_fwd_bn with counter == NULL):
+ * every block derives scale / shift from f->accum (fp64 [2][roundup16(c)] sums), block 0 writes f->scale / shift / mean /
+ * invstd (+ batch or running statistics exactly like b200seg_bn_finalize). f->counter is ignored. */
+int b200seg_bn_apply_cells(const void* y, int32_t y_ld, const b200seg_bn_fold* f, const void* res, int32_t res_ld,
+                           const float* post_scale, int32_t relu, void* z, int32_t z_ld, int64_t npix, int32_t hw,
+                           int32_t c, void* stream);
 /* backward: g = dz * post_scale * (mask > 0); partials[grid][2][c] of (sum g, sum g*xhat), grid from _bn_bwd_grid */
 int32_t b200seg_bn_bwd_grid(int64_t npix, int32_t c);
 int b200seg_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld, const float* post_scale,
@@ -264,6 +286,13 @@ int b200seg_bn_bwd_reduce_finalize(const void* dz, int32_t dz_ld, const void* ma
 int b200seg_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld, const float* post_scale,
                          const void* y, int32_t y_ld, const float* mean, const float* invstd, const float* gamma,
                          const float* c1, const float* c2, void* dy, int32_t dy_ld, void* g_out, int32_t g_ld,
+                         int32_t g_accumulate, int64_t npix, int32_t hw, int32_t c, void* stream);
+/* reduce + gradient pass with deferred finalisation (two launches): the reduction adds its sums to cells ([2][c] fp64,
+ * zeroed by the caller once per step), the gradient pass folds them in its prologue and accumulates dgamma / dbeta
+ * (either may be NULL). Per-GPU statistics only (SyncBN: _reduce + _finalize + _apply). */
+int b200seg_bn_bwd_cells(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld, const float* post_scale,
+                         const void* y, int32_t y_ld, const float* mean, const float* invstd, const float* gamma,
+                         float* dgamma, float* dbeta, double* cells, void* dy, int32_t dy_ld, void* g_out, int32_t g_ld,
                          int32_t g_accumulate, int64_t npix, int32_t hw, int32_t c, void* stream);
 /* dst (=|+=) src * (mask > 0) */
 int b200seg_masked_accum(const void* src, int32_t src_ld, const void* mask, int32_t mask_ld, void* dst, int32_t dst_ld,
@@ -390,6 +419,28 @@ int b200seg_resize_nchw(const float* src, int32_t planes, int32_t h, int32_t w, 
 /* a: [n,1,hw]; mode 0: out = a*x + (1-a)*y; 1: out = x + (1-a)*y; 2: out = a*x   (x, y, out: [n,c,hw]) */
 int b200seg_blend(const float* a, const float* x, const float* y, float* out, int32_t n, int32_t c, int64_t hw,
                   int32_t mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pooling / broadcast glue of the DeepLabV3+ / WideResNet-38 path: NHWC bf16.
+ * ------------------------------------------------------------------------------------------------ */
+/* nn.MaxPool2d(3, stride=2, padding=1) (network/wider_resnet.py:347-349); y: [n, (h-1)/2+1, (w-1)/2+1, c] */
+int b200seg_maxpool3x3s2_fwd(const void* x, int32_t x_ld, int32_t n, int32_t h, int32_t w, int32_t c, void* y,
+                             int32_t y_ld, void* stream);
+/* dx (=|+=) adjoint of the above; x is the forward input (the argmax is recomputed, first maximum wins) */
+int b200seg_maxpool3x3s2_bwd(const void* x, int32_t x_ld, const void* dy, int32_t dy_ld, int32_t n, int32_t h, int32_t w,
+                             int32_t c, void* dx, int32_t dx_ld, int32_t accumulate, void* stream);
+/* per-channel sum / sum of squares of an activation: partials fp32 [grid][2][c], grid = _channel_stats_grid(npix, c);
+ * same layout as the convolution epilogues' statistics (feed b200seg_bn_finalize with cpad = c) */
+int32_t b200seg_channel_stats_grid(int64_t npix, int32_t c);
+int b200seg_channel_stats(const void* x, int32_t x_ld, int64_t npix, int32_t c, float* partials, void* stream);
+/* out[n][c] (bf16, pitch out_ld, =|+=) scale * sum over the p pixels of x[n][pix][c]  (nn.AdaptiveAvgPool2d(1) with
+ * scale = 1/p, network/utils.py:194-210; adjoint of the broadcast below with scale = 1); ws: fp32 [n][splits(p)][c] */
+int32_t b200seg_spatial_sum_splits(int32_t p);
+int b200seg_spatial_sum(const void* x, int32_t x_ld, int32_t n, int32_t p, int32_t c, float scale, float* ws, void* out,
+                        int32_t out_ld, int32_t accumulate, void* stream);
+/* out[n][pix][c] (=|+=) scale * v[n][c]: Upsample of a 1x1 map; adjoint of the image pooling with scale = 1/p */
+int b200seg_broadcast_pixels(const void* v, int32_t v_ld, int32_t n, int32_t p, int32_t c, float scale, void* out,
+                             int32_t out_ld, int32_t accumulate, void* stream);
 
 /* Evaluation tail on the device (utils/trnval_utils.py:116-196 eval_minibatch, utils/misc.py:50-85 fast_hist):
  * out (=|+=) pred [n,c,h,w] fp32, optionally mirrored along w (the do_flip / multi-scale averaging loop) */

@@ -20,7 +20,7 @@ P32 = ctypes.POINTER(c_int32)
 class ConvDesc(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "n", "h", "w", "cin", "cout", "ksize", "stride", "pad", "x_ld", "y_ld",
-        "out_fp32", "has_bias", "emit_stats", "reserved")]
+        "out_fp32", "has_bias", "emit_stats", "reserved", "dilation")]
 
 
 class FuseTerm(ctypes.Structure):
@@ -79,7 +79,8 @@ SIGNATURES = {
     "b200seg_conv2d_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V, P32, V]),
     "b200seg_set_smem_reserve": (ctypes.c_int, [I32]),
     "b200seg_conv2d_fwd_bn": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, ctypes.POINTER(BnFold), V]),
-    "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
+    "b200seg_conv2d_fwd_add": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, I32, V, V, P32, V]),
+    "b200seg_conv2d_fwd_affine": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, I32, V, I32, V, V]),
     "b200seg_pack_weight": (ctypes.c_int, [V, I32, I32, I32, V, V, I32, V]),
     "b200seg_pack_chunk": (I32, []),
     "b200seg_pack_weights": (ctypes.c_int, [V, V, V, I32, I32, V]),
@@ -102,12 +103,15 @@ SIGNATURES = {
     "b200seg_sgd_step": (ctypes.c_int, [V, V, V, I32, F, F, F, F, I32, I32, V]),
     "b200seg_bn_eval_params": (ctypes.c_int, [I32, V, V, F, V, V, V, V, V]),
     "b200seg_bn_apply": (ctypes.c_int, [V, I32, V, V, V, I32, V, I32, V, I32, I64, I32, I32, V]),
+    "b200seg_bn_apply_cells": (ctypes.c_int, [V, I32, ctypes.POINTER(BnFold), V, I32, V, I32, V, I32, I64, I32, I32, V]),
     "b200seg_bn_bwd_grid": (I32, [I64, I32]),
     "b200seg_bn_bwd_reduce": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, I64, I32, I32, V, V]),
     "b200seg_bn_bwd_finalize": (ctypes.c_int, [V, I32, I32, F, V, V, V, V, ctypes.POINTER(BnSync), V]),
     "b200seg_bn_bwd_reduce_finalize": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, I64, I32, I32, V, V, V, V, V, V,
                                                       V]),
     "b200seg_bn_bwd_apply": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, V, V, V, V, I32, V, I32, I32, I64, I32,
+                                            I32, V]),
+    "b200seg_bn_bwd_cells": (ctypes.c_int, [V, I32, V, I32, V, V, I32, V, V, V, V, V, V, V, I32, V, I32, I32, I64, I32,
                                             I32, V]),
     "b200seg_masked_accum": (ctypes.c_int, [V, I32, V, I32, V, I32, I32, I64, I32, V]),
     "b200seg_fuse_fwd": (ctypes.c_int, [ctypes.POINTER(FuseDesc), V, I32, V]),
@@ -134,11 +138,19 @@ SIGNATURES = {
     "b200seg_resize_to_nchw": (ctypes.c_int, [V, I32, I32, I32, I32, I32, I32, V, I32, I32, V]),
     "b200seg_resize_nchw": (ctypes.c_int, [V, I32, I32, I32, V, I32, I32, V]),
     "b200seg_blend": (ctypes.c_int, [V, V, V, V, I32, I32, I64, I32, V]),
+    "b200seg_maxpool3x3s2_fwd": (ctypes.c_int, [V, I32, I32, I32, I32, I32, V, I32, V]),
+    "b200seg_maxpool3x3s2_bwd": (ctypes.c_int, [V, I32, V, I32, I32, I32, I32, I32, V, I32, I32, V]),
+    "b200seg_channel_stats_grid": (I32, [I64, I32]),
+    "b200seg_channel_stats": (ctypes.c_int, [V, I32, I64, I32, V, V]),
+    "b200seg_spatial_sum_splits": (I32, [I32]),
+    "b200seg_spatial_sum": (ctypes.c_int, [V, I32, I32, I32, I32, F, V, V, I32, I32, V]),
+    "b200seg_broadcast_pixels": (ctypes.c_int, [V, I32, I32, I32, I32, F, V, I32, I32, V]),
     "b200seg_accum_pred": (ctypes.c_int, [V, V, I32, I32, I32, I32, I32, I32, V]),
     "b200seg_argmax_hist": (ctypes.c_int, [V, I32, I32, I64, F, V, V, V, V, V]),
 }
-# test-only probe entry point (csrc/probe.h), not part of include/b200seg.h
+# test-only entry points (csrc/probe.h, libb200seg_test.so), not part of include/b200seg.h / the product library
 PROBE_SIGNATURES = {
+    "b200seg_conv2d_fwd_direct": (ctypes.c_int, [ctypes.POINTER(ConvDesc), V, V, V, V, V]),
     "b200seg_umma_probe": (ctypes.c_int, [ctypes.POINTER(ProbeDesc), V, V, V, V]),
 }
 
@@ -158,13 +170,31 @@ def lib():
                 "libb200seg.so not found at %s - run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU / PyTorch fallback for the hot path)" % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
-        for table in (SIGNATURES, PROBE_SIGNATURES):
-            for name, (res, args) in table.items():
-                fn = getattr(L, name)
-                fn.restype = res
-                fn.argtypes = args
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
         _lib = L
     return _lib
+
+
+TEST_LIB_PATH = os.path.join(_HERE, "lib", "libb200seg_test.so")
+_test_lib = None
+
+
+def test_lib():
+    """The test-only library (direct cross-check convolution, descriptor probe); never loaded by the product path."""
+    global _test_lib
+    if _test_lib is None:
+        if not os.path.exists(TEST_LIB_PATH):
+            raise B200SegError("libb200seg_test.so not found at %s (make -C csrc)" % TEST_LIB_PATH)
+        L = ctypes.CDLL(TEST_LIB_PATH)
+        for name, (res, args) in PROBE_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _test_lib = L
+    return _test_lib
 
 
 KERNEL_LAUNCHES = 0   # running count of kernels launched through the ABI by this process (bench.py reports it)

@@ -18,7 +18,7 @@ HRNET_W48 = dict(
 # config.py:157-159 (OCR), :130 (SEGATTN_BOT_CH), network/ocrnet.py:63 (dropout)
 OCR_DEFAULT = dict(mid_channels=512, key_channels=256, num_classes=19, segattn_bot_ch=256, dropout=0.05)
 
-ARCHS = ("ocrnet.HRNet_Mscale", "ocrnet.HRNet", "basic.HRNet", "mscale.HRNet")
+ARCHS = ("ocrnet.HRNet_Mscale", "ocrnet.HRNet", "basic.HRNet", "mscale.HRNet", "deepv3.DeepV3PlusW38")
 
 
 def is_two_scale(arch):
@@ -50,6 +50,12 @@ def wrn_block_plan(wcfg=WRN38):
                          dil, drop))
             in_ch = wcfg["channels"][mod_id][-1]
     return plan
+
+
+def wrn_drop_layout(wcfg=WRN38):
+    """(block prefix, channels of the dropped activation, p) for every bottleneck block that carries a dropout."""
+    return [("backbone.%s.%s" % (mod, blk), ch[1], drop) for mod, blk, _i, ch, _s, _d, drop in wrn_block_plan(wcfg)
+            if drop is not None and len(ch) == 3]
 
 
 def deepv3_tensor_specs(num_classes=19, wcfg=WRN38):
@@ -109,6 +115,8 @@ def high_level_channels(hcfg):
 
 def tensor_specs(arch, hcfg=HRNET_W48, ocfg=OCR_DEFAULT):
     """-> list of (name, shape, kind) with kind in {'conv_w','conv_b','bn_w','bn_b','bn_rm','bn_rv','bn_nbt'}."""
+    if arch == "deepv3.DeepV3PlusW38":
+        return deepv3_tensor_specs(ocfg["num_classes"], hcfg if "structure" in hcfg else WRN38)
     out = []
 
     def conv(name, o, i, k, bias=False):

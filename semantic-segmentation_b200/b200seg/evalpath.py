@@ -6,6 +6,7 @@ reference's output assembly in fp32 NCHW on the device.
   mscale.HRNet        : MscaleBase.nscale_forward / two_scale_forward eval branches (network/mscale.py:114-231)
   ocrnet.HRNet        : OCRNet.forward eval branch (:104-122)
   basic.HRNet         : Basic.forward eval branch (network/basic.py:50-64)
+  deepv3.DeepV3PlusW38: DeepV3Plus.forward eval branch (network/deepv3.py:73-96)
 """
 import torch
 
@@ -39,7 +40,15 @@ def eval_forward(module, images):
     n, _, H, W = images.shape
     tensors = {k: v.detach() for k, v in module._tensors().items()}
     E = Engine(tensors, {}, module._packed, False, None)
+    # BatchNorm from running statistics: every layer's scale / shift up front; conv + BN (+ residual) + ReLU then run as
+    # ONE launch each (raw.conv2d_fwd_affine). B200SEG_EVAL_FUSED=0: separate bn_eval_params / bn_apply launches.
+    import os
+    if os.environ.get("B200SEG_EVAL_FUSED", "1") == "1":
+        E.eval_bn = module._eval_bn_params()
     arch = module.arch
+    if arch == "deepv3.DeepV3PlusW38":          # DeepV3Plus.forward eval branch (network/deepv3.py:73-96)
+        head = M.deepv3_pass(E, images, module.hcfg)
+        return {"pred": raw.resize_to_nchw(head.logits, 19, H, W)}
     if not A.is_two_scale(arch):
         return {"pred": _pass(module, E, images, (H, W))["cls_out"]}
 

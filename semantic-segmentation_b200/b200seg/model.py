@@ -235,6 +235,66 @@ def seg_head(E, x, p="seg_head"):
     return E.conv_head(t, p + ".6", bias=False)
 
 
+# ----------------------------------------------------------------------------------------------- DeepLabV3+ / WRN-38 (f2)
+def wrn_block(E, p, x, in_ch, ch, stride, dil, drop_mask):
+    """IdentityResidualBlock.forward (network/wider_resnet.py:170-183). x: raw (pre-activation) Act carrying its batch
+    statistics; returns the raw residual sum (+ statistics from the last convolution's epilogue)."""
+    a = E.preact(x, p + ".bn1.0")
+    need_proj = stride != 1 or in_ch != ch[-1]
+    short = E.conv_sum(a, p + ".proj_conv", 1, stride) if need_proj else x
+    c = p + ".convs"
+    if len(ch) == 2:
+        t = E.conv_bn(a, c + ".conv1", c + ".bn2.0", 3, stride=stride, dilation=dil)
+        return E.conv_sum(t, c + ".conv2", 3, 1, dil, addend=short, want_stats=True)
+    t = E.conv_bn(a, c + ".conv1", c + ".bn2.0", 1, stride=stride)
+    t = E.conv_bn(t, c + ".conv2", c + ".bn3.0", 3, dilation=dil, post_scale=drop_mask)
+    return E.conv_sum(t, c + ".conv3", 1, 1, 1, addend=short, want_stats=True)
+
+
+def deepv3_pass(E, images, wcfg):
+    """DeepV3Plus.forward up to the half-resolution logits (network/deepv3.py:75-88): WRN-38 trunk (output stride 8),
+    ASPP (network/utils.py:204-216), decoder. Returns the logit HeadRec [n, H/2, W/2, 19]."""
+    from . import arch as A
+    n, _, H, W = images.shape
+    x16 = Act(raw.image_prep(images, H, W), needs_grad=False)
+    x = E.conv_sum(x16, "backbone.mod1.conv1", 3)
+    feats = {}
+    drop_masks = {}
+    if E.training and E.drop_mask is not None:
+        off = 0
+        for bp, c, _p in A.wrn_drop_layout(wcfg):
+            drop_masks[bp] = E.drop_mask[off:off + n * c].view(n, c)
+            off += n * c
+    for mod, blk, in_ch, ch, stride, dil, drop in A.wrn_block_plan(wcfg):
+        if blk == "block1" and mod in ("mod2", "mod3"):
+            x = E.maxpool(x)                                               # pool2 / pool3
+        bp = "backbone.%s.%s" % (mod, blk)
+        dm = drop_masks.get(bp)
+        x = wrn_block(E, bp, x, in_ch, ch, stride, dil, dm)
+        feats[mod] = x
+    s2, final = feats["mod2"], x
+    dev = final.t.device
+    h8, w8 = final.t.shape[1:3]
+    cat = Act(raw._new((n, h8, w8, 5 * 256), dtype=BF16, device=dev))      # [img | 1x1 | d12 | d24 | d36]
+    img = E.conv_bn(E.image_pool(final), "aspp.img_conv.0", "aspp.img_conv.1", 1)
+    pieces = [(E.broadcast(img, h8, w8, cat.t[..., 0:256]), 0, 256)]
+    pieces.append((E.conv_bn(final, "aspp.features.0.0", "aspp.features.0.1", 1, out=cat.t[..., 256:512]), 256, 512))
+    for i, r in enumerate(A.ASPP_RATES):
+        c0 = 512 + 256 * i
+        f = "aspp.features.%d" % (i + 1)
+        pieces.append((E.conv_bn(final, f + ".0", f + ".1", 3, dilation=r, out=cat.t[..., c0:c0 + 256]), c0, c0 + 256))
+    E.slice_marker(cat, pieces)
+    conv_aspp = E.conv_sum(cat, "bot_aspp", 1)
+    h2, w2 = s2.t.shape[1:3]
+    cat2 = Act(raw._new((n, h2, w2, 48 + 256), dtype=BF16, device=dev))
+    conv_s2 = E.conv_sum(s2, "bot_fine", 1, out=cat2.t[..., :48])
+    up = E.fuse((n, h2, w2, 256), [("id", conv_aspp)], relu=False, out=cat2.t[..., 48:])
+    E.slice_marker(cat2, [(conv_s2, 0, 48), (up, 48, 304)])
+    t = E.conv_bn(cat2, "final.0", "final.1", 3)
+    t = E.conv_bn(t, "final.3", "final.4", 3)
+    return E.conv_head(t, "final.6", bias=False)
+
+
 # ----------------------------------------------------------------------------------------------- per-scale pass
 def scale_pass(E, images, size_hw, arch, hcfg, ocfg):
     """MscaleOCR._fwd (network/ocrnet.py:170-183) up to the quarter-resolution maps (the x4 Upsample is fused into the
@@ -269,6 +329,7 @@ def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, su
     two_scale = A.is_two_scale(arch)
     lo = None
     main = torch.cuda.current_stream() if images.is_cuda else None
+    deepv3 = arch == "deepv3.DeepV3PlusW38"
     par = two_scale and E_lo is not None and E_lo.stream is not None
     if not par:
         E_lo = E
@@ -280,7 +341,10 @@ def train_loss(E, images, gts, arch, hcfg, ocfg, lo_scale=0.5, ocr_alpha=0.4, su
                 lo = scale_pass(E_lo, images, (hm, wm), arch, hcfg, ocfg)
         else:
             lo = scale_pass(E, images, (hm, wm), arch, hcfg, ocfg)
-    hi = scale_pass(E, images, (H, W), arch, hcfg, ocfg)
+    if deepv3:
+        hi = dict(cls=deepv3_pass(E, images, hcfg), aux=None, attn=None)
+    else:
+        hi = scale_pass(E, images, (H, W), arch, hcfg, ocfg)
     if par:
         main.wait_stream(E_lo.stream)
     nheads = 2 if A.has_ocr(arch) else 1

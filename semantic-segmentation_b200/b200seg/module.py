@@ -86,7 +86,10 @@ class B200SegModule(nn.Module):
         self.arch = arch
         self.criterion = criterion
         self.loss_kind = _criterion_kind(criterion)
-        self.hcfg = hcfg or A.HRNET_W48
+        self.is_deepv3 = arch == "deepv3.DeepV3PlusW38"
+        self.hcfg = hcfg or (A.WRN38 if self.is_deepv3 else A.HRNET_W48)
+        self._stem = "backbone.mod1.conv1.weight" if self.is_deepv3 else "backbone.conv1.weight"
+        self.wrn_dropout_scale = 1.0     # tests set 0.0 for a dropout-free step
         self.ocfg = dict(ocfg or A.OCR_DEFAULT)
         self.ocfg["num_classes"] = num_classes
         if num_classes != 19:
@@ -106,6 +109,10 @@ class B200SegModule(nn.Module):
         # clear end-to-end gain, so it is opt-in (B200SEG_FUSED_BN=1); SyncBN always uses the separate finaliser.
         import os
         self.fused_bn_finalize = os.environ.get("B200SEG_FUSED_BN", "0") == "1"
+        # Deferred finalisation (default): the convolution / the backward reduction add their sums to per-layer fp64
+        # cells and the consuming apply pass folds them in its prologue - no finaliser launch and no last-CTA tail on
+        # the chain conv -> BN -> conv (B200SEG_BN_CELLS=0: separate bn_finalize / bn_bwd_finalize launches).
+        self.bn_cells = os.environ.get("B200SEG_BN_CELLS", "1") == "1" and not self.fused_bn_finalize
         self._sync = None
         self._run_flat = None
         self._specs = A.tensor_specs(arch, self.hcfg, self.ocfg)
@@ -136,7 +143,14 @@ class B200SegModule(nn.Module):
             in_backbone = parts[0] == "backbone"
             if kind == "conv_w":
                 w = torch.empty(shape)
-                if in_backbone:
+                if self.is_deepv3:
+                    # WRN-38 trunk: nn.Conv2d default; ASPP / bot_* / final: initialize_weights = kaiming_normal_
+                    # (network/deepv3.py:66-69, network/mynn.py:27-39)
+                    if in_backbone:
+                        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+                    else:
+                        nn.init.kaiming_normal_(w)
+                elif in_backbone:
                     nn.init.normal_(w, std=0.001)
                 else:
                     nn.init.kaiming_uniform_(w, a=math.sqrt(5))
@@ -295,9 +309,44 @@ class B200SegModule(nn.Module):
                 cells[b] = (acc[o:o + 2 * cp], tickets[li:li + 1])
                 o += 2 * cp
             self._bnfold.append(cells)
+        # deferred BatchNorm finalisation (csrc/bn_fold.cuh, counter == NULL): per pass and layer a forward cell pair
+        # [2 * roundup16(c)] and a backward one [2 * c], one fp64 arena zeroed at the start of every step
+        n_cells = sum(2 * ((c_ + 15) // 16 * 16) + 2 * c_ for _o, c_ in self._bn_slots.values())
+        self._bncell_arena = torch.zeros(2 * n_cells, dtype=torch.float64, device=dev)
+        self._bncells = []
+        o = 0
+        for _pass in range(2):
+            cells = {}
+            for b, (_o, c_) in self._bn_slots.items():
+                cp = (c_ + 15) // 16 * 16
+                cells[b] = (self._bncell_arena[o:o + 2 * cp], self._bncell_arena[o + 2 * cp:o + 2 * cp + 2 * c_])
+                o += 2 * cp + 2 * c_
+            self._bncells.append(cells)
         self._bstat = [torch.zeros(total, dtype=F32, device=dev) for _ in range(2)]
         self._bstat_views = [{b: t[o_:o_ + 2 * c_] for b, (o_, c_) in self._bn_slots.items()} for t in self._bstat]
         self._graphs = {}
+
+    def _eval_bn_params(self):
+        """Evaluation: scale / shift of EVERY BatchNorm layer from the running statistics in a handful of launches
+        (instead of one bn_eval_params launch per layer and pass): name -> (scale, shift) fp32 views."""
+        dev = self._run_flat.device
+        names = list(self._bn_slots)
+        if getattr(self, "_eval_idx", None) is None or self._eval_idx[0].device != dev:
+            im, iv, spans, o = [], [], {}, 0
+            for b in names:
+                off, c = self._bn_slots[b]
+                im.append(torch.arange(off, off + c))
+                iv.append(torch.arange(off + c, off + 2 * c))
+                spans[b] = (o, o + c)
+                o += c
+            self._eval_idx = (torch.cat(im).to(dev), torch.cat(iv).to(dev), spans)
+        im, iv, spans = self._eval_idx
+        t = self._tensors()
+        gamma = torch.cat([t[b + ".weight"].detach().reshape(-1) for b in names]).float()
+        beta = torch.cat([t[b + ".bias"].detach().reshape(-1) for b in names]).float()
+        scale = gamma * torch.rsqrt(self._run_flat[iv] + BN_EPS)
+        shift = beta - self._run_flat[im] * scale
+        return {b: (scale[a:z], shift[a:z]) for b, (a, z) in spans.items()}
 
     def _repack(self, side=None):
         """fp32 OIHW master weights -> bf16 kernel layouts, one launch for the whole model (inside the captured step:
@@ -361,6 +410,10 @@ class B200SegModule(nn.Module):
             sync.advance()
         tensors = {k: v.detach() for k, v in self._tensors().items()}
         par = self.parallel_scales and A.is_two_scale(self.arch)
+        # (one engine per scale pass, or a single pass: a layer's cells are used once per step)
+        use_cells = self.bn_cells and sync is None and (par or not A.is_two_scale(self.arch))
+        if use_cells:
+            self._bncell_arena.zero_()
         self._acc_hi.zero_()         # two memsets (45 us each) beat clearing inside the fold's transposed gather
         if par:
             self._acc_lo.zero_()
@@ -380,14 +433,16 @@ class B200SegModule(nn.Module):
             E_lo = Engine(tensors, grads_lo, self._packed, True, drop_mask, side_stream=self._side_stream_lo,
                           bstat=self._bstat_views[0], stream=self._lo_stream, sync=sync, pass_id=0,
                           branch_streams=self._bstreams["lo"], ws_holder=self._ws_holders["lo"],
-                          bnfold=self._bnfold[0] if self.fused_bn_finalize else None)
+                          bnfold=self._bnfold[0] if self.fused_bn_finalize else None,
+                          bncells=self._bncells[0] if use_cells else None)
         two_pass = A.is_two_scale(self.arch)
         if sync is not None and two_pass and not par:
             raise RuntimeError("SyncBN needs parallel_scales=True for the two-scale step (one engine per pass)")
         E = Engine(tensors, grads, self._packed, True, drop_mask, side_stream=self._side_stream,
                    bstat=self._bstat_views[1] if par else None, sync=sync, pass_id=1 if two_pass else 0,
                    branch_streams=self._bstreams["hi"], ws_holder=self._ws_holders["hi"],
-                   bnfold=self._bnfold[1] if self.fused_bn_finalize else None)
+                   bnfold=self._bnfold[1] if self.fused_bn_finalize else None,
+                   bncells=self._bncells[1] if use_cells else None)
         loss = M.train_loss(E, images, gts, self.arch, self.hcfg, self.ocfg, self.lo_scale, self.ocr_alpha, self.sup_wt,
                             self.ignore_index, E_lo=E_lo, loss_kind=self.loss_kind)
         E.pre_backward_event = wd_ready
@@ -464,6 +519,15 @@ class B200SegModule(nn.Module):
 
     def _drop_mask(self, n, device):
         """Dropout2d(0.05) channel mask (network/ocr_utils.py:146) drawn from torch's generator, folded with 1/(1-p)."""
+        if self.is_deepv3:
+            # WRN-38 mod6 / mod7: Dropout2d(0.3) / Dropout2d(0.5) in front of conv3 (network/wider_resnet.py:302 patches
+            # nn.Dropout to Dropout2d; :336-338). One flat fp32 buffer, [n, c] per block in A.wrn_drop_layout order.
+            parts = []
+            for _bp, c, p in A.wrn_drop_layout(self.hcfg):
+                p = p * self.wrn_dropout_scale
+                keep = torch.bernoulli(torch.full((n * c,), 1.0 - p, dtype=F32, device=device))
+                parts.append(keep / (1.0 - p))
+            return torch.cat(parts) if parts else None
         if not A.has_ocr(self.arch):
             return None
         p = self.ocfg["dropout"]

@@ -101,22 +101,24 @@ def pack_weights(table, which=3):
 
 
 def conv_desc(n, h, w, cin, cout, ksize, stride, x_ld, y_ld, out_fp32=False, has_bias=False, emit_stats=False,
-              force_kc=0):
+              force_kc=0, dilation=1):
     d = ConvDesc()
     d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
-    d.ksize, d.stride, d.pad = ksize, stride, (1 if ksize == 3 else 0)
+    d.ksize, d.stride, d.pad = ksize, stride, (dilation if ksize == 3 else 0)
     d.x_ld, d.y_ld = x_ld, y_ld
     d.out_fp32, d.has_bias, d.emit_stats, d.reserved = int(out_fp32), int(has_bias), int(emit_stats), force_kc
+    d.dilation = dilation
     return d
 
 
-def out_hw(h, w, ksize, stride):
-    pad = 1 if ksize == 3 else 0
-    return (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
+def out_hw(h, w, ksize, stride, dilation=1):
+    pad = dilation if ksize == 3 else 0
+    span = dilation * (ksize - 1) + 1
+    return (h + 2 * pad - span) // stride + 1, (w + 2 * pad - span) // stride + 1
 
 
 def conv2d_fwd(x, w_ohwi, bias=None, stride=1, out=None, out_fp32=False, emit_stats=False, force_kc=0,
-               direct=False, out_ld=None):
+               direct=False, out_ld=None, dilation=1, addend=None):
     """x: [N,H,W,Cin] bf16; w_ohwi: [Cout][k*k][Cin] bf16. Returns y (and with emit_stats the per-CTA partials
     [grid][2][cout_pad] fp32)."""
     assert x.is_cuda and x.dtype == BF16
@@ -124,15 +126,16 @@ def conv2d_fwd(x, w_ohwi, bias=None, stride=1, out=None, out_fp32=False, emit_st
     assert cin == x.shape[3], (cin, x.shape)
     ksize = 3 if taps == 9 else 1
     n, h, w, _ = x.shape
-    ho, wo = out_hw(h, w, ksize, stride)
+    ho, wo = out_hw(h, w, ksize, stride, dilation)
     if out is None:
         width = cout if out_ld is None else out_ld
         buf = _new((n, ho, wo, width), dtype=F32 if out_fp32 else BF16, device=x.device)
         out = buf[..., :cout] if width != cout else buf
     d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(out), out_fp32, bias is not None, emit_stats,
-                  force_kc)
+                  force_kc, dilation)
     if direct:
-        check(lib().b200seg_conv2d_fwd_direct(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out),
+        from ._lib import test_lib        # test-only library (tests/test_gpu_ops.py cross-check)
+        check(test_lib().b200seg_conv2d_fwd_direct(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out),
                                               stream_ptr()), "conv2d_fwd_direct")
         return out
     stats = None
@@ -140,8 +143,12 @@ def conv2d_fwd(x, w_ohwi, bias=None, stride=1, out=None, out_fp32=False, emit_st
     if emit_stats:
         nelem = lib().b200seg_conv2d_stats_elems(ctypes.byref(d))
         stats = _new(nelem, dtype=F32, device=x.device)
-    check(lib().b200seg_conv2d_fwd(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out), ptr(stats),
-                                   ctypes.byref(grid), stream_ptr()), "conv2d_fwd")
+    if addend is not None:      # y = conv(x) + addend (identity-mapping residual sum in the convolution epilogue)
+        check(lib().b200seg_conv2d_fwd_add(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(addend), _ld(addend),
+                                           ptr(out), ptr(stats), ctypes.byref(grid), stream_ptr()), "conv2d_fwd_add")
+    else:
+        check(lib().b200seg_conv2d_fwd(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out), ptr(stats),
+                                       ctypes.byref(grid), stream_ptr()), "conv2d_fwd")
     if emit_stats:
         cout_pad = (cout + 15) // 16 * 16
         return out, (stats, grid.value, cout_pad)
@@ -149,7 +156,7 @@ def conv2d_fwd(x, w_ohwi, bias=None, stride=1, out=None, out_fp32=False, emit_st
 
 
 def conv2d_fwd_bn(x, w_ohwi, bias, stride, gamma, beta, eps, momentum, accum, counter, batch_out=None,
-                  running_mean=None, running_var=None, nbt=None, out=None):
+                  running_mean=None, running_var=None, nbt=None, out=None, dilation=1):
     """Convolution + training-mode BatchNorm statistics finalised inside the launch (b200seg_conv2d_fwd_bn): returns
     (y, params fp32 [4, cout] = scale, shift, mean, invstd). accum (fp64 [2*roundup16(cout)]) / counter (int32 [1]) are
     the layer's private, self-clearing reduction cells."""
@@ -158,10 +165,11 @@ def conv2d_fwd_bn(x, w_ohwi, bias, stride, gamma, beta, eps, momentum, accum, co
     assert cin == x.shape[3], (cin, x.shape)
     ksize = 3 if taps == 9 else 1
     n, h, w, _ = x.shape
-    ho, wo = out_hw(h, w, ksize, stride)
+    ho, wo = out_hw(h, w, ksize, stride, dilation)
     if out is None:
         out = _new((n, ho, wo, cout), dtype=BF16, device=x.device)
-    d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(out), False, bias is not None, True)
+    d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(out), False, bias is not None, True,
+                  dilation=dilation)
     par = _new((4, cout), dtype=F32, device=x.device)
     f = BnFold()
     f.accum, f.counter = ptr(accum), ptr(counter)
@@ -175,28 +183,95 @@ def conv2d_fwd_bn(x, w_ohwi, bias, stride, gamma, beta, eps, momentum, accum, co
     return out, par
 
 
-def conv2d_dgrad(dy, w_dgrad, x_shape, ksize, stride, addend=None, out=None, force_kc=0):
+def conv2d_fwd_affine(x, w_ohwi, scale, shift, relu, stride=1, addend=None, out=None, dilation=1):
+    """Evaluation: y = relu?(conv(x) * scale + shift (+ addend)) in one launch (BatchNorm from running statistics)."""
+    assert x.is_cuda and x.dtype == BF16
+    cout, taps, cin = w_ohwi.shape
+    assert cin == x.shape[3], (cin, x.shape)
+    ksize = 3 if taps == 9 else 1
+    n, h, w, _ = x.shape
+    ho, wo = out_hw(h, w, ksize, stride, dilation)
+    if out is None:
+        out = _new((n, ho, wo, cout), dtype=BF16, device=x.device)
+    d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(out), dilation=dilation)
+    check(lib().b200seg_conv2d_fwd_affine(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(scale), ptr(shift), int(relu),
+                                          ptr(addend), _ld(addend) if addend is not None else 0, ptr(out),
+                                          stream_ptr()), "conv2d_fwd_affine")
+    return out
+
+
+def _cells_fold(cells, par, gamma, beta, eps, momentum, count, c, batch_out, running_mean, running_var, nbt):
+    f = BnFold()
+    f.accum, f.counter = ptr(cells), None          # counter NULL = deferred finalisation (csrc/bn_fold.cuh)
+    f.gamma, f.beta = ptr(gamma), ptr(beta)
+    f.scale, f.shift, f.mean, f.invstd = ptr(par[0]), ptr(par[1]), ptr(par[2]), ptr(par[3])
+    f.batch_stats_out = ptr(batch_out)
+    f.running_mean, f.running_var, f.num_batches_tracked = ptr(running_mean), ptr(running_var), ptr(nbt)
+    f.eps, f.momentum, f.count, f.c = eps, momentum, float(count), c
+    return f
+
+
+def conv2d_fwd_cells(x, w_ohwi, bias, stride, cells, out=None, dilation=1):
+    """Convolution whose epilogue adds the batch statistics of the stored output to `cells` (fp64 [2*roundup16(cout)],
+    zero at the start of the step) and nothing else: the consuming bn_apply_cells finalises them. Returns y."""
+    assert x.is_cuda and x.dtype == BF16
+    cout, taps, cin = w_ohwi.shape
+    assert cin == x.shape[3], (cin, x.shape)
+    ksize = 3 if taps == 9 else 1
+    n, h, w, _ = x.shape
+    ho, wo = out_hw(h, w, ksize, stride, dilation)
+    if out is None:
+        out = _new((n, ho, wo, cout), dtype=BF16, device=x.device)
+    d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(out), False, bias is not None, True,
+                  dilation=dilation)
+    f = BnFold()
+    f.accum, f.counter, f.c = ptr(cells), None, cout
+    check(lib().b200seg_conv2d_fwd_bn(ctypes.byref(d), ptr(x), ptr(w_ohwi), ptr(bias), ptr(out), ctypes.byref(f),
+                                      stream_ptr()), "conv2d_fwd_bn(cells)")
+    return out
+
+
+def bn_apply_cells(y, cells, par, gamma, beta, eps, momentum, res=None, post_scale=None, relu=True, out=None,
+                   batch_out=None, running_mean=None, running_var=None, nbt=None):
+    """bn_apply as the consumer of conv2d_fwd_cells: finalises the statistics in its prologue and fills par (fp32
+    [4, c] = scale, shift, mean, invstd) and the batch / running statistics."""
+    n, h, w, c = y.shape
+    if out is None:
+        out = _new((n, h, w, c), dtype=BF16, device=y.device)
+    f = _cells_fold(cells, par, gamma, beta, eps, momentum, n * h * w, c, batch_out, running_mean, running_var, nbt)
+    check(lib().b200seg_bn_apply_cells(ptr(y), _ld(y), ctypes.byref(f), ptr(res), _ld(res) if res is not None else 0,
+                                       ptr(post_scale), int(relu), ptr(out), _ld(out), n * h * w, h * w, c,
+                                       stream_ptr()), "bn_apply_cells")
+    return out
+
+
+def conv2d_dgrad(dy, w_dgrad, x_shape, ksize, stride, addend=None, out=None, force_kc=0, dilation=1):
     """dy: [N,Ho,Wo,roundup8(Cout)] bf16; w_dgrad: [Cin][k*k][roundup8(Cout)]; x_shape = (N,H,W,Cin)."""
     n, h, w, cin = x_shape
     cout_pad = w_dgrad.shape[2]
     assert dy.shape[3] >= cout_pad or dy.shape[3] == cout_pad, (dy.shape, w_dgrad.shape)
     if out is None:
-        out = addend if addend is not None else _new((n, h, w, cin), dtype=BF16, device=dy.device)
-    d = conv_desc(n, h, w, cin, cout_pad, ksize, stride, _ld(out), _ld(out), force_kc=force_kc)
+        if addend is not None:
+            out = addend
+        elif ksize == 1 and stride == 2:     # only the even lattice is written by the kernel
+            out = _newz((n, h, w, cin), dtype=BF16, device=dy.device)
+        else:
+            out = _new((n, h, w, cin), dtype=BF16, device=dy.device)
+    d = conv_desc(n, h, w, cin, cout_pad, ksize, stride, _ld(out), _ld(out), force_kc=force_kc, dilation=dilation)
     check(lib().b200seg_conv2d_dgrad(ctypes.byref(d), ptr(dy), _ld(dy), ptr(w_dgrad), ptr(addend),
                                      _ld(addend) if addend is not None else 0, ptr(out), _ld(out), stream_ptr()),
-          "conv2d_dgrad", 4 if stride == 2 else 1)
+          "conv2d_dgrad", (4 if ksize == 3 else 1) if stride == 2 else 1)
     return out
 
 
-def conv2d_wgrad(x, dy, dw_ohwi, cout, ksize, stride, ws_holder=None):
+def conv2d_wgrad(x, dy, dw_ohwi, cout, ksize, stride, ws_holder=None, dilation=1):
     """dw_ohwi (fp32 accumulator [Cout][k*k][Cin], contiguous; a [Cout,Cin,1,1] tensor is the same memory for 1x1)
     += sum_pixels dy x shifted(x). Returns the workspace tensor (keep it alive while the launch is in flight).
     ws_holder: optional one-element list holding a reusable workspace of the calling stream (grown on demand): all
     weight gradients of one side stream run back to back, so they can share one slab buffer."""
     n, h, w, cin = x.shape
     assert dw_ohwi.is_contiguous() and dw_ohwi.dtype == F32 and dw_ohwi.numel() == cout * cin * ksize * ksize
-    d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(dy))
+    d = conv_desc(n, h, w, cin, cout, ksize, stride, _ld(x), _ld(dy), dilation=dilation)
     L = lib()
     nbytes = L.b200seg_conv2d_wgrad_ws_bytes(ctypes.byref(d))
     need = max(nbytes, 16) // 4
@@ -296,12 +371,20 @@ def bn_apply(y, scale, shift, res=None, post_scale=None, relu=True, out=None):
 
 
 def bn_bwd(dz, mask, post_scale, y, mean, invstd, gamma, dgamma, dbeta, g_out=None, g_accumulate=False, dy_out=None,
-           sync=None, fold=None):
+           sync=None, fold=None, cells=None):
     """Returns dy (gradient w.r.t. the BN input). dgamma/dbeta (fp32 views) are accumulated into. fold = (fp64
-    accumulator [2*c], int32 ticket): finalise inside the reduce launch (per-GPU statistics, no bn_bwd_finalize)."""
+    accumulator [2*c], int32 ticket): finalise inside the reduce launch (per-GPU statistics, no bn_bwd_finalize).
+    cells (fp64 [2*c], zero at the start of the step): deferred finalisation inside the gradient pass (two launches)."""
     n, h, w, c = y.shape
     npix = n * h * w
     L = lib()
+    if cells is not None and sync is None:
+        dy = dy_out if dy_out is not None else _new((n, h, w, c), dtype=BF16, device=y.device)
+        check(L.b200seg_bn_bwd_cells(ptr(dz), _ld(dz), ptr(mask), _ld(mask) if mask is not None else 0, ptr(post_scale),
+                                     ptr(y), _ld(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(dgamma), ptr(dbeta),
+                                     ptr(cells), ptr(dy), _ld(dy), ptr(g_out), _ld(g_out) if g_out is not None else 0,
+                                     int(g_accumulate), npix, h * w, c, stream_ptr()), "bn_bwd_cells", launches=2)
+        return dy
     cc = _new((2, c), dtype=F32, device=y.device)
     if fold is not None and sync is None:
         check(L.b200seg_bn_bwd_reduce_finalize(ptr(dz), _ld(dz), ptr(mask), _ld(mask) if mask is not None else 0,
@@ -562,3 +645,55 @@ def argmax_hist(pred, labels=None, scale=1.0, hist=None):
     check(lib().b200seg_argmax_hist(ptr(pred), n, c, h * w, float(scale), ptr(labels), ptr(pm), ptr(mp), ptr(hist),
                                     stream_ptr()), "argmax_hist")
     return pm, mp, hist
+
+
+# ----------------------------------------------------------------------------------------------- pooling / broadcast (f2)
+def maxpool3x3s2(x):
+    n, h, w, c = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = _new((n, ho, wo, c), dtype=BF16, device=x.device)
+    check(lib().b200seg_maxpool3x3s2_fwd(ptr(x), _ld(x), n, h, w, c, ptr(y), _ld(y), stream_ptr()), "maxpool_fwd")
+    return y
+
+
+def maxpool3x3s2_bwd(x, dy, out=None, accumulate=False):
+    n, h, w, c = x.shape
+    if out is None:
+        out = _new((n, h, w, c), dtype=BF16, device=x.device)
+    check(lib().b200seg_maxpool3x3s2_bwd(ptr(x), _ld(x), ptr(dy), _ld(dy), n, h, w, c, ptr(out), _ld(out),
+                                         int(accumulate), stream_ptr()), "maxpool_bwd")
+    return out
+
+
+def channel_stats(x):
+    """-> (partials, grid, cpad) in the layout bn_finalize consumes (statistics of an activation that did not come out
+    of a convolution epilogue)."""
+    n, h, w, c = x.shape
+    npix = n * h * w
+    grid = lib().b200seg_channel_stats_grid(npix, c)
+    partials = _new((grid * 2 * c,), dtype=F32, device=x.device)
+    check(lib().b200seg_channel_stats(ptr(x), _ld(x), npix, c, ptr(partials), stream_ptr()), "channel_stats")
+    return partials, grid, c
+
+
+def spatial_sum(x, scale, out=None, accumulate=False):
+    """x [n,h,w,c] -> [n,1,1,c] bf16: scale * sum over pixels (per image)."""
+    n, h, w, c = x.shape
+    L = lib()
+    ws = _new((n * L.b200seg_spatial_sum_splits(h * w) * c,), dtype=F32, device=x.device)
+    if out is None:
+        out = _new((n, 1, 1, c), dtype=BF16, device=x.device)
+    check(L.b200seg_spatial_sum(ptr(x), _ld(x), n, h * w, c, float(scale), ptr(ws), ptr(out), out.stride(0),
+                                int(accumulate), stream_ptr()), "spatial_sum", 2)
+    return out
+
+
+def broadcast_pixels(v, h, w, out=None, scale=1.0, accumulate=False):
+    """v [n,1,1,c] -> out [n,h,w,c] (=|+=) scale * v at every pixel."""
+    n, _, _, c = v.shape
+    if out is None:
+        assert not accumulate
+        out = _new((n, h, w, c), dtype=BF16, device=v.device)
+    check(lib().b200seg_broadcast_pixels(ptr(v), v.stride(0), n, h * w, c, float(scale), ptr(out), _ld(out),
+                                         int(accumulate), stream_ptr()), "broadcast_pixels")
+    return out

@@ -5,6 +5,11 @@
 // clears accumulator and ticket for the next launch. Replaces one bn_finalize launch (a pure latency chain of ~10 us
 // between every convolution and its consumer) per BatchNorm layer and scale pass; arithmetic identical to
 // bn_finalize_kernel (bn_kernels.cu). SyncBN keeps the separate finaliser (the cross-GPU exchange lives there).
+// Deferred variant (counter == nullptr, the default of the training step): the CTAs only add their sums to the cells; the
+// BatchNorm apply pass that consumes the layer folds the totals in its prologue (b200seg_bn_apply_cells), so neither a
+// finaliser launch nor a last-CTA tail sits between the convolution and its consumer. The cells are zeroed by the caller
+// once per step. A sum of <= 296 fp32 partials in fp64 is exact unless their magnitudes differ by more than 2^20, so
+// the order of the adds does not change the result in practice.
 #pragma once
 #include <cstdint>
 
@@ -25,7 +30,11 @@ struct BnFoldDev {
   long long* nbt;
   float eps, momentum, count;
   int C;
+  int relu;                 // affine-epilogue mode only (below)
 };
+// Affine-epilogue mode (evaluation: BatchNorm from running statistics folded into the convolution, accum == nullptr and
+// scale != nullptr): the epilogue stores relu?(acc * scale[c] + shift[c] (+ addend)) - one launch per conv + BN (+ residual)
+// + ReLU instead of three (b200seg_conv2d_fwd_affine). A convolution bias is folded into shift by the caller.
 
 // Called by ALL threads of the CTA after its last tile (s_stats = [4 quarters][2][cout_pad] per-CTA sums in shared memory,
 // already synchronised; s_ticket_p = one free word of the CTA's dynamic shared memory). Returns after the layer's parameters are written if this CTA drew the last ticket.
@@ -38,6 +47,9 @@ __device__ __forceinline__ void bn_fold_tail(const BnFoldDev& f, const float* s_
   }
   // Only the threads that added to the accumulator fence (their adds must be visible before the ticket is drawn): a
   // fence in the epilogue threads would also wait for their outstanding output stores, which nobody here depends on.
+  // Deferred mode (counter == nullptr): the consumer of the layer (bn_apply_kernel's prologue) turns the totals into the
+  // parameters; nothing to wait for here - the adds are complete when this grid is (stream order / griddepcontrol.wait).
+  if (f.counter == nullptr) return;
   if ((int)threadIdx.x < 2 * cout_pad) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) *s_ticket_p = atomicAdd(f.counter, 1u);

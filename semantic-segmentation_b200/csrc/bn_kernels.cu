@@ -10,6 +10,7 @@
 #include "launch.h"
 #include "../../include/b200seg.h"
 #include "vec.cuh"
+#include "conv_common.h"
 #include <cstring>
 
 namespace b200seg {
@@ -287,14 +288,50 @@ __global__ void bn_eval_params_kernel(int C, const float* __restrict__ gamma, co
   shift[c] = beta[c] - running_mean[c] * g_ * invstd;
 }
 
+// Deferred finalisation of the producing convolution's statistics (bn_fold.cuh, counter == nullptr): every block of the
+// apply pass turns the fp64 totals into scale / shift for itself; block 0 also publishes the layer's parameters (the
+// backward pass reads mean / invstd, fuse layers scale / shift) and the batch / running statistics. cells == nullptr:
+// scale / shift come from bn_finalize (SyncBN, evaluation, statistics that did not come from a convolution epilogue).
+struct BnLazy {
+  const double* cells;      // [2][cpad] = per-channel sum | sum of squares
+  int cpad;
+  float count, eps, momentum;
+  const float* gamma;
+  const float* beta;
+  float* mean_out;          // [C] each; scale / shift outputs are the kernel's own scale / shift arguments
+  float* invstd_out;
+  float* batch_stats_out;   // [2*C] or nullptr
+  float* running_mean;      // nullable
+  float* running_var;
+  long long* nbt;
+};
+
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const float* __restrict__ scale,
-                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_ld,
+bn_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, float* __restrict__ scale,
+                float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_ld,
                 const float* __restrict__ post_scale, int relu, __nv_bfloat16* __restrict__ z, int z_ld,
-                long long npix, int hw, int C) {
+                long long npix, int hw, int C, const BnLazy lazy) {
   pdl_sync();
   extern __shared__ float s_par[];   // [2][C]
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = scale[i]; s_par[C + i] = shift[i]; }
+  if (lazy.cells != nullptr) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double s1 = lazy.cells[c], s2 = lazy.cells[lazy.cpad + c];
+      if (blockIdx.x == 0) {         // same arithmetic as below: every block derives identical values
+        bn_write_params(s1, s2, lazy.count, c, C, lazy.gamma, lazy.beta, lazy.eps, lazy.momentum, lazy.running_mean,
+                        lazy.running_var, scale, shift, lazy.mean_out, lazy.invstd_out, lazy.batch_stats_out);
+      }
+      const double mean = s1 / lazy.count;
+      double var = s2 / lazy.count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)lazy.eps));
+      const float g_ = lazy.gamma ? lazy.gamma[c] : 1.f, b_ = lazy.beta ? lazy.beta[c] : 0.f;
+      s_par[c] = g_ * invstd;
+      s_par[C + c] = b_ - (float)mean * g_ * invstd;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && lazy.nbt) *lazy.nbt += 1;
+  } else {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = scale[i]; s_par[C + i] = shift[i]; }
+  }
   __syncthreads();
   const int groups = C >> 3;
   const long long total = npix * groups;
@@ -420,7 +457,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv
     if (fold.accum != nullptr) atomicAdd(fold.accum + (k >> 3) * C + c, (double)acc);
     else partials[(size_t)blockIdx.x * 2 * C + (k >> 3) * C + c] = acc;
   }
-  if (fold.accum == nullptr) return;
+  if (fold.accum == nullptr || fold.counter == nullptr) return;   // counter == nullptr: bn_bwd_apply folds the cells
   // In-launch finalisation (per-GPU statistics): the last CTA to finish turns the fp64 totals into dgamma / dbeta
   // (accumulated) and the two mean terms of the input gradient, and clears the cells (see bn_fold.cuh for the pattern).
   __shared__ unsigned s_ticket;
@@ -491,15 +528,27 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv_
                     int mask_ld, const float* __restrict__ post_scale, const __nv_bfloat16* __restrict__ y, int y_ld,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ c1, const float* __restrict__ c2, __nv_bfloat16* __restrict__ dy, int dy_ld,
-                    __nv_bfloat16* __restrict__ g_out, int g_ld, int g_accumulate, long long npix, int hw, int C) {
+                    __nv_bfloat16* __restrict__ g_out, int g_ld, int g_accumulate, long long npix, int hw, int C,
+                    const double* __restrict__ cells, float count, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta) {
   pdl_sync();
   extern __shared__ float s_par[];   // [5][C]: mean, invstd, gamma*invstd, c1, c2
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     s_par[i] = mean[i];
     s_par[C + i] = invstd[i];
     s_par[2 * C + i] = (gamma ? gamma[i] : 1.f) * invstd[i];
-    s_par[3 * C + i] = c1[i];
-    s_par[4 * C + i] = c2[i];
+    if (cells != nullptr) {          // deferred finalisation of bn_bwd_reduce's totals ([2][C] fp64): see BnLazy
+      const double s1 = cells[i], s2 = cells[C + i];
+      s_par[3 * C + i] = (float)(s1 / (double)count);
+      s_par[4 * C + i] = (float)(s2 / (double)count);
+      if (blockIdx.x == 0) {         // parameter gradients: local sums, accumulated once
+        if (dbeta) dbeta[i] += (float)s1;
+        if (dgamma) dgamma[i] += (float)s2;
+      }
+    } else {
+      s_par[3 * C + i] = c1[i];
+      s_par[4 * C + i] = c2[i];
+    }
   }
   __syncthreads();
   const int groups = C >> 3;
@@ -590,9 +639,12 @@ masked_accum_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, const __n
   }
 }
 
+// Grid of the element-wise passes: one 256-thread block per 256 x ew_items 16-byte items (the kernels keep several
+// independent items in flight per thread only when the grid leaves them more than one), capped at ew_ctas_per_sm x 148.
 static inline int ew_grid(long long total_threads) {
-  long long b = (total_threads + 255) / 256;
-  const long long cap = 148LL * 8;
+  const long long per = 256LL * (tune().ew_items > 0 ? tune().ew_items : 1);
+  long long b = (total_threads + per - 1) / per;
+  const long long cap = 148LL * (tune().ew_ctas_per_sm > 0 ? tune().ew_ctas_per_sm : 8);
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
@@ -673,9 +725,30 @@ extern "C" int b200seg_bn_apply(const void* y, int32_t y_ld, const float* scale,
                                 int32_t res_ld, const float* post_scale, int32_t relu, void* z, int32_t z_ld,
                                 int64_t npix, int32_t hw, int32_t c, void* stream) {
   if (!y || !z || !scale || !shift || c % 8 || y_ld % 8 || z_ld % 8 || (res && res_ld % 8)) return B200SEG_E_BADARG;
+  BnLazy lazy;
+  memset(&lazy, 0, sizeof(lazy));
   launch_k(bn_apply_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 2 * c * sizeof(float), (cudaStream_t)stream,
-           (const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, post_scale, relu,
-           (__nv_bfloat16*)z, z_ld, npix, hw, c);
+           (const __nv_bfloat16*)y, y_ld, const_cast<float*>(scale), const_cast<float*>(shift),
+           (const __nv_bfloat16*)res, res_ld, post_scale, relu, (__nv_bfloat16*)z, z_ld, npix, hw, c, lazy);
+  CHECK_LAUNCH();
+}
+
+extern "C" int b200seg_bn_apply_cells(const void* y, int32_t y_ld, const b200seg_bn_fold* f, const void* res,
+                                      int32_t res_ld, const float* post_scale, int32_t relu, void* z, int32_t z_ld,
+                                      int64_t npix, int32_t hw, int32_t c, void* stream) {
+  if (!y || !z || !f || c % 8 || y_ld % 8 || z_ld % 8 || (res && res_ld % 8)) return B200SEG_E_BADARG;
+  if (!f->accum || !f->scale || !f->shift || !f->mean || !f->invstd || f->c != c || f->count <= 0.f ||
+      (reinterpret_cast<uintptr_t>(f->accum) & 7))
+    return B200SEG_E_BADARG;
+  BnLazy lazy;
+  lazy.cells = f->accum; lazy.cpad = (c + 15) / 16 * 16;
+  lazy.count = f->count; lazy.eps = f->eps; lazy.momentum = f->momentum;
+  lazy.gamma = f->gamma; lazy.beta = f->beta; lazy.mean_out = f->mean; lazy.invstd_out = f->invstd;
+  lazy.batch_stats_out = f->batch_stats_out; lazy.running_mean = f->running_mean; lazy.running_var = f->running_var;
+  lazy.nbt = (long long*)f->num_batches_tracked;
+  launch_k(bn_apply_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 2 * c * sizeof(float), (cudaStream_t)stream,
+           (const __nv_bfloat16*)y, y_ld, f->scale, f->shift, (const __nv_bfloat16*)res, res_ld, post_scale, relu,
+           (__nv_bfloat16*)z, z_ld, npix, hw, c, lazy);
   CHECK_LAUNCH();
 }
 
@@ -690,9 +763,10 @@ static inline void reduce_shape(int c, int* rows, int* threads) {
 extern "C" int32_t b200seg_bn_bwd_grid(int64_t npix, int32_t c) {
   int rows, threads;
   reduce_shape(c, &rows, &threads);
-  long long b = (npix + rows - 1) / rows;
-  const long long cap = 148LL * 2;
-  return (int32_t)(b < cap ? b : cap);
+  const long long per = (long long)rows * (tune().red_items > 0 ? tune().red_items : 1);
+  long long b = (npix + per - 1) / per;
+  const long long cap = 148LL * (tune().red_ctas_per_sm > 0 ? tune().red_ctas_per_sm : 2);
+  return (int32_t)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
 static int bn_bwd_reduce_launch(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld,
@@ -758,7 +832,31 @@ extern "C" int b200seg_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* m
   launch_k(bn_bwd_apply_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 5 * c * sizeof(float), (cudaStream_t)stream,
            (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y,
            y_ld, mean, invstd, gamma, c1, c2, (__nv_bfloat16*)dy, dy_ld, (__nv_bfloat16*)g_out, g_ld, g_accumulate,
-           npix, hw, c);
+           npix, hw, c, (const double*)nullptr, 0.f, (float*)nullptr, (float*)nullptr);
+  CHECK_LAUNCH();
+}
+
+// BatchNorm backward with deferred finalisation: bn_bwd_reduce adds its per-block sums to `cells` ([2][c] fp64, zeroed by
+// the caller once per step), bn_bwd_apply folds them in its prologue (and accumulates dgamma / dbeta): two launches
+// instead of three, nothing between the reduction and the gradient pass. Per-GPU statistics only.
+extern "C" int b200seg_bn_bwd_cells(const void* dz, int32_t dz_ld, const void* mask, int32_t mask_ld,
+                                    const float* post_scale, const void* y, int32_t y_ld, const float* mean,
+                                    const float* invstd, const float* gamma, float* dgamma, float* dbeta, double* cells,
+                                    void* dy, int32_t dy_ld, void* g_out, int32_t g_ld, int32_t g_accumulate,
+                                    int64_t npix, int32_t hw, int32_t c, void* stream) {
+  if (!dz || !y || !dy || !mean || !invstd || !cells || c % 8 || (reinterpret_cast<uintptr_t>(cells) & 7))
+    return B200SEG_E_BADARG;
+  BnBwdFold fold;
+  memset(&fold, 0, sizeof(fold));
+  fold.accum = cells;                 // counter == nullptr: cells only
+  fold.count = (float)npix;
+  if (int rc = bn_bwd_reduce_launch(dz, dz_ld, mask, mask_ld, post_scale, y, y_ld, mean, invstd, npix, hw, c, nullptr,
+                                    fold, stream))
+    return rc;
+  launch_k(bn_bwd_apply_kernel, dim3(ew_grid(npix * (c / 8))), dim3(256), 5 * c * sizeof(float), (cudaStream_t)stream,
+           (const __nv_bfloat16*)dz, dz_ld, (const __nv_bfloat16*)mask, mask_ld, post_scale, (const __nv_bfloat16*)y,
+           y_ld, mean, invstd, gamma, (const float*)nullptr, (const float*)nullptr, (__nv_bfloat16*)dy, dy_ld,
+           (__nv_bfloat16*)g_out, g_ld, g_accumulate, npix, hw, c, (const double*)cells, (float)npix, dgamma, dbeta);
   CHECK_LAUNCH();
 }
 

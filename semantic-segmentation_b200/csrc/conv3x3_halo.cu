@@ -366,6 +366,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.Cout) ? __ldg(bias + c0 + j) : 0.f;
         }
+        const bool affine = fold.accum == nullptr && fold.scale != nullptr;   // evaluation: BN folded into the epilogue
+        if (affine) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.Cout) v[j] = v[j] * __ldg(fold.scale + c0 + j) + __ldg(fold.shift + c0 + j);
+        }
         if (addend != nullptr && valid && c0 + 16 <= p.Cout) {
           const __nv_bfloat16* ap = addend + pix * p.addend_ld + c0;
           float a0[8], a1[8];
@@ -373,6 +379,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           load8(ap + 8, a1);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
+        }
+        if (affine && fold.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         uint32_t pk[8];
 #pragma unroll
@@ -542,7 +552,7 @@ static int halo_plan(int n, int h, int w, int cin, int cout, HaloParams& p, size
   // one CTA per SM unless the co-resident configuration was chosen (occupancy is bounded by shared memory and registers)
   if (occ == 1 && smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   const int slots = occ == 2 ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
-  grid = p.total_tiles < slots ? p.total_tiles : slots;
+  grid = conv_grid_for(p.total_tiles, slots, (double)k16 * (p.BN / 2 > 32 ? p.BN / 2 : 32));
   return 0;
 }
 
@@ -561,10 +571,14 @@ int make_bn_fold(const b200seg_bn_fold* f, int cout, BnFoldDev* out);
 int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
                         const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
                         const void* addend, int addend_ld, int emit_stats, cudaStream_t stream,
-                        const b200seg_bn_fold* fold) {
+                        const b200seg_bn_fold* fold, const BnFoldDev* affine) {
   if (in_ld % 8 || out_ld % 8) return B200SEG_E_BADARG;
   BnFoldDev fd;
   if (int frc = make_bn_fold(emit_stats ? fold : nullptr, cout, &fd)) return frc;
+  if (affine) {                       // evaluation: BatchNorm folded into the epilogue (no statistics)
+    if (emit_stats) return B200SEG_E_BADARG;
+    fd = *affine;
+  }
   if (emit_stats && !stats_partials && !fold) return B200SEG_E_BADARG;
   HaloParams p;
   size_t smem_bytes;
@@ -613,6 +627,7 @@ int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in,
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
+  if (affine && p.stage_bytes) return B200SEG_E_BADARG;   // the staged epilogue (opt-in, training) has no affine mode
   cudaError_t e =
       p.stage_bytes ? launch_k(conv3x3_halo_kernel<1, true>, dim3(grid), dim3(kHThreads), smem_bytes, stream, tmA, tmB, tmY, p,
                                (__nv_bfloat16*)out, bias, stats_partials, (const __nv_bfloat16*)addend, fd)

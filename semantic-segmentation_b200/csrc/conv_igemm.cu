@@ -199,6 +199,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.Cout) ? __ldg(bias + c0 + j) : 0.f;
         }
+        const bool affine = fold.accum == nullptr && fold.scale != nullptr;   // evaluation: BN folded into the epilogue
+        if (affine) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.Cout) v[j] = v[j] * __ldg(fold.scale + c0 + j) + __ldg(fold.shift + c0 + j);
+        }
         if (addend != nullptr && valid && c0 + 16 <= p.Cout) {
           const __nv_bfloat16* ap = addend + pix * p.addend_ld + c0;
           float a0[8], a1[8];
@@ -206,6 +212,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           load8(ap + 8, a1);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { v[j] += a0[j]; v[8 + j] += a1[j]; }
+        }
+        if (affine && fold.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (p.out_fp32) {
           if (valid) {
@@ -369,15 +379,24 @@ static int plan_geom(const LaunchGeom& g, ConvPlan* pl) {
   pl->smem_bytes = fixed + (size_t)nst * pl->stage_bytes;
   if (occ == 1 && pl->smem_bytes < 120 * 1024) pl->smem_bytes = 120 * 1024;   // one CTA per SM
   const int slots = occ == 2 ? B200SEG_MAX_GRID : B200SEG_MAX_CTAS;
-  pl->grid = pl->total_tiles < slots ? pl->total_tiles : slots;
+  {
+    const int k16 = g.ntaps * pl->cchunks * (KC / 16);
+    pl->grid = conv_grid_for(pl->total_tiles, slots, (double)k16 * (64.0 + pl->BN / 2));
+  }
   return 0;
+}
+
+static inline int conv_dil(const b200seg_conv_desc* d) { return d->dilation > 1 ? d->dilation : 1; }
+static inline int conv_out(int in, const b200seg_conv_desc* d) {
+  return (in + 2 * d->pad - conv_dil(d) * (d->ksize - 1) - 1) / d->stride + 1;
 }
 
 static LaunchGeom fwd_geom(const b200seg_conv_desc* d) {
   LaunchGeom g{};
+  const int dil = conv_dil(d);
   g.n = d->n; g.in_h = d->h; g.in_w = d->w; g.in_c = d->cin; g.in_ld = d->x_ld;
-  g.out_h = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
-  g.out_w = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
+  g.out_h = conv_out(d->h, d);
+  g.out_w = conv_out(d->w, d);
   g.out_c = d->cout; g.out_ld = d->y_ld;
   g.sub_h = g.out_h; g.sub_w = g.out_w;
   g.in_stride = d->stride; g.out_stride = 1; g.out_off_h = g.out_off_w = 0;
@@ -385,7 +404,7 @@ static LaunchGeom fwd_geom(const b200seg_conv_desc* d) {
   for (int kh = 0; kh < d->ksize; ++kh)
     for (int kw = 0; kw < d->ksize; ++kw) {
       const int t = kh * d->ksize + kw;
-      g.tap_dh[t] = kh - d->pad; g.tap_dw[t] = kw - d->pad; g.tap_w[t] = t;
+      g.tap_dh[t] = kh * dil - d->pad; g.tap_dw[t] = kw * dil - d->pad; g.tap_w[t] = t;
     }
   g.out_fp32 = d->out_fp32; g.has_bias = d->has_bias; g.emit_stats = d->emit_stats; g.force_kc = d->reserved;
   return g;
@@ -393,13 +412,39 @@ static LaunchGeom fwd_geom(const b200seg_conv_desc* d) {
 
 static bool desc_ok(const b200seg_conv_desc* d) {
   if (!d || d->n <= 0 || d->h <= 0 || d->w <= 0) return false;
-  if (!((d->ksize == 1 && d->pad == 0) || (d->ksize == 3 && d->pad == 1))) return false;
+  const int dil = d->dilation > 1 ? d->dilation : 1;
+  if (!((d->ksize == 1 && d->pad == 0 && dil == 1) || (d->ksize == 3 && d->pad == dil))) return false;
   if (d->stride != 1 && d->stride != 2) return false;
+  if (dil > 1 && d->stride != 1) return false;       // dilated layers of the path are all stride 1
   return true;
 }
 
 static int g_smem_reserve = 0;
 int smem_reserve() { return g_smem_reserve; }
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+const Tune& tune() {
+  static const Tune t = {env_int("B200SEG_CONV_MIN_CLK", 0),    env_int("B200SEG_WGRAD_MIN_CLK", 0),
+                         env_int("B200SEG_EW_ITEMS", 8),        env_int("B200SEG_EW_CTAS_PER_SM", 8),
+                         env_int("B200SEG_RED_ITEMS", 4),       env_int("B200SEG_RED_CTAS_PER_SM", 2),
+                         env_int("B200SEG_RS_ITEMS", 1)};
+  return t;
+}
+// grid of a persistent convolution launch: every CTA gets at least conv_min_clk modelled clocks of tiles
+static int conv_grid(long long total_tiles, int slots, double tile_clk) {
+  long long g = total_tiles < slots ? total_tiles : slots;
+  const int min_clk = tune().conv_min_clk;
+  if (min_clk > 0) {
+    long long want = (long long)((double)total_tiles * tile_clk / (double)min_clk + 0.999);
+    if (want < 1) want = 1;
+    if (want < g) g = want;
+  }
+  return (int)g;
+}
+int conv_grid_for(long long total_tiles, int slots, double tile_clk) { return conv_grid(total_tiles, slots, tile_clk); }
 
 int conv_plan(const b200seg_conv_desc* d, ConvPlan* pl) {
   if (!desc_ok(d)) return B200SEG_E_BADARG;
@@ -410,9 +455,9 @@ int make_bn_fold(const b200seg_bn_fold* f, int cout, BnFoldDev* out) {
   BnFoldDev d;
   memset(&d, 0, sizeof(d));
   if (f) {
-    if (!f->accum || !f->counter || !f->scale || !f->shift || !f->mean || !f->invstd || f->c != cout || f->count <= 0.f ||
-        (reinterpret_cast<uintptr_t>(f->accum) & 7))
-      return B200SEG_E_BADARG;
+    if (!f->accum || f->c != cout || (reinterpret_cast<uintptr_t>(f->accum) & 7)) return B200SEG_E_BADARG;
+    // counter == NULL: deferred mode, only the cells are touched (see bn_fold.cuh)
+    if (f->counter && (!f->scale || !f->shift || !f->mean || !f->invstd || f->count <= 0.f)) return B200SEG_E_BADARG;
     d.accum = f->accum; d.counter = f->counter; d.gamma = f->gamma; d.beta = f->beta;
     d.scale = f->scale; d.shift = f->shift; d.mean = f->mean; d.invstd = f->invstd; d.batch_out = f->batch_stats_out;
     d.running_mean = f->running_mean; d.running_var = f->running_var; d.nbt = (long long*)f->num_batches_tracked;
@@ -424,7 +469,7 @@ int make_bn_fold(const b200seg_bn_fold* f, int cout, BnFoldDev* out) {
 
 static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const float* bias, void* out,
                        float* stats_partials, int32_t* stats_grid, const void* addend, int addend_ld,
-                       cudaStream_t stream, const b200seg_bn_fold* fold = nullptr) {
+                       cudaStream_t stream, const b200seg_bn_fold* fold = nullptr, const BnFoldDev* affine = nullptr) {
   ConvPlan pl;
   int rc = plan_geom(g, &pl);
   if (rc) return rc;
@@ -433,6 +478,10 @@ static int launch_geom(const LaunchGeom& g, const void* a, const void* w, const 
   if (g.emit_stats && ((!stats_partials && !fold) || g.out_fp32)) return B200SEG_E_BADARG;
   BnFoldDev fd;
   if (int frc = make_bn_fold(g.emit_stats ? fold : nullptr, g.out_c, &fd)) return frc;
+  if (affine) {                       // evaluation: BatchNorm folded into the epilogue (no statistics)
+    if (g.emit_stats) return B200SEG_E_BADARG;
+    fd = *affine;
+  }
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
       (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15))
     return B200SEG_E_BADARG;
@@ -517,7 +566,7 @@ void conv_igemm_occupancy_report() {
 int conv3x3_halo_launch(int n, int h, int w, int cin, int in_ld, const void* in, int cout, const void* wts,
                         const float* bias, void* out, int out_ld, float* stats_partials, int32_t* stats_grid,
                         const void* addend, int addend_ld, int emit_stats, cudaStream_t stream,
-                        const b200seg_bn_fold* fold = nullptr);
+                        const b200seg_bn_fold* fold = nullptr, const BnFoldDev* affine = nullptr);
 int conv3x3_halo_plan_info(int n, int h, int w, int cin, int cout, int32_t* out);
 
 }  // namespace b200seg
@@ -555,7 +604,7 @@ extern "C" int b200seg_conv2d_plan_info(const b200seg_conv_desc* d, int32_t whic
 extern "C" int b200seg_conv2d_fwd(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
                                   void* y, float* stats_partials, int32_t* stats_grid, void* stream) {
   if (!desc_ok(d)) return B200SEG_E_BADARG;
-  if (d->ksize == 3 && d->stride == 1 && !d->out_fp32 && d->cout % 16 == 0 && d->reserved == 0) {
+  if (d->ksize == 3 && d->stride == 1 && !d->out_fp32 && d->cout % 16 == 0 && d->reserved == 0 && conv_dil(d) == 1) {
     if (d->emit_stats && !stats_partials) return B200SEG_E_BADARG;
     // halo-tile kernel: the input is read once per tile instead of once per filter tap (conv3x3_halo.cu)
     return conv3x3_halo_launch(d->n, d->h, d->w, d->cin, d->x_ld, x, d->cout, w_ohwi, d->has_bias ? bias : nullptr, y,
@@ -573,10 +622,43 @@ extern "C" int b200seg_set_smem_reserve(int32_t bytes) {
 extern "C" int b200seg_conv2d_fwd_bn(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
                                      void* y, const b200seg_bn_fold* fold, void* stream) {
   if (!desc_ok(d) || !fold || !d->emit_stats || d->out_fp32) return B200SEG_E_BADARG;
-  if (d->ksize == 3 && d->stride == 1 && d->cout % 16 == 0 && d->reserved == 0)
+  if (d->ksize == 3 && d->stride == 1 && d->cout % 16 == 0 && d->reserved == 0 && conv_dil(d) == 1)
     return conv3x3_halo_launch(d->n, d->h, d->w, d->cin, d->x_ld, x, d->cout, w_ohwi, d->has_bias ? bias : nullptr, y,
                                d->y_ld, nullptr, nullptr, nullptr, 0, 1, (cudaStream_t)stream, fold);
   return launch_geom(fwd_geom(d), x, w_ohwi, bias, y, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream, fold);
+}
+
+// Forward convolution with a residual addend in the epilogue: y = conv(x) (+ bias) + addend, statistics of the stored sum.
+// The identity-mapping blocks of WideResNet-38 (network/wider_resnet.py:170-183 `out.add_(shortcut)`) feed that sum into
+// the next block's pre-activation BatchNorm, so the batch statistics come for free from this epilogue.
+extern "C" int b200seg_conv2d_fwd_add(const b200seg_conv_desc* d, const void* x, const void* w_ohwi, const float* bias,
+                                      const void* addend, int32_t addend_ld, void* y, float* stats_partials,
+                                      int32_t* stats_grid, void* stream) {
+  if (!desc_ok(d) || !addend || d->out_fp32) return B200SEG_E_BADARG;
+  if (d->emit_stats && !stats_partials) return B200SEG_E_BADARG;
+  if (d->ksize == 3 && d->stride == 1 && d->cout % 16 == 0 && d->reserved == 0 && conv_dil(d) == 1)
+    return conv3x3_halo_launch(d->n, d->h, d->w, d->cin, d->x_ld, x, d->cout, w_ohwi, d->has_bias ? bias : nullptr, y,
+                               d->y_ld, stats_partials, stats_grid, addend, addend_ld, d->emit_stats, (cudaStream_t)stream);
+  return launch_geom(fwd_geom(d), x, w_ohwi, bias, y, stats_partials, stats_grid, addend, addend_ld, (cudaStream_t)stream);
+}
+
+// Evaluation: y = relu?(conv(x) * scale[co] + shift[co] (+ addend)) in the convolution epilogue (BatchNorm from running
+// statistics, residual sum and ReLU of network/hrnetv2.py:50-66,86-106 in one launch). bf16 output, no statistics.
+extern "C" int b200seg_conv2d_fwd_affine(const b200seg_conv_desc* d, const void* x, const void* w_ohwi,
+                                         const float* scale, const float* shift, int32_t relu, const void* addend,
+                                         int32_t addend_ld, void* y, void* stream) {
+  if (!desc_ok(d) || !scale || !shift || d->out_fp32 || d->emit_stats || d->has_bias) return B200SEG_E_BADARG;
+  BnFoldDev fd;
+  memset(&fd, 0, sizeof(fd));
+  fd.scale = const_cast<float*>(scale);
+  fd.shift = const_cast<float*>(shift);
+  fd.relu = relu ? 1 : 0;
+  fd.C = d->cout;
+  if (d->ksize == 3 && d->stride == 1 && d->cout % 16 == 0 && d->reserved == 0 && conv_dil(d) == 1)
+    return conv3x3_halo_launch(d->n, d->h, d->w, d->cin, d->x_ld, x, d->cout, w_ohwi, nullptr, y, d->y_ld, nullptr,
+                               nullptr, addend, addend_ld, 0, (cudaStream_t)stream, nullptr, &fd);
+  return launch_geom(fwd_geom(d), x, w_ohwi, nullptr, y, nullptr, nullptr, addend, addend_ld, (cudaStream_t)stream,
+                     nullptr, &fd);
 }
 
 // Data gradient. d describes the FORWARD convolution. dx[n,h,w,cin] = sum_taps dy[...] * W  (+ addend).
@@ -586,15 +668,16 @@ extern "C" int b200seg_conv2d_fwd_bn(const b200seg_conv_desc* d, const void* x, 
 extern "C" int b200seg_conv2d_dgrad(const b200seg_conv_desc* d, const void* dy, int32_t dy_ld, const void* w_dgrad,
                                     const void* addend, int32_t addend_ld, void* dx, int32_t dx_ld, void* stream) {
   if (!desc_ok(d)) return B200SEG_E_BADARG;
-  const int Ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
-  const int Wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
+  const int Ho = conv_out(d->h, d);
+  const int Wo = conv_out(d->w, d);
   const int K = d->ksize, taps = K * K;
+  const int dil = conv_dil(d);
   LaunchGeom g{};
   g.n = d->n; g.in_h = Ho; g.in_w = Wo; g.in_c = (d->cout + 7) / 8 * 8; g.in_ld = dy_ld;
   g.out_h = d->h; g.out_w = d->w; g.out_c = d->cin; g.out_ld = dx_ld;
   g.in_stride = 1; g.wtaps = taps;
   g.out_fp32 = 0; g.has_bias = 0; g.emit_stats = 0; g.force_kc = d->reserved;
-  if (d->stride == 1 && K == 3 && d->cin % 16 == 0 && d->reserved == 0)
+  if (d->stride == 1 && K == 3 && d->cin % 16 == 0 && d->reserved == 0 && dil == 1)
     return conv3x3_halo_launch(d->n, d->h, d->w, g.in_c, dy_ld, dy, d->cin, w_dgrad, nullptr, dx, dx_ld, nullptr, nullptr,
                                addend, addend_ld, 0, (cudaStream_t)stream);
   if (d->stride == 1) {
@@ -603,11 +686,19 @@ extern "C" int b200seg_conv2d_dgrad(const b200seg_conv_desc* d, const void* dy, 
     for (int kh = 0; kh < K; ++kh)
       for (int kw = 0; kw < K; ++kw) {
         const int t = kh * K + kw;
-        g.tap_dh[t] = d->pad - kh; g.tap_dw[t] = d->pad - kw; g.tap_w[t] = taps - 1 - t;
+        g.tap_dh[t] = d->pad - kh * dil; g.tap_dw[t] = d->pad - kw * dil; g.tap_w[t] = taps - 1 - t;
       }
     return launch_geom(g, dy, w_dgrad, nullptr, dx, nullptr, nullptr, addend, addend_ld, (cudaStream_t)stream);
   }
-  if (K != 3) return B200SEG_E_BADARG;
+  if (K == 1) {
+    // 1x1 stride-2 (WideResNet-38 proj_conv of mod4.block1): only the even lattice receives a gradient. The caller hands
+    // in dx either zero-filled or as the in-place accumulation target (addend == dx); the odd lattice is left untouched.
+    if (addend != nullptr && addend != dx) return B200SEG_E_BADARG;
+    g.sub_h = (d->h + 1) / 2; g.sub_w = (d->w + 1) / 2;
+    g.out_stride = 2; g.out_off_h = 0; g.out_off_w = 0;
+    g.ntaps = 1; g.tap_dh[0] = 0; g.tap_dw[0] = 0; g.tap_w[0] = 0;
+    return launch_geom(g, dy, w_dgrad, nullptr, dx, nullptr, nullptr, addend, addend_ld, (cudaStream_t)stream);
+  }
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       g.sub_h = (d->h - a + 1) / 2; g.sub_w = (d->w - b + 1) / 2;

@@ -9,6 +9,7 @@
 //                      (network/mynn.py:102-114; scale 0.5 == 2x2 mean) folded in.
 #include "ptx.cuh"
 #include "launch.h"
+#include "conv_common.h"
 #include "../../include/b200seg.h"
 #include "vec.cuh"
 
@@ -198,7 +199,8 @@ image_prep_kernel(const float* __restrict__ img, int N, int H, int W, __nv_bfloa
 }
 
 static inline int ew_grid(long long total_threads) {
-  long long b = (total_threads + 255) / 256;
+  const long long per = 256LL * (tune().rs_items > 0 ? tune().rs_items : 1);
+  long long b = (total_threads + per - 1) / per;
   const long long cap = 148LL * 8;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }

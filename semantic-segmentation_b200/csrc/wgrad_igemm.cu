@@ -27,7 +27,7 @@ namespace b200seg {
 
 struct WgradParams {
   int N, Ho, Wo, Cout, Cin;
-  int ksize, stride, pad, taps;
+  int ksize, stride, pad, taps, dil;
   int TH, TW, tiles_h, tiles_w, pix_tiles;
   int m_tiles, n_tiles, tap_groups, taps_per_group, splits, total_units;
   int nblocksB_max;
@@ -124,7 +124,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
             mbar_arrive_expect_tx(&b_full[b_slot], nblk * kABlock);
             for (int b = 0; b < nblk; ++b)
               tma_load_4d(&tmX, &b_full[b_slot], sb + (size_t)b * kABlock, n0 + b * 64,
-                          tw_i * p.TW * p.stride + kw - p.pad, th_i * p.TH * p.stride + kh - p.pad, img);
+                          tw_i * p.TW * p.stride + kw * p.dil - p.pad, th_i * p.TH * p.stride + kh * p.dil - p.pad,
+                          img);
             if (++b_slot == p.b_slots) { b_slot = 0; b_phase ^= 1; }
           }
         }
@@ -379,14 +380,16 @@ using namespace b200seg;
 
 static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
   if (!d) return B200SEG_E_BADARG;
-  if (!((d->ksize == 1 && d->pad == 0) || (d->ksize == 3 && d->pad == 1))) return B200SEG_E_BADARG;
+  const int dil = d->dilation > 1 ? d->dilation : 1;
+  if (!((d->ksize == 1 && d->pad == 0 && dil == 1) || (d->ksize == 3 && d->pad == dil))) return B200SEG_E_BADARG;
   if (d->stride != 1 && d->stride != 2) return B200SEG_E_BADARG;
+  if (dil > 1 && d->stride != 1) return B200SEG_E_BADARG;
   if (d->cin % 16 || d->x_ld % 8) return B200SEG_E_BADARG;
   p.N = d->n; p.Cout = d->cout; p.Cin = d->cin;
-  p.ksize = d->ksize; p.stride = d->stride; p.pad = d->pad; p.taps = d->ksize * d->ksize;
-  p.Ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
-  p.Wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
-  p.halo = (d->ksize == 3 && d->stride == 1 && d->reserved == 0) ? 1 : 0;
+  p.ksize = d->ksize; p.stride = d->stride; p.pad = d->pad; p.taps = d->ksize * d->ksize; p.dil = dil;
+  p.Ho = (d->h + 2 * d->pad - dil * (d->ksize - 1) - 1) / d->stride + 1;
+  p.Wo = (d->w + 2 * d->pad - dil * (d->ksize - 1) - 1) / d->stride + 1;
+  p.halo = (d->ksize == 3 && d->stride == 1 && d->reserved == 0 && dil == 1) ? 1 : 0;
   p.b_block_bytes = p.halo ? 24576 : kABlock;
   p.TW = 16; p.TH = 8;
   if (p.Wo <= 8 || p.halo) { p.TW = 8; p.TH = 16; }
@@ -418,13 +421,18 @@ static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
       int sp_max = B200SEG_MAX_CTAS / items;
       if (sp_max > p.pix_tiles) sp_max = p.pix_tiles;
       if (sp_max < 1) sp_max = 1;
+      const double mma = (double)tpg * 8.0 * (Nmax / 2 > 32 ? Nmax / 2 : 32);
+      const double bytes = (a_two ? 32768.0 : 16384.0) + (p.halo ? nblk * 23040.0 : (double)tpg * nblk * 16384.0);
+      const double per_tile = mma > bytes / 64.0 ? mma : bytes / 64.0;
+      if (tune().wgrad_min_clk > 0) {     // every unit reduces at least wgrad_min_clk modelled clocks of pixel tiles
+        int sp_w = (int)((double)p.pix_tiles * per_tile / (double)tune().wgrad_min_clk);
+        if (sp_w < 1) sp_w = 1;
+        if (sp_w < sp_max) sp_max = sp_w;
+      }
       for (int pass = 0; pass < 2; ++pass) {
         const int splits = pass == 0 ? 1 : sp_max;
         if (pass == 1 && sp_max == 1) break;
         const double tiles_per_unit = (double)((p.pix_tiles + splits - 1) / splits);
-        const double mma = (double)tpg * 8.0 * (Nmax / 2 > 32 ? Nmax / 2 : 32);
-        const double bytes = (a_two ? 32768.0 : 16384.0) + (p.halo ? nblk * 23040.0 : (double)tpg * nblk * 16384.0);
-        const double per_tile = mma > bytes / 64.0 ? mma : bytes / 64.0;
         const double unit = tiles_per_unit * per_tile + (double)tpg * Nmax * 4.0 + 1500.0;
         const double waves = (double)(((long long)items * splits + B200SEG_MAX_CTAS - 1) / B200SEG_MAX_CTAS);
         double cost = waves * unit;

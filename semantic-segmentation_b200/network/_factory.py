@@ -14,7 +14,8 @@ def build(arch, num_classes, criterion):
     kw = {}
     try:
         from config import cfg
-        kw["hcfg"] = A.hrnet_cfg_from_reference_cfg(cfg)
+        if not arch.startswith("deepv3."):
+            kw["hcfg"] = A.hrnet_cfg_from_reference_cfg(cfg)
         ocfg = dict(A.OCR_DEFAULT)
         ocfg["mid_channels"] = cfg.MODEL.OCR.MID_CHANNELS
         ocfg["key_channels"] = cfg.MODEL.OCR.KEY_CHANNELS

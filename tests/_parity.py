@@ -29,6 +29,8 @@ def oracle_train_step(O, arch, hcfg, sd0, images, gts, sup_wt=0.0, crit=None, em
         loss = O.mscale_two_scale(ctx, images, gts, criterion=crit, hcfg=hcfg, supervised_mscale_wt=sup_wt)
     elif arch == "ocrnet.HRNet":
         loss = O.ocrnet_forward(ctx, images, gts, criterion=crit, hcfg=hcfg)
+    elif arch == "deepv3.DeepV3PlusW38":
+        loss = O.deepv3_forward(ctx, images, gts, criterion=crit, wcfg=hcfg)
     else:
         loss = O.basic_forward(ctx, images, gts, criterion=crit, hcfg=hcfg)
     loss.backward()

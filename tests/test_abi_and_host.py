@@ -28,6 +28,10 @@ def test_library_exports_every_declared_symbol():
         assert s in _lib.SIGNATURES, "ctypes table lacks %s" % s
     for s in _lib.SIGNATURES:
         assert s in syms, "%s is bound but not declared in include/b200seg.h" % s
+    # the test-only kernels live in their own library: the product library does not export them
+    T = _lib.test_lib()
+    for s in _lib.PROBE_SIGNATURES:
+        assert hasattr(T, s) and not hasattr(L, s), s
 
 
 def test_no_torch_types_in_the_abi():
@@ -65,8 +69,9 @@ def test_factory_contract_and_cpu_refusal():
     assert type(net).__name__ == "B200SegModule" and net.arch == "ocrnet.HRNet_Mscale"
     assert network.get_model("network.basic.HRNet", 19, None).arch == "basic.HRNet"
     assert network.get_model("network.mscale.HRNet", 19, None).arch == "mscale.HRNet"      # network/mscale.py:473-475
+    assert network.get_model("network.deepv3.DeepV3PlusW38", 19, None).arch == "deepv3.DeepV3PlusW38"
     with pytest.raises((ImportError, ModuleNotFoundError, AttributeError)):
-        network.get_model("network.deepv3.DeepV3PlusW38", 19, None)     # outside the hot path: not provided
+        network.get_model("network.deepv3.DeepV3PlusSRNX50V3PlusD_m1", 19, None)   # other trunks: not provided
     net.train()
     with pytest.raises(RuntimeError, match="CUDA only"):                 # no CPU fallback
         net({"images": torch.zeros(1, 3, 64, 64), "gts": torch.zeros(1, 64, 64, dtype=torch.long)})

@@ -131,6 +131,59 @@ def test_conv_with_in_launch_bn_finalize(case):
     close(yr * par1[0] + par1[1], ref, 2e-5, "affine vs F.batch_norm")
 
 
+@pytest.mark.parametrize("case", [(1, 64, 96, 48, 48, 3, 1, False), (2, 40, 72, 64, 64, 3, 1, False),
+                                  (1, 32, 64, 720, 512, 3, 1, True), (1, 32, 64, 96, 48, 1, 1, False),
+                                  (1, 64, 128, 48, 96, 3, 2, False), (1, 256, 512, 48, 48, 3, 1, False)])
+@pytest.mark.parametrize("res,relu", [(True, True), (False, False)])
+def test_conv_with_deferred_bn_finalize(case, res, relu):
+    """Deferred finalisation (the training default): conv2d_fwd_cells adds its statistics to fp64 cells, bn_apply_cells
+    folds them in its prologue. Against the three-launch path (conv2d_fwd partials + bn_finalize + bn_apply): same conv
+    bits, same z bits up to one bf16 ulp, same scale / shift / mean / invstd / batch + running statistics."""
+    raw = _setup()
+    n, h, w, cin, cout, k, s, bias = case
+    x = rnd((n, h, w, cin), 1)
+    wt = rnd((cout, cin, k, k), 2, scale=(cin * k * k) ** -0.5, dtype=torch.float32).contiguous()
+    b = rnd((cout,), 3, dtype=torch.float32) if bias else None
+    gamma = 1.0 + 0.1 * rnd((cout,), 4, dtype=torch.float32)
+    beta = 0.1 * rnd((cout,), 5, dtype=torch.float32)
+    w_f, _ = raw.pack_weight(wt, want_dgrad=False)
+    y0, stats = raw.conv2d_fwd(x, w_f, b, stride=s, emit_stats=True)
+    npix = y0.shape[0] * y0.shape[1] * y0.shape[2]
+    rm0, rv0 = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+    nbt0 = torch.zeros((), dtype=torch.long, device="cuda")
+    par0 = raw.bn_finalize(stats, npix, gamma, beta, 1e-5, 0.1, rm0, rv0, nbt0, cout)
+    r = rnd(tuple(y0.shape), 6) if res else None
+    z0 = raw.bn_apply(y0, par0[0], par0[1], r, None, relu)
+    cpad = (cout + 15) // 16 * 16
+    rm1, rv1 = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+    nbt1 = torch.zeros((), dtype=torch.long, device="cuda")
+    for rep in range(2):
+        cells = torch.zeros(2 * cpad, dtype=torch.float64, device="cuda")
+        par1 = torch.full((4, cout), float("nan"), device="cuda")
+        batch = torch.zeros(2 * cout, device="cuda")
+        y1 = raw.conv2d_fwd_cells(x, w_f, b, s, cells)
+        if rep == 0:
+            z1 = raw.bn_apply_cells(y1, cells, par1, gamma, beta, 1e-5, 0.1, r, None, relu, running_mean=rm1,
+                                    running_var=rv1, nbt=nbt1)
+        else:
+            z1 = raw.bn_apply_cells(y1, cells, par1, gamma, beta, 1e-5, 0.1, r, None, relu, batch_out=batch)
+        torch.cuda.synchronize()
+        assert torch.equal(y1, y0)
+        yr = y0.double().reshape(-1, cout)
+        close(cells[:cout].float(), yr.sum(0).float(), 1e-5, "cell sums")
+        close(cells[cpad:cpad + cout].float(), (yr * yr).sum(0).float(), 1e-5, "cell sums of squares")
+        for i, name in enumerate(("scale", "shift", "mean", "invstd")):
+            close(par1[i], par0[i], 2e-6, name)
+        close(z1, z0, 2.0 ** -8, "z")
+        if rep:
+            close(batch[:cout], par0[2], 2e-6, "batch mean")
+            var_b = yr.var(0, unbiased=True).float()
+            close(batch[cout:], var_b, 1e-4, "batch var")
+    close(rm1, rm0, 2e-6, "running mean")
+    close(rv1, rv0, 2e-6, "running var")
+    assert int(nbt1) == int(nbt0) == 1
+
+
 def test_grad_fold_layouts_and_clearing():
     """End-of-step fold: OHWI accumulators of two passes -> OIHW gradient (+= or overwrite), vectors of both passes, the
     stem accumulating on 16 padded input channels at its own accumulator offset, accumulators cleared on request."""
@@ -285,6 +338,18 @@ def test_batchnorm_train_fwd_bwd(c, res, relu, size):
         close(dgamma2, dgamma, 1e-5, "fused dgamma")
         close(dbeta2, dbeta, 1e-5, "fused dbeta")
         assert float(acc.abs().max()) == 0.0 and int(ticket) == 0
+    # deferred finalisation (the training default): the reduce only adds to the cells, the gradient pass folds them
+    cells = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+    dgamma3, dbeta3 = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    g_out3 = torch.empty((n, h, w, c), dtype=torch.bfloat16, device="cuda") if res else None
+    dy3 = raw.bn_bwd(dz, z if relu else None, ps, y, par[2], par[3], gamma, dgamma3, dbeta3, g_out=g_out3, cells=cells)
+    torch.cuda.synchronize()
+    close(dy3, dy, 2.0 ** -8, "deferred dx")
+    close(dgamma3, dgamma, 1e-5, "deferred dgamma")
+    close(dbeta3, dbeta, 1e-5, "deferred dbeta")
+    if res:
+        assert torch.equal(g_out3, g_out)
+    close(cells[:c].float(), dbeta, 1e-5, "cells hold the sums")
 
 
 def test_fuse_and_upsample_adjoint():

@@ -36,6 +36,14 @@ def test_two_scale_step_flops_and_launch_structure():
     assert f["conv2d_fwd_bn"][0] == 2 * 316 and "bn_finalize" not in f and "bn_bwd_finalize" not in f
     assert f["conv2d_fwd_bn"][0] + f["conv2d_fwd"][0] == 2 * 322
     assert r["total"][0] - f["total"][0] == 2 * 316 + r["bn_bwd_finalize"][0]     # launches the fused finalisers save
+    # default training program with per-GPU statistics (B200SEG_BN_CELLS=1): deferred finalisation - a bn_finalize launch
+    # remains only in front of the fuse layers (their consumers read scale / shift), no bn_bwd_finalize at all
+    c = _trace("--arch", "ocrnet.HRNet_Mscale", "--bn-cells")
+    assert c["bn_apply_cells"][0] + c["bn_finalize"][0] == 2 * 316 and "bn_bwd_finalize" not in c
+    assert c["bn_bwd_cells"][0] == r["bn_bwd_reduce"][0] and "bn_bwd_reduce" not in c
+    assert c["bn_apply_cells"][0] + c.get("bn_apply", (0,))[0] == r["bn_apply"][0]
+    assert c["conv2d_fwd_bn"][0] == c["bn_apply_cells"][0]
+    assert abs(c["total"][1] - total[1]) < 1e-6
     assert 60.0 < total[2] < 90.0                                        # GB of tensors handed to kernels per crop
 
 
@@ -55,3 +63,10 @@ def test_mscale_basic_architecture_traces():
     want = 1.25 * fwd1 + 2.0 * (1.25 * fwd1 - 2.0 * 294.7e-3)
     assert abs(r["total"][1] - want) <= 0.01 * want, (r["total"], want)
     assert r["conv2d_wgrad"][0] == r["conv2d_fwd"][0] - 3
+
+
+def test_deepv3_wrn38_program_traces():
+    r = _trace("--arch", "deepv3.DeepV3PlusW38")
+    assert abs(r["total"][1] - 34.95) <= 0.35, r["total"]                # 3 x 11.65 TFLOP
+    assert r["maxpool3x3s2_fwd"][0] == 2 and r["maxpool3x3s2_bwd"][0] == 2
+    assert r["conv2d_fwd"][0] + r.get("conv2d_fwd_bn", (0,))[0] + r["conv2d_fwd_add"][0] == r["conv2d_wgrad"][0]

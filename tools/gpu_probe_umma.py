@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "semantic-segmentation_b200"))
 import torch
 
-from b200seg._lib import ProbeDesc, lib, ptr, stream_ptr
+from b200seg._lib import ProbeDesc, ptr, stream_ptr, test_lib
 
 
 def operand(o, rows, cols, box_cols, box_rows, nboxes=1, c0=0, r0=0, dcol=0, drow=0, smem_stride=0, swz=128):
@@ -25,7 +25,7 @@ def operand(o, rows, cols, box_cols, box_rows, nboxes=1, c0=0, r0=0, dcol=0, dro
 
 def run(p, A, B, N):
     D = torch.full((128, N), float("nan"), device="cuda")
-    rc = lib().b200seg_umma_probe(ctypes.byref(p), ptr(A), ptr(B), ptr(D), stream_ptr())
+    rc = test_lib().b200seg_umma_probe(ctypes.byref(p), ptr(A), ptr(B), ptr(D), stream_ptr())
     assert rc == 0, rc
     torch.cuda.synchronize()
     return D
