@@ -429,7 +429,7 @@ static int env_int(const char* name, int dflt) {
 const Tune& tune() {
   static const Tune t = {env_int("B200SEG_CONV_MIN_CLK", 0),    env_int("B200SEG_WGRAD_MIN_CLK", 0),
                          env_int("B200SEG_EW_ITEMS", 8),        env_int("B200SEG_EW_CTAS_PER_SM", 8),
-                         env_int("B200SEG_RED_ITEMS", 4),       env_int("B200SEG_RED_CTAS_PER_SM", 2),
+                         env_int("B200SEG_RED_ITEMS", 8),       env_int("B200SEG_RED_CTAS_PER_SM", 2),
                          env_int("B200SEG_RS_ITEMS", 1)};
   return t;
 }

@@ -38,6 +38,7 @@ struct WgradParams {
   long long unit_stride; // floats per unit slab
   int a_slot_bytes, b_slot_bytes, b_slots;
   int direct;            // splits == 1: units add straight into the gradient accumulator
+  int tmem_cols;         // TMEM allocation: 512, or a power of two <= 256 in the co-resident configuration
 };
 
 constexpr int kWThreads = 256;
@@ -69,7 +70,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
     mbar_init(acc_empty, 4);
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  if (warp == 2) { tmem_alloc(tmem_ptr_smem, p.tmem_cols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -242,7 +243,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
 
@@ -378,6 +379,16 @@ publish_grads_kernel(float* __restrict__ dst, const float* __restrict__ src, lon
 
 using namespace b200seg;
 
+// B200SEG_WGRAD_CORES=1 (experiment): narrow layers (Cout <= 64, one 64-channel block of x per N tile) run in a
+// configuration that can share an SM with a co-resident convolution CTA or another weight-gradient CTA: at most 256 TMEM
+// columns (more, smaller tap groups), one 16 KB dy block per stage and a shared-memory footprint below half an SM.
+// Default off: a full-SM weight-gradient CTA excludes every other tensor-core CTA from its SM and vice versa.
+static bool wgrad_coresident_enabled() {
+  static const bool on = []() { const char* e = getenv("B200SEG_WGRAD_CORES"); return e && e[0] == '1'; }();
+  return on;
+}
+constexpr size_t kWgradHalfSm = 115712;   // (228 KB - 2 x 1 KB reserved) / 2
+
 static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
   if (!d) return B200SEG_E_BADARG;
   const int dil = d->dilation > 1 ? d->dilation : 1;
@@ -412,7 +423,8 @@ static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
     const int n_tiles = (d->cin + ntw - 1) / ntw;
     const int Nmax = d->cin < ntw ? d->cin : ntw;
     const int nblk = (Nmax + 63) / 64;
-    int tpg_max = 512 / Nmax;
+    const bool cores = wgrad_coresident_enabled() && d->cout <= 64 && ntw == 64;
+    int tpg_max = (cores ? 256 : 512) / Nmax;
     if (tpg_max > p.taps) tpg_max = p.taps;
     for (int tg = (p.taps + tpg_max - 1) / tpg_max; tg <= p.taps; ++tg) {
       const int tpg = (p.taps + tg - 1) / tg;
@@ -459,6 +471,13 @@ static int wgrad_plan(const b200seg_conv_desc* d, WgradParams& p) {
   p.unit_stride = (long long)p.taps_per_group * 128 * Nmax;
   p.a_slot_bytes = 2 * kABlock;
   p.b_slot_bytes = p.nblocksB_max * p.b_block_bytes;
+  p.tmem_cols = 512;
+  if (wgrad_coresident_enabled() && d->cout <= 64 && p.ntile_w == 64 && p.taps_per_group * Nmax <= 256) {
+    p.a_slot_bytes = kABlock;                    // Cout <= 64: the second dy block is never loaded
+    int cols = 32;
+    while (cols < p.taps_per_group * Nmax) cols *= 2;
+    p.tmem_cols = cols;
+  }
   return 0;
 }
 
@@ -482,12 +501,14 @@ extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, c
     if (reinterpret_cast<uintptr_t>(workspace) & 15) return B200SEG_E_BADARG;
   }
   const size_t fixed = 1024 + 2 * (size_t)p.a_slot_bytes + (4 + 2 * kMaxBSlots + 2) * 8 + 16;
-  int bs = (int)((227 * 1024 - smem_reserve() - fixed) / p.b_slot_bytes);
+  const bool cores = p.tmem_cols <= 256;
+  const size_t budget = cores ? kWgradHalfSm - (size_t)smem_reserve() / 2 : (size_t)227 * 1024 - smem_reserve();
+  int bs = (int)((budget - fixed) / p.b_slot_bytes);
   if (bs > kMaxBSlots) bs = kMaxBSlots;
   if (bs < 2) return B200SEG_E_BADARG;
   p.b_slots = bs;
   size_t smem_bytes = fixed + (size_t)bs * p.b_slot_bytes;
-  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
+  if (!cores && smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;      // one CTA per SM
 
   CUtensorMap tmDy, tmX;
   {
@@ -509,6 +530,8 @@ extern "C" int b200seg_conv2d_wgrad(const b200seg_conv_desc* d, const void* x, c
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
