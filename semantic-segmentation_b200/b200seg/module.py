@@ -20,7 +20,7 @@ from torch import nn
 from . import arch as A
 from . import model as M
 from . import raw
-from .engine import BN_MOMENTUM, Engine
+from .engine import BN_EPS, BN_MOMENTUM, Engine
 
 F32 = torch.float32
 

@@ -379,12 +379,14 @@ publish_grads_kernel(float* __restrict__ dst, const float* __restrict__ src, lon
 
 using namespace b200seg;
 
-// B200SEG_WGRAD_CORES=1 (experiment): narrow layers (Cout <= 64, one 64-channel block of x per N tile) run in a
-// configuration that can share an SM with a co-resident convolution CTA or another weight-gradient CTA: at most 256 TMEM
-// columns (more, smaller tap groups), one 16 KB dy block per stage and a shared-memory footprint below half an SM.
-// Default off: a full-SM weight-gradient CTA excludes every other tensor-core CTA from its SM and vice versa.
+// Narrow layers (Cout <= 64, one 64-channel block of x per N tile: the 48 / 64-channel high-resolution branch and the
+// stem) run in a configuration that can share an SM with a co-resident convolution CTA or another weight-gradient CTA:
+// at most 256 TMEM columns (more, smaller tap groups), one 16 KB dy block per stage and a shared-memory footprint below
+// half an SM. A full-SM weight-gradient CTA (512 columns, > 200 KB) excludes every other tensor-core CTA from its SM
+// and vice versa; measured on the two-scale step: 38.37 vs 38.93 ms (profiles/r2_ab_switches.txt).
+// B200SEG_WGRAD_CORES=0 restores the full-SM configuration everywhere.
 static bool wgrad_coresident_enabled() {
-  static const bool on = []() { const char* e = getenv("B200SEG_WGRAD_CORES"); return e && e[0] == '1'; }();
+  static const bool on = []() { const char* e = getenv("B200SEG_WGRAD_CORES"); return !(e && e[0] == '0'); }();
   return on;
 }
 constexpr size_t kWgradHalfSm = 115712;   // (228 KB - 2 x 1 KB reserved) / 2
