@@ -377,6 +377,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, float* __restrict
       store8(z + pix[u] * z_ld + c0[u], v);
     }
   }
+  pdl_launch_late();
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -447,6 +448,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dst[j] = s1[j]; dst[8 + j] = s2[j]; }
   }
+  pdl_launch_late();
   __syncthreads();
   // deterministic in-block reduction over rows
   for (int i = threadIdx.x; i < groups * 16; i += blockDim.x) {
@@ -608,6 +610,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld, const __nv_
       }
     }
   }
+  pdl_launch_late();
 }
 
 // dst = (accumulate ? dst : 0) + src * (mask > 0)    (ReLU backward into a fan-out gradient)
@@ -637,6 +640,7 @@ masked_accum_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, const __n
     }
     store8(dst + pix * dst_ld + c0, g);
   }
+  pdl_launch_late();
 }
 
 // Grid of the element-wise passes: one 256-thread block per 256 x ew_items 16-byte items (the kernels keep several

@@ -240,6 +240,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++a_slot == p.a_slots) { a_slot = 0; a_phase ^= 1; }
         }
       }
+      pdl_launch_late();    // every MMA of this CTA is issued: only the last epilogue and the statistics remain
     }
     __syncwarp();
   } else if (warp >= 4) {

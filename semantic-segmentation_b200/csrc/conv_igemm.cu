@@ -161,6 +161,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (++stage == p.nstages) { stage = 0; phase ^= 1; }
         }
       }
+      pdl_launch_late();    // every MMA of this CTA is issued: only the last epilogue and the statistics remain
     }
     __syncwarp();
   } else if (warp >= 4) {

@@ -71,7 +71,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 // Because *every* kernel executes pdl_wait before it completes, completion is transitive along the stream.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// B200SEG_PDL_LATE (build variant, A/B in profiles/r2_ab_switches.txt): a dependent grid that becomes resident at the START
+// of its predecessor holds registers, shared memory and TMEM on the SMs for the predecessor's whole duration while it
+// sits in griddepcontrol.wait - on a step bound by what fits on the SMs that residency is paid by the other streams. The
+// late variant triggers the dependent when a CTA has finished its main loop (pdl_launch_late), so only the successor's
+// prologue overlaps the predecessor's tail; kernels without an explicit late trigger fall back to the implicit one at exit.
+#ifdef B200SEG_PDL_LATE
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); }
+__device__ __forceinline__ void pdl_launch_late() { pdl_launch(); }
+#else
 __device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_launch(); }
+__device__ __forceinline__ void pdl_launch_late() {}
+#endif
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -194,6 +194,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
         }
         umma_commit(acc_full);
       }
+      pdl_launch_late();
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -290,6 +291,7 @@ wgrad_reduce_kernel(const WgradParams p, const float* __restrict__ ws, float* __
     acc = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
   }
   sh[slice][lane] = acc;
+  pdl_launch_late();
   __syncthreads();
   if (slice == 0 && live) {
     float4 t = sh[0][lane];
