@@ -452,6 +452,38 @@ int b200seg_accum_pred(const float* pred, float* out, int32_t n, int32_t c, int3
 int b200seg_argmax_hist(const float* pred_nchw, int32_t n, int32_t c, int64_t hw, float scale, const int64_t* labels,
                         int64_t* pred_out, float* maxprob_out, int64_t* hist, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training input pipeline on the device: the reference's per-sample transform chain
+ * (datasets/__init__.py:72-108) on the decoded uint8 frame, bit-exact with Pillow. Host side: b200seg/augment.py.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200seg_aug_geom {
+  int32_t src_h, src_w;        /* decoded frame: rgb uint8 [src_h][src_w][3], label ids uint8 [src_h][src_w] */
+  int32_t out_h, out_w;        /* crop size */
+  int32_t win_y0, win_x0;      /* first crop row / column (before the flip) that shows a pixel of the resized frame */
+  int32_t n_y, n_x;            /* rows / columns of that window = extents of the tables (0: the crop is all padding) */
+  int32_t ksize_v, ksize_h;    /* row pitch of kk_v / kk_h */
+  int32_t flip;                /* RandomHorizontallyFlip (transforms/joint_transforms.py:276-281) */
+  int32_t ignore_label;        /* label of the padding (RandomCrop, :171-176) */
+} b200seg_aug_geom;
+/* RandomSizeAndCrop + RandomCrop padding + flip. kk_* int32 [n][ksize] / bounds_* int32 [n][2]: Pillow's BICUBIC taps of the
+ * window's output positions (22-bit fixed point; first source index, tap count); near_* int32 [n]: NEAREST source index;
+ * id_lut uint8 [256] or NULL (datasets/base_loader.py:177-181). out_rgb uint8 [out_h][out_w][3], out_label int64. */
+int b200seg_aug_resize_crop(const b200seg_aug_geom* d, const uint8_t* src_rgb, const uint8_t* src_mask,
+                            const int32_t* kk_h, const int32_t* bounds_h, const int32_t* kk_v, const int32_t* bounds_v,
+                            const int32_t* near_x, const int32_t* near_y, const uint8_t* id_lut, uint8_t* out_rgb,
+                            int64_t* out_label, void* stream);
+typedef struct b200seg_aug_color {
+  int32_t n_ops;               /* 0..4 ColorJitter ops in their drawn order (transforms/transforms.py:326-348) */
+  int32_t kind[4];             /* 0 brightness, 1 contrast, 2 saturation, 3 hue */
+  float factor[4];             /* ImageEnhance factor of ops 0-2 */
+  int32_t hue_shift[4];        /* np.uint8(hue_factor * 255) of the hue op */
+  float mean[3], std[3];       /* Normalize (config.py:96-97) */
+} b200seg_aug_color;
+/* ColorJitter -> ToTensor -> Normalize: rgb uint8 [h][w][3] -> fp32 [3][h][w]. luma_sum_ws: 8 bytes of device memory
+ * (needed when a contrast op is present: ImageEnhance.Contrast blends with the mean grey level). */
+int b200seg_aug_color_normalize(const b200seg_aug_color* c, const uint8_t* rgb, int32_t h, int32_t w,
+                                uint64_t* luma_sum_ws, float* out_chw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

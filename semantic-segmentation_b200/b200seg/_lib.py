@@ -56,6 +56,16 @@ class BnFold(ctypes.Structure):
                 ("c", c_int32)]
 
 
+class AugGeom(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in ("src_h", "src_w", "out_h", "out_w", "win_y0", "win_x0", "n_y", "n_x", "ksize_v",
+                                       "ksize_h", "flip", "ignore_label")]
+
+
+class AugColor(ctypes.Structure):
+    _fields_ = [("n_ops", c_int32), ("kind", c_int32 * 4), ("factor", c_float * 4), ("hue_shift", c_int32 * 4),
+                ("mean", c_float * 3), ("std", c_float * 3)]
+
+
 class ProbeOperand(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "rows", "cols", "box_cols", "box_rows", "nboxes", "c0", "r0", "dcol", "drow", "smem_stride",
@@ -148,6 +158,8 @@ SIGNATURES = {
     "b200seg_spatial_sum": (ctypes.c_int, [V, I32, I32, I32, I32, F, V, V, I32, I32, V]),
     "b200seg_broadcast_pixels": (ctypes.c_int, [V, I32, I32, I32, I32, F, V, I32, I32, V]),
     "b200seg_accum_pred": (ctypes.c_int, [V, V, I32, I32, I32, I32, I32, I32, V]),
+    "b200seg_aug_resize_crop": (ctypes.c_int, [ctypes.POINTER(AugGeom), V, V, V, V, V, V, V, V, V, V, V, V]),
+    "b200seg_aug_color_normalize": (ctypes.c_int, [ctypes.POINTER(AugColor), V, I32, I32, V, V, V]),
     "b200seg_argmax_hist": (ctypes.c_int, [V, I32, I32, I64, F, V, V, V, V, V]),
 }
 # test-only entry points (csrc/probe.h, libb200seg_test.so), not part of include/b200seg.h / the product library

@@ -7,7 +7,7 @@ import ctypes
 
 import torch
 
-from ._lib import BnFold, ConvDesc, FuseDesc, MscaleDesc, check, lib, ptr, stream_ptr
+from ._lib import AugColor, AugGeom, BnFold, ConvDesc, FuseDesc, MscaleDesc, check, lib, ptr, stream_ptr
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -697,3 +697,46 @@ def broadcast_pixels(v, h, w, out=None, scale=1.0, accumulate=False):
     check(lib().b200seg_broadcast_pixels(ptr(v), v.stride(0), n, h * w, c, float(scale), ptr(out), _ld(out),
                                          int(accumulate), stream_ptr()), "broadcast_pixels")
     return out
+
+
+# ----------------------------------------------------------------------------------------------- input pipeline (f4)
+def augment(image_u8, mask_u8, p, t, id_lut, ignore_label, mean, std, out_image=None, out_label=None):
+    """b200seg.augment.DeviceTrainTransform: resize + crop + flip (uint8), colour jitter + ToTensor + Normalize.
+    p: AugParams, t: the window tables of DeviceTrainTransform.tables. Returns (fp32 [3,th,tw], int64 [th,tw])."""
+    import numpy as np
+    dev = image_u8.device
+    h, w = image_u8.shape[:2]
+    th, tw = t["th"], t["tw"]
+    g = AugGeom()
+    g.src_h, g.src_w, g.out_h, g.out_w = h, w, th, tw
+    g.win_y0, g.win_x0 = t["lo_y"] - (p.y1 - p.pad_y), t["lo_x"] - (p.x1 - p.pad_x)
+    g.n_y, g.n_x = t["n_y"], t["n_x"]
+    g.ksize_v, g.ksize_h = t["kv"].shape[1], t["kh"].shape[1]
+    g.flip, g.ignore_label = int(bool(p.flip)), int(ignore_label)
+    # one upload for all six tables
+    parts = [t["kh"].ravel(), t["bh"].ravel(), t["kv"].ravel(), t["bv"].ravel(), t["nx"].ravel(), t["ny"].ravel()]
+    flat = torch.from_numpy(np.concatenate(parts).astype(np.int32)).to(dev, non_blocking=True)
+    offs = np.cumsum([0] + [x.size for x in parts])
+    tab = [flat[offs[i]:offs[i + 1]] for i in range(6)]
+    rgb = _new((th, tw, 3), dtype=torch.uint8, device=dev)
+    if out_label is None:
+        out_label = _new((th, tw), dtype=torch.int64, device=dev)
+    check(lib().b200seg_aug_resize_crop(ctypes.byref(g), ptr(image_u8), ptr(mask_u8), ptr(tab[0]), ptr(tab[1]),
+                                        ptr(tab[2]), ptr(tab[3]), ptr(tab[4]), ptr(tab[5]), ptr(id_lut), ptr(rgb),
+                                        ptr(out_label), stream_ptr()), "aug_resize_crop")
+    c = AugColor()
+    c.n_ops = len(p.ops)
+    has_contrast = False
+    for i, (kind, factor) in enumerate(p.ops):
+        c.kind[i], c.factor[i] = kind, factor
+        if kind == 3:          # transforms.py:289-290: np_h += np.uint8(hue_factor * 255): C cast (truncate, wrap mod 256)
+            c.hue_shift[i] = int(factor * 255) & 0xFF
+        has_contrast |= kind == 1
+    for i in range(3):
+        c.mean[i], c.std[i] = mean[i], std[i]
+    ws = _new((1,), dtype=torch.int64, device=dev) if has_contrast else None
+    if out_image is None:
+        out_image = _new((3, th, tw), dtype=F32, device=dev)
+    check(lib().b200seg_aug_color_normalize(ctypes.byref(c), ptr(rgb), th, tw, ptr(ws), ptr(out_image), stream_ptr()),
+          "aug_color_normalize", launches=2 if has_contrast else 1)
+    return out_image, out_label, rgb

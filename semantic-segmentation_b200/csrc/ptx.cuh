@@ -65,18 +65,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // Every kernel of the library is launched with the programmatic-stream-serialization attribute (launch.h) and runs
-//   <prologue that touches no global data>; pdl_wait(); pdl_launch(); <main work>
+//   <prologue that touches no global data>; pdl_wait(); <main work>; pdl_launch_late(); <tail>
 // pdl_wait blocks until the preceding grid on the stream has completed and flushed its writes; pdl_launch lets the next
 // grid on the stream start its own prologue (barrier init, TMEM allocation, descriptor prefetch) under this grid's body.
 // Because *every* kernel executes pdl_wait before it completes, completion is transitive along the stream.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-// B200SEG_PDL_LATE (build variant, A/B in profiles/r2_ab_switches.txt): a dependent grid that becomes resident at the START
+// Late trigger (default; -DB200SEG_PDL_EARLY builds the variant that triggers at the start of every kernel; measured 37.95
+// vs 38.24 ms on the two-scale step, profiles/r2_ab_switches.txt): a dependent grid that becomes resident at the START
 // of its predecessor holds registers, shared memory and TMEM on the SMs for the predecessor's whole duration while it
 // sits in griddepcontrol.wait - on a step bound by what fits on the SMs that residency is paid by the other streams. The
-// late variant triggers the dependent when a CTA has finished its main loop (pdl_launch_late), so only the successor's
+// default therefore triggers the dependent when a CTA has finished its main loop (pdl_launch_late), so only the successor's
 // prologue overlaps the predecessor's tail; kernels without an explicit late trigger fall back to the implicit one at exit.
-#ifdef B200SEG_PDL_LATE
+#ifndef B200SEG_PDL_EARLY
 __device__ __forceinline__ void pdl_sync() { pdl_wait(); }
 __device__ __forceinline__ void pdl_launch_late() { pdl_launch(); }
 #else
