@@ -38,49 +38,56 @@ def _bicubic(x):
 
 def bicubic_tables(in_size, out_size, lo=0, hi=None):
     """Pillow's ImagingResample coefficient tables (BICUBIC, 8 bpc) of output positions [lo, hi): int32 kk[hi-lo, ksize]
-    (22-bit fixed point, rows zero padded) and int32 bounds[hi-lo, 2] = (first source index, tap count)."""
+    (22-bit fixed point, rows zero padded) and int32 bounds[hi-lo, 2] = (first source index, tap count).
+    Vectorised over the output positions; every double operation and the left-to-right order of the normalising sum are
+    those of precompute_coeffs / normalize_coeffs_8bpc (tests/test_augment_host.py compares with Image.resize)."""
     hi = out_size if hi is None else hi
     scale = filterscale = float(in_size) / out_size
     if filterscale < 1.0:
         filterscale = 1.0
     support = 2.0 * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
-    kk = np.zeros((hi - lo, ksize), dtype=np.int32)
-    bounds = np.zeros((hi - lo, 2), dtype=np.int32)
+    n = max(0, hi - lo)
+    kk = np.zeros((n, ksize), dtype=np.int32)
+    bounds = np.zeros((n, 2), dtype=np.int32)
+    if n == 0:
+        return kk, bounds
     ss = 1.0 / filterscale
-    for xx in range(lo, hi):
-        center = (xx + 0.5) * scale
-        xmin = int(center - support + 0.5)
-        if xmin < 0:
-            xmin = 0
-        xmax = int(center + support + 0.5)
-        if xmax > in_size:
-            xmax = in_size
-        xmax -= xmin
-        w = [_bicubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
-        ww = 0.0
-        for v in w:
-            ww += v
-        for x, v in enumerate(w):
-            if ww != 0.0:
-                v = v / ww
-            kk[xx - lo, x] = int(-0.5 + v * (1 << PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << PRECISION_BITS))
-        bounds[xx - lo] = (xmin, xmax)
+    center = (np.arange(lo, hi, dtype=np.float64) + 0.5) * scale
+    xmin = np.trunc(center - support + 0.5).astype(np.int64)          # (int) of a double: truncation
+    xmin = np.maximum(xmin, 0)
+    xmax = np.trunc(center + support + 0.5).astype(np.int64)
+    xmax = np.minimum(xmax, in_size) - xmin
+    a = -0.5
+    w = np.zeros((n, ksize), dtype=np.float64)
+    ww = np.zeros(n, dtype=np.float64)
+    for x in range(ksize):                                             # taps in order: ww accumulates left to right
+        live = x < xmax
+        t = np.abs((x + xmin - center + 0.5) * ss)
+        f = np.where(t < 1.0, ((a + 2.0) * t - (a + 3.0)) * t * t + 1, np.where(t < 2.0, (((t - 5) * t + 8) * t - 4) * a, 0.0))
+        f = np.where(live, f, 0.0)
+        w[:, x] = f
+        ww = np.where(live, ww + f, ww)
+    nz = ww != 0.0
+    w = np.where(nz[:, None], w / np.where(nz, ww, 1.0)[:, None], w)
+    fixed = np.where(w < 0, np.trunc(-0.5 + w * (1 << PRECISION_BITS)), np.trunc(0.5 + w * (1 << PRECISION_BITS)))
+    kk[:] = np.where(np.arange(ksize)[None, :] < xmax[:, None], fixed, 0).astype(np.int32)
+    bounds[:, 0], bounds[:, 1] = xmin, xmax
     return kk, bounds
 
 
 def nearest_table(in_size, out_size, lo=0, hi=None):
     """Source index of every NEAREST output position in [lo, hi): Pillow's affine scaler accumulates xo += in/out in
-    double starting at in/out * 0.5 (the accumulated value, not (x + 0.5) * scale, decides ties)."""
+    double starting at in/out * 0.5 (the accumulated value, not (x + 0.5) * scale, decides ties); numpy's cumsum adds
+    left to right in double, i.e. the same sequence of roundings."""
     hi = out_size if hi is None else hi
+    if hi <= lo:
+        return np.zeros(0, dtype=np.int32)
     a0 = float(in_size) / out_size
-    xo = a0 * 0.5
-    tab = np.zeros(hi - lo, dtype=np.int32)
-    for x in range(hi):
-        if x >= lo:
-            tab[x - lo] = min(max(int(math.floor(xo)), 0), in_size - 1)
-        xo += a0
-    return tab
+    steps = np.full(hi, a0, dtype=np.float64)
+    steps[0] = a0 * 0.5
+    xo = np.cumsum(steps)
+    return np.clip(np.floor(xo[lo:hi]), 0, in_size - 1).astype(np.int32)
 
 
 # ----------------------------------------------------------------------------------------------- parameters
@@ -186,3 +193,28 @@ class DeviceTrainTransform:
         img, lab, self.last_rgb_u8 = raw.augment(image_u8.contiguous(), mask_u8.contiguous(), p, t, self._lut,
                                                  self.ignore_label, self.mean, self.std, out_image, out_label)
         return img, lab
+
+
+class DeviceAugmentedBatches:
+    """Wraps an iterable of decoded batches - (images uint8 [N, H, W, 3], label ids uint8 [N, H, W]) host (pinned) or CUDA
+    tensors, optionally a third item with one centroid (x, y) or None per sample (class-uniform sampling,
+    datasets/uniform.py) - and yields {'images': fp32 [N, 3, th, tw], 'gts': int64 [N, th, tw]} on the device, the dict
+    the reference's training loop feeds the network (train.py:485-488). The random decisions of sample i are drawn on
+    the host in loader order, like the reference's dataset workers draw them per sample."""
+
+    def __init__(self, batches, transform, device="cuda"):
+        self.batches, self.t, self.device = batches, transform, torch.device(device)
+
+    def __iter__(self):
+        for batch in self.batches:
+            imgs, masks = batch[0], batch[1]
+            cents = batch[2] if len(batch) > 2 else [None] * imgs.shape[0]
+            imgs = imgs.to(self.device, non_blocking=True)
+            masks = masks.to(self.device, non_blocking=True)
+            n, h, w = masks.shape
+            th, tw = (h, w) if self.t.full_size else self.t.crop_hw
+            out_i = torch.empty((n, 3, th, tw), dtype=torch.float32, device=self.device)
+            out_l = torch.empty((n, th, tw), dtype=torch.int64, device=self.device)
+            for i in range(n):
+                self.t(imgs[i], masks[i], centroid=cents[i], out_image=out_i[i], out_label=out_l[i])
+            yield {"images": out_i, "gts": out_l}

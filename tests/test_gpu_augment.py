@@ -74,3 +74,24 @@ def test_full_size_crop_with_label_lookup():
     """BASELINE shape: a 1024x2048 crop of a 1024x2048 Cityscapes-size frame, label ids -> train ids on the device."""
     for seed in (3, 4):
         _run(1024, 2048, (1024, 2048), 0.5, 2.0, 0.25, seed, lut=CITYSCAPES_IDS)
+
+
+def test_batch_wrapper_draws_in_loader_order():
+    """DeviceAugmentedBatches: sample i of a batch gets the i-th draw; the batch dict is what train.py feeds the network."""
+    from b200seg import augment as AUG
+    from oracle import augment_oracle as AO
+    frames = [AO.synth_frame(96, 160, s) for s in (41, 42, 43)]
+    imgs = torch.from_numpy(np.stack([f[0] for f in frames])).pin_memory()
+    masks = torch.from_numpy(np.stack([f[1] for f in frames])).pin_memory()
+    t = AUG.DeviceTrainTransform((64, 96))
+    random.seed(7)
+    np.random.seed(7)
+    batch = next(iter(AUG.DeviceAugmentedBatches([(imgs, masks)], t)))
+    torch.cuda.synchronize()
+    assert tuple(batch["images"].shape) == (3, 3, 64, 96) and batch["gts"].dtype == torch.int64
+    random.seed(7)
+    np.random.seed(7)
+    for i, (img_u8, mask_u8) in enumerate(frames):
+        p = t.draw(160, 96)
+        ref_img, ref_lab, _ = AO.reference_chain(img_u8, mask_u8, p, (64, 96), 255, t.mean, t.std)
+        assert torch.equal(batch["images"][i].cpu(), ref_img) and torch.equal(batch["gts"][i].cpu(), ref_lab), i
