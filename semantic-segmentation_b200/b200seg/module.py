@@ -376,10 +376,28 @@ class B200SegModule(nn.Module):
         from . import _lib
         launches0 = _lib.KERNEL_LAUNCHES
         try:
-            return self._step_body(images, gts, drop_mask)
+            if not self._prio():
+                return self._step_body(images, gts, drop_mask)
+            # B200SEG_PRIO=1 (experiment): the scale passes and their branch streams run on high-priority streams, the
+            # weight-gradient / repack side streams (which feed nothing downstream inside the step) stay at the default
+            # priority; kernel-node priorities are captured into the graph
+            if getattr(self, "_prio_stream", None) is None:
+                self._prio_stream = torch.cuda.Stream(priority=-1)
+            cur = torch.cuda.current_stream()
+            self._prio_stream.wait_stream(cur)
+            with torch.cuda.stream(self._prio_stream):
+                loss = self._step_body(images, gts, drop_mask)
+            cur.wait_stream(self._prio_stream)
+            loss.record_stream(cur)
+            return loss
         finally:
             raw.KEEP = None
             self.kernels_per_step = _lib.KERNEL_LAUNCHES - launches0   # same count when the captured graph replays
+
+    @staticmethod
+    def _prio():
+        import os
+        return os.environ.get("B200SEG_PRIO", "0") == "1"
 
     def _sync_context(self):
         """Lazily builds the SyncBN mailboxes (collective: every rank must reach its first training step)."""
@@ -421,14 +439,16 @@ class B200SegModule(nn.Module):
         raw.KEEP = [] if wide else None
         if getattr(self, "_bstreams", None) is None:
             use_b = self.parallel_branches and wide
-            mk = lambda: [torch.cuda.Stream() for _ in range(3)] if use_b else []
+            pr = -1 if self._prio() else 0
+            mk = lambda: [torch.cuda.Stream(priority=pr) for _ in range(3)] if use_b else []
             self._bstreams = {"hi": mk(), "lo": mk()}
             self._ws_holders = {"hi": [None] if wide else None, "lo": [None] if wide else None}
         grads = self._engine_grads("hi")
         E_lo = None
         if par:
             if getattr(self, "_lo_stream", None) is None:
-                self._lo_stream, self._side_stream_lo = torch.cuda.Stream(), torch.cuda.Stream()
+                self._lo_stream = torch.cuda.Stream(priority=-1 if self._prio() else 0)
+                self._side_stream_lo = torch.cuda.Stream()
             grads_lo = self._engine_grads("lo")
             E_lo = Engine(tensors, grads_lo, self._packed, True, drop_mask, side_stream=self._side_stream_lo,
                           bstat=self._bstat_views[0], stream=self._lo_stream, sync=sync, pass_id=0,
