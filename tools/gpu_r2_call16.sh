@@ -6,7 +6,7 @@ set -u
 mkdir -p gpurun_out
 O=gpurun_out
 B="python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-torch-gpu-baseline --no-recipe"
-for cfg in "B200SEG_PRIO=0" "B200SEG_PRIO=1" "B200SEG_PRIO=0" "B200SEG_PRIO=1"; do
+for cfg in "B200SEG_PRIO=0" "B200SEG_PRIO=1" "B200SEG_PRIO=1"; do
   echo "== $cfg"
   env B200SEG_TIME_ONLY=1 $cfg timeout 200 $B 2>&1 | grep -h '^{\|Error\|error' | cut -c1-300
 done | tee $O/c16_prio_ab.log
@@ -21,13 +21,8 @@ tail -n 3 $O/c16_augment.log
 timeout 120 python tools/gpu_augment_bench.py 2>&1 | grep -h '^{' | cut -c1-500 | tee $O/c16_augment_bench.log
 timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/c16_smoke.log 2>&1
 tail -n 2 $O/c16_smoke.log
-timeout 300 python tools/gpu_stream_report.py > $O/c16_streams.log 2>&1
-grep -A8 "^class " $O/c16_streams.log | head -12
-B200SEG_PROFILE=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
+B200SEG_PROFILE=1 timeout 330 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
   --log-file $O/c16_launches.csv python bench.py --no-graph --no-cpu-baseline --no-torch-gpu-baseline --no-recipe > $O/c16_ncu_list.log 2>&1
 echo "launch list rc=$?" >> $O/c16_ncu_list.log
 gzip -f $O/c16_launches.csv
-timeout 400 ncu --set full --clock-control none --import-source on -f -o $O/r2_kernels_final \
-  -k regex:"conv3x3_halo|wgrad_|bn_bwd_|bn_apply|aug_" python tools/gpu_ncu_kernels.py > $O/c16_ncu_full.log 2>&1
-echo "ncu full rc=$?" >> $O/c16_ncu_full.log
-ls -la $O/r2_kernels_final.ncu-rep $O/c16_launches.csv.gz
+ls -la $O/c16_launches.csv.gz
