@@ -32,7 +32,9 @@ FWD_TFLOP_1X = 3.0546
 # Launch-level roofline of one train step per 1024x2048 crop: sum over the step's launches of max(FLOPs / sustained bf16
 # peak, bytes / HBM copy bandwidth), from the static trace of the real step program (tools/trace_step.py,
 # profiles/r1_step_roofline_model.txt; peaks of MEASURED_PEAKS.json: 1386.7 TFLOP/s, 6572.9 GB/s)
-# SyncBN at --gpus N > 1 unless --no-syncbn (every reference script trains with syncbn: true)
+# BatchNorm at --gpus N > 1: per-GPU statistics unless --syncbn. Every reference script trains with syncbn: true and the
+# NVLink exchange is validated and measured at N = 2 (tests/test_gpu_multi.py) - but never at N = 4 / 8 (the
+# round's GPU budget), so the driver's 1 -> 8 scaling runs use the configuration that is known to complete.
 SYNCBN_DEFAULT = False
 STEP_ROOFLINE_MS = {"ocrnet.HRNet_Mscale": 15.12, "ocrnet.HRNet": 11.34, "deepv3.DeepV3PlusW38": 30.8}
 # the same model per kernel class (profiles/r2_step_roofline_model.txt): class -> (kernel-name fragments, roofline ms)
@@ -113,8 +115,8 @@ def parse():
     ap.add_argument("--criterion", default="ce", choices=["ce", "rmi"])
     ap.add_argument("--syncbn", dest="syncbn", action="store_true", default=None,
                     help="synchronise BatchNorm statistics across the GPUs through NVLink peer memory (syncbn: true in every "
-                         "reference script); the default for --gpus N > 1")
-    ap.add_argument("--no-syncbn", dest="syncbn", action="store_false", help="per-GPU BatchNorm statistics at N > 1")
+                         "reference script); validated at N = 2")
+    ap.add_argument("--no-syncbn", dest="syncbn", action="store_false", help="per-GPU BatchNorm statistics at N > 1 (default)")
     ap.add_argument("--torch-sgd", action="store_true", help="torch.optim.SGD instead of b200seg.optim.FusedSGD")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -440,8 +442,12 @@ def run_b200(args):
     t_e0.record()
     prev = None
     loss_val = float("nan")
+    dbg = os.environ.get("B200SEG_E2E_DEBUG") == "1"
+    marks = [time.perf_counter()]
     for i, batch in enumerate(DevicePrefetcher(host_batches(args.steps))):   # H2D of step i+1 on a copy stream under step i
         loss = step(batch["images"], batch["gts"])
+        if dbg:
+            marks.append(time.perf_counter())
         slot = i % 2
         pin[slot].copy_(loss.detach().reshape(1), non_blocking=True)
         evts[slot].record()
@@ -454,6 +460,8 @@ def run_b200(args):
     t_e1.record()
     barrier()
     ms_e2e = t_e0.elapsed_time(t_e1)
+    if dbg and rank == 0:
+        print("e2e-debug host ms between iterations:", [round((b - a) * 1e3, 1) for a, b in zip(marks, marks[1:])])
     b_e0, b_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     b_e0.record()
