@@ -39,6 +39,22 @@ def test_draws_and_oracle_chain_reproduce_the_reference():
     assert seen_pad >= 1 and seen_flip >= 1 and seen_ops >= 4     # the cases exercise padding, flips and the jitter
 
 
+def test_centroid_pre_size_and_full_size_draws_reproduce_the_reference():
+    """The other arguments of RandomSizeAndCrop: class-uniform centroids (crop_in_image with a centroid,
+    joint_transforms.py:104-116), --pre_size (:448-456), --full_crop_training (:458-459)."""
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "reference_augment.pt"), weights_only=False)
+    for i, (h, w, crop, smin, smax, caug, seed, centroid, pre_size, full_size) in enumerate(gold["cases2"]):
+        img_u8, mask_u8 = AO.synth_frame(h, w, seed)
+        random.seed(seed)
+        np.random.seed(seed)
+        p = AUG.draw_params(w, h, tuple(crop), smin, smax, caug, centroid=centroid, pre_size=pre_size, full_size=full_size)
+        image, label, _ = AO.reference_chain(img_u8, mask_u8, p, tuple(crop), 255, gold["mean"], gold["std"],
+                                             full_size=full_size)
+        sha = (hashlib.sha256(image.numpy().tobytes()).hexdigest(), hashlib.sha256(label.numpy().tobytes()).hexdigest())
+        assert tuple(image.shape) == tuple(gold["sha256_2"][i][2]), (i, p)
+        assert sha == tuple(gold["sha256_2"][i][:2]), (i, p)
+
+
 def _apply_bicubic(a, kk, bounds, axis):
     """Pillow's pass along `axis` with the product's tables (integer arithmetic, test only)."""
     a = np.moveaxis(a.astype(np.int64), axis, 0)
