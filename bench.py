@@ -470,7 +470,7 @@ def run_b200(args):
     # (a) pipelined read: the loss of step i is copied to pinned memory asynchronously and read on the host while step
     #     i+1 is already running (what a training loop that logs asynchronously does);
     # (b) blocking read: loss.item() right after every step (the reference's train.py:499-512 pattern) - this also
-    #     exposes the launch latency of the ~6 000-node graph on an idle GPU every step.
+    #     exposes the launch latency of the ~4 900-node graph on an idle GPU every step.
     from b200seg.prefetch import DevicePrefetcher
 
     def host_batches(n):
