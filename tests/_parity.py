@@ -3,7 +3,7 @@ GPU through stock PyTorch fp32, TF32 off, bf16-storage emulation) on identical w
 matched-precision agreement figures (loss, per-tensor gradient cosine / relative L2, running statistics, eval maps).
 
 Test infrastructure only (imports oracle/); used by tests/test_gpu_model.py, tests/test_gpu_zz_fullsize.py and
-tools/gpu_parity_report.py."""
+tests/diag/gpu_parity_report.py."""
 import torch
 
 

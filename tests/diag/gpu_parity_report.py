@@ -10,7 +10,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "semantic-segmentation_b200"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)

@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 timeout 300 python tools/gpu_occupancy.py > $O/c1_occupancy.log 2>&1
 timeout 900 python -m pytest tests -m gpu -q > $O/c1_tests.log 2>&1
 echo "tests rc=$?" >> $O/c1_tests.log
-timeout 600 python tools/gpu_parity_report.py $O/c1_parity.json > $O/c1_parity.log 2>&1
+timeout 600 python tests/diag/gpu_parity_report.py $O/c1_parity.json > $O/c1_parity.log 2>&1
 timeout 600 python bench.py --steps 20 > $O/c1_bench_on.log 2>&1
 B200SEG_CORESIDENT=0 timeout 300 python bench.py --steps 20 --no-cpu-baseline --no-torch-gpu-baseline > $O/c1_bench_off.log 2>&1
 B200SEG_PROFILE=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv \

@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 300 python tools/gpu_deepv3_diag.py > $O/c10_deepv3_diag.log 2>&1
+timeout 300 python tests/diag/gpu_deepv3_diag.py > $O/c10_deepv3_diag.log 2>&1
 echo "diag rc=$?" >> $O/c10_deepv3_diag.log
 B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-torch-gpu-baseline --no-recipe"
 export B200SEG_TIME_ONLY=1

@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 400 python tools/gpu_deepv3_diag.py > $O/c11_deepv3_diag.log 2>&1
+timeout 400 python tests/diag/gpu_deepv3_diag.py > $O/c11_deepv3_diag.log 2>&1
 echo "diag rc=$?" >> $O/c11_deepv3_diag.log
 grep '^\[' $O/c11_deepv3_diag.log | cut -c1-400
 timeout 700 python tools/gpu_tune_sweep.py --budget-s 400 > $O/c11_sweep.log 2>&1

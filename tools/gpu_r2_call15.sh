@@ -6,4 +6,4 @@ O=gpurun_out
 timeout 600 python -m pytest tests/test_gpu_augment.py -m gpu -q -p no:cacheprovider --tb=short > $O/c15_augment.log 2>&1
 echo "augment rc=$?" >> $O/c15_augment.log
 tail -n 30 $O/c15_augment.log | cut -c1-400
-timeout 300 python tools/gpu_augment_bench.py 2>&1 | grep -h '^{\|Error\|error' | cut -c1-600 | tee $O/c15_augment_bench.log
+timeout 300 python tests/diag/gpu_augment_bench.py 2>&1 | grep -h '^{\|Error\|error' | cut -c1-600 | tee $O/c15_augment_bench.log

@@ -18,7 +18,7 @@ grep -h '^{' $O/c16_bench_ref.log | cut -c1-400
 timeout 300 python -m pytest tests/test_gpu_augment.py -m gpu -q -p no:cacheprovider > $O/c16_augment.log 2>&1
 echo "augment rc=$?" >> $O/c16_augment.log
 tail -n 3 $O/c16_augment.log
-timeout 120 python tools/gpu_augment_bench.py 2>&1 | grep -h '^{' | cut -c1-500 | tee $O/c16_augment_bench.log
+timeout 120 python tests/diag/gpu_augment_bench.py 2>&1 | grep -h '^{' | cut -c1-500 | tee $O/c16_augment_bench.log
 timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/c16_smoke.log 2>&1
 tail -n 2 $O/c16_smoke.log
 B200SEG_PROFILE=1 timeout 330 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
