@@ -562,10 +562,14 @@ def run_b200(args):
                  api="b200seg.prefetch.DevicePrefetcher(pinned host batches) -> net({'images','gts'}) -> loss.backward() -> "
                      "optimizer.step(); every step's inputs are copied host->device (copy stream, double buffer, "
                      "overlapping the previous step), the loss of every step is copied to pinned host memory and read while "
-                     "the next step runs",
+                     "the next step runs. Steady state of the pipeline after 2 untimed iterations through this path: the copy "
+                     "of step i's inputs is issued while step i-1 runs, so the first timed step's inputs crossed PCIe just "
+                     "before the region and the region contains steps-2 of the steps copies; blocking_read is the strict "
+                     "variant (copy, step, loss.item() inside every timed iteration)",
                  blocking_read=dict(value=crops / (ms_e2e_block * 1e-3), ms_per_step=ms_e2e_block / args.steps,
-                                    note="loss.item() immediately after every step (exposes the graph-launch latency "
-                                         "on an idle GPU each step)")),
+                                    note="H2D copy of the step's inputs on the compute stream, the step, loss.item() - all "
+                                         "inside every timed iteration (exposes the graph-launch latency on an idle GPU "
+                                         "each step)")),
         gpu_launches=int(kernels_per_step * args.steps * 3),
         gpu_launches_note="%d b200seg kernels per step (inside one CUDA graph replay), three timed loops" % kernels_per_step,
         model_flops_utilisation=dict(achieved_tflops=step_tflops / 1.0, peak=pk["tf_sust"],
